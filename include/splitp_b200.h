@@ -1,0 +1,174 @@
+/* splitp_b200 -- C ABI of the B200 (sm_100a) engine for the SplitP hot path.
+ *
+ * The reference (js51/SplitP v0.3.2) is pure Python and has no FFI layer: its boundary is the set of
+ * callables re-exported at splitp/__init__.py:15-18.  The entry points below are what a ctypes
+ * binding inside those callables would call; each one names the reference
+ * function it replaces.  All pointers are DEVICE pointers unless the name says `h_`; the caller owns
+ * every buffer; the library keeps no state besides a thread-local error string.  Every call is
+ * asynchronous on `stream` (a cudaStream_t passed as void*) unless documented as synchronising.
+ * Return value: 0 = ok, otherwise an spb_status; spb_last_error() describes the failure.
+ *
+ * Encodings (fixed by splitp/constants.py:7-8): A=0 C=1 G=2 T=3.
+ *   key      : base-4 number of a site pattern, taxon 0 most significant (same significance as
+ *              `__index_of`, splitp/constructions.py:166-171).  n <= 31 taxa -> uint64.
+ *   sm       : "site-major" packed alignment, a little-endian bit stream of 2n-bit keys, site s at
+ *              bits [2n*s, 2n*s+2n).  N*n/4 bytes.  Allocate spb_sm_words(n, N) uint32.
+ *   planes   : "taxon-major" bit planes, uint32 [n][2][Wp]; plane 0 = low code bit, plane 1 = high
+ *              code bit, site s = bit (s%32) of word s/32.  N*n/4 bytes.  Wp = spb_plane_words(N).
+ *   valid    : uint32 [Wp] bit mask, 1 = every taxon has A/C/G/T at that site
+ *              (splitp/parsers/fasta.py:55-57).
+ *   split    : spb_split -- ordered taxon positions of both sides; order = digit significance.
+ */
+#ifndef SPLITP_B200_H
+#define SPLITP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SPB_OK = 0,
+  SPB_ERR_ARG = 1,      /* maps to ValueError */
+  SPB_ERR_CUDA = 2,     /* maps to RuntimeError */
+  SPB_ERR_CAPACITY = 3, /* a caller-provided buffer is too small; maps to MemoryError */
+  SPB_ERR_UNSUPPORTED = 4 /* maps to NotImplementedError */
+} spb_status;
+
+#define SPB_MAX_TAXA 64
+#define SPB_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+typedef struct {
+  int32_t n;            /* taxa in the pattern */
+  int32_t a, b;         /* side sizes */
+  uint8_t idx_a[SPB_MAX_TAXA]; /* positions (0..n-1) of side A, most significant digit first */
+  uint8_t idx_b[SPB_MAX_TAXA];
+} spb_split;
+
+int spb_version(void);
+const char* spb_last_error(void);
+/* number of SMs / compute capability of the current device; -1 when there is no device */
+int spb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+int64_t spb_sm_words(int n_taxa, int64_t n_sites);
+int64_t spb_plane_words(int64_t n_sites);
+
+/* ---- f1: FASTA text -> packed alignment (parsers/fasta.py:20-35 reads, :48-57 validity rule) ---- */
+/* d_chars: uint8 [n][row_stride]; is_ascii=1: bytes are characters (ACGTacgt valid), 0: bytes are
+ * codes 0..3 (anything else invalid).  Any of d_sm / d_planes may be NULL.  d_sm needs n <= 32. */
+int spb_pack(const uint8_t* d_chars, int n_taxa, int64_t n_sites, int64_t row_stride, int is_ascii,
+             uint32_t* d_sm, uint32_t* d_planes, uint32_t* d_valid, void* stream);
+
+/* ---- a1: get_pattern_counts (parsers/fasta.py:48-63) ---- */
+/* Direct-indexed table, n <= 14: d_table uint32 [4^n] must be zeroed by the caller (or hold partial
+ * counts to accumulate into, e.g. another site range).  d_first (optional, uint32 [4^n], filled with
+ * 0xFFFFFFFF) receives the first site index of each pattern (dict insertion order).
+ * d_usable (uint64, optional) accumulates the number of valid sites in [site_begin, site_end). */
+int spb_count_direct(const uint32_t* d_sm, const uint32_t* d_valid, int n_taxa, int64_t site_begin,
+                     int64_t site_end, uint32_t* d_table, uint32_t* d_first, uint64_t* d_usable,
+                     void* stream);
+/* Non-zero cells of a direct table -> (keys ascending = lexicographic A<C<G<T order of
+ * simulation.py:50-54, counts, first).  d_tmp: uint32 [spb_compact_tmp_words(cells)].
+ * Writes P to d_num (uint64).  capacity = length of the output arrays. */
+int64_t spb_compact_tmp_words(int64_t cells);
+int spb_compact_direct(const uint32_t* d_table, const uint32_t* d_first, int64_t cells, uint64_t* d_keys,
+                       uint32_t* d_counts, uint32_t* d_first_out, int64_t capacity, uint64_t* d_num,
+                       uint32_t* d_tmp, void* stream);
+/* Open-addressing hash table for 15 <= n <= 31 (works for any n <= 31): d_hkeys uint64 [cap] filled
+ * with 0xFF bytes, d_hcounts uint32 [cap] zeroed, d_hfirst optional (0xFF filled).  cap = power of 2.
+ * d_overflow (uint32) is set non-zero if the table filled up (SPB_ERR_CAPACITY must then be raised
+ * by the caller after reading it). */
+int spb_count_hash(const uint32_t* d_sm, const uint32_t* d_valid, int n_taxa, int64_t site_begin,
+                   int64_t site_end, uint64_t* d_hkeys, uint32_t* d_hcounts, uint32_t* d_hfirst,
+                   int64_t cap, uint64_t* d_usable, uint32_t* d_overflow, void* stream);
+int spb_compact_hash(const uint64_t* d_hkeys, const uint32_t* d_hcounts, const uint32_t* d_hfirst,
+                     int64_t cap, uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first_out,
+                     int64_t capacity, uint64_t* d_num, uint32_t* d_tmp, void* stream);
+/* Merge a (keys, counts) list into a hash table (multi-GPU merge of hashed tables). */
+int spb_hash_merge(const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_first, int64_t num,
+                   uint64_t* d_hkeys, uint32_t* d_hcounts, uint32_t* d_hfirst, int64_t cap,
+                   uint32_t* d_overflow, void* stream);
+
+/* ---- a7-a10: flattening (constructions.py:7-102) ---- */
+/* value kinds for the pattern table handed to the flattening kernels */
+#define SPB_VAL_U32 0 /* counts; written value = count / divisor (one IEEE division, fasta.py:66-70), divisor<=0 -> count */
+#define SPB_VAL_F64 1 /* values copied verbatim (dict inputs) */
+/* rows/cols of every pattern (int64) -- the COO triplets behind FlatFormat.sparse (:86-102) */
+int spb_flatten_coo(const uint64_t* d_keys, int64_t num, const spb_split* split, int64_t* d_rows,
+                    int64_t* d_cols, void* stream);
+/* FlatFormat.dense := sparse.todense(): d_out double [4^a][4^b], zero-filled by this call. */
+int spb_flatten_dense(const uint64_t* d_keys, const void* d_vals, int val_kind, double divisor, int64_t num,
+                      const spb_split* split, double* d_out, void* stream);
+/* FlatFormat.reduced (:31-55) in two steps.  plan: marks used rows/cols and ranks them
+ * (sorted-unique), returns the reduced shape in h_shape[2] (SYNCHRONISES).  d_rank_r uint32 [4^a + 1],
+ * d_rank_c uint32 [4^b + 1], d_tmp uint32 [spb_compact_tmp_words(max(4^a,4^b))].  Sides are limited to
+ * 13 taxa each.  fill: d_out double [R][C] zero-filled by the call. */
+int spb_flatten_reduced_plan(const uint64_t* d_keys, int64_t num, const spb_split* split, uint32_t* d_rank_r,
+                             uint32_t* d_rank_c, uint32_t* d_tmp, int64_t* h_shape, void* stream);
+int spb_flatten_reduced_fill(const uint64_t* d_keys, const void* d_vals, int val_kind, double divisor,
+                             int64_t num, const spb_split* split, const uint32_t* d_rank_r,
+                             const uint32_t* d_rank_c, int64_t R, int64_t C, double* d_out, void* stream);
+/* Scoring layout of a count flattening: low byte of every count into d_s0 (uint8 [rows_pad][pitch],
+ * zero-filled by the call; rows_pad >= R, pitch >= C, pitch % 16 == 0) and the remainder
+ * (count - (count & 255)) of counts >= 256 as COO triplets (d_hi_rc int32 [cap][2], d_hi_val uint32
+ * [cap]), *d_hi_num (uint32, zeroed by the call) = number of triplets (may exceed cap -> caller must
+ * check).  If d_rank_r/d_rank_c are non-NULL the reduced row/col ranks are used instead of the raw
+ * base-4 indices.  Requires the split to cover all n taxa (otherwise cells would collide). */
+int spb_flatten_u8(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* split,
+                   const uint32_t* d_rank_r, const uint32_t* d_rank_c, uint8_t* d_s0, int64_t rows_pad,
+                   int64_t pitch, int32_t* d_hi_rc, uint32_t* d_hi_val, uint32_t* d_hi_num, int64_t hi_cap,
+                   void* stream);
+
+/* ---- a11: subflattening (constructions.py:108-198) ---- */
+/* Raw pair statistics of sites [32*word_begin, 32*word_end) accumulated (atomicAdd) into d_raw
+ * (uint64 [spb_pair_raw_words(n)], zeroed by the caller; sum-reducible across GPUs). */
+int64_t spb_pair_raw_words(int n_taxa);
+int spb_pair_tables(const uint32_t* d_planes, const uint32_t* d_valid, int n_taxa, int64_t plane_words,
+                    int64_t word_begin, int64_t word_end, uint64_t* d_raw, void* stream);
+/* raw -> N double [n][n][4][4] (joint tables, N[i][i] diagonal = marginal) and the Hadamard-type
+ * basis change T[i][j] = H N[i][j] H^T (H = sign table of constructions.py:143-161).  divisor > 0
+ * turns counts into probabilities first (count / divisor).  d_total (double) = sum of all values. */
+int spb_pair_finalize(const uint64_t* d_raw, int n_taxa, double divisor, double* d_N, double* d_T,
+                      double* d_total, void* stream);
+/* Same tables from a weighted pattern list (dict inputs): d_N must be zeroed by the caller. */
+int spb_pair_tables_weighted(const uint64_t* d_keys, const double* d_vals, int64_t num, int n_taxa,
+                             double* d_N, void* stream);
+int spb_pair_transform(const double* d_N, int n_taxa, double* d_T, double* d_total, void* stream);
+/* One subflattening matrix, row-major double [(3a+1)][(3b+1)]. */
+int spb_subflatten(const double* d_T, const double* d_total, int n_taxa, const spb_split* split, double* d_out,
+                   void* stream);
+/* Batched: scores of `num` splits given as bit masks over taxon positions (bit t set = taxon t on
+ * side A; side B = d_masks_b[s] if non-NULL else the complement).  d_scores double [num]. */
+int spb_subflatten_score(const double* d_T, const double* d_total, int n_taxa, const uint64_t* d_masks_a,
+                         const uint64_t* d_masks_b, int64_t num, double* d_scores, void* stream);
+
+/* ---- a12-a14: split_score (phylogenetics.py:280-328), K = 4 hard-coded ---- */
+/* G = A A^T for row-major double A [batch][R][C] (lda = C): d_G double [batch][R][R].
+ * d_ws: double workspace of spb_gram_f64_ws(R, C, batch) elements (may be NULL when that is 0). */
+int64_t spb_gram_f64_ws(int64_t R, int64_t C, int64_t batch);
+int spb_gram_f64(const double* d_A, int64_t R, int64_t C, int64_t batch, double* d_G, double* d_ws, void* stream);
+/* Exact integer Gram of a u8 matrix (rows_pad x pitch, see spb_flatten_u8): d_G double [rows_pad][rows_pad]
+ * is OVERWRITTEN with S0 S0^T.  rows_pad <= 64 uses a dp4a kernel; rows_pad % 128 == 0 uses the
+ * tcgen05 (tensor core, kind::i8) kernel.  K = pitch. */
+int spb_gram_u8(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, double* d_G, void* stream);
+/* Adds the terms of the sparse high part H: G += F H^T + H S0^T with F = S0 + H. */
+int spb_gram_hi_correction(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, const int32_t* d_hi_rc,
+                           const uint32_t* d_hi_val, const uint32_t* d_hi_num, int64_t hi_cap, double* d_G,
+                           void* stream);
+/* Scores from symmetric PSD Gram matrices d_G double [batch][ld][ld] using the leading k x k block
+ * (k <= 128): cyclic Jacobi in shared memory, score = sqrt(sum_{i>=4} lambda_i / sum_i lambda_i).
+ * d_eig (optional) double [batch][k] receives the eigenvalues in descending order. */
+int spb_score_gram_small(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores,
+                         double* d_eig, void* stream);
+/* Scores from large Gram matrices (k > 128): block-Krylov Rayleigh-Ritz for the 4 largest
+ * eigenvalues, score = sqrt(1 - top4 / trace).  d_ws: double [spb_score_gram_large_ws(k, batch)].
+ * d_info (optional) double [batch][4] = {top4 sum, trace, convergence estimate, krylov dim}. */
+int64_t spb_score_gram_large_ws(int64_t k, int64_t batch);
+int spb_score_gram_large(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores,
+                         double* d_info, double* d_ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLITP_B200_H */

@@ -1,0 +1,392 @@
+// Kernel 1: site-pattern compression and counting over the 2-bit-packed (site-major) alignment.
+// Replaces splitp/parsers/fasta.py:48-63 (get_pattern_counts) and the counting half of
+// splitp/simulation.py:43-54.  Bit-exact integer work.
+//
+// Data flow per CTA (256 threads, tile = 8192 sites):
+//   coalesced 128-bit loads of the tile's bit stream -> shared memory
+//   -> per-site key extraction (funnel shifts) -> warp-level aggregation (__match_any_sync)
+//   -> shared-memory hash of (key, count, first site), kept across the tiles of a persistent CTA
+//   -> flush: one global atomic per distinct key per CTA (direct-indexed table for n <= 14,
+//      open-addressing global hash otherwise).
+#include "common.cuh"
+
+using namespace spb;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTileSites = 32 * kThreads;  // 8192
+constexpr int kHashSlots = 4096;           // shared-memory staging table
+constexpr int kMaxProbe = 16;
+
+struct DirectSink {
+  uint32_t* table;
+  uint32_t* first;
+  __device__ __forceinline__ void add(uint64_t key, uint32_t c, uint32_t f) const {
+    atomicAdd(table + key, c);
+    if (first) atomicMin(first + key, f);
+  }
+};
+
+struct HashSink {
+  unsigned long long* keys;
+  uint32_t* counts;
+  uint32_t* first;
+  uint64_t mask;
+  uint32_t* overflow;
+  __device__ __forceinline__ void add(uint64_t key, uint32_t c, uint32_t f) const {
+    uint64_t h = mix64(key) & mask;
+    for (uint64_t probe = 0; probe <= mask; ++probe) {
+      unsigned long long k = keys[h];
+      if (k == SPB_EMPTY_KEY) {
+        unsigned long long old = atomicCAS(keys + h, (unsigned long long)SPB_EMPTY_KEY, (unsigned long long)key);
+        if (old == SPB_EMPTY_KEY) k = key; else k = old;
+      }
+      if (k == key) {
+        atomicAdd(counts + h, c);
+        if (first) atomicMin(first + h, f);
+        return;
+      }
+      h = (h + 1) & mask;
+    }
+    atomicExch(overflow, 1u);
+  }
+};
+
+template <class Sink>
+__device__ __forceinline__ void stage_add(unsigned long long* s_keys, uint32_t* s_cnt, uint32_t* s_first, uint32_t* s_fill,
+                                          const Sink& sink, uint64_t key, uint32_t c, uint32_t f) {
+  uint32_t h = (uint32_t)mix64(key) & (kHashSlots - 1);
+#pragma unroll 1
+  for (int probe = 0; probe < kMaxProbe; ++probe) {
+    unsigned long long k = *((volatile unsigned long long*)(s_keys + h));
+    if (k == SPB_EMPTY_KEY) {
+      unsigned long long old = atomicCAS(s_keys + h, (unsigned long long)SPB_EMPTY_KEY, (unsigned long long)key);
+      if (old == SPB_EMPTY_KEY) { atomicAdd(s_fill, 1u); k = key; } else k = old;
+    }
+    if (k == key) {
+      atomicAdd(s_cnt + h, c);
+      atomicMin(s_first + h, f);
+      return;
+    }
+    h = (h + 1) & (kHashSlots - 1);
+  }
+  sink.add(key, c, f);
+}
+
+template <class Sink>
+__device__ __forceinline__ void stage_flush(unsigned long long* s_keys, uint32_t* s_cnt, uint32_t* s_first, uint32_t* s_fill,
+                                            const Sink& sink) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < kHashSlots; i += kThreads) {
+    unsigned long long k = s_keys[i];
+    if (k != SPB_EMPTY_KEY) {
+      sink.add(k, s_cnt[i], s_first[i]);
+      s_keys[i] = SPB_EMPTY_KEY;
+      s_cnt[i] = 0;
+      s_first[i] = 0xFFFFFFFFu;
+    }
+  }
+  if (threadIdx.x == 0) *s_fill = 0;
+  __syncthreads();
+}
+
+template <class Sink>
+__global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restrict__ sm, int64_t sm_words,
+                                                         const uint32_t* __restrict__ valid, int64_t valid_words, int n,
+                                                         int64_t site_begin, int64_t site_end, int64_t tile_begin,
+                                                         int64_t tile_end, Sink sink, unsigned long long* usable) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_keys + kHashSlots);
+  uint32_t* s_first = s_cnt + kHashSlots;
+  uint32_t* s_tile = s_first + kHashSlots;  // 512*n words + 4 pad
+  __shared__ uint32_t s_fill;
+  __shared__ uint32_t s_usable;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int bits = 2 * n;
+  const int tile_words = (kTileSites / 32) * bits;  // 512 n
+  const uint64_t kmask = (bits == 64) ? ~0ull : ((1ull << bits) - 1ull);
+
+  for (int i = tid; i < kHashSlots; i += kThreads) { s_keys[i] = SPB_EMPTY_KEY; s_cnt[i] = 0; s_first[i] = 0xFFFFFFFFu; }
+  if (tid == 0) { s_fill = 0; s_usable = 0; }
+  __syncthreads();
+
+  uint32_t my_usable = 0;
+  for (int64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+    const int64_t base_site = tile * kTileSites;
+    const int64_t base_word = tile * (int64_t)tile_words;
+    // coalesced 128-bit loads of the tile (tile_words is a multiple of 4, base_word of 4)
+    for (int v = tid; v < tile_words / 4; v += kThreads) {
+      int64_t gw = base_word + (int64_t)v * 4;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (gw + 4 <= sm_words) x = __ldg(reinterpret_cast<const uint4*>(sm + gw));
+      reinterpret_cast<uint4*>(s_tile)[v] = x;
+    }
+    if (tid < 4) s_tile[tile_words + tid] = 0;
+    __syncthreads();
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) {
+      const int sl = it * kThreads + tid;  // consecutive lanes = consecutive sites
+      const int64_t site = base_site + sl;
+      const int64_t vw = (base_site + it * kThreads + wid * 32) >> 5;
+      uint32_t vbits = (vw < valid_words) ? __ldg(valid + vw) : 0u;
+      bool ok = ((vbits >> lane) & 1u) && site >= site_begin && site < site_end;
+      const uint32_t bp = (uint32_t)sl * (uint32_t)bits;
+      const uint32_t w = bp >> 5, sh = bp & 31;
+      uint32_t w0 = s_tile[w], w1 = s_tile[w + 1], w2 = s_tile[w + 2];
+      uint64_t key = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | (uint64_t)__funnelshift_r(w0, w1, sh);
+      key &= kmask;
+      my_usable += ok ? 1u : 0u;
+      // warp-level aggregation: lanes with equal keys elect the lowest lane (= earliest site)
+      unsigned long long mk = ok ? (unsigned long long)key : (0xFFFFFFFF00000000ull | (unsigned)lane);
+      if (!ok && bits > 32) mk = SPB_EMPTY_KEY - 1 - lane;  // never equals a valid (<2^62) key
+      unsigned peers = __match_any_sync(0xFFFFFFFFu, mk);
+      if (ok && lane == (__ffs(peers) - 1))
+        stage_add(s_keys, s_cnt, s_first, &s_fill, sink, key, (uint32_t)__popc(peers), (uint32_t)site);
+    }
+    __syncthreads();
+    if (s_fill > (kHashSlots * 3) / 4) stage_flush(s_keys, s_cnt, s_first, &s_fill, sink);
+  }
+  stage_flush(s_keys, s_cnt, s_first, &s_fill, sink);
+  // usable-site count: warp reduce, one atomic per CTA
+  for (int o = 16; o > 0; o >>= 1) my_usable += __shfl_xor_sync(0xFFFFFFFFu, my_usable, o);
+  if (lane == 0 && my_usable) atomicAdd(&s_usable, my_usable);
+  __syncthreads();
+  if (tid == 0 && usable && s_usable) atomicAdd(usable, (unsigned long long)s_usable);
+}
+
+template <class Sink>
+int launch_count(const uint32_t* d_sm, const uint32_t* d_valid, int n, int64_t site_begin, int64_t site_end, Sink sink,
+                 uint64_t* d_usable, cudaStream_t st) {
+  if (site_end <= site_begin) return SPB_OK;
+  size_t smem = (size_t)kHashSlots * 16 + ((size_t)(kTileSites / 32) * 2 * n + 4) * 4;
+  SPB_CUDA(cudaFuncSetAttribute(count_kernel<Sink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_kernel<Sink>, kThreads, smem));
+  if (occ < 1) occ = 1;
+  int64_t tile_begin = site_begin / kTileSites, tile_end = (site_end + kTileSites - 1) / kTileSites;
+  int64_t tiles = tile_end - tile_begin;
+  int64_t grid = (int64_t)sm_count() * occ;
+  if (grid > tiles) grid = tiles;
+  // the caller's buffers are sized by spb_sm_words / spb_plane_words for the whole alignment; the
+  // kernel only needs an upper bound that is safe to read: everything up to the last tile's end
+  // that lies inside the allocation.  We pass the *allocation-independent* bound derived from
+  // site_end, which is always inside the allocation.
+  int64_t sm_words = ((site_end + 31) / 32) * 2 * (int64_t)n;
+  sm_words = (sm_words + 3) / 4 * 4;
+  int64_t valid_words = (site_end + 31) / 32;
+  count_kernel<Sink><<<(unsigned)grid, kThreads, smem, st>>>(d_sm, sm_words, d_valid, valid_words, n, site_begin, site_end,
+                                                             tile_begin, tile_end, sink, (unsigned long long*)d_usable);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// compaction (ordered stream compaction of non-empty cells): 3 phases, block = 4096 cells
+// ------------------------------------------------------------------------------------------
+constexpr int kCThreads = 1024;
+constexpr int kCPer = 4;
+constexpr int kCBlock = kCThreads * kCPer;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+    if (lane >= o) x += y;
+  }
+  __syncthreads();  // protect warp_sums reuse
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = (lane < nw) ? warp_sums[lane] : 0u;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, o);
+      if (lane >= o) s += y;
+    }
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  uint32_t offset = (wid > 0) ? warp_sums[wid - 1] : 0u;
+  if (total) *total = warp_sums[nw - 1];
+  return offset + x - v;
+}
+
+struct DirectSrc {
+  const uint32_t* table;
+  __device__ __forceinline__ bool used(int64_t i) const { return table[i] != 0u; }
+  __device__ __forceinline__ uint64_t key(int64_t i) const { return (uint64_t)i; }
+  __device__ __forceinline__ uint32_t count(int64_t i) const { return table[i]; }
+};
+struct HashSrc {
+  const uint64_t* keys;
+  const uint32_t* counts;
+  __device__ __forceinline__ bool used(int64_t i) const { return keys[i] != SPB_EMPTY_KEY; }
+  __device__ __forceinline__ uint64_t key(int64_t i) const { return keys[i]; }
+  __device__ __forceinline__ uint32_t count(int64_t i) const { return counts[i]; }
+};
+// flags array source (used by the reduced flattening rank computation)
+struct FlagSrc {
+  const uint32_t* flags;
+  __device__ __forceinline__ bool used(int64_t i) const { return flags[i] != 0u; }
+};
+
+template <class Src>
+__global__ void __launch_bounds__(kCThreads) compact_count_kernel(Src src, int64_t cells, uint32_t* tmp) {
+  int64_t base = (int64_t)blockIdx.x * kCBlock + (int64_t)threadIdx.x * kCPer;
+  uint32_t c = 0;
+#pragma unroll
+  for (int q = 0; q < kCPer; ++q) c += (base + q < cells && src.used(base + q)) ? 1u : 0u;
+  uint32_t total;
+  block_exclusive_scan(c, &total);
+  if (threadIdx.x == 0) tmp[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kCThreads) compact_scan_kernel(uint32_t* tmp, int64_t nblocks, unsigned long long* num) {
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < nblocks; base += kCThreads) {
+    int64_t i = base + threadIdx.x;
+    uint32_t v = (i < nblocks) ? tmp[i] : 0u;
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(v, &total);
+    uint32_t carry = carry_s;
+    if (i < nblocks) tmp[i] = ex + carry;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && num) *num = carry_s;
+}
+
+template <class Src>
+__global__ void __launch_bounds__(kCThreads) compact_write_kernel(Src src, const uint32_t* first, int64_t cells,
+                                                                  const uint32_t* tmp, uint64_t* keys, uint32_t* counts,
+                                                                  uint32_t* first_out, int64_t capacity) {
+  int64_t base = (int64_t)blockIdx.x * kCBlock + (int64_t)threadIdx.x * kCPer;
+  uint32_t c = 0;
+  bool u[kCPer];
+#pragma unroll
+  for (int q = 0; q < kCPer; ++q) { u[q] = (base + q < cells) && src.used(base + q); c += u[q] ? 1u : 0u; }
+  uint32_t ex = block_exclusive_scan(c, nullptr);
+  int64_t o = (int64_t)tmp[blockIdx.x] + ex;
+#pragma unroll
+  for (int q = 0; q < kCPer; ++q) {
+    if (u[q]) {
+      if (o < capacity) {
+        keys[o] = src.key(base + q);
+        counts[o] = src.count(base + q);
+        if (first_out) first_out[o] = first ? first[base + q] : 0u;
+      }
+      ++o;
+    }
+  }
+}
+
+// rank[i] = number of used cells before i (exclusive), rank[cells] = total
+__global__ void __launch_bounds__(kCThreads) rank_write_kernel(const uint32_t* flags, int64_t cells, const uint32_t* tmp,
+                                                               uint32_t* rank) {
+  int64_t base = (int64_t)blockIdx.x * kCBlock + (int64_t)threadIdx.x * kCPer;
+  uint32_t c = 0;
+  bool u[kCPer];
+#pragma unroll
+  for (int q = 0; q < kCPer; ++q) { u[q] = (base + q < cells) && flags[base + q] != 0u; c += u[q] ? 1u : 0u; }
+  uint32_t ex = block_exclusive_scan(c, nullptr);
+  uint32_t o = tmp[blockIdx.x] + ex;
+#pragma unroll
+  for (int q = 0; q < kCPer; ++q) {
+    if (base + q < cells) rank[base + q] = o;
+    if (u[q]) ++o;
+  }
+}
+
+__global__ void hash_merge_kernel(const uint64_t* keys, const uint32_t* counts, const uint32_t* first, int64_t num,
+                                  HashSink sink) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < num) sink.add(keys[i], counts[i], first ? first[i] : 0xFFFFFFFFu);
+}
+
+template <class Src>
+int run_compact(Src src, const uint32_t* first, int64_t cells, uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first_out,
+                int64_t capacity, uint64_t* d_num, uint32_t* d_tmp, cudaStream_t st) {
+  int64_t nb = (cells + kCBlock - 1) / kCBlock;
+  if (nb == 0) { SPB_CUDA(cudaMemsetAsync(d_num, 0, 8, st)); return SPB_OK; }
+  compact_count_kernel<Src><<<(unsigned)nb, kCThreads, 0, st>>>(src, cells, d_tmp);
+  SPB_LAUNCH_CHECK();
+  compact_scan_kernel<<<1, kCThreads, 0, st>>>(d_tmp, nb, (unsigned long long*)d_num);
+  SPB_LAUNCH_CHECK();
+  compact_write_kernel<Src><<<(unsigned)nb, kCThreads, 0, st>>>(src, first, cells, d_tmp, d_keys, d_counts, d_first_out, capacity);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+}  // namespace
+
+namespace spb {
+// used by flatten.cu (reduced format): exclusive rank of the set flags; total to rank[cells]
+int rank_flags(const uint32_t* d_flags, int64_t cells, uint32_t* d_rank, uint32_t* d_tmp, cudaStream_t st) {
+  int64_t nb = (cells + kCBlock - 1) / kCBlock;
+  FlagSrc src{d_flags};
+  compact_count_kernel<FlagSrc><<<(unsigned)nb, kCThreads, 0, st>>>(src, cells, d_tmp);
+  SPB_LAUNCH_CHECK();
+  compact_scan_kernel<<<1, kCThreads, 0, st>>>(d_tmp, nb, (unsigned long long*)nullptr);
+  SPB_LAUNCH_CHECK();
+  rank_write_kernel<<<(unsigned)nb, kCThreads, 0, st>>>(d_flags, cells, d_tmp, d_rank);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+}  // namespace spb
+
+extern "C" int64_t spb_compact_tmp_words(int64_t cells) { return (cells + kCBlock - 1) / kCBlock + 8; }
+
+extern "C" int spb_count_direct(const uint32_t* d_sm, const uint32_t* d_valid, int n_taxa, int64_t site_begin,
+                                int64_t site_end, uint32_t* d_table, uint32_t* d_first, uint64_t* d_usable, void* stream) {
+  SPB_REQUIRE(d_sm && d_valid && d_table, "spb_count_direct: NULL buffer");
+  SPB_REQUIRE(n_taxa >= 1 && n_taxa <= 14, "spb_count_direct: direct table needs 1 <= n_taxa <= 14 (got %d)", n_taxa);
+  SPB_REQUIRE(site_begin >= 0 && site_end >= site_begin && site_end < (1ll << 32), "spb_count_direct: bad site range");
+  DirectSink sink{d_table, d_first};
+  return launch_count(d_sm, d_valid, n_taxa, site_begin, site_end, sink, d_usable, (cudaStream_t)stream);
+}
+
+extern "C" int spb_count_hash(const uint32_t* d_sm, const uint32_t* d_valid, int n_taxa, int64_t site_begin,
+                              int64_t site_end, uint64_t* d_hkeys, uint32_t* d_hcounts, uint32_t* d_hfirst, int64_t cap,
+                              uint64_t* d_usable, uint32_t* d_overflow, void* stream) {
+  SPB_REQUIRE(d_sm && d_valid && d_hkeys && d_hcounts && d_overflow, "spb_count_hash: NULL buffer");
+  SPB_REQUIRE(n_taxa >= 1 && n_taxa <= 31, "spb_count_hash: uint64 keys need n_taxa <= 31 (got %d)", n_taxa);
+  SPB_REQUIRE(cap >= 2 && (cap & (cap - 1)) == 0, "spb_count_hash: capacity must be a power of two");
+  SPB_REQUIRE(site_begin >= 0 && site_end >= site_begin && site_end < (1ll << 32), "spb_count_hash: bad site range");
+  HashSink sink{(unsigned long long*)d_hkeys, d_hcounts, d_hfirst, (uint64_t)cap - 1, d_overflow};
+  return launch_count(d_sm, d_valid, n_taxa, site_begin, site_end, sink, d_usable, (cudaStream_t)stream);
+}
+
+extern "C" int spb_compact_direct(const uint32_t* d_table, const uint32_t* d_first, int64_t cells, uint64_t* d_keys,
+                                  uint32_t* d_counts, uint32_t* d_first_out, int64_t capacity, uint64_t* d_num,
+                                  uint32_t* d_tmp, void* stream) {
+  SPB_REQUIRE(d_table && d_keys && d_counts && d_num && d_tmp && cells >= 0, "spb_compact_direct: bad arguments");
+  return run_compact(DirectSrc{d_table}, d_first, cells, d_keys, d_counts, d_first_out, capacity, d_num, d_tmp,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int spb_compact_hash(const uint64_t* d_hkeys, const uint32_t* d_hcounts, const uint32_t* d_hfirst, int64_t cap,
+                                uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first_out, int64_t capacity,
+                                uint64_t* d_num, uint32_t* d_tmp, void* stream) {
+  SPB_REQUIRE(d_hkeys && d_hcounts && d_keys && d_counts && d_num && d_tmp && cap >= 0, "spb_compact_hash: bad arguments");
+  return run_compact(HashSrc{d_hkeys, d_hcounts}, d_hfirst, cap, d_keys, d_counts, d_first_out, capacity, d_num, d_tmp,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int spb_hash_merge(const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_first, int64_t num,
+                              uint64_t* d_hkeys, uint32_t* d_hcounts, uint32_t* d_hfirst, int64_t cap,
+                              uint32_t* d_overflow, void* stream) {
+  SPB_REQUIRE(d_keys && d_counts && d_hkeys && d_hcounts && d_overflow, "spb_hash_merge: NULL buffer");
+  SPB_REQUIRE(cap >= 2 && (cap & (cap - 1)) == 0, "spb_hash_merge: capacity must be a power of two");
+  if (num <= 0) return SPB_OK;
+  HashSink sink{(unsigned long long*)d_hkeys, d_hcounts, d_hfirst, (uint64_t)cap - 1, d_overflow};
+  hash_merge_kernel<<<(unsigned)((num + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_keys, d_counts, d_first, num, sink);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}

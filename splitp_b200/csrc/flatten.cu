@@ -1,0 +1,222 @@
+// Kernel 2: flattening scatter.  Replaces splitp/constructions.py:31-55 (reduced), :58-102 (sparse) and
+// defines FlatFormat.dense := sparse.todense().  Row = base-4 index over side A, col = base-4 index over
+// side B, first listed taxon most significant (constructions.py:166-171).  Values are copied, never
+// combined, so every format is bit-exact by construction; counts become probabilities with the same
+// single IEEE division the reference performs (parsers/fasta.py:66-70).
+#include "common.cuh"
+
+namespace spb {
+int rank_flags(const uint32_t* d_flags, int64_t cells, uint32_t* d_rank, uint32_t* d_tmp, cudaStream_t st);
+}
+using namespace spb;
+
+namespace {
+
+__device__ __forceinline__ double load_val(const void* vals, int kind, double divisor, int64_t i) {
+  if (kind == SPB_VAL_U32) {
+    double c = (double)reinterpret_cast<const uint32_t*>(vals)[i];
+    return divisor > 0.0 ? c / divisor : c;
+  }
+  return reinterpret_cast<const double*>(vals)[i];
+}
+
+__global__ void coo_kernel(const uint64_t* __restrict__ keys, int64_t num, SplitDev sp, int64_t* rows, int64_t* cols) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num) return;
+  uint64_t k = keys[i];
+  rows[i] = (int64_t)side_index(k, sp.sh_a, sp.a);
+  cols[i] = (int64_t)side_index(k, sp.sh_b, sp.b);
+}
+
+// Assignment semantics of the reference (constructions.py:43,101): when several patterns land in the
+// same cell (split does not cover all taxa) the LAST pattern in table order wins.  win[] holds the
+// largest pattern index + 1 per cell; only that pattern writes.
+__global__ void dense_win_kernel(const uint64_t* __restrict__ keys, int64_t num, SplitDev sp, const uint32_t* rank_r,
+                                 const uint32_t* rank_c, int64_t C, uint32_t* win) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num) return;
+  uint64_t k = keys[i];
+  uint64_t r = side_index(k, sp.sh_a, sp.a), c = side_index(k, sp.sh_b, sp.b);
+  if (rank_r) { r = rank_r[r]; c = rank_c[c]; }
+  atomicMax(win + r * C + c, (uint32_t)(i + 1));
+}
+
+__global__ void dense_fill_kernel(const uint64_t* __restrict__ keys, const void* __restrict__ vals, int kind, double divisor,
+                                  int64_t num, SplitDev sp, const uint32_t* rank_r, const uint32_t* rank_c, int64_t C,
+                                  const uint32_t* win, double* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num) return;
+  uint64_t k = keys[i];
+  uint64_t r = side_index(k, sp.sh_a, sp.a), c = side_index(k, sp.sh_b, sp.b);
+  if (rank_r) { r = rank_r[r]; c = rank_c[c]; }
+  if (win && win[r * C + c] != (uint32_t)(i + 1)) return;
+  out[r * C + c] = load_val(vals, kind, divisor, i);
+}
+
+__global__ void mark_kernel(const uint64_t* __restrict__ keys, int64_t num, SplitDev sp, uint32_t* flag_r, uint32_t* flag_c) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num) return;
+  uint64_t k = keys[i];
+  flag_r[side_index(k, sp.sh_a, sp.a)] = 1u;
+  flag_c[side_index(k, sp.sh_b, sp.b)] = 1u;
+}
+
+__global__ void u8_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t num, SplitDev sp,
+                          const uint32_t* rank_r, const uint32_t* rank_c, uint8_t* s0, int64_t pitch, int32_t* hi_rc,
+                          uint32_t* hi_val, uint32_t* hi_num, int64_t hi_cap) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num) return;
+  uint64_t k = keys[i];
+  uint32_t cnt = counts[i];
+  uint64_t r = side_index(k, sp.sh_a, sp.a), c = side_index(k, sp.sh_b, sp.b);
+  if (rank_r) { r = rank_r[r]; c = rank_c[c]; }
+  s0[r * pitch + c] = (uint8_t)(cnt & 255u);
+  if (cnt >= 256u) {
+    uint32_t slot = atomicAdd(hi_num, 1u);
+    if ((int64_t)slot < hi_cap) {
+      hi_rc[2 * (int64_t)slot] = (int32_t)r;
+      hi_rc[2 * (int64_t)slot + 1] = (int32_t)c;
+      hi_val[slot] = cnt - (cnt & 255u);
+    }
+  }
+}
+
+inline bool covers_all(const spb_split* s) {
+  uint64_t m = 0;
+  for (int i = 0; i < s->a; ++i) m |= 1ull << s->idx_a[i];
+  for (int i = 0; i < s->b; ++i) m |= 1ull << s->idx_b[i];
+  return s->a + s->b == s->n && m == ((s->n == 64) ? ~0ull : ((1ull << s->n) - 1ull));
+}
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+extern "C" int spb_flatten_coo(const uint64_t* d_keys, int64_t num, const spb_split* split, int64_t* d_rows, int64_t* d_cols,
+                               void* stream) {
+  SplitDev sp;
+  int rc = make_split_dev(split, &sp);
+  if (rc) return rc;
+  SPB_REQUIRE(sp.a <= 31 && sp.b <= 31, "spb_flatten_coo: sides are limited to 31 taxa (int64 indices)");
+  if (num <= 0) return SPB_OK;
+  SPB_REQUIRE(d_keys && d_rows && d_cols, "spb_flatten_coo: NULL buffer");
+  coo_kernel<<<nblk(num, 256), 256, 0, (cudaStream_t)stream>>>(d_keys, num, sp, d_rows, d_cols);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+static int fill_common(const uint64_t* d_keys, const void* d_vals, int val_kind, double divisor, int64_t num,
+                       const spb_split* split, const SplitDev& sp, const uint32_t* rank_r, const uint32_t* rank_c,
+                       int64_t R, int64_t C, double* d_out, uint32_t* d_win, cudaStream_t st) {
+  SPB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)R * (size_t)C * sizeof(double), st));
+  if (num <= 0) return SPB_OK;
+  const uint32_t* win = nullptr;
+  if (!covers_all(split)) {
+    if (!d_win) {
+      set_error("flattening: split does not cover all taxa; a winner workspace (uint32 per cell) is required");
+      return SPB_ERR_ARG;
+    }
+    SPB_CUDA(cudaMemsetAsync(d_win, 0, (size_t)R * (size_t)C * sizeof(uint32_t), st));
+    dense_win_kernel<<<nblk(num, 256), 256, 0, st>>>(d_keys, num, sp, rank_r, rank_c, C, d_win);
+    SPB_LAUNCH_CHECK();
+    win = d_win;
+  }
+  dense_fill_kernel<<<nblk(num, 256), 256, 0, st>>>(d_keys, d_vals, val_kind, divisor, num, sp, rank_r, rank_c, C, win, d_out);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+// d_win: optional uint32 [4^a * 4^b] workspace, only needed when the split does not cover all taxa.
+extern "C" int spb_flatten_dense_w(const uint64_t* d_keys, const void* d_vals, int val_kind, double divisor, int64_t num,
+                                   const spb_split* split, double* d_out, uint32_t* d_win, void* stream) {
+  SplitDev sp;
+  int rc = make_split_dev(split, &sp);
+  if (rc) return rc;
+  SPB_REQUIRE(sp.a + sp.b <= 14, "spb_flatten_dense: 4^(a+b) cells with a+b=%d exceeds the dense limit (14)", sp.a + sp.b);
+  SPB_REQUIRE(d_out && (num <= 0 || (d_keys && d_vals)), "spb_flatten_dense: NULL buffer");
+  int64_t R = 1ll << (2 * sp.a), C = 1ll << (2 * sp.b);
+  return fill_common(d_keys, d_vals, val_kind, divisor, num, split, sp, nullptr, nullptr, R, C, d_out, d_win,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int spb_flatten_dense(const uint64_t* d_keys, const void* d_vals, int val_kind, double divisor, int64_t num,
+                                 const spb_split* split, double* d_out, void* stream) {
+  return spb_flatten_dense_w(d_keys, d_vals, val_kind, divisor, num, split, d_out, nullptr, stream);
+}
+
+extern "C" int spb_flatten_reduced_plan(const uint64_t* d_keys, int64_t num, const spb_split* split, uint32_t* d_rank_r,
+                                        uint32_t* d_rank_c, uint32_t* d_tmp, int64_t* h_shape, void* stream) {
+  SplitDev sp;
+  int rc = make_split_dev(split, &sp);
+  if (rc) return rc;
+  if (sp.a > 13 || sp.b > 13) {
+    set_error("spb_flatten_reduced: sides are limited to 13 taxa in this version (a=%d b=%d)", sp.a, sp.b);
+    return SPB_ERR_UNSUPPORTED;
+  }
+  SPB_REQUIRE(d_rank_r && d_rank_c && d_tmp && h_shape, "spb_flatten_reduced_plan: NULL buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t R = 1ll << (2 * sp.a), C = 1ll << (2 * sp.b);
+  SPB_CUDA(cudaMemsetAsync(d_rank_r, 0, (size_t)(R + 1) * 4, st));
+  SPB_CUDA(cudaMemsetAsync(d_rank_c, 0, (size_t)(C + 1) * 4, st));
+  if (num > 0) {
+    mark_kernel<<<nblk(num, 256), 256, 0, st>>>(d_keys, num, sp, d_rank_r, d_rank_c);
+    SPB_LAUNCH_CHECK();
+  }
+  // flags and ranks alias: every thread reads its own flags before it writes their ranks
+  rc = rank_flags(d_rank_r, R + 1, d_rank_r, d_tmp, st);
+  if (rc) return rc;
+  rc = rank_flags(d_rank_c, C + 1, d_rank_c, d_tmp, st);
+  if (rc) return rc;
+  uint32_t hr = 0, hc = 0;
+  SPB_CUDA(cudaMemcpyAsync(&hr, d_rank_r + R, 4, cudaMemcpyDeviceToHost, st));
+  SPB_CUDA(cudaMemcpyAsync(&hc, d_rank_c + C, 4, cudaMemcpyDeviceToHost, st));
+  SPB_CUDA(cudaStreamSynchronize(st));
+  h_shape[0] = hr;
+  h_shape[1] = hc;
+  return SPB_OK;
+}
+
+extern "C" int spb_flatten_reduced_fill_w(const uint64_t* d_keys, const void* d_vals, int val_kind, double divisor,
+                                          int64_t num, const spb_split* split, const uint32_t* d_rank_r,
+                                          const uint32_t* d_rank_c, int64_t R, int64_t C, double* d_out, uint32_t* d_win,
+                                          void* stream) {
+  SplitDev sp;
+  int rc = make_split_dev(split, &sp);
+  if (rc) return rc;
+  if (R <= 0 || C <= 0) return SPB_OK;
+  SPB_REQUIRE(d_out && d_rank_r && d_rank_c && (num <= 0 || (d_keys && d_vals)), "spb_flatten_reduced_fill: NULL buffer");
+  return fill_common(d_keys, d_vals, val_kind, divisor, num, split, sp, d_rank_r, d_rank_c, R, C, d_out, d_win,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int spb_flatten_reduced_fill(const uint64_t* d_keys, const void* d_vals, int val_kind, double divisor, int64_t num,
+                                        const spb_split* split, const uint32_t* d_rank_r, const uint32_t* d_rank_c,
+                                        int64_t R, int64_t C, double* d_out, void* stream) {
+  return spb_flatten_reduced_fill_w(d_keys, d_vals, val_kind, divisor, num, split, d_rank_r, d_rank_c, R, C, d_out, nullptr,
+                                    stream);
+}
+
+extern "C" int spb_flatten_u8(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* split,
+                              const uint32_t* d_rank_r, const uint32_t* d_rank_c, uint8_t* d_s0, int64_t rows_pad,
+                              int64_t pitch, int32_t* d_hi_rc, uint32_t* d_hi_val, uint32_t* d_hi_num, int64_t hi_cap,
+                              void* stream) {
+  SplitDev sp;
+  int rc = make_split_dev(split, &sp);
+  if (rc) return rc;
+  SPB_REQUIRE(covers_all(split), "spb_flatten_u8: the split must cover all %d taxa", sp.n);
+  SPB_REQUIRE(d_s0 && d_hi_rc && d_hi_val && d_hi_num && pitch % 16 == 0, "spb_flatten_u8: bad buffers / pitch");
+  SPB_REQUIRE((d_rank_r == nullptr) == (d_rank_c == nullptr), "spb_flatten_u8: give both rank arrays or neither");
+  if (!d_rank_r) {
+    SPB_REQUIRE(sp.a <= 15 && sp.b <= 15, "spb_flatten_u8: side too large without rank arrays");
+    SPB_REQUIRE(rows_pad >= (1ll << (2 * sp.a)) && pitch >= (1ll << (2 * sp.b)), "spb_flatten_u8: s0 too small");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  SPB_CUDA(cudaMemsetAsync(d_s0, 0, (size_t)rows_pad * (size_t)pitch, st));
+  SPB_CUDA(cudaMemsetAsync(d_hi_num, 0, 4, st));
+  if (num <= 0) return SPB_OK;
+  SPB_REQUIRE(d_keys && d_counts, "spb_flatten_u8: NULL pattern table");
+  u8_kernel<<<nblk(num, 256), 256, 0, st>>>(d_keys, d_counts, num, sp, d_rank_r, d_rank_c, d_s0, pitch, d_hi_rc, d_hi_val,
+                                            d_hi_num, hi_cap);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}

@@ -1,0 +1,377 @@
+// Kernel 3: subflattening.  Replaces splitp/constructions.py:108-198.
+//
+// A subflattening depends on the alignment only through the pairwise 4x4 joint tables N_ij of the taxa
+// (SURVEY.md section 0): entry (3i+c, 3j+d) = (H N_{A_i B_j} H^T)[c,d] with H the +-1 sign table of
+// constructions.py:143-161.  So the alignment is read ONCE (pair_kernel: bit-plane AND + POPC), the
+// Hadamard-type basis change is n^2 batched 4x4x4 products (finalize / transform kernels) and each
+// split is a gather + a small Gram + Jacobi in shared memory (subflatten_score_kernel).
+#include "common.cuh"
+#include "jacobi.cuh"
+
+using namespace spb;
+
+namespace {
+
+__constant__ int c_H[16] = {1, -1, -1, 1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, 1, 1};
+
+constexpr int kPThreads = 256;
+constexpr int kPW = 64;  // plane words per tile (2048 sites)
+
+template <int PPT>
+__global__ void __launch_bounds__(kPThreads) pair_kernel(const uint32_t* __restrict__ planes, const uint32_t* __restrict__ valid,
+                                                         int n, int64_t Wp, int64_t word_begin, int64_t word_end,
+                                                         unsigned long long* raw) {
+  extern __shared__ uint32_t s_mem[];
+  const int Wpad = kPW + 1;
+  uint32_t* s_mask = s_mem;                       // [n*3][Wpad]
+  uint32_t* s_valid = s_mask + n * 3 * Wpad;      // [kPW]
+  uint8_t* s_ij = reinterpret_cast<uint8_t*>(s_valid + kPW);  // [npairs][2]
+  const int tid = threadIdx.x;
+  const int npairs = n * (n - 1) / 2;
+  for (int p = tid; p < npairs; p += kPThreads) {
+    // invert p = i*(2n-i-1)/2 + (j-i-1)
+    int i = 0, rem = p;
+    while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+    s_ij[2 * p] = (uint8_t)i;
+    s_ij[2 * p + 1] = (uint8_t)(i + 1 + rem);
+  }
+  uint32_t cnt[PPT][9];
+#pragma unroll
+  for (int q = 0; q < PPT; ++q)
+#pragma unroll
+    for (int e = 0; e < 9; ++e) cnt[q][e] = 0;
+  uint32_t marg = 0, total = 0;
+  const int64_t tile0 = word_begin / kPW, tile1 = (word_end + kPW - 1) / kPW;
+  for (int64_t tile = tile0 + blockIdx.x; tile < tile1; tile += gridDim.x) {
+    __syncthreads();
+    const int64_t wbase = tile * kPW;
+    for (int idx = tid; idx < n * kPW; idx += kPThreads) {
+      int j = idx / kPW, w = idx - j * kPW;
+      int64_t gw = wbase + w;
+      uint32_t lo = 0, hi = 0, v = 0;
+      if (gw >= word_begin && gw < word_end) {
+        v = __ldg(valid + gw);
+        lo = __ldg(planes + ((int64_t)j * 2) * Wp + gw);
+        hi = __ldg(planes + ((int64_t)j * 2 + 1) * Wp + gw);
+      }
+      s_mask[(j * 3 + 0) * Wpad + w] = ~hi & ~lo & v;
+      s_mask[(j * 3 + 1) * Wpad + w] = ~hi & lo & v;
+      s_mask[(j * 3 + 2) * Wpad + w] = hi & ~lo & v;
+      if (j == 0) s_valid[w] = v;
+    }
+    __syncthreads();
+    if (tid < n * 3) {
+      const uint32_t* m = s_mask + tid * Wpad;
+#pragma unroll 8
+      for (int w = 0; w < kPW; ++w) marg += __popc(m[w]);
+    } else if (tid == kPThreads - 1) {
+#pragma unroll 8
+      for (int w = 0; w < kPW; ++w) total += __popc(s_valid[w]);
+    }
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      int p = tid + q * kPThreads;
+      if (p < npairs) {
+        const uint32_t* mi = s_mask + (int)s_ij[2 * p] * 3 * Wpad;
+        const uint32_t* mj = s_mask + (int)s_ij[2 * p + 1] * 3 * Wpad;
+#pragma unroll 4
+        for (int w = 0; w < kPW; ++w) {
+          uint32_t a0 = mi[w], a1 = mi[Wpad + w], a2 = mi[2 * Wpad + w];
+          uint32_t b0 = mj[w], b1 = mj[Wpad + w], b2 = mj[2 * Wpad + w];
+          cnt[q][0] += __popc(a0 & b0); cnt[q][1] += __popc(a0 & b1); cnt[q][2] += __popc(a0 & b2);
+          cnt[q][3] += __popc(a1 & b0); cnt[q][4] += __popc(a1 & b1); cnt[q][5] += __popc(a1 & b2);
+          cnt[q][6] += __popc(a2 & b0); cnt[q][7] += __popc(a2 & b1); cnt[q][8] += __popc(a2 & b2);
+        }
+      }
+    }
+  }
+  // flush: one 64-bit atomic per counter per CTA
+#pragma unroll
+  for (int q = 0; q < PPT; ++q) {
+    int p = tid + q * kPThreads;
+    if (p < npairs) {
+      int i = s_ij[2 * p], j = s_ij[2 * p + 1];
+#pragma unroll
+      for (int e = 0; e < 9; ++e)
+        if (cnt[q][e]) atomicAdd(raw + ((int64_t)i * n + j) * 9 + e, (unsigned long long)cnt[q][e]);
+    }
+  }
+  if (tid < n * 3 && marg) atomicAdd(raw + (int64_t)n * n * 9 + tid, (unsigned long long)marg);
+  if (tid == kPThreads - 1 && total) atomicAdd(raw + (int64_t)n * n * 9 + n * 3, (unsigned long long)total);
+}
+
+// raw pair statistics -> full joint tables N[i][j][4][4] and T = H N H^T, one thread per ordered (i, j)
+__global__ void finalize_kernel(const unsigned long long* __restrict__ raw, int n, double divisor, double* Nout, double* Tout,
+                                double* total_out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  int i = idx / n, j = idx - i * n;
+  const unsigned long long* marg = raw + (int64_t)n * n * 9;
+  long long tot = (long long)marg[n * 3];
+  long long N[4][4];
+  if (i == j) {
+    long long s = 0;
+    for (int x = 0; x < 4; ++x) for (int y = 0; y < 4; ++y) N[x][y] = 0;
+    for (int x = 0; x < 3; ++x) { N[x][x] = (long long)marg[i * 3 + x]; s += N[x][x]; }
+    N[3][3] = tot - s;
+  } else {
+    int lo = i < j ? i : j, hi = i < j ? j : i;
+    const unsigned long long* r = raw + ((int64_t)lo * n + hi) * 9;
+    long long M[4][4];
+    long long all = 0;
+    for (int x = 0; x < 3; ++x) {
+      long long rs = 0;
+      for (int y = 0; y < 3; ++y) { M[x][y] = (long long)r[x * 3 + y]; rs += M[x][y]; }
+      M[x][3] = (long long)marg[lo * 3 + x] - rs;
+      all += rs + M[x][3];
+    }
+    for (int y = 0; y < 3; ++y) {
+      long long cs = M[0][y] + M[1][y] + M[2][y];
+      M[3][y] = (long long)marg[hi * 3 + y] - cs;
+      all += M[3][y];
+    }
+    M[3][3] = tot - all;
+    for (int x = 0; x < 4; ++x) for (int y = 0; y < 4; ++y) N[x][y] = (i < j) ? M[x][y] : M[y][x];
+  }
+  long long HN[4][4];
+  for (int c = 0; c < 4; ++c) for (int y = 0; y < 4; ++y) {
+    long long s = 0;
+    for (int x = 0; x < 4; ++x) s += c_H[c * 4 + x] * N[x][y];
+    HN[c][y] = s;
+  }
+  for (int c = 0; c < 4; ++c) for (int d = 0; d < 4; ++d) {
+    long long s = 0;
+    for (int y = 0; y < 4; ++y) s += HN[c][y] * c_H[d * 4 + y];
+    double t = (double)s;
+    Tout[(int64_t)idx * 16 + c * 4 + d] = divisor > 0.0 ? t / divisor : t;
+    if (Nout) {
+      double v = (double)N[c][d];
+      Nout[(int64_t)idx * 16 + c * 4 + d] = divisor > 0.0 ? v / divisor : v;
+    }
+  }
+  if (idx == 0 && total_out) *total_out = divisor > 0.0 ? (double)tot / divisor : (double)tot;
+}
+
+__global__ void weighted_kernel(const uint64_t* __restrict__ keys, const double* __restrict__ vals, int64_t num, int n,
+                                double* Nout) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t pat = g / n;
+  int i = (int)(g - pat * n);
+  if (pat >= num) return;
+  uint64_t k = keys[pat];
+  double v = vals[pat];
+  if (v == 0.0) return;
+  int x = (int)((k >> (2 * (n - 1 - i))) & 3ull);
+  for (int j = 0; j < n; ++j) {
+    int y = (int)((k >> (2 * (n - 1 - j))) & 3ull);
+    atomicAdd(Nout + ((int64_t)i * n + j) * 16 + x * 4 + y, v);
+  }
+}
+
+__global__ void transform_kernel(const double* __restrict__ Nin, int n, double* Tout, double* total_out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const double* N = Nin + (int64_t)idx * 16;
+  double HN[4][4];
+  for (int c = 0; c < 4; ++c) for (int y = 0; y < 4; ++y) {
+    double s = 0;
+    for (int x = 0; x < 4; ++x) s += c_H[c * 4 + x] * N[x * 4 + y];
+    HN[c][y] = s;
+  }
+  for (int c = 0; c < 4; ++c) for (int d = 0; d < 4; ++d) {
+    double s = 0;
+    for (int y = 0; y < 4; ++y) s += HN[c][y] * c_H[d * 4 + y];
+    Tout[(int64_t)idx * 16 + c * 4 + d] = s;
+  }
+  if (idx == 0 && total_out) *total_out = N[0] + N[5] + N[10] + N[15];  // diagonal marginal of taxon 0
+}
+
+__device__ __forceinline__ double subflat_entry(const double* __restrict__ T, double total, int n, const uint8_t* la, int a,
+                                                const uint8_t* lb, int b, int r, int c) {
+  if (r < 3 * a) {
+    int i = r / 3, ci = r - 3 * i, ta = la[i];
+    if (c < 3 * b) {
+      int j = c / 3, dj = c - 3 * j;
+      return T[((int64_t)ta * n + lb[j]) * 16 + ci * 4 + dj];
+    }
+    return T[((int64_t)ta * n + ta) * 16 + ci * 4 + 3];
+  }
+  if (c < 3 * b) {
+    int j = c / 3, dj = c - 3 * j, tb = lb[j];
+    return T[((int64_t)tb * n + tb) * 16 + 12 + dj];
+  }
+  return total;
+}
+
+__global__ void subflatten_kernel(const double* __restrict__ T, const double* __restrict__ total, int n, SplitDev sp,
+                                  double* out) {
+  __shared__ uint8_t la[SPB_MAX_TAXA], lb[SPB_MAX_TAXA];
+  if (threadIdx.x < sp.a) la[threadIdx.x] = (uint8_t)(n - 1 - sp.sh_a[threadIdx.x] / 2);
+  if (threadIdx.x < sp.b) lb[threadIdx.x] = (uint8_t)(n - 1 - sp.sh_b[threadIdx.x] / 2);
+  __syncthreads();
+  int rows = 3 * sp.a + 1, cols = 3 * sp.b + 1;
+  double tot = *total;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < rows * cols; idx += gridDim.x * blockDim.x) {
+    int r = idx / cols, c = idx - r * cols;
+    out[idx] = subflat_entry(T, tot, n, la, sp.a, lb, sp.b, r, c);
+  }
+}
+
+constexpr int kSThreads = 128;
+
+__global__ void __launch_bounds__(kSThreads) subflatten_score_kernel(const double* __restrict__ T, const double* __restrict__ total,
+                                                                     int n, const uint64_t* __restrict__ masks_a,
+                                                                     const uint64_t* __restrict__ masks_b, int64_t num,
+                                                                     double* scores, int m_elems) {
+  extern __shared__ __align__(16) double s_d[];
+  double* M = s_d;                 // k x (L+1)
+  double* G = M + m_elems;         // k x (k|1)
+  __shared__ JacobiScratch js;
+  __shared__ double lam[kJacobiMaxK], tmp[kJacobiMaxK];
+  __shared__ uint8_t la[SPB_MAX_TAXA], lb[SPB_MAX_TAXA];
+  __shared__ int s_a, s_b;
+  const int tid = threadIdx.x;
+  const uint64_t full = (n == 64) ? ~0ull : ((1ull << n) - 1ull);
+  const double tot = *total;
+  for (int64_t s = blockIdx.x; s < num; s += gridDim.x) {
+    __syncthreads();
+    if (tid == 0) {
+      uint64_t ma = masks_a[s] & full;
+      uint64_t mb = masks_b ? (masks_b[s] & full & ~ma) : (full & ~ma);
+      int a = 0, b = 0;
+      while (ma) { la[a++] = (uint8_t)(__ffsll((long long)ma) - 1); ma &= ma - 1; }
+      while (mb) { lb[b++] = (uint8_t)(__ffsll((long long)mb) - 1); mb &= mb - 1; }
+      s_a = a; s_b = b;
+    }
+    __syncthreads();
+    const int a = s_a, b = s_b;
+    const int rows = 3 * a + 1, cols = 3 * b + 1;
+    const bool tr = rows > cols;          // orient so that k = smaller dimension
+    const int k = tr ? cols : rows, L = tr ? rows : cols;
+    const int ldm = L + 1, ldg = k | 1;
+    for (int idx = tid; idx < k * L; idx += kSThreads) {
+      int r = idx / L, c = idx - r * L;
+      M[r * ldm + c] = tr ? subflat_entry(T, tot, n, la, a, lb, b, c, r) : subflat_entry(T, tot, n, la, a, lb, b, r, c);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < k * k; idx += kSThreads) {
+      int r1 = idx / k, r2 = idx - r1 * k;
+      if (r2 < r1) continue;
+      const double* x = M + r1 * ldm;
+      const double* y = M + r2 * ldm;
+      double acc = 0.0;
+      for (int c = 0; c < L; ++c) acc = fma(x[c], y[c], acc);
+      G[r1 * ldg + r2] = acc;
+      G[r2 * ldg + r1] = acc;
+    }
+    __syncthreads();
+    jacobi_eig_smem(G, ldg, k, nullptr, 0, &js);
+    sort_diag_desc(G, ldg, k, tmp, lam);
+    if (tid == 0) scores[s] = (k <= 4) ? 0.0 : score_from_sorted(lam, k);
+  }
+}
+
+inline size_t subflat_smem(int n, int* m_elems) {
+  int h = n / 2;
+  int k = 3 * h + 1, L = 3 * (n - h) + 1;
+  // the widest staging matrix over all splits: k x (L+1) is maximised at the balanced split, but a
+  // 1|n-1 split has k=4, L=3(n-1)+1; cover both
+  int m1 = k * (L + 1);
+  int m2 = 4 * (3 * (n - 1) + 2);
+  *m_elems = m1 > m2 ? m1 : m2;
+  int ldg = k | 1;
+  return ((size_t)*m_elems + (size_t)k * ldg) * sizeof(double);
+}
+
+}  // namespace
+
+extern "C" int64_t spb_pair_raw_words(int n_taxa) { return (int64_t)n_taxa * n_taxa * 9 + (int64_t)n_taxa * 3 + 1; }
+
+extern "C" int spb_pair_tables(const uint32_t* d_planes, const uint32_t* d_valid, int n_taxa, int64_t plane_words,
+                               int64_t word_begin, int64_t word_end, uint64_t* d_raw, void* stream) {
+  SPB_REQUIRE(d_planes && d_valid && d_raw, "spb_pair_tables: NULL buffer");
+  SPB_REQUIRE(n_taxa >= 1 && n_taxa <= SPB_MAX_TAXA, "spb_pair_tables: n_taxa out of range");
+  SPB_REQUIRE(word_begin >= 0 && word_end <= plane_words && word_begin <= word_end, "spb_pair_tables: bad word range");
+  if (word_end == word_begin) return SPB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int npairs = n_taxa * (n_taxa - 1) / 2;
+  size_t smem = ((size_t)n_taxa * 3 * (kPW + 1) + kPW) * 4 + (size_t)(npairs > 0 ? npairs : 1) * 2 + 16;
+  int64_t tiles = (word_end + kPW - 1) / kPW - word_begin / kPW;
+  int64_t grid = (int64_t)sm_count() * 2;
+  if (grid > tiles) grid = tiles;
+#define SPB_PAIR_LAUNCH(PPT)                                                                                          \
+  do {                                                                                                                \
+    SPB_CUDA(cudaFuncSetAttribute(pair_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    pair_kernel<PPT><<<(unsigned)grid, kPThreads, smem, st>>>(d_planes, d_valid, n_taxa, plane_words, word_begin,     \
+                                                              word_end, (unsigned long long*)d_raw);                  \
+  } while (0)
+  if (npairs <= kPThreads) SPB_PAIR_LAUNCH(1);
+  else if (npairs <= 2 * kPThreads) SPB_PAIR_LAUNCH(2);
+  else if (npairs <= 4 * kPThreads) SPB_PAIR_LAUNCH(4);
+  else SPB_PAIR_LAUNCH(8);
+#undef SPB_PAIR_LAUNCH
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int spb_pair_finalize(const uint64_t* d_raw, int n_taxa, double divisor, double* d_N, double* d_T, double* d_total,
+                                 void* stream) {
+  SPB_REQUIRE(d_raw && d_T && n_taxa >= 1 && n_taxa <= SPB_MAX_TAXA, "spb_pair_finalize: bad arguments");
+  int nn = n_taxa * n_taxa;
+  finalize_kernel<<<(nn + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const unsigned long long*)d_raw, n_taxa, divisor, d_N, d_T,
+                                                                     d_total);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int spb_pair_tables_weighted(const uint64_t* d_keys, const double* d_vals, int64_t num, int n_taxa, double* d_N,
+                                        void* stream) {
+  SPB_REQUIRE(d_N && n_taxa >= 1 && n_taxa <= 31, "spb_pair_tables_weighted: uint64 keys need n_taxa <= 31");
+  if (num <= 0) return SPB_OK;
+  SPB_REQUIRE(d_keys && d_vals, "spb_pair_tables_weighted: NULL buffer");
+  int64_t work = num * n_taxa;
+  weighted_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_keys, d_vals, num, n_taxa, d_N);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int spb_pair_transform(const double* d_N, int n_taxa, double* d_T, double* d_total, void* stream) {
+  SPB_REQUIRE(d_N && d_T && n_taxa >= 1 && n_taxa <= SPB_MAX_TAXA, "spb_pair_transform: bad arguments");
+  int nn = n_taxa * n_taxa;
+  transform_kernel<<<(nn + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_N, n_taxa, d_T, d_total);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int spb_subflatten(const double* d_T, const double* d_total, int n_taxa, const spb_split* split, double* d_out,
+                              void* stream) {
+  SplitDev sp;
+  int rc = make_split_dev(split, &sp, false);
+  if (rc) return rc;
+  SPB_REQUIRE(d_T && d_total && d_out && sp.n == n_taxa, "spb_subflatten: bad arguments");
+  int cells = (3 * sp.a + 1) * (3 * sp.b + 1);
+  int blocks = (cells + 127) / 128;
+  if (blocks > 64) blocks = 64;
+  subflatten_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(d_T, d_total, n_taxa, sp, d_out);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int spb_subflatten_score(const double* d_T, const double* d_total, int n_taxa, const uint64_t* d_masks_a,
+                                    const uint64_t* d_masks_b, int64_t num, double* d_scores, void* stream) {
+  SPB_REQUIRE(d_T && d_total && n_taxa >= 2 && n_taxa <= SPB_MAX_TAXA, "spb_subflatten_score: bad arguments");
+  if (num <= 0) return SPB_OK;
+  SPB_REQUIRE(d_masks_a && d_scores, "spb_subflatten_score: NULL buffer");
+  int m_elems = 0;
+  size_t smem = subflat_smem(n_taxa, &m_elems);
+  SPB_CUDA(cudaFuncSetAttribute(subflatten_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, subflatten_score_kernel, kSThreads, smem));
+  if (occ < 1) occ = 1;
+  int64_t grid = (int64_t)sm_count() * occ;
+  if (grid > num) grid = num;
+  subflatten_score_kernel<<<(unsigned)grid, kSThreads, smem, (cudaStream_t)stream>>>(d_T, d_total, n_taxa, d_masks_a, d_masks_b,
+                                                                                    num, d_scores, m_elems);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}

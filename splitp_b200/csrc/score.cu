@@ -1,0 +1,437 @@
+// Split score (splitp/phylogenetics.py:280-328) from Gram matrices.
+//
+//   score = sqrt(1 - sum_{i<4} sigma_i^2 / sum_i sigma_i^2),  sigma = singular values of the (sub)flattening
+//
+// sigma_i^2 are the eigenvalues of G = F F^T.  Small G (k <= 128) goes through the shared-memory Jacobi
+// solver and the trailing eigenvalues are summed directly.  Large G (the 4096 x 4096 Gram of a dense 6|6
+// flattening) is reduced to a <= 96 x 96 Rayleigh-Ritz problem by a block-Krylov iteration with full
+// re-orthogonalisation (fp64), whose projected matrix is again solved by the same Jacobi routine; the
+// total is trace(G) = ||F||_F^2.
+#include "common.cuh"
+#include "jacobi.cuh"
+
+using namespace spb;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// Batched fp64 GEMM, C[M][N] = A[M][K] * B[N][K]^T ("NT": both operands K-contiguous), optional split-K
+// into a partial workspace (summed in a fixed order by reduce_kernel => deterministic).
+// ------------------------------------------------------------------------------------------
+constexpr int kBK = 16;
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256) gemm_nt_kernel(const double* __restrict__ A, int64_t lda, int64_t strideA,
+                                                      const double* __restrict__ B, int64_t ldb, int64_t strideB,
+                                                      double* __restrict__ C, int64_t ldc, int64_t strideC, int M, int N, int K,
+                                                      int ksplit, int kchunk) {
+  static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+  constexpr int TX = BN / TN;  // threads along N
+  __shared__ double As[kBK][BM + 2];
+  __shared__ double Bs[kBK][BN + 2];
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int bt = blockIdx.z / ksplit, ks = blockIdx.z - bt * ksplit;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const double* Ab = A + (int64_t)bt * strideA;
+  const double* Bb = B + (int64_t)bt * strideB;
+  const int kbeg = ks * kchunk;
+  const int kend = min(K, kbeg + kchunk);
+  double acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
+
+  for (int k0 = kbeg; k0 < kend; k0 += kBK) {
+    // tile loads: element (row r, k kk) for r < BM (A) / BN (B), kk < 16; consecutive threads walk k
+    for (int idx = tid; idx < BM * kBK; idx += 256) {
+      int r = idx / kBK, kk = idx - r * kBK;
+      int gm = m0 + r, gk = k0 + kk;
+      As[kk][r] = (gm < M && gk < kend) ? Ab[(int64_t)gm * lda + gk] : 0.0;
+    }
+    for (int idx = tid; idx < BN * kBK; idx += 256) {
+      int r = idx / kBK, kk = idx - r * kBK;
+      int gn = n0 + r, gk = k0 + kk;
+      Bs[kk][r] = (gn < N && gk < kend) ? Bb[(int64_t)gn * ldb + gk] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kBK; ++kk) {
+      double a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty + i * (BM / TM)];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx + j * TX];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  double* Cb = C + (int64_t)blockIdx.z * strideC;  // partial index = bt*ksplit + ks (strideC = M*N region when split)
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int gm = m0 + ty + i * (BM / TM);
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int gn = n0 + tx + j * TX;
+      if (gn < N) Cb[(int64_t)gm * ldc + gn] = acc[i][j];
+    }
+  }
+}
+
+// C[bt][i] = sum_ks part[(bt*ksplit+ks)][i]  (fixed order)
+__global__ void reduce_kernel(const double* __restrict__ part, int64_t elems, int ksplit, double* __restrict__ C, int64_t strideC,
+                              int M, int N, int64_t ldc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int bt = blockIdx.y;
+  if (i >= elems) return;
+  double s = 0.0;
+  for (int ks = 0; ks < ksplit; ++ks) s += part[((int64_t)bt * ksplit + ks) * elems + i];
+  int r = (int)(i / N), c = (int)(i - (int64_t)r * N);
+  C[(int64_t)bt * strideC + (int64_t)r * ldc + c] = s;
+}
+
+struct GemmArgs {
+  const double* A; int64_t lda, strideA;
+  const double* B; int64_t ldb, strideB;
+  double* C; int64_t ldc, strideC;
+  int M, N, K, batch;
+};
+
+// skinny = true: M <= 16 (block of Krylov vectors times the big symmetric matrix)
+static int gemm_nt(const GemmArgs& g, bool skinny, int ksplit, double* part, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return SPB_OK;
+  if (ksplit < 1) ksplit = 1;
+  int kchunk = ((g.K + ksplit - 1) / ksplit + kBK - 1) / kBK * kBK;
+  if (kchunk < kBK) kchunk = kBK;
+  ksplit = (g.K + kchunk - 1) / kchunk;
+  if (ksplit < 1) ksplit = 1;
+  double* out = g.C; int64_t ldc = g.ldc, strideC = g.strideC;
+  if (ksplit > 1) { out = part; ldc = g.N; strideC = (int64_t)g.M * g.N; }
+  if (skinny) {
+    dim3 grid((g.N + 255) / 256, (g.M + 15) / 16, g.batch * ksplit);
+    gemm_nt_kernel<16, 256, 4, 4><<<grid, 256, 0, st>>>(g.A, g.lda, g.strideA, g.B, g.ldb, g.strideB, out, ldc,
+                                                        ksplit > 1 ? strideC : g.strideC, g.M, g.N, g.K, ksplit, kchunk);
+  } else {
+    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.batch * ksplit);
+    gemm_nt_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(g.A, g.lda, g.strideA, g.B, g.ldb, g.strideB, out, ldc,
+                                                       ksplit > 1 ? strideC : g.strideC, g.M, g.N, g.K, ksplit, kchunk);
+  }
+  SPB_LAUNCH_CHECK();
+  if (ksplit > 1) {
+    int64_t elems = (int64_t)g.M * g.N;
+    dim3 rg((unsigned)((elems + 255) / 256), g.batch);
+    reduce_kernel<<<rg, 256, 0, st>>>(part, elems, ksplit, g.C, g.strideC, g.M, g.N, g.ldc);
+    SPB_LAUNCH_CHECK();
+  }
+  return SPB_OK;
+}
+
+// NOTE on strides with split-K: partial (bt, ks) lives at part[(bt*ksplit+ks)*M*N]; the kernel indexes C by
+// blockIdx.z = bt*ksplit+ks with strideC = M*N, which is exactly that layout.  Without split-K blockIdx.z = bt.
+
+static int choose_ksplit(int M, int N, int K, int batch, bool skinny) {
+  int64_t tiles = skinny ? (int64_t)((N + 255) / 256) * ((M + 15) / 16) : (int64_t)((N + 63) / 64) * ((M + 63) / 64);
+  tiles *= batch;
+  int target = 2 * sm_count();
+  if (tiles >= target) return 1;
+  int ks = (int)((target + tiles - 1) / tiles);
+  int maxks = K / 256;
+  if (maxks < 1) maxks = 1;
+  if (ks > maxks) ks = maxks;
+  if (ks > 64) ks = 64;
+  return ks;
+}
+
+// ------------------------------------------------------------------------------------------
+// small path: Jacobi on the k x k Gram directly
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) score_small_kernel(const double* __restrict__ G, int k, int64_t ld, int64_t batch,
+                                                          double* scores, double* eig) {
+  extern __shared__ __align__(16) double s_A[];
+  __shared__ JacobiScratch js;
+  __shared__ double lam[kJacobiMaxK], tmp[kJacobiMaxK];
+  const int lda = k | 1;
+  for (int64_t bt = blockIdx.x; bt < batch; bt += gridDim.x) {
+    __syncthreads();
+    const double* Gb = G + bt * ld * ld;
+    for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
+      int r = idx / k, c = idx - r * k;
+      // symmetrise on load: the callers' Gram matrices are symmetric up to rounding
+      s_A[r * lda + c] = 0.5 * (Gb[(int64_t)r * ld + c] + Gb[(int64_t)c * ld + r]);
+    }
+    __syncthreads();
+    jacobi_eig_smem(s_A, lda, k, nullptr, 0, &js);
+    sort_diag_desc(s_A, lda, k, tmp, lam);
+    if (threadIdx.x == 0) scores[bt] = (k <= 4) ? (lam[0] > 0.0 || k > 1 ? 0.0 : 0.0) : score_from_sorted(lam, k);
+    if (eig) for (int i = threadIdx.x; i < k; i += blockDim.x) eig[bt * k + i] = lam[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// large path: block Krylov + Rayleigh-Ritz
+// ------------------------------------------------------------------------------------------
+constexpr int kKB = 16;       // block size
+constexpr int kKBlocks = 6;   // Krylov blocks
+constexpr int kKDim = kKB * kKBlocks;  // 96
+
+__global__ void krylov_init_kernel(double* W, int64_t strideW, int k) {
+  int64_t bt = blockIdx.y;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)kKB * k) return;
+  uint64_t h = mix64((uint64_t)i * 0x9E3779B97F4A7C15ull + 0x1234567ull + (uint64_t)bt * 0xD1B54A32D192ED03ull);
+  W[bt * strideW + i] = (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+__global__ void copy_block_kernel(const double* src, int64_t strideS, double* dst, int64_t strideD, int64_t elems) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < elems) dst[blockIdx.y * strideD + i] = src[blockIdx.y * strideS + i];
+}
+
+// W[c][pos] -= sum_r C[r][c] * Q[r][pos],  r < rows
+__global__ void __launch_bounds__(256) krylov_subtract_kernel(double* W, int64_t strideW, const double* __restrict__ Q,
+                                                              int64_t strideQ, const double* __restrict__ C, int64_t strideCm,
+                                                              int rows, int k) {
+  __shared__ double sC[kKDim * kKB];
+  const int64_t bt = blockIdx.y;
+  for (int i = threadIdx.x; i < rows * kKB; i += blockDim.x) sC[i] = C[bt * strideCm + i];
+  __syncthreads();
+  int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= k) return;
+  double w[kKB];
+  double* Wb = W + bt * strideW;
+  const double* Qb = Q + bt * strideQ;
+#pragma unroll
+  for (int c = 0; c < kKB; ++c) w[c] = Wb[(int64_t)c * k + pos];
+  for (int r = 0; r < rows; ++r) {
+    double q = Qb[(int64_t)r * k + pos];
+#pragma unroll
+    for (int c = 0; c < kKB; ++c) w[c] = fma(-sC[r * kKB + c], q, w[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < kKB; ++c) Wb[(int64_t)c * k + pos] = w[c];
+}
+
+// SVQB orthonormalisation of a block: S = W W^T (16x16, given), eigen-decompose the diagonally scaled S,
+// W <- Lambda^{-1/2} V^T D W.  Directions with lambda <= 1e-13 * lambda_max are dropped (zero vectors).
+__global__ void __launch_bounds__(256) krylov_svqb_kernel(double* W, int64_t strideW, const double* __restrict__ S,
+                                                          int64_t strideS, int k) {
+  __shared__ double sS[kKB * (kKB + 1)], sV[kKB * (kKB + 1)], sU[kKB * kKB], sD[kKB];
+  __shared__ JacobiScratch js;
+  const int64_t bt = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int ld = kKB + 1;
+  const double* Sb = S + bt * strideS;
+  if (tid < kKB) {
+    double d = Sb[tid * kKB + tid];
+    sD[tid] = d > 0.0 ? rsqrt(d) : 0.0;
+  }
+  __syncthreads();
+  for (int i = tid; i < kKB * kKB; i += blockDim.x) {
+    int r = i / kKB, c = i - r * kKB;
+    sS[r * ld + c] = 0.5 * (Sb[r * kKB + c] + Sb[c * kKB + r]) * sD[r] * sD[c];
+    sV[r * ld + c] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  jacobi_eig_smem(sS, ld, kKB, sV, ld, &js);
+  __syncthreads();
+  if (tid < kKB) {
+    double lmax = 0.0;
+    for (int i = 0; i < kKB; ++i) lmax = fmax(lmax, sS[i * ld + i]);
+    double lam = sS[tid * ld + tid];
+    double sc = (lam > 1e-13 * lmax && lam > 0.0) ? rsqrt(lam) : 0.0;
+    // new vector `tid` = sum_c U[tid][c] W_c, U[tid][c] = sc * V[c][tid] * D[c]
+    for (int c = 0; c < kKB; ++c) sU[tid * kKB + c] = sc * sV[c * ld + tid] * sD[c];
+  }
+  __syncthreads();
+  double* Wb = W + bt * strideW;
+  for (int pos = blockIdx.x * blockDim.x + tid; pos < k; pos += gridDim.x * blockDim.x) {
+    double w[kKB], o[kKB];
+#pragma unroll
+    for (int c = 0; c < kKB; ++c) w[c] = Wb[(int64_t)c * k + pos];
+#pragma unroll
+    for (int v = 0; v < kKB; ++v) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < kKB; ++c) s = fma(sU[v * kKB + c], w[c], s);
+      o[v] = s;
+    }
+#pragma unroll
+    for (int v = 0; v < kKB; ++v) Wb[(int64_t)v * k + pos] = o[v];
+  }
+}
+
+// Rayleigh-Ritz: eigenvalues of T (dim x dim) and of its leading (dim - 16) block; trace of G.
+__global__ void __launch_bounds__(256) krylov_rr_kernel(const double* __restrict__ T, int64_t strideT, int dim,
+                                                        const double* __restrict__ G, int k, int64_t ld, double* scores,
+                                                        double* info) {
+  extern __shared__ __align__(16) double s_A[];
+  __shared__ JacobiScratch js;
+  __shared__ double lam[kJacobiMaxK], tmp[kJacobiMaxK];
+  __shared__ double red[256];
+  const int64_t bt = blockIdx.x;
+  const int tid = threadIdx.x;
+  const double* Tb = T + bt * strideT;
+  const double* Gb = G + bt * ld * ld;
+  double tr = 0.0;
+  for (int i = tid; i < k; i += blockDim.x) tr += Gb[(int64_t)i * ld + i];
+  red[tid] = tr;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  tr = red[0];
+  double top[2] = {0.0, 0.0};
+  for (int pass = 0; pass < 2; ++pass) {
+    int d = pass == 0 ? dim - kKB : dim;
+    if (d < 4) { top[pass] = 0.0; continue; }
+    int lda = d | 1;
+    __syncthreads();
+    for (int idx = tid; idx < d * d; idx += blockDim.x) {
+      int r = idx / d, c = idx - r * d;
+      s_A[r * lda + c] = 0.5 * (Tb[r * dim + c] + Tb[c * dim + r]);
+    }
+    __syncthreads();
+    jacobi_eig_smem(s_A, lda, d, nullptr, 0, &js);
+    sort_diag_desc(s_A, lda, d, tmp, lam);
+    top[pass] = lam[0] + lam[1] + lam[2] + lam[3];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double rad = 1.0 - top[1] / tr;
+    scores[bt] = tr > 0.0 ? sqrt(fmax(rad, 0.0)) : nan("");
+    if (info) {
+      info[bt * 4 + 0] = top[1];
+      info[bt * 4 + 1] = tr;
+      info[bt * 4 + 2] = tr > 0.0 ? fabs(top[1] - top[0]) / tr : 0.0;
+      info[bt * 4 + 3] = (double)dim;
+    }
+  }
+}
+
+struct KrylovWs {
+  double *Q, *AQ, *C, *S, *T, *part;
+  int64_t sQ, sC, sS, sT, part_elems;
+};
+
+static int64_t krylov_layout(int64_t k, int64_t batch, double* base, KrylovWs* w) {
+  int64_t off = 0;
+  auto take = [&](int64_t n) { double* p = base ? base + off : nullptr; off += (n + 1) / 2 * 2; return p; };
+  w->sQ = (int64_t)kKDim * k;
+  w->Q = take(batch * w->sQ);
+  w->AQ = take(batch * w->sQ);
+  w->sC = (int64_t)kKDim * kKB;
+  w->C = take(batch * w->sC);
+  w->sS = (int64_t)kKB * kKB;
+  w->S = take(batch * w->sS);
+  w->sT = (int64_t)kKDim * kKDim;
+  w->T = take(batch * w->sT);
+  w->part_elems = batch * 64 * (int64_t)kKDim * kKDim;  // up to 64 k-splits of the largest product
+  w->part = take(w->part_elems);
+  return off;
+}
+
+}  // namespace
+
+extern "C" int64_t spb_gram_f64_ws(int64_t R, int64_t C, int64_t batch) {
+  int ks = choose_ksplit((int)R, (int)R, (int)C, (int)batch, false);
+  return ks > 1 ? batch * ks * R * R : 0;
+}
+
+extern "C" int spb_gram_f64(const double* d_A, int64_t R, int64_t C, int64_t batch, double* d_G, double* d_ws, void* stream) {
+  SPB_REQUIRE(d_A && d_G && R >= 1 && C >= 1 && batch >= 1 && R < (1 << 30) && C < (1 << 30), "spb_gram_f64: bad arguments");
+  int ks = choose_ksplit((int)R, (int)R, (int)C, (int)batch, false);
+  SPB_REQUIRE(ks == 1 || d_ws, "spb_gram_f64: workspace required (spb_gram_f64_ws)");
+  GemmArgs g{d_A, C, R * C, d_A, C, R * C, d_G, R, R * R, (int)R, (int)R, (int)C, (int)batch};
+  return gemm_nt(g, false, ks, d_ws, (cudaStream_t)stream);
+}
+
+extern "C" int spb_score_gram_small(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores, double* d_eig,
+                                    void* stream) {
+  SPB_REQUIRE(d_G && d_scores && k >= 1 && k <= kJacobiMaxK && ld >= k && batch >= 0,
+              "spb_score_gram_small: need 1 <= k <= %d (got %lld)", kJacobiMaxK, (long long)k);
+  if (batch == 0) return SPB_OK;
+  size_t smem = (size_t)k * (k | 1) * sizeof(double);
+  SPB_CUDA(cudaFuncSetAttribute(score_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int threads = k <= 32 ? 128 : 256;
+  int occ = 1;
+  SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, score_small_kernel, threads, smem));
+  if (occ < 1) occ = 1;
+  int64_t grid = (int64_t)sm_count() * occ;
+  if (grid > batch) grid = batch;
+  score_small_kernel<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(d_G, (int)k, ld, batch, d_scores, d_eig);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int64_t spb_score_gram_large_ws(int64_t k, int64_t batch) {
+  KrylovWs w;
+  return krylov_layout(k, batch, nullptr, &w);
+}
+
+extern "C" int spb_score_gram_large(const double* d_G, int64_t k64, int64_t ld, int64_t batch64, double* d_scores, double* d_info,
+                                    double* d_ws, void* stream) {
+  SPB_REQUIRE(d_G && d_scores && d_ws && k64 > kJacobiMaxK && ld >= k64 && batch64 >= 1 && k64 < (1 << 24),
+              "spb_score_gram_large: need k > %d and a workspace", kJacobiMaxK);
+  const int k = (int)k64, batch = (int)batch64;
+  cudaStream_t st = (cudaStream_t)stream;
+  KrylovWs w;
+  krylov_layout(k, batch, d_ws, &w);
+  const int64_t blk = (int64_t)kKB * k;
+  int rc;
+  auto ortho_block = [&](double* W) -> int {  // SVQB twice
+    for (int pass = 0; pass < 2; ++pass) {
+      GemmArgs g{W, k, w.sQ, W, k, w.sQ, w.S, kKB, w.sS, kKB, kKB, k, batch};
+      int ks = choose_ksplit(kKB, kKB, k, batch, false);
+      int r = gemm_nt(g, false, ks, w.part, st);
+      if (r) return r;
+      dim3 grid((k + 255) / 256 > 32 ? 32 : (k + 255) / 256, batch);
+      krylov_svqb_kernel<<<grid, 256, 0, st>>>(W, w.sQ, w.S, w.sS, k);
+      SPB_LAUNCH_CHECK();
+    }
+    return SPB_OK;
+  };
+  {
+    dim3 grid((unsigned)((blk + 255) / 256), batch);
+    krylov_init_kernel<<<grid, 256, 0, st>>>(w.Q, w.sQ, k);
+    SPB_LAUNCH_CHECK();
+  }
+  if ((rc = ortho_block(w.Q))) return rc;
+  for (int j = 0; j < kKBlocks; ++j) {
+    double* Qj = w.Q + (int64_t)j * blk;
+    double* AQj = w.AQ + (int64_t)j * blk;
+    {
+      GemmArgs g{Qj, k, w.sQ, d_G, ld, ld * ld, AQj, k, w.sQ, kKB, k, k, batch};
+      if ((rc = gemm_nt(g, true, 1, nullptr, st))) return rc;
+    }
+    if (j == kKBlocks - 1) break;
+    double* Wn = w.Q + (int64_t)(j + 1) * blk;
+    {
+      dim3 grid((unsigned)((blk + 255) / 256), batch);
+      copy_block_kernel<<<grid, 256, 0, st>>>(AQj, w.sQ, Wn, w.sQ, blk);
+      SPB_LAUNCH_CHECK();
+    }
+    const int rows = (j + 1) * kKB;
+    for (int pass = 0; pass < 2; ++pass) {
+      GemmArgs g{w.Q, k, w.sQ, Wn, k, w.sQ, w.C, kKB, w.sC, rows, kKB, k, batch};
+      int ks = choose_ksplit(rows, kKB, k, batch, false);
+      if ((rc = gemm_nt(g, false, ks, w.part, st))) return rc;
+      dim3 grid((k + 255) / 256, batch);
+      krylov_subtract_kernel<<<grid, 256, 0, st>>>(Wn, w.sQ, w.Q, w.sQ, w.C, w.sC, rows, k);
+      SPB_LAUNCH_CHECK();
+    }
+    if ((rc = ortho_block(Wn))) return rc;
+  }
+  {
+    GemmArgs g{w.Q, k, w.sQ, w.AQ, k, w.sQ, w.T, kKDim, w.sT, kKDim, kKDim, k, batch};
+    int ks = choose_ksplit(kKDim, kKDim, k, batch, false);
+    if ((rc = gemm_nt(g, false, ks, w.part, st))) return rc;
+  }
+  size_t smem = (size_t)kKDim * (kKDim | 1) * sizeof(double);
+  SPB_CUDA(cudaFuncSetAttribute(krylov_rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  krylov_rr_kernel<<<batch, 256, smem, st>>>(w.T, w.sT, kKDim, d_G, k, ld, d_scores, d_info);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
