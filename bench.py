@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the SplitP hot path on B200 (contract: see the task statement; metric: BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c3] [--impl reference]
+
+Workload c2 (default; BASELINE.json configs[1]): balanced 12-taxon Jukes-Cantor tree, branch length 0.05,
+1,000,000 sites (seeded synthetic alignment), ALL 2,035 splits scored from dense count flattenings
+(4^a x 4^b, 4096 x 4096 for the 462 6|6 splits) through the exact-integer tensor-core Gram + eigen-solver.
+One step = one pass of the whole path: pack -> pattern count -> (count allreduce) -> per split
+flatten + Gram + high-part correction + score -> (score all-gather).
+Workload c3 (configs[2], scaled by --sites): 20-taxon GTR tree, pair tables from the bit planes, subflattening
+scores of all 524,267 splits.
+
+N > 1 (torchrun): sites are sharded for counting (integer allreduce of the count table / pair statistics)
+and splits are sharded for scoring; total work is fixed => "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(n=12, sites=1_000_000, bl=0.05, model="JC", seed=2,
+               desc="BASELINE configs[1]: balanced 12-taxon JC tree bl=0.05, 1M sites, all 2035 splits, dense count "
+                    "flattenings (6|6 = 4096x4096), exact u8 tensor-core Gram + eigen score"),
+    "c3": dict(n=20, sites=10_000_000, bl=0.05, model="GTR", seed=3,
+               desc="BASELINE configs[2]: balanced 20-taxon GTR tree bl=0.05, 10M sites, subflattening scores of all "
+                    "524267 splits"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--sites", type=int, default=None, help="override the number of sites (parity/debug runs)")
+    ap.add_argument("--max-splits", type=int, default=None, help="score only the first M splits (debug runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_model(sim, name):
+    return sim.GTR.JukesCantor(0.5) if name == "JC" else sim.GTR((0.1, 0.2, 0.3, 0.4), (1, 2, 3, 4, 5, 6))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (nvidia-smi sampled DURING the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy / LAPACK restatement of the reference path) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(workload, codes_np, tree, splits, budget_s=25.0):
+    """Times the oracle on the host cores.  c2: pattern counting of ALL sites once, then one split per side
+    size (reduced flattening + LAPACK split score, the reference's README loop); the whole-job rate is the
+    size-weighted estimate 2035 / (t_count + sum_a n_a * t_a).  c3: pattern counting + pair-table
+    subflattening + score of a bounded number of splits."""
+    from oracle import splitp_oracle as O
+    cores = os.cpu_count() or 1
+    n = codes_np.shape[0]
+    t0 = time.perf_counter()
+    keys, counts, usable = O.get_pattern_counts_arrays(codes_np)
+    t_count = time.perf_counter() - t0
+    vals = counts / float(usable)
+    pos = {t: i for i, t in enumerate(tree.taxa)}
+    by_size = {}
+    for s in splits:
+        by_size.setdefault(min(len(s[0]), len(s[1])), []).append(s)
+    per_size, spent = {}, 0.0
+    if workload == "c2":
+        for a in sorted(by_size):
+            s = by_size[a][len(by_size[a]) // 2]
+            ia, ib = [pos[x] for x in s[0]], [pos[x] for x in s[1]]
+            t1 = time.perf_counter()
+            O.split_score(O.flattening_reduced(keys, vals, n, ia, ib))
+            per_size[a] = time.perf_counter() - t1
+            spent += per_size[a]
+        total = t_count + sum(len(by_size[a]) * per_size[a] for a in per_size)
+        value = len(splits) / total
+        sample = (f"oracle port: pattern count of all {codes_np.shape[1]} sites ({t_count:.2f} s) + one split per side size "
+                  f"{sorted(per_size)} (reduced flattening + LAPACK gesdd score: "
+                  + ", ".join(f"{a}:{per_size[a]:.3f}s" for a in sorted(per_size))
+                  + f"); value = {len(splits)} / (t_count + sum_a n_a t_a)")
+    else:
+        t1 = time.perf_counter()
+        tables = O.pair_tables(keys, vals, n)
+        t_pairs = time.perf_counter() - t1
+        done, t2 = 0, time.perf_counter()
+        tot = vals.sum()
+        while done < len(splits) and time.perf_counter() - t2 < budget_s:
+            s = splits[(done * 7919) % len(splits)]
+            O.split_score(O.subflattening_from_tables(tables, tot, [pos[x] for x in s[0]], [pos[x] for x in s[1]]))
+            done += 1
+        t_split = (time.perf_counter() - t2) / max(done, 1)
+        value = len(splits) / (t_count + t_pairs + len(splits) * t_split)
+        sample = (f"oracle port: pattern count of all {codes_np.shape[1]} sites ({t_count:.2f} s) + numpy pair tables "
+                  f"({t_pairs:.2f} s) + {done} splits ({t_split * 1e3:.3f} ms each, subflattening from tables + LAPACK "
+                  f"score); value = {len(splits)} / (t_count + t_pairs + S * t_split)")
+    return {"value": value, "unit": "split-scores/s", "cores": cores, "kind": "port", "sample": sample,
+            "sites_per_s": codes_np.shape[1] / t_count}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    wl = dict(WORKLOADS[args.workload])
+    if args.sites:
+        wl["sites"] = args.sites
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import torch
+        from splitp_b200 import simulation, splits as splits_mod, trees
+        tree = trees.balanced_tree(wl["n"], wl["bl"])
+        codes = simulation.simulate_codes(tree, make_model(simulation, wl["model"]), wl["sites"], wl["seed"], device="cpu").numpy()
+        splits = list(splits_mod.all_splits(tree))[: args.max_splits]
+        vals = []
+        for _ in range(args.warmup):
+            cpu_reference_sample(args.workload, codes, tree, splits, budget_s=3.0)
+        t0 = time.perf_counter()
+        for _ in range(max(args.steps, 1)):
+            cb = cpu_reference_sample(args.workload, codes, tree, splits, budget_s=10.0)
+            vals.append(cb["value"])
+        dt = (time.perf_counter() - t0) / max(args.steps, 1)
+        v = float(np.mean(vals))
+        cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": "split_scores_per_sec", "value": v, "unit": "split-scores/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": wl["desc"], "sites": wl["sites"], "splits": len(splits)},
+                          "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": "split-scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import splitp_b200 as sp
+    from splitp_b200 import distributed as spd
+    eng = sp.engine
+    rank, local, world = spd.init_from_env()
+    dev = eng.device()
+
+    tree = sp.trees.balanced_tree(wl["n"], wl["bl"])
+    n, N = wl["n"], wl["sites"]
+    codes_full = sp.simulation.simulate_codes(tree, make_model(sp.simulation, wl["model"]), N, wl["seed"])  # same on every rank
+    sb, se = spd.shard_range(N, rank, world, 32)
+    codes_dev = codes_full[:, sb:se].contiguous()          # this rank's site shard, resident in HBM
+    codes_pin = codes_dev.cpu().pin_memory()               # e2e: host buffer
+    splits = list(sp.all_splits(tree))[: args.max_splits]
+    S = len(splits)
+    idx_all = [eng.split_positions(s, tree.taxa) for s in splits]
+    pb, pe = spd.shard_range(S, rank, world)
+    idx_mine = idx_all[pb:pe]
+    reduce_fn = spd.make_reduce_fn() if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    prof = {"gram": [], "pairs": [], "count": []}
+    state = {}
+    if args.workload == "c3":
+        ma_np, mb_np = eng.masks_from_splits(idx_mine)
+        ma = torch.from_numpy(ma_np.view(np.int64)).to(dev)
+        mb = torch.from_numpy(mb_np.view(np.int64)).to(dev)
+
+    def timed(key, fn):
+        if not state.get("profile"):
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        prof[key].append((a, b))
+        return r
+
+    def step(codes):
+        """One pass of the hot path over this rank's shard.  Returns the scores of ALL splits (device)."""
+        if args.workload == "c2":
+            aln = eng.pack(codes, want_planes=False)
+            table = timed("count", lambda: eng.count_patterns(aln, reduce_fn=reduce_fn))
+            scorer = state.get("scorer")
+            if scorer is None:
+                scorer = state["scorer"] = eng.CountScorer(table)
+            scorer.table = table
+            out = torch.empty(len(idx_mine), dtype=torch.float64, device=dev)
+            for s, (ia, ib) in enumerate(idx_mine):
+                big = min(len(ia), len(ib)) == 6
+                if big and state.get("profile"):
+                    scorer.gram_hook = lambda f: timed("gram", f)
+                else:
+                    scorer.gram_hook = None
+                out[s:s + 1] = scorer.score(ia, ib)
+            scorer.check_hi()
+        else:
+            aln = eng.pack(codes, want_sm=False)
+            raw = timed("pairs", lambda: eng.pair_raw(aln))
+            if world > 1:
+                dist.all_reduce(raw)
+            pt = eng.pair_finalize(raw, n, float(N))
+            out = eng.subflatten_scores(pt, ma, mb)
+        return spd.gather_scores(out, S, rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        scores = step(codes_dev)
+    barrier()
+
+    # ---- timed: device-resident inputs ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = int(eng.lib.spb_launch_count())
+    state["profile"] = True
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)  # L2 flush between timed iterations (outside the per-step event pair)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        scores = step(codes_dev)
+        b.record()
+        evs.append((a, b))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    state["profile"] = False
+    launches = int(eng.lib.spb_launch_count()) - launches0
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = S / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the public call, H2D + D2H inside the timed region ----
+    for _ in range(2):
+        step(codes_pin.to(dev, non_blocking=True)).cpu()
+    barrier()
+    evs2 = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        host_scores = step(codes_pin.to(dev, non_blocking=True)).cpu()
+        b.record()
+        evs2.append((a, b))
+    barrier()
+    t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in evs2)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2.item()) / args.steps
+    e2e = {"value": S / (e2e_ms * 1e-3), "unit": "split-scores/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(codes_pin.numel()) * world, "d2h_bytes_per_step": S * 8,
+           "call": "engine.pack + count_patterns + CountScorer.score per split" if args.workload == "c2" else
+                   "engine.pack + pair_raw/pair_finalize + subflatten_scores"}
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the launch stream ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    roof = None
+    if args.workload == "c2" and prof["gram"]:
+        ms = float(np.mean([a.elapsed_time(b) for a, b in prof["gram"]]))
+        flops = 2.0 * 4096 ** 3  # 2 R^2 C per 6|6 split (GEMM convention)
+        tiles_done, tiles_all = 272, 512
+        bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
+        which = "measured (MEASURED_PEAKS.json bf16 sustained x2: kind::i8 has K=32 per instruction vs 16 for bf16)" if peaks else \
+            "fallback 1.59 PFLOP/s x2"
+        roof = {"kernel": "gram_u8_umma_kernel<256> (tcgen05.mma kind::i8, 4096x4096x4096 per 6|6 split)", "bound": "tensor",
+                "achieved": flops / (ms * 1e-3) / 1e12, "peak": 2 * bf16, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / (2 * bf16),
+                "traffic": None, "peak_source": which, "launch_ms": ms, "launches_timed": len(prof["gram"]),
+                "executed_frac_of_algorithmic": tiles_done / tiles_all,
+                "note": "algorithmic flops = full 2*R^2*C; the kernel computes only the 272 of 512 tiles touching the upper "
+                        "triangle and mirrors the rest"}
+    elif args.workload == "c3" and prof["pairs"]:
+        ms = float(np.mean([a.elapsed_time(b) for a, b in prof["pairs"]]))
+        nbytes = (se - sb) * n / 4.0 + (se - sb) / 8.0  # N n / 4 (+ N / 8 validity mask)
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        roof = {"kernel": "pair_kernel (bit-plane AND + POPC pair statistics)", "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9,
+                "peak": hbm, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s", "launch_ms": ms}
+    count_ms = float(np.mean([a.elapsed_time(b) for a, b in prof["count"]])) if prof["count"] else None
+
+    if rank == 0:
+        out = {"metric": "split_scores_per_sec", "value": value, "unit": "split-scores/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "u8" if args.workload == "c2" else "f64", "data": "synthetic",
+               "config": {"workload": wl["desc"], "taxa": n, "sites": N, "splits": S, "l2": "flushed between timed steps (256 MB fill)",
+                          "parallelism": f"sites+splits sharded x{world}"},
+               "sites_per_sec": (N / (count_ms * 1e-3)) if count_ms else N / (ms_per_step * 1e-3),
+               "count_stage_ms": count_ms, "wall_s_timed_region": t_wall,
+               "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof}
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_reference_sample(args.workload, codes_full.cpu().numpy(), tree, splits, budget_s=15.0)
+        elif world > 1:
+            out["cpu_baseline"] = None
+        # cheap sanity: the scores are finite and the tree's true splits rank first among their size
+        sc = scores.cpu().numpy()
+        out["checks"] = {"finite": bool(np.isfinite(sc).all()), "host_equals_device": bool(np.array_equal(sc, host_scores.numpy()))}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

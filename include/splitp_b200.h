@@ -48,6 +48,8 @@ typedef struct {
 
 int spb_version(void);
 const char* spb_last_error(void);
+/* number of CUDA kernels this library has launched in this process so far (bench.py's gpu_launches) */
+uint64_t spb_launch_count(void);
 /* number of SMs / compute capability of the current device; -1 when there is no device */
 int spb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -109,16 +111,35 @@ int spb_flatten_reduced_plan(const uint64_t* d_keys, int64_t num, const spb_spli
 int spb_flatten_reduced_fill(const uint64_t* d_keys, const void* d_vals, int val_kind, double divisor,
                              int64_t num, const spb_split* split, const uint32_t* d_rank_r,
                              const uint32_t* d_rank_c, int64_t R, int64_t C, double* d_out, void* stream);
-/* Scoring layout of a count flattening: low byte of every count into d_s0 (uint8 [rows_pad][pitch],
- * zero-filled by the call; rows_pad >= R, pitch >= C, pitch % 16 == 0) and the remainder
- * (count - (count & 255)) of counts >= 256 as COO triplets (d_hi_rc int32 [cap][2], d_hi_val uint32
- * [cap]), *d_hi_num (uint32, zeroed by the call) = number of triplets (may exceed cap -> caller must
- * check).  If d_rank_r/d_rank_c are non-NULL the reduced row/col ranks are used instead of the raw
+/* Variants with a winner workspace d_win (uint32 per output cell): required only when the split does not
+ * cover all taxa, where the reference's assignment semantics (last pattern wins, constructions.py:43,101)
+ * need a tie-break.  The plain entry points above pass d_win = NULL and fail with SPB_ERR_ARG in that case. */
+int spb_flatten_dense_w(const uint64_t* d_keys, const void* d_vals, int val_kind, double divisor, int64_t num,
+                        const spb_split* split, double* d_out, uint32_t* d_win, void* stream);
+int spb_flatten_reduced_fill_w(const uint64_t* d_keys, const void* d_vals, int val_kind, double divisor,
+                               int64_t num, const spb_split* split, const uint32_t* d_rank_r,
+                               const uint32_t* d_rank_c, int64_t R, int64_t C, double* d_out, uint32_t* d_win,
+                               void* stream);
+/* Scoring layout of a count flattening: low byte of every count into d_s0 (uint8, rows_pad x pitch cells;
+ * rows_pad >= R, pitch >= C) and the remainder (count - (count & 255)) of counts >= 256 as COO triplets
+ * (d_hi_rc int32 [cap][2], d_hi_val uint32 [cap]), *d_hi_num (uint32, zeroed by the call) = number of
+ * triplets (may exceed cap -> caller must check).  layout: SPB_S0_ROWMAJOR = [rows_pad][pitch], pitch % 16 == 0;
+ * SPB_S0_TILED = 128 x 128-byte tiles in the tensor-core operand layout (see csrc/gram.cu), rows_pad % 128 ==
+ * 0 and pitch % 128 == 0.  flags & SPB_U8_NO_MEMSET: d_s0 is known to be all zero (see spb_flatten_u8_clear),
+ * skip the memset.  If d_rank_r/d_rank_c are non-NULL the reduced row/col ranks are used instead of the raw
  * base-4 indices.  Requires the split to cover all n taxa (otherwise cells would collide). */
+#define SPB_S0_ROWMAJOR 0
+#define SPB_S0_TILED 1
+#define SPB_U8_NO_MEMSET 1
 int spb_flatten_u8(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* split,
                    const uint32_t* d_rank_r, const uint32_t* d_rank_c, uint8_t* d_s0, int64_t rows_pad,
-                   int64_t pitch, int32_t* d_hi_rc, uint32_t* d_hi_val, uint32_t* d_hi_num, int64_t hi_cap,
-                   void* stream);
+                   int64_t pitch, int layout, int flags, int32_t* d_hi_rc, uint32_t* d_hi_val, uint32_t* d_hi_num,
+                   int64_t hi_cap, void* stream);
+/* Writes zeros back to exactly the cells spb_flatten_u8 touched for this split (P byte stores instead of a
+ * rows_pad * pitch memset), restoring the all-zero state for the next split. */
+int spb_flatten_u8_clear(const uint64_t* d_keys, int64_t num, const spb_split* split, const uint32_t* d_rank_r,
+                         const uint32_t* d_rank_c, uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout,
+                         void* stream);
 
 /* ---- a11: subflattening (constructions.py:108-198) ---- */
 /* Raw pair statistics of sites [32*word_begin, 32*word_end) accumulated (atomicAdd) into d_raw
@@ -148,12 +169,18 @@ int spb_subflatten_score(const double* d_T, const double* d_total, int n_taxa, c
  * d_ws: double workspace of spb_gram_f64_ws(R, C, batch) elements (may be NULL when that is 0). */
 int64_t spb_gram_f64_ws(int64_t R, int64_t C, int64_t batch);
 int spb_gram_f64(const double* d_A, int64_t R, int64_t C, int64_t batch, double* d_G, double* d_ws, void* stream);
-/* Exact integer Gram of a u8 matrix (rows_pad x pitch, see spb_flatten_u8): d_G double [rows_pad][rows_pad]
- * is OVERWRITTEN with S0 S0^T.  rows_pad <= 64 uses a dp4a kernel; rows_pad % 128 == 0 uses the
- * tcgen05 (tensor core, kind::i8) kernel.  K = pitch. */
-int spb_gram_u8(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, double* d_G, void* stream);
-/* Adds the terms of the sparse high part H: G += F H^T + H S0^T with F = S0 + H. */
-int spb_gram_hi_correction(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, const int32_t* d_hi_rc,
+/* Exact integer Gram of a u8 matrix (see spb_flatten_u8): d_G double [rows_pad][rows_pad] is OVERWRITTEN with
+ * S0 S0^T.  SPB_S0_ROWMAJOR: rows_pad <= 64, dp4a kernel.  SPB_S0_TILED: rows_pad == 128 or rows_pad % 256 == 0,
+ * tcgen05 (tensor core, kind::i8) kernel.  K = pitch.  d_ws: uint64 [spb_gram_u8_ws(...)] (NULL when that is 0);
+ * it holds exact 64-bit partial sums when K is split across CTAs. */
+int64_t spb_s0_bytes(int64_t rows_pad, int64_t pitch);
+int64_t spb_gram_u8_ws(int64_t rows_pad, int64_t pitch, int layout);
+int spb_gram_u8(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, double* d_G, uint64_t* d_ws,
+                void* stream);
+/* Same result from a plain SIMT loop, any layout and size: the on-device cross-check used by the tests. */
+int spb_gram_u8_simt(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, double* d_G, void* stream);
+/* Adds the terms of the sparse high part H (F = S0 + H): G += S0 H^T + H S0^T + H H^T, so that G = F F^T. */
+int spb_gram_hi_correction(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, const int32_t* d_hi_rc,
                            const uint32_t* d_hi_val, const uint32_t* d_hi_num, int64_t hi_cap, double* d_G,
                            void* stream);
 /* Scores from symmetric PSD Gram matrices d_G double [batch][ld][ld] using the leading k x k block

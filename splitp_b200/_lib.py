@@ -1,0 +1,108 @@
+"""ctypes binding of the C-ABI library (include/splitp_b200.h).
+
+The product path has no CPU fallback: if `libsplitp_b200.so` is missing or a symbol is absent this
+module raises at import time.  Build with `python splitp_b200/build.py`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsplitp_b200.so")
+
+SPB_MAX_TAXA = 64
+SPB_VAL_U32, SPB_VAL_F64 = 0, 1
+SPB_S0_ROWMAJOR, SPB_S0_TILED = 0, 1
+SPB_U8_NO_MEMSET = 1
+EMPTY_KEY = 0xFFFFFFFFFFFFFFFF
+
+
+class SpbSplit(C.Structure):
+    _fields_ = [("n", C.c_int32), ("a", C.c_int32), ("b", C.c_int32),
+                ("idx_a", C.c_uint8 * SPB_MAX_TAXA), ("idx_b", C.c_uint8 * SPB_MAX_TAXA)]
+
+
+def make_split(n, idx_a, idx_b):
+    """Encoded split: ordered taxon positions of both sides (order = digit significance,
+    splitp/constructions.py:166-171)."""
+    if n > SPB_MAX_TAXA or len(idx_a) > SPB_MAX_TAXA or len(idx_b) > SPB_MAX_TAXA:
+        raise ValueError(f"at most {SPB_MAX_TAXA} taxa are supported")
+    s = SpbSplit()
+    s.n, s.a, s.b = n, len(idx_a), len(idx_b)
+    for i, t in enumerate(idx_a):
+        s.idx_a[i] = t
+    for i, t in enumerate(idx_b):
+        s.idx_b[i] = t
+    return s
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: the sm_100a library has not been built (python splitp_b200/build.py). "
+        "splitp_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_p, _i, _l, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+_sp = C.POINTER(SpbSplit)
+
+# name -> (restype, argtypes); mirrors include/splitp_b200.h line by line
+PROTOTYPES = {
+    "spb_version": (_i, []),
+    "spb_last_error": (C.c_char_p, []),
+    "spb_launch_count": (C.c_uint64, []),
+    "spb_device_info": (_i, [C.POINTER(_i)] * 3),
+    "spb_sm_words": (_l, [_i, _l]),
+    "spb_plane_words": (_l, [_l]),
+    "spb_pack": (_i, [_p, _i, _l, _l, _i, _p, _p, _p, _p]),
+    "spb_count_direct": (_i, [_p, _p, _i, _l, _l, _p, _p, _p, _p]),
+    "spb_compact_tmp_words": (_l, [_l]),
+    "spb_compact_direct": (_i, [_p, _p, _l, _p, _p, _p, _l, _p, _p, _p]),
+    "spb_count_hash": (_i, [_p, _p, _i, _l, _l, _p, _p, _p, _l, _p, _p, _p]),
+    "spb_compact_hash": (_i, [_p, _p, _p, _l, _p, _p, _p, _l, _p, _p, _p]),
+    "spb_hash_merge": (_i, [_p, _p, _p, _l, _p, _p, _p, _l, _p, _p]),
+    "spb_flatten_coo": (_i, [_p, _l, _sp, _p, _p, _p]),
+    "spb_flatten_dense": (_i, [_p, _p, _i, _d, _l, _sp, _p, _p]),
+    "spb_flatten_dense_w": (_i, [_p, _p, _i, _d, _l, _sp, _p, _p, _p]),
+    "spb_flatten_reduced_plan": (_i, [_p, _l, _sp, _p, _p, _p, C.POINTER(_l), _p]),
+    "spb_flatten_reduced_fill": (_i, [_p, _p, _i, _d, _l, _sp, _p, _p, _l, _l, _p, _p]),
+    "spb_flatten_reduced_fill_w": (_i, [_p, _p, _i, _d, _l, _sp, _p, _p, _l, _l, _p, _p, _p]),
+    "spb_flatten_u8": (_i, [_p, _p, _l, _sp, _p, _p, _p, _l, _l, _i, _i, _p, _p, _p, _l, _p]),
+    "spb_flatten_u8_clear": (_i, [_p, _l, _sp, _p, _p, _p, _l, _l, _i, _p]),
+    "spb_pair_raw_words": (_l, [_i]),
+    "spb_pair_tables": (_i, [_p, _p, _i, _l, _l, _l, _p, _p]),
+    "spb_pair_finalize": (_i, [_p, _i, _d, _p, _p, _p, _p]),
+    "spb_pair_tables_weighted": (_i, [_p, _p, _l, _i, _p, _p]),
+    "spb_pair_transform": (_i, [_p, _i, _p, _p, _p]),
+    "spb_subflatten": (_i, [_p, _p, _i, _sp, _p, _p]),
+    "spb_subflatten_score": (_i, [_p, _p, _i, _p, _p, _l, _p, _p]),
+    "spb_gram_f64_ws": (_l, [_l, _l, _l]),
+    "spb_gram_f64": (_i, [_p, _l, _l, _l, _p, _p, _p]),
+    "spb_s0_bytes": (_l, [_l, _l]),
+    "spb_gram_u8_ws": (_l, [_l, _l, _i]),
+    "spb_gram_u8": (_i, [_p, _l, _l, _i, _p, _p, _p]),
+    "spb_gram_u8_simt": (_i, [_p, _l, _l, _i, _p, _p]),
+    "spb_gram_hi_correction": (_i, [_p, _l, _l, _i, _p, _p, _p, _l, _p, _p]),
+    "spb_score_gram_small": (_i, [_p, _l, _l, _l, _p, _p, _p]),
+    "spb_score_gram_large_ws": (_l, [_l, _l]),
+    "spb_score_gram_large": (_i, [_p, _l, _l, _l, _p, _p, _p, _p]),
+}
+
+for _name, (_res, _args) in PROTOTYPES.items():
+    _f = getattr(lib, _name)  # AttributeError here = the library is stale: rebuild it
+    _f.restype = _res
+    _f.argtypes = _args
+
+_ERRORS = {1: ValueError, 2: RuntimeError, 3: MemoryError, 4: NotImplementedError}
+
+
+def check(rc):
+    """Maps an spb_status to the Python exception the reference would raise for that condition."""
+    if rc != 0:
+        msg = lib.spb_last_error().decode("utf-8", "replace")
+        raise _ERRORS.get(rc, RuntimeError)(f"splitp_b200: {msg}")
+
+
+def call(name, *args):
+    check(getattr(lib, name)(*args))

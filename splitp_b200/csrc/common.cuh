@@ -9,6 +9,7 @@
 namespace spb {
 
 void set_error(const char* fmt, ...);
+extern unsigned long long g_launches;  // kernels launched by this library (spb_launch_count)
 
 inline int sm_count() {
   static int cached = 0;
@@ -34,6 +35,7 @@ inline int sm_count() {
 
 #define SPB_LAUNCH_CHECK()                                                                \
   do {                                                                                    \
+    __atomic_fetch_add(&spb::g_launches, 1ull, __ATOMIC_RELAXED);                         \
     cudaError_t e__ = cudaGetLastError();                                                 \
     if (e__ != cudaSuccess) {                                                             \
       spb::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \

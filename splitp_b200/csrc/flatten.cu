@@ -61,16 +61,25 @@ __global__ void mark_kernel(const uint64_t* __restrict__ keys, int64_t num, Spli
   flag_c[side_index(k, sp.sh_b, sp.b)] = 1u;
 }
 
+__device__ __forceinline__ int64_t s0_cell(int layout, int64_t pitch, uint64_t r, uint64_t c) {
+  if (layout == SPB_S0_ROWMAJOR) return (int64_t)(r * (uint64_t)pitch + c);
+  // 128 x 128-byte tiles, K-major SWIZZLE_128B inside the tile (the tcgen05 operand layout, csrc/gram.cu)
+  uint64_t KT = (uint64_t)pitch >> 7;
+  uint64_t rt = r >> 7, kt = c >> 7;
+  uint32_t rr = (uint32_t)(r & 127), kk = (uint32_t)(c & 127);
+  return (int64_t)((rt * KT + kt) * 16384ull + rr * 128u + ((((kk >> 4) ^ (rr & 7u))) << 4) + (kk & 15u));
+}
+
 __global__ void u8_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t num, SplitDev sp,
-                          const uint32_t* rank_r, const uint32_t* rank_c, uint8_t* s0, int64_t pitch, int32_t* hi_rc,
+                          const uint32_t* rank_r, const uint32_t* rank_c, uint8_t* s0, int64_t pitch, int layout, int32_t* hi_rc,
                           uint32_t* hi_val, uint32_t* hi_num, int64_t hi_cap) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= num) return;
   uint64_t k = keys[i];
-  uint32_t cnt = counts[i];
+  uint32_t cnt = counts ? counts[i] : 0u;  // counts == NULL: clear pass
   uint64_t r = side_index(k, sp.sh_a, sp.a), c = side_index(k, sp.sh_b, sp.b);
   if (rank_r) { r = rank_r[r]; c = rank_c[c]; }
-  s0[r * pitch + c] = (uint8_t)(cnt & 255u);
+  s0[s0_cell(layout, pitch, r, c)] = (uint8_t)(cnt & 255u);
   if (cnt >= 256u) {
     uint32_t slot = atomicAdd(hi_num, 1u);
     if ((int64_t)slot < hi_cap) {
@@ -196,27 +205,52 @@ extern "C" int spb_flatten_reduced_fill(const uint64_t* d_keys, const void* d_va
                                     stream);
 }
 
-extern "C" int spb_flatten_u8(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* split,
-                              const uint32_t* d_rank_r, const uint32_t* d_rank_c, uint8_t* d_s0, int64_t rows_pad,
-                              int64_t pitch, int32_t* d_hi_rc, uint32_t* d_hi_val, uint32_t* d_hi_num, int64_t hi_cap,
-                              void* stream) {
-  SplitDev sp;
-  int rc = make_split_dev(split, &sp);
+static int u8_check(const spb_split* split, SplitDev* sp, const uint32_t* d_rank_r, const uint32_t* d_rank_c, uint8_t* d_s0,
+                    int64_t rows_pad, int64_t pitch, int layout) {
+  int rc = make_split_dev(split, sp);
   if (rc) return rc;
-  SPB_REQUIRE(covers_all(split), "spb_flatten_u8: the split must cover all %d taxa", sp.n);
-  SPB_REQUIRE(d_s0 && d_hi_rc && d_hi_val && d_hi_num && pitch % 16 == 0, "spb_flatten_u8: bad buffers / pitch");
+  SPB_REQUIRE(covers_all(split), "spb_flatten_u8: the split must cover all %d taxa", sp->n);
+  SPB_REQUIRE(d_s0 && rows_pad >= 1 && pitch >= 1, "spb_flatten_u8: bad buffers");
+  SPB_REQUIRE(layout == SPB_S0_ROWMAJOR || layout == SPB_S0_TILED, "spb_flatten_u8: unknown layout %d", layout);
+  if (layout == SPB_S0_ROWMAJOR) SPB_REQUIRE(pitch % 16 == 0, "spb_flatten_u8: row-major pitch must be a multiple of 16");
+  else SPB_REQUIRE(pitch % 128 == 0 && rows_pad % 128 == 0, "spb_flatten_u8: tiled layout needs rows_pad, pitch multiples of 128");
   SPB_REQUIRE((d_rank_r == nullptr) == (d_rank_c == nullptr), "spb_flatten_u8: give both rank arrays or neither");
   if (!d_rank_r) {
-    SPB_REQUIRE(sp.a <= 15 && sp.b <= 15, "spb_flatten_u8: side too large without rank arrays");
-    SPB_REQUIRE(rows_pad >= (1ll << (2 * sp.a)) && pitch >= (1ll << (2 * sp.b)), "spb_flatten_u8: s0 too small");
+    SPB_REQUIRE(sp->a <= 15 && sp->b <= 15, "spb_flatten_u8: side too large without rank arrays");
+    SPB_REQUIRE(rows_pad >= (1ll << (2 * sp->a)) && pitch >= (1ll << (2 * sp->b)), "spb_flatten_u8: s0 too small");
   }
+  return SPB_OK;
+}
+
+extern "C" int spb_flatten_u8(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* split,
+                              const uint32_t* d_rank_r, const uint32_t* d_rank_c, uint8_t* d_s0, int64_t rows_pad,
+                              int64_t pitch, int layout, int flags, int32_t* d_hi_rc, uint32_t* d_hi_val, uint32_t* d_hi_num,
+                              int64_t hi_cap, void* stream) {
+  SplitDev sp;
+  int rc = u8_check(split, &sp, d_rank_r, d_rank_c, d_s0, rows_pad, pitch, layout);
+  if (rc) return rc;
+  SPB_REQUIRE(d_hi_rc && d_hi_val && d_hi_num, "spb_flatten_u8: NULL high-part buffers");
   cudaStream_t st = (cudaStream_t)stream;
-  SPB_CUDA(cudaMemsetAsync(d_s0, 0, (size_t)rows_pad * (size_t)pitch, st));
+  if (!(flags & SPB_U8_NO_MEMSET)) SPB_CUDA(cudaMemsetAsync(d_s0, 0, (size_t)rows_pad * (size_t)pitch, st));
   SPB_CUDA(cudaMemsetAsync(d_hi_num, 0, 4, st));
   if (num <= 0) return SPB_OK;
   SPB_REQUIRE(d_keys && d_counts, "spb_flatten_u8: NULL pattern table");
-  u8_kernel<<<nblk(num, 256), 256, 0, st>>>(d_keys, d_counts, num, sp, d_rank_r, d_rank_c, d_s0, pitch, d_hi_rc, d_hi_val,
+  u8_kernel<<<nblk(num, 256), 256, 0, st>>>(d_keys, d_counts, num, sp, d_rank_r, d_rank_c, d_s0, pitch, layout, d_hi_rc, d_hi_val,
                                             d_hi_num, hi_cap);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int spb_flatten_u8_clear(const uint64_t* d_keys, int64_t num, const spb_split* split, const uint32_t* d_rank_r,
+                                    const uint32_t* d_rank_c, uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout,
+                                    void* stream) {
+  SplitDev sp;
+  int rc = u8_check(split, &sp, d_rank_r, d_rank_c, d_s0, rows_pad, pitch, layout);
+  if (rc) return rc;
+  if (num <= 0) return SPB_OK;
+  SPB_REQUIRE(d_keys, "spb_flatten_u8_clear: NULL pattern table");
+  u8_kernel<<<nblk(num, 256), 256, 0, (cudaStream_t)stream>>>(d_keys, nullptr, num, sp, d_rank_r, d_rank_c, d_s0, pitch, layout,
+                                                              nullptr, nullptr, nullptr, 0);
   SPB_LAUNCH_CHECK();
   return SPB_OK;
 }

@@ -1,0 +1,544 @@
+// Kernel 4: exact integer Gram contraction G = S0 * S0^T of a u8 matrix on the 5th-generation tensor cores.
+//
+// Why u8: a flattening built from site-pattern COUNTS is an integer matrix, so F F^T is an integer matrix.
+// The split score (splitp/phylogenetics.py:293-300) is 1 - top4/total, a difference of nearly equal numbers
+// for a true split, and SURVEY.md 7.3 shows that any fp32-accumulated Gram misses the tolerance.  We split
+// F = S0 + H with S0 = low byte of every count (dense, u8) and H = the few counts >= 256 (sparse triplets):
+//     F F^T = S0 S0^T + S0 H^T + H S0^T + H H^T.
+// S0 S0^T runs on tcgen05.mma kind::i8 (u8 x u8 -> s32 in TMEM, exact: 255^2 * K < 2^31 for K <= 33025 per
+// accumulation, enforced through the split-K chunk size) and the three sparse terms are added by
+// spb_gram_hi_correction with integer-valued fp64 atomics (exact below 2^53).
+//
+// Operand layout ("tiled"): S0 is stored as [rows_pad/128][pitch/128] tiles of 128 rows x 128 bytes, each tile
+// 16 KB contiguous in the K-major SWIZZLE_128B canonical layout of the UMMA shared-memory descriptor
+//     offset(r, k) = r*128 + (((k >> 4) ^ (r & 7)) << 4) + (k & 15).
+// The flattening scatter (spb_flatten_u8, layout = SPB_S0_TILED) writes this layout directly, so a whole operand
+// tile is ONE 1-D bulk-TMA copy (cp.async.bulk, 16 KB) completing on an mbarrier: no tensor map, no swizzle
+// work on the load path, perfectly coalesced HBM/L2 reads.
+//
+// Kernel structure (persistent, one CTA per SM, 192 threads):
+//   warp 0   : TMA producer   (bulk copies into a 4-stage shared-memory ring)
+//   warp 1   : MMA issuer     (tcgen05.mma M=128, N=BN, K=32 x 4 per stage; accumulators in TMEM, 2 stages)
+//   warps 2-5: epilogue       (tcgen05.ld -> fp64 stores incl. the mirrored half, or 64-bit integer atomics
+//                              when K is split across CTAs)
+// Only tiles touching the upper triangle (in 256-wide blocks) are computed; the rest is mirrored.
+#include "common.cuh"
+
+using namespace spb;
+
+namespace {
+
+constexpr int kTile = 128;               // rows and K-bytes per operand tile
+constexpr int kTileBytes = kTile * kTile;  // 16 KB
+constexpr int kStages = 4;
+constexpr int kUmmaThreads = 192;
+constexpr uint32_t kSpinLimit = 1u << 28;  // watchdog: a broken pipeline traps instead of hanging the GPU
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 1-D bulk TMA copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, u8 x u8 -> s32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): rows are 128 B apart, 8-row groups
+// 1024 B apart (SBO); LBO is unused for swizzled K-major operands.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                     // leading byte offset (ignored), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                     // layout type: SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor, kind::i8: D = s32, A = B = u8, both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
+  return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// work decomposition shared by all roles.  Tiles: row tile i (128 rows) x column tile j (BN columns), computed
+// only if the tile's 256-block column index >= its 256-block row index.  Work item = (tile, k-split).
+// ---------------------------------------------------------------------------------------------------
+struct Work {
+  int i, j, ks;
+};
+
+template <int BN>
+__device__ __forceinline__ bool tile_needed(int i, int j) {
+  // 256-granular block indices of the tile's first row and LAST column
+  int rb = (i * kTile) >> 8;
+  int cb = (j * BN + BN - 1) >> 8;
+  return cb >= rb;
+}
+
+template <int BN>
+__device__ __forceinline__ bool get_work(int w, int T, int TN, int ksplit, Work* out) {
+  int tile = w / ksplit;
+  int ks = w - tile * ksplit;
+  int seen = 0;
+  for (int i = 0; i < T; ++i) {
+    for (int j = 0; j < TN; ++j) {
+      if (!tile_needed<BN>(i, j)) continue;
+      if (seen == tile) { out->i = i; out->j = j; out->ks = ks; return true; }
+      ++seen;
+    }
+  }
+  return false;
+}
+
+template <int BN>
+int count_tiles(int T, int TN) {
+  int c = 0;
+  for (int i = 0; i < T; ++i)
+    for (int j = 0; j < TN; ++j) {
+      int rb = (i * kTile) >> 8, cb = (j * BN + BN - 1) >> 8;
+      if (cb >= rb) ++c;
+    }
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the tensor-core kernel
+// ---------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+gram_u8_umma_kernel(const uint8_t* __restrict__ s0t, int T, int KT, int ksplit, int kt_per_split, int num_work, int64_t ldg,
+                    double* __restrict__ G, unsigned long long* __restrict__ acc64) {
+  constexpr int kStageBytes = kTileBytes + BN * kTile;  // A tile + B tile(s)
+  constexpr uint32_t kTmemCols = 2 * BN;                 // two accumulator stages (power of two >= 32)
+  constexpr uint32_t kIdesc = make_idesc_i8(kTile, BN);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // carve-up: [stages][A | B] then barriers
+  // SWIZZLE_128B operands need 1024-byte aligned tiles: align the ring by hand (the launch adds 1 KB of slack)
+  uint8_t* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)kStages * kStageBytes);
+  uint64_t* full_bar = bars;                  // [kStages]
+  uint64_t* empty_bar = bars + kStages;       // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;   // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int TN = (T * kTile) / BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        Work wk;
+        if (!get_work<BN>(w, T, TN, ksplit, &wk)) break;
+        const int kt0 = wk.ks * kt_per_split;
+        const int kt1 = min(KT, kt0 + kt_per_split);
+        for (int kt = kt0; kt < kt1; ++kt) {
+          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+          const uint32_t fb = smem_u32(full_bar + stage);
+          mbar_expect_tx(fb, (uint32_t)kStageBytes);
+          uint8_t* sa = ring + (size_t)stage * kStageBytes;
+          bulk_g2s(smem_u32(sa), s0t + ((size_t)wk.i * KT + kt) * kTileBytes, kTileBytes, fb);
+#pragma unroll
+          for (int h = 0; h < BN / kTile; ++h) {
+            const int rt = wk.j * (BN / kTile) + h;
+            bulk_g2s(smem_u32(sa + kTileBytes + h * kTileBytes), s0t + ((size_t)rt * KT + kt) * kTileBytes, kTileBytes, fb);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        Work wk;
+        if (!get_work<BN>(w, T, TN, ksplit, &wk)) break;
+        const int kt0 = wk.ks * kt_per_split;
+        const int kt1 = min(KT, kt0 + kt_per_split);
+        mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kt = kt0; kt < kt1; ++kt) {
+          mbar_wait(smem_u32(full_bar + stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + (size_t)stage * kStageBytes);
+          const uint64_t da = make_desc_sw128(sa);
+          const uint64_t db = make_desc_sw128(sa + kTileBytes);
+#pragma unroll
+          for (int k = 0; k < kTile / 32; ++k) {
+            // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_i8(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kt > kt0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(empty_bar + stage));  // frees the smem slot once the MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(tfull_bar + acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: 4 warps, warp q = warp % 4 owns TMEM lanes [32q, 32q+32) =====
+    const int q = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      Work wk;
+      if (!get_work<BN>(w, T, TN, ksplit, &wk)) break;
+      mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+      tc_fence_after();
+      const int row = wk.i * kTile + q * 32 + lane;
+      const int rb = row >> 8;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
+        const int col0 = wk.j * BN + c0;
+        if (acc64) {
+          // split-K: exact 64-bit integer accumulation; the finalize kernel converts and mirrors
+          unsigned long long* dst = acc64 + (size_t)row * ldg + col0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (v[e]) atomicAdd(dst + e, (unsigned long long)v[e]);
+        } else {
+          double* dst = G + (size_t)row * ldg + col0;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            double2 d2 = make_double2((double)(int)v[e], (double)(int)v[e + 1]);
+            *reinterpret_cast<double2*>(dst + e) = d2;
+          }
+          if ((col0 >> 8) > rb) {  // mirrored half: lanes walk consecutive rows => coalesced
+#pragma unroll
+            for (int e = 0; e < 32; ++e) G[(size_t)(col0 + e) * ldg + row] = (double)(int)v[e];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// split-K finalize: 64-bit integer accumulators (upper 256-block triangle valid) -> symmetric fp64 G
+__global__ void gram_finalize_kernel(const unsigned long long* __restrict__ acc64, int64_t R, int64_t ldg, double* __restrict__ G) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * R) return;
+  int64_t r = idx / R, c = idx - r * R;
+  unsigned long long v = ((c >> 8) >= (r >> 8)) ? acc64[r * ldg + c] : acc64[c * ldg + r];
+  G[r * ldg + c] = (double)(long long)v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small row counts (rows_pad <= 64, row-major layout): dp4a over K chunks, 64-bit integer atomics
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSmallChunk = 2048;  // K bytes per CTA iteration (255^2 * 2048 < 2^32: u32 partials are exact)
+
+__global__ void __launch_bounds__(256) gram_u8_small_kernel(const uint8_t* __restrict__ s0, int R, int64_t pitch,
+                                                            unsigned long long* __restrict__ acc64) {
+  extern __shared__ uint32_t s_rows[];  // [R][kSmallChunk/4 + 1]
+  const int ldw = kSmallChunk / 4 + 1;
+  const int tid = threadIdx.x;
+  const int64_t nchunks = (pitch + kSmallChunk - 1) / kSmallChunk;
+  const int nb = (R + 15) / 16;          // 16 x 16 output blocks
+  const int tr = tid >> 4, tc = tid & 15;
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int64_t k0 = ch * kSmallChunk;
+    __syncthreads();
+    // coalesced 128-bit loads of R rows x chunk (pitch % 16 == 0)
+    for (int idx = tid; idx < R * (kSmallChunk / 16); idx += 256) {
+      int r = idx / (kSmallChunk / 16), v = idx - r * (kSmallChunk / 16);
+      int64_t k = k0 + (int64_t)v * 16;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (k < pitch) x = __ldg(reinterpret_cast<const uint4*>(s0 + (int64_t)r * pitch + k));
+      uint32_t* d = s_rows + r * ldw + v * 4;
+      d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+    }
+    __syncthreads();
+    for (int bi = 0; bi < nb; ++bi)
+      for (int bj = bi; bj < nb; ++bj) {
+        int r1 = bi * 16 + tr, r2 = bj * 16 + tc;
+        if (r1 < R && r2 < R) {
+          const uint32_t* x = s_rows + r1 * ldw;
+          const uint32_t* y = s_rows + r2 * ldw;
+          uint32_t s = 0;
+#pragma unroll 8
+          for (int w = 0; w < kSmallChunk / 4; ++w) s = __dp4a(x[w], y[w], s);
+          if (s) atomicAdd(acc64 + (int64_t)r1 * R + r2, (unsigned long long)s);
+        }
+      }
+  }
+}
+
+// acc64 [R][R] (upper 16-block triangle valid) -> symmetric fp64 G [ld][ld] leading R x R block
+__global__ void gram_small_finalize_kernel(const unsigned long long* __restrict__ acc64, int R, int64_t ld, double* __restrict__ G) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * R) return;
+  int r = idx / R, c = idx - r * R;
+  unsigned long long v = ((c >> 4) >= (r >> 4)) ? acc64[(int64_t)r * R + c] : acc64[(int64_t)c * R + r];
+  G[(int64_t)r * ld + c] = (double)(long long)v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generic SIMT Gram for any layout / size: the on-device cross-check of the tensor-core kernel (tests)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t s0_offset(int layout, int64_t pitch, int64_t r, int64_t k) {
+  if (layout == SPB_S0_ROWMAJOR) return r * pitch + k;
+  int64_t KT = pitch / kTile;
+  int64_t rt = r / kTile, kt = k / kTile;
+  int rr = (int)(r - rt * kTile), kk = (int)(k - kt * kTile);
+  return (rt * KT + kt) * kTileBytes + rr * 128 + ((((kk >> 4) ^ (rr & 7))) << 4) + (kk & 15);
+}
+
+__global__ void gram_u8_simt_kernel(const uint8_t* __restrict__ s0, int layout, int64_t R, int64_t pitch, int64_t ldg,
+                                    double* __restrict__ G) {
+  int64_t r1 = blockIdx.y, r2 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r2 >= R) return;
+  unsigned long long s = 0;
+  for (int64_t k = 0; k < pitch; ++k)
+    s += (unsigned long long)s0[s0_offset(layout, pitch, r1, k)] * (unsigned long long)s0[s0_offset(layout, pitch, r2, k)];
+  G[r1 * ldg + r2] = (double)s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sparse high-part corrections: G += S0 H^T + H S0^T + H H^T
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hi_cross_kernel(const uint8_t* __restrict__ s0, int layout, int64_t R, int64_t pitch,
+                                                       const int32_t* __restrict__ hi_rc, const uint32_t* __restrict__ hi_val,
+                                                       const uint32_t* __restrict__ hi_num, int64_t hi_cap, int64_t ldg,
+                                                       double* __restrict__ G) {
+  int64_t n = *hi_num;
+  if (n > hi_cap) n = hi_cap;
+  for (int64_t e = blockIdx.y; e < n; e += gridDim.y) {
+    const int64_t r = hi_rc[2 * e], c = hi_rc[2 * e + 1];
+    const double v = (double)hi_val[e];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.x * blockDim.x) {
+      uint32_t s = s0[s0_offset(layout, pitch, i, c)];
+      if (s) {
+        double t = v * (double)s;
+        atomicAdd(G + i * ldg + r, t);  // (S0 H^T)[i][r]
+        atomicAdd(G + r * ldg + i, t);  // (H S0^T)[r][i]
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) hi_self_kernel(const int32_t* __restrict__ hi_rc, const uint32_t* __restrict__ hi_val,
+                                                      const uint32_t* __restrict__ hi_num, int64_t hi_cap, int64_t ldg,
+                                                      double* __restrict__ G) {
+  int64_t n = *hi_num;
+  if (n > hi_cap) n = hi_cap;
+  for (int64_t e1 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e1 < n; e1 += (int64_t)gridDim.x * blockDim.x) {
+    const int r1 = hi_rc[2 * e1], c1 = hi_rc[2 * e1 + 1];
+    const double v1 = (double)hi_val[e1];
+    for (int64_t e2 = 0; e2 < n; ++e2)
+      if (hi_rc[2 * e2 + 1] == c1) atomicAdd(G + (int64_t)r1 * ldg + hi_rc[2 * e2], v1 * (double)hi_val[e2]);  // (H H^T)[r1][r2]
+  }
+}
+
+struct UmmaPlan {
+  int BN, T, KT, tiles, ksplit, kt_per_split, num_work;
+  size_t smem;
+};
+
+UmmaPlan plan_umma(int64_t rows_pad, int64_t pitch) {
+  UmmaPlan p;
+  p.BN = rows_pad >= 256 ? 256 : 128;
+  p.T = (int)(rows_pad / kTile);
+  p.KT = (int)(pitch / kTile);
+  int TN = (int)(rows_pad / p.BN);
+  p.tiles = p.BN == 256 ? count_tiles<256>(p.T, TN) : count_tiles<128>(p.T, TN);
+  // split K so that every SM has work; one s32 accumulation must stay below 2^31: 255^2 * 128 * kt <= 2^31 -> kt <= 258
+  int sms = sm_count();
+  int ks = 1;
+  if (p.tiles < sms) ks = (sms + p.tiles - 1) / p.tiles;
+  if (ks > p.KT) ks = p.KT;
+  int per = (p.KT + ks - 1) / ks;
+  if (per > 256) per = 256;
+  ks = (p.KT + per - 1) / per;
+  p.ksplit = ks;
+  p.kt_per_split = per;
+  p.num_work = p.tiles * ks;
+  p.smem = (size_t)kStages * (kTileBytes + p.BN * kTile) + 16 * 8 + 1024;
+  return p;
+}
+
+}  // namespace
+
+extern "C" int64_t spb_s0_bytes(int64_t rows_pad, int64_t pitch) { return rows_pad * pitch; }
+
+extern "C" int64_t spb_gram_u8_ws(int64_t rows_pad, int64_t pitch, int layout) {
+  if (layout == SPB_S0_ROWMAJOR) return rows_pad * rows_pad;
+  if (rows_pad % kTile || pitch % kTile) return 0;
+  UmmaPlan p = plan_umma(rows_pad, pitch);
+  return p.ksplit > 1 ? rows_pad * rows_pad : 0;
+}
+
+extern "C" int spb_gram_u8(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, double* d_G, uint64_t* d_ws,
+                           void* stream) {
+  SPB_REQUIRE(d_s0 && d_G && rows_pad >= 1 && pitch >= 16 && pitch % 16 == 0, "spb_gram_u8: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (layout == SPB_S0_ROWMAJOR) {
+    SPB_REQUIRE(rows_pad <= 64, "spb_gram_u8: the row-major (dp4a) path handles rows_pad <= 64, got %lld; use the tiled layout",
+                (long long)rows_pad);
+    SPB_REQUIRE(d_ws, "spb_gram_u8: workspace required (spb_gram_u8_ws)");
+    int R = (int)rows_pad;
+    SPB_CUDA(cudaMemsetAsync(d_ws, 0, (size_t)R * R * 8, st));
+    size_t smem = (size_t)R * (kSmallChunk / 4 + 1) * 4;
+    SPB_CUDA(cudaFuncSetAttribute(gram_u8_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t nchunks = (pitch + kSmallChunk - 1) / kSmallChunk;
+    int64_t grid = (int64_t)sm_count() * (smem > 110 * 1024 ? 1 : 2);
+    if (grid > nchunks) grid = nchunks;
+    gram_u8_small_kernel<<<(unsigned)grid, 256, smem, st>>>(d_s0, R, pitch, (unsigned long long*)d_ws);
+    SPB_LAUNCH_CHECK();
+    gram_small_finalize_kernel<<<(R * R + 255) / 256, 256, 0, st>>>((const unsigned long long*)d_ws, R, rows_pad, d_G);
+    SPB_LAUNCH_CHECK();
+    return SPB_OK;
+  }
+  SPB_REQUIRE(layout == SPB_S0_TILED, "spb_gram_u8: unknown layout %d", layout);
+  SPB_REQUIRE(rows_pad % kTile == 0 && pitch % kTile == 0 && (rows_pad == kTile || rows_pad % 256 == 0),
+              "spb_gram_u8: the tiled (tcgen05) path needs pitch %% 128 == 0 and rows_pad == 128 or a multiple of 256 "
+              "(got rows_pad=%lld pitch=%lld)", (long long)rows_pad, (long long)pitch);
+  SPB_REQUIRE(rows_pad <= 32768, "spb_gram_u8: rows_pad too large");
+  UmmaPlan p = plan_umma(rows_pad, pitch);
+  unsigned long long* acc = nullptr;
+  if (p.ksplit > 1) {
+    SPB_REQUIRE(d_ws, "spb_gram_u8: workspace required (spb_gram_u8_ws)");
+    acc = (unsigned long long*)d_ws;
+    SPB_CUDA(cudaMemsetAsync(acc, 0, (size_t)rows_pad * rows_pad * 8, st));
+  }
+  int grid = p.num_work < sm_count() ? p.num_work : sm_count();
+  if (p.BN == 256) {
+    SPB_CUDA(cudaFuncSetAttribute(gram_u8_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    gram_u8_umma_kernel<256><<<grid, kUmmaThreads, p.smem, st>>>(d_s0, p.T, p.KT, p.ksplit, p.kt_per_split, p.num_work, rows_pad,
+                                                               d_G, acc);
+  } else {
+    SPB_CUDA(cudaFuncSetAttribute(gram_u8_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    gram_u8_umma_kernel<128><<<grid, kUmmaThreads, p.smem, st>>>(d_s0, p.T, p.KT, p.ksplit, p.kt_per_split, p.num_work, rows_pad,
+                                                               d_G, acc);
+  }
+  SPB_LAUNCH_CHECK();
+  if (acc) {
+    int64_t cells = rows_pad * rows_pad;
+    gram_finalize_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(acc, rows_pad, rows_pad, d_G);
+    SPB_LAUNCH_CHECK();
+  }
+  return SPB_OK;
+}
+
+// Test / cross-check entry: same result as spb_gram_u8 from a plain SIMT loop (any layout, any size).
+extern "C" int spb_gram_u8_simt(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, double* d_G, void* stream) {
+  SPB_REQUIRE(d_s0 && d_G && rows_pad >= 1 && pitch >= 1, "spb_gram_u8_simt: bad arguments");
+  SPB_REQUIRE(layout == SPB_S0_ROWMAJOR || (rows_pad % kTile == 0 && pitch % kTile == 0), "spb_gram_u8_simt: bad tiled shape");
+  dim3 grid((unsigned)((rows_pad + 127) / 128), (unsigned)rows_pad);
+  gram_u8_simt_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_s0, layout, rows_pad, pitch, rows_pad, d_G);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int spb_gram_hi_correction(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, const int32_t* d_hi_rc,
+                                      const uint32_t* d_hi_val, const uint32_t* d_hi_num, int64_t hi_cap, double* d_G,
+                                      void* stream) {
+  SPB_REQUIRE(d_s0 && d_hi_rc && d_hi_val && d_hi_num && d_G && hi_cap >= 0, "spb_gram_hi_correction: bad arguments");
+  if (hi_cap == 0) return SPB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t gy = hi_cap < 1024 ? hi_cap : 1024;
+  dim3 grid((unsigned)((rows_pad + 255) / 256 > 16 ? 16 : (rows_pad + 255) / 256), (unsigned)gy);
+  hi_cross_kernel<<<grid, 256, 0, st>>>(d_s0, layout, rows_pad, pitch, d_hi_rc, d_hi_val, d_hi_num, hi_cap, rows_pad, d_G);
+  SPB_LAUNCH_CHECK();
+  int64_t gx = (hi_cap + 255) / 256;
+  if (gx > 1024) gx = 1024;
+  hi_self_kernel<<<(unsigned)gx, 256, 0, st>>>(d_hi_rc, d_hi_val, d_hi_num, hi_cap, rows_pad, d_G);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}

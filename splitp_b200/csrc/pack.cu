@@ -5,6 +5,7 @@
 
 namespace spb {
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -17,6 +18,7 @@ using namespace spb;
 
 extern "C" int spb_version(void) { return 100; }
 extern "C" const char* spb_last_error(void) { return spb::g_err; }
+extern "C" uint64_t spb_launch_count(void) { return __atomic_load_n(&spb::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int spb_device_info(int* sms, int* major, int* minor) {
   int dev = 0;

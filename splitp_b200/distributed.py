@@ -1,0 +1,116 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, torch.distributed (NCCL over NVLink).
+
+The path shards two ways (BASELINE.json north_star):
+  * counting  -- alignment SITES are split into contiguous ranges, one per rank; every rank counts its
+                 range and the count tables are summed with an allreduce (direct-indexed table, n <= 12
+                 taxa) or, for hashed tables, gathered as (key, count) lists and merged on every rank.
+                 The pair-statistics table of the subflattening path is reduced the same way.
+  * scoring   -- the SPLIT list is cut into contiguous ranges, one per rank; no collective during the
+                 compute; the scores are all-gathered at the end.
+All reductions are integer sums, so the sharded result is bit-identical to the single-GPU result.
+The host-side logic (ranges, gathers) is backend-agnostic and is tested with gloo on CPU tensors.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env():
+    """Process-group setup under torchrun (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
+    return rank, local, world
+
+
+def shard_range(total, rank, world, align=1):
+    """Contiguous [begin, end) share of `total` units for `rank`; boundaries are multiples of `align`
+    (sites are aligned to 32 so that a shard starts on a validity / bit-plane word)."""
+    blocks = (total + align - 1) // align
+    per, extra = divmod(blocks, world)
+    b = rank * per + min(rank, extra)
+    e = b + per + (1 if rank < extra else 0)
+    return min(b * align, total), min(e * align, total)
+
+
+def make_reduce_fn(group=None):
+    """reduce_fn(tensor, op) hook for engine.count_patterns: in-place allreduce of integer tables."""
+    def reduce_fn(t, op):
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return t
+        if op == "sum":
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        elif op == "min_u32":  # uint32 stored in int32: widen so that 0xFFFFFFFF stays the largest value
+            w = t.to(torch.int64) & 0xFFFFFFFF
+            dist.all_reduce(w, op=dist.ReduceOp.MIN, group=group)
+            t.copy_(torch.where(w > 0x7FFFFFFF, w - (1 << 32), w).to(torch.int32))
+        else:
+            raise ValueError(op)
+        return t
+    return reduce_fn
+
+
+def all_gather_varlen(t, group=None):
+    """Concatenation over ranks of 1-D tensors of different lengths (rank order)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return t
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes)
+    pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+
+
+def gather_scores(local_scores, total, rank, world, group=None):
+    """Scores of split range shard_range(total, rank, world) from every rank -> all `total` scores."""
+    if world == 1:
+        return local_scores
+    out = all_gather_varlen(local_scores, group)
+    assert out.shape[0] == total
+    return out
+
+
+def count_patterns_sharded(aln, rank, world, group=None, want_first=False):
+    """Pattern table of the WHOLE alignment when every rank holds (at least) its site range of `aln`:
+    rank r counts sites shard_range(N, r, world, 32) and the tables are combined."""
+    from . import engine
+    b, e = shard_range(aln.N, rank, world, 32)
+    if world == 1:
+        return engine.count_patterns(aln, want_first=want_first)
+    if aln.n <= engine.DIRECT_MAX_TAXA:
+        return engine.count_patterns(aln, b, e, want_first=want_first, reduce_fn=make_reduce_fn(group))
+    # hashed tables: gather the per-rank (key, count) lists and merge them into one table on every rank
+    local = engine.count_patterns(aln, b, e, want_first=want_first, sort=False)
+    keys = all_gather_varlen(local.keys, group)
+    counts = all_gather_varlen(local.counts, group)
+    first = all_gather_varlen(local.first, group) if want_first else None
+    usable = torch.tensor([int(local.divisor)], dtype=torch.int64, device=keys.device)
+    dist.all_reduce(usable, group=group)
+    merged = engine.merge_tables(aln.n, keys, counts, first)
+    merged.divisor = float(int(usable.item()))
+    merged.taxa = aln.taxa
+    return merged
+
+
+def pair_tables_sharded(aln, rank, world, group=None, as_counts=False):
+    """Pair tables of the whole alignment: each rank reduces its word range, raw statistics are summed."""
+    from . import engine
+    words = (aln.N + 31) // 32
+    b, e = shard_range(words, rank, world)
+    raw = engine.pair_raw(aln, b, e)
+    if world > 1:
+        dist.all_reduce(raw, group=group)
+    return engine.pair_finalize(raw, aln.n, 0.0 if as_counts else float(int(raw[-1].item())))

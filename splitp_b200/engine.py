@@ -1,0 +1,565 @@
+"""Device-side engine behind the drop-in functions.
+
+Everything here drives the C-ABI library (`include/splitp_b200.h`) with torch tensors used purely
+as device buffers (`tensor.data_ptr()`), on the current torch CUDA stream.  There is no CPU
+fallback: without a CUDA device or without the built library every entry point raises.
+
+Objects
+  DeviceAlignment  2-bit packed alignment (site-major bit stream + taxon-major bit planes + validity)
+  PatternTable     compressed site patterns: keys (base-4 number of the pattern, taxon 0 most
+                   significant, as `__index_of`, splitp/constructions.py:166-171) with integer
+                   counts (from an alignment) or float64 values (from a {pattern: value} mapping)
+  PairTables       4x4 joint tables of every taxon pair and their Hadamard-type transform: all a
+                   subflattening needs
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SPB_S0_ROWMAJOR, SPB_S0_TILED, SPB_U8_NO_MEMSET, SPB_VAL_F64, SPB_VAL_U32, call, lib, make_split
+
+STATES = "ACGT"
+_UPPER_LUT = np.full(256, 255, dtype=np.uint8)
+for _i, _c in enumerate(STATES):
+    _UPPER_LUT[ord(_c)] = _i
+DIRECT_MAX_TAXA = 12   # direct-indexed count table up to 4^12 cells (64 MB); hash table above
+JACOBI_MAX_K = 128
+
+
+# --------------------------------------------------------------------------------------------
+# plumbing
+# --------------------------------------------------------------------------------------------
+def device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("splitp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _zeros(shape, dtype):
+    return torch.zeros(shape, dtype=dtype, device=device())
+
+
+def _empty(shape, dtype):
+    return torch.empty(shape, dtype=dtype, device=device())
+
+
+def split_positions(split, taxa):
+    """Taxon labels of both sides -> positions in `taxa` (order kept: it is the digit significance)."""
+    indexer = {t: i for i, t in enumerate(taxa)}
+    return [indexer[s] for s in split[0]], [indexer[s] for s in split[1]]
+
+
+def covers_all(n, idx_a, idx_b):
+    return len(idx_a) + len(idx_b) == n and set(idx_a) | set(idx_b) == set(range(n))
+
+
+# --------------------------------------------------------------------------------------------
+# alignment packing (validity rule of splitp/parsers/fasta.py:54-57)
+# --------------------------------------------------------------------------------------------
+class DeviceAlignment:
+    def __init__(self, n, N, sm, planes, valid, taxa=None):
+        self.n, self.N, self.sm, self.planes, self.valid = n, N, sm, planes, valid
+        self.taxa = tuple(taxa) if taxa is not None else None
+        self.plane_words = int(lib.spb_plane_words(N))
+
+
+def pack(chars, is_ascii=False, taxa=None, want_sm=True, want_planes=True):
+    """chars: uint8 [n, N] (torch tensor on the device, or anything np.asarray accepts on the host).
+    is_ascii: bytes are characters (ACGTacgt valid) rather than codes 0..3."""
+    if not isinstance(chars, torch.Tensor):
+        host = torch.from_numpy(np.ascontiguousarray(np.asarray(chars, dtype=np.uint8)))
+        chars = host.to(device(), non_blocking=False)
+    if chars.dtype != torch.uint8 or chars.dim() != 2:
+        raise ValueError("pack: expected a uint8 [n_taxa, n_sites] array")
+    chars = chars.contiguous()
+    n, N = int(chars.shape[0]), int(chars.shape[1])
+    Wp = int(lib.spb_plane_words(N))
+    sm = _empty(int(lib.spb_sm_words(n, N)), torch.int32) if (want_sm and n <= 32) else None
+    planes = _empty((n, 2, Wp), torch.int32) if want_planes else None
+    valid = _zeros(Wp, torch.int32)
+    if N > 0:
+        call("spb_pack", _p(chars), n, N, N, int(bool(is_ascii)), _p(sm), _p(planes), _p(valid), _st())
+    return DeviceAlignment(n, N, sm, planes, valid, taxa)
+
+
+# --------------------------------------------------------------------------------------------
+# pattern tables
+# --------------------------------------------------------------------------------------------
+class PatternTable:
+    def __init__(self, n, keys, counts=None, values=None, divisor=0.0, first=None, taxa=None):
+        self.n, self.keys, self.counts, self.values = n, keys, counts, values
+        self.divisor = float(divisor)  # counts / divisor = probabilities (fasta.py:66-70); 0 = leave counts
+        self.first, self.taxa = first, (tuple(taxa) if taxa is not None else None)
+
+    @property
+    def num(self):
+        return int(self.keys.shape[0])
+
+    def val_args(self, as_counts=False):
+        """(pointer, kind, divisor) triple of the flattening entry points."""
+        if self.counts is not None:
+            return _p(self.counts), SPB_VAL_U32, 0.0 if as_counts else self.divisor
+        return _p(self.values), SPB_VAL_F64, 0.0
+
+    def values_f64(self):
+        if self.values is not None:
+            return self.values
+        v = self.counts.to(torch.float64)
+        return v / self.divisor if self.divisor > 0 else v
+
+
+def count_patterns(aln, site_begin=0, site_end=None, want_first=False, force_hash=False, sort=True, reduce_fn=None):
+    """Kernel 1: {pattern: count} of the usable sites in [site_begin, site_end)
+    (splitp/parsers/fasta.py:48-63).  Keys come back ascending (= lexicographic A<C<G<T order of
+    splitp/simulation.py:50-54); `first` holds the first site of each pattern (dict insertion order).
+    reduce_fn(tensor) (optional) is applied to the direct table / usable counter before compaction:
+    the hook the multi-GPU path uses for its count allreduce."""
+    n = aln.n
+    if aln.sm is None:
+        raise NotImplementedError("pattern counting uses uint64 keys: at most 31 taxa (site-major stream <= 32)")
+    if n > 31:
+        raise NotImplementedError("pattern counting uses uint64 keys: at most 31 taxa")
+    site_end = aln.N if site_end is None else site_end
+    nsites = max(0, site_end - site_begin)
+    usable = _zeros(1, torch.int64)
+    num = _zeros(1, torch.int64)
+    if n <= DIRECT_MAX_TAXA and not force_hash:
+        cells = 4 ** n
+        table = _zeros(cells, torch.int32)
+        first = torch.full((cells,), -1, dtype=torch.int32, device=device()) if want_first else None
+        call("spb_count_direct", _p(aln.sm), _p(aln.valid), n, site_begin, site_end, _p(table), _p(first), _p(usable), _st())
+        if reduce_fn is not None:
+            reduce_fn(table, "sum")
+            reduce_fn(usable, "sum")
+            if first is not None:
+                reduce_fn(first, "min_u32")
+        cap = min(cells, max(nsites, 1)) if reduce_fn is None else cells
+        tmp = _empty(int(lib.spb_compact_tmp_words(cells)), torch.int32)
+        keys, counts = _empty(cap, torch.int64), _empty(cap, torch.int32)
+        fo = _empty(cap, torch.int32) if want_first else None
+        call("spb_compact_direct", _p(table), _p(first), cells, _p(keys), _p(counts), _p(fo), cap, _p(num), _p(tmp), _st())
+        P = int(num.item())
+        keys, counts = keys[:P], counts[:P]
+        fo = fo[:P] if fo is not None else None
+    else:
+        cap = 1024
+        while cap < 2 * min(4 ** n, max(nsites, 1)):
+            cap *= 2
+        hk = torch.full((cap,), -1, dtype=torch.int64, device=device())
+        hc = _zeros(cap, torch.int32)
+        hf = torch.full((cap,), -1, dtype=torch.int32, device=device()) if want_first else None
+        ovf = _zeros(1, torch.int32)
+        call("spb_count_hash", _p(aln.sm), _p(aln.valid), n, site_begin, site_end, _p(hk), _p(hc), _p(hf), cap, _p(usable),
+             _p(ovf), _st())
+        outcap = min(cap, max(nsites, 1))
+        tmp = _empty(int(lib.spb_compact_tmp_words(cap)), torch.int32)
+        keys, counts = _empty(outcap, torch.int64), _empty(outcap, torch.int32)
+        fo = _empty(outcap, torch.int32) if want_first else None
+        call("spb_compact_hash", _p(hk), _p(hc), _p(hf), cap, _p(keys), _p(counts), _p(fo), outcap, _p(num), _p(tmp), _st())
+        if int(ovf.item()):
+            raise MemoryError("splitp_b200: pattern hash table overflow")
+        P = int(num.item())
+        keys, counts = keys[:P], counts[:P]
+        fo = fo[:P] if fo is not None else None
+        if reduce_fn is not None:
+            reduce_fn(usable, "sum")
+        if sort and P > 1:
+            keys, perm = torch.sort(keys)  # keys < 2^62: signed order = unsigned order
+            counts = counts[perm]
+            fo = fo[perm] if fo is not None else None
+    return PatternTable(n, keys, counts=counts, divisor=float(int(usable.item())), first=fo, taxa=aln.taxa)
+
+
+def merge_tables(n, keys, counts, first=None, sort=True):
+    """Sums the counts of equal keys of a concatenated (key, count) list: the merge step of the sharded
+    hashed counting (one spb_hash_merge pass into a fresh open-addressing table, then compaction)."""
+    total = int(keys.shape[0])
+    cap = 1024
+    while cap < 2 * max(total, 1):
+        cap *= 2
+    hk = torch.full((cap,), -1, dtype=torch.int64, device=device())
+    hc = _zeros(cap, torch.int32)
+    hf = torch.full((cap,), -1, dtype=torch.int32, device=device()) if first is not None else None
+    ovf, num = _zeros(1, torch.int32), _zeros(1, torch.int64)
+    call("spb_hash_merge", _p(keys.contiguous()), _p(counts.contiguous()), _p(first), total, _p(hk), _p(hc), _p(hf), cap, _p(ovf), _st())
+    outcap = max(total, 1)
+    tmp = _empty(int(lib.spb_compact_tmp_words(cap)), torch.int32)
+    ok, oc = _empty(outcap, torch.int64), _empty(outcap, torch.int32)
+    of = _empty(outcap, torch.int32) if first is not None else None
+    call("spb_compact_hash", _p(hk), _p(hc), _p(hf), cap, _p(ok), _p(oc), _p(of), outcap, _p(num), _p(tmp), _st())
+    if int(ovf.item()):
+        raise MemoryError("splitp_b200: pattern hash table overflow")
+    P = int(num.item())
+    ok, oc = ok[:P], oc[:P]
+    of = of[:P] if of is not None else None
+    if sort and P > 1:
+        ok, perm = torch.sort(ok)
+        oc = oc[perm]
+        of = of[perm] if of is not None else None
+    return PatternTable(n, ok, counts=oc, first=of)
+
+
+def encode_patterns(patterns):
+    """list of equal-length ACGT strings -> (uint64 keys, n).  Any other character raises KeyError
+    exactly like `__index_of` (constructions.py:166-171) does."""
+    P = len(patterns)
+    if P == 0:
+        return np.zeros(0, dtype=np.uint64), 0
+    n = len(patterns[0])
+    joined = "".join(patterns)
+    if len(joined) != P * n:
+        raise KeyError("patterns of unequal length")
+    if n > 31:
+        raise NotImplementedError("pattern keys are uint64: at most 31 taxa")
+    raw = np.frombuffer(joined.encode("latin-1", errors="replace"), dtype=np.uint8).reshape(P, n)
+    codes = _UPPER_LUT[raw]
+    bad = np.argwhere(codes > 3)
+    if len(bad):
+        raise KeyError(chr(raw[bad[0][0], bad[0][1]]))
+    weights = (np.uint64(4) ** np.arange(n - 1, -1, -1, dtype=np.uint64)) if n else np.zeros(0, np.uint64)
+    return (codes.astype(np.uint64) * weights).sum(axis=1, dtype=np.uint64), n
+
+
+def decode_keys(keys, n):
+    """uint64 keys -> list of pattern strings."""
+    keys = np.asarray(keys, dtype=np.uint64)
+    if len(keys) == 0:
+        return []
+    shifts = (2 * np.arange(n - 1, -1, -1)).astype(np.uint64)
+    codes = ((keys[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)
+    chars = np.frombuffer(STATES.encode(), dtype=np.uint8)[codes]
+    flat = chars.tobytes().decode("ascii")
+    return [flat[i * n:(i + 1) * n] for i in range(len(keys))]
+
+
+_TABLE_CACHE = {}
+
+
+def table_from_mapping(mapping):
+    """{pattern: value} mapping (plain dict or Alignment) -> PatternTable with float64 values, in the
+    mapping's iteration order.  A one-entry-per-object cache avoids re-uploading an unchanged mapping
+    (validated against the joined keys and the values, so a mutated mapping is re-encoded)."""
+    if isinstance(mapping, PatternTable):
+        return mapping
+    pats = list(mapping.keys())
+    vals = np.fromiter((float(v) for v in mapping.values()), dtype=np.float64, count=len(pats))
+    joined = "".join(pats)
+    hit = _TABLE_CACHE.get(id(mapping))
+    if hit is not None and hit[0] == joined and hit[1].shape == vals.shape and np.array_equal(hit[1], vals, equal_nan=True):
+        table = hit[2]
+    else:
+        keys, n = encode_patterns(pats)
+        dev = device()
+        table = PatternTable(n, torch.from_numpy(keys.view(np.int64)).to(dev), values=torch.from_numpy(vals).to(dev))
+        if len(_TABLE_CACHE) > 16:
+            _TABLE_CACHE.clear()
+        _TABLE_CACHE[id(mapping)] = (joined, vals, table)
+    table.taxa = tuple(mapping.taxa) if hasattr(mapping, "taxa") else None
+    return table
+
+
+def table_to_dict(table, as_counts=False):
+    keys = table.keys.cpu().numpy().view(np.uint64)
+    pats = decode_keys(keys, table.n)
+    if table.counts is not None:
+        cnt = table.counts.cpu().numpy().view(np.uint32)
+        if as_counts or table.divisor <= 0:
+            return {p: int(c) for p, c in zip(pats, cnt)}
+        return {p: int(c) / table.divisor for p, c in zip(pats, cnt)}  # one IEEE division, fasta.py:66-70
+    return dict(zip(pats, table.values.cpu().numpy().tolist()))
+
+
+# --------------------------------------------------------------------------------------------
+# flattenings (kernel 2)
+# --------------------------------------------------------------------------------------------
+def flatten_coo(table, idx_a, idx_b):
+    """(rows, cols) int64 of every pattern: the triplets behind FlatFormat.sparse (constructions.py:86-102)."""
+    sp = make_split(table.n, idx_a, idx_b)
+    rows, cols = _empty(table.num, torch.int64), _empty(table.num, torch.int64)
+    call("spb_flatten_coo", _p(table.keys), table.num, C.byref(sp), _p(rows), _p(cols), _st())
+    return rows, cols
+
+
+def flatten_dense(table, idx_a, idx_b, as_counts=False):
+    a, b = len(idx_a), len(idx_b)
+    sp = make_split(table.n, idx_a, idx_b)
+    out = _empty((4 ** a, 4 ** b), torch.float64)
+    win = None if covers_all(table.n, idx_a, idx_b) else _empty(4 ** (a + b), torch.int32)
+    vp, kind, div = table.val_args(as_counts)
+    call("spb_flatten_dense_w", _p(table.keys), vp, kind, div, table.num, C.byref(sp), _p(out), _p(win), _st())
+    return out
+
+
+def reduced_plan(table, idx_a, idx_b):
+    a, b = len(idx_a), len(idx_b)
+    sp = make_split(table.n, idx_a, idx_b)
+    rank_r, rank_c = _empty(4 ** a + 1, torch.int32), _empty(4 ** b + 1, torch.int32)
+    tmp = _empty(int(lib.spb_compact_tmp_words(max(4 ** a, 4 ** b) + 1)), torch.int32)
+    shape = (C.c_int64 * 2)()
+    call("spb_flatten_reduced_plan", _p(table.keys), table.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(tmp), shape, _st())
+    return sp, rank_r, rank_c, int(shape[0]), int(shape[1])
+
+
+def flatten_reduced(table, idx_a, idx_b, as_counts=False):
+    """constructions.py:31-55: all-zero rows / columns dropped, rows and columns in ascending index order."""
+    if max(len(idx_a), len(idx_b)) > 13:
+        return _flatten_reduced_large(table, idx_a, idx_b, as_counts)
+    sp, rank_r, rank_c, R, Cc = reduced_plan(table, idx_a, idx_b)
+    out = _empty((R, Cc), torch.float64)
+    if R == 0 or Cc == 0:
+        return out
+    win = None if covers_all(table.n, idx_a, idx_b) else _empty(R * Cc, torch.int32)
+    vp, kind, div = table.val_args(as_counts)
+    call("spb_flatten_reduced_fill_w", _p(table.keys), vp, kind, div, table.num, C.byref(sp), _p(rank_r), _p(rank_c), R, Cc,
+         _p(out), _p(win), _st())
+    return out
+
+
+def _flatten_reduced_large(table, idx_a, idx_b, as_counts):
+    # sides above 13 taxa: the used-index flag arrays (4^side cells) no longer fit, so the ranks come from a
+    # sort-unique of the per-pattern indices (torch.unique: library sort, documented in DESIGN.md)
+    if max(len(idx_a), len(idx_b)) > 31:
+        raise NotImplementedError("reduced flattening: sides are limited to 31 taxa (int64 indices)")
+    rows, cols = flatten_coo(table, idx_a, idx_b)
+    ur, ri = torch.unique(rows, return_inverse=True)
+    uc, ci = torch.unique(cols, return_inverse=True)
+    out = _zeros((len(ur), len(uc)), torch.float64)
+    vals = table.counts.to(torch.float64) if (as_counts and table.counts is not None) else table.values_f64()
+    if not covers_all(table.n, idx_a, idx_b):
+        cell = ri * len(uc) + ci
+        order = torch.arange(table.num, device=cell.device)
+        last = torch.zeros(len(ur) * len(uc), dtype=torch.int64, device=cell.device).scatter_reduce_(0, cell, order, "amax")
+        keep = last[cell] == order
+        ri, ci, vals = ri[keep], ci[keep], vals[keep]
+    out[ri, ci] = vals
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# scores (kernels 4 and 5)
+# --------------------------------------------------------------------------------------------
+def gram_f64(A):
+    """G = A A^T, A float64 [batch, R, C] (or [R, C]) -> [batch, R, R]."""
+    if A.dim() == 2:
+        A = A.unsqueeze(0)
+    A = A.contiguous()
+    batch, R, Cc = (int(x) for x in A.shape)
+    G = _empty((batch, R, R), torch.float64)
+    ws_elems = int(lib.spb_gram_f64_ws(R, Cc, batch))
+    ws = _empty(ws_elems, torch.float64) if ws_elems else None
+    call("spb_gram_f64", _p(A), R, Cc, batch, _p(G), _p(ws), _st())
+    return G
+
+
+def score_gram(G, k=None, want_info=False):
+    """Scores from symmetric PSD Gram matrices G [batch, ld, ld] using the leading k x k block.
+    k <= 4 -> 0.0 (at most 4 singular values: 1 - top4/total vanishes, phylogenetics.py:293-300)."""
+    if G.dim() == 2:
+        G = G.unsqueeze(0)
+    G = G.contiguous()
+    batch, ld = int(G.shape[0]), int(G.shape[1])
+    k = ld if k is None else int(k)
+    scores = _empty(batch, torch.float64)
+    info = None
+    if k <= JACOBI_MAX_K:
+        info = _empty((batch, k), torch.float64) if want_info else None
+        call("spb_score_gram_small", _p(G), k, ld, batch, _p(scores), _p(info), _st())
+    else:
+        ws = _empty(int(lib.spb_score_gram_large_ws(k, batch)), torch.float64)
+        info = _empty((batch, 4), torch.float64) if want_info else None
+        call("spb_score_gram_large", _p(G), k, ld, batch, _p(scores), _p(info), _p(ws), _st())
+    return (scores, info) if want_info else scores
+
+
+def score_matrix(A):
+    """split_score of a float64 device matrix [R, C] (or a batch [B, R, C]): Gram on the short side."""
+    if A.dim() == 2:
+        A = A.unsqueeze(0)
+    if A.shape[1] > A.shape[2]:
+        A = A.transpose(1, 2)
+    if min(A.shape[1], A.shape[2]) == 0:
+        return torch.full((A.shape[0],), float("nan"), dtype=torch.float64, device=A.device)
+    return score_gram(gram_f64(A.contiguous()))
+
+
+class CountScorer:
+    """Exact-integer scoring of count flattenings: u8 low-byte matrix -> Gram on the tensor cores
+    (tcgen05 kind::i8) or dp4a for <= 64 rows -> sparse high-part correction -> eigen-solver.
+    Buffers are allocated once and reused across splits."""
+
+    def __init__(self, table, hi_cap=None):
+        if table.counts is None:
+            raise ValueError("CountScorer needs a PatternTable with integer counts")
+        self.table = table
+        self.hi_cap = int(hi_cap if hi_cap is not None else max(1024, min(table.num, 1 << 20)))
+        self.hi_rc = _empty((self.hi_cap, 2), torch.int32)
+        self.hi_val = _empty(self.hi_cap, torch.int32)
+        self.hi_num = _zeros(1, torch.int32)
+        self._s0 = {}
+        self._G = {}
+        self._ws = {}
+        self.gram_hook = None  # optional wrapper around the Gram launch (bench.py times it with CUDA events)
+
+    @staticmethod
+    def geometry(rows, cols):
+        """(layout, rows_pad, pitch) for a rows x cols count matrix with rows <= cols."""
+        if rows <= 64:
+            return SPB_S0_ROWMAJOR, max(rows, 1), (cols + 15) // 16 * 16
+        rp = 128 if rows <= 128 else (rows + 255) // 256 * 256
+        return SPB_S0_TILED, rp, (cols + 127) // 128 * 128
+
+    def _buffers(self, layout, rows_pad, pitch):
+        key = (layout, rows_pad, pitch)
+        if key not in self._s0:
+            self._s0[key] = _zeros(rows_pad * pitch, torch.uint8)
+        if rows_pad not in self._G:
+            self._G[rows_pad] = _empty((rows_pad, rows_pad), torch.float64)
+        wkey = (layout, rows_pad, pitch)
+        if wkey not in self._ws:
+            n = int(lib.spb_gram_u8_ws(rows_pad, pitch, layout))
+            self._ws[wkey] = _empty(n, torch.int64) if n else None
+        return self._s0[key], self._G[rows_pad], self._ws[wkey]
+
+    def gram(self, idx_a, idx_b, reduced=False):
+        """Exact F F^T (short side) of the count flattening of one split.  Returns (G, k)."""
+        t = self.table
+        if not covers_all(t.n, idx_a, idx_b):
+            raise ValueError("CountScorer: the split must cover all taxa")
+        rank_r = rank_c = None
+        if reduced:
+            sp, rank_r, rank_c, R, Cc = reduced_plan(t, idx_a, idx_b)
+            if R > Cc:  # Gram on the short side: swap the roles of the two sides
+                idx_a, idx_b, rank_r, rank_c, R, Cc = idx_b, idx_a, rank_c, rank_r, Cc, R
+                sp = make_split(t.n, idx_a, idx_b)
+        else:
+            if len(idx_a) > len(idx_b):
+                idx_a, idx_b = idx_b, idx_a
+            sp = make_split(t.n, idx_a, idx_b)
+            R, Cc = 4 ** len(idx_a), 4 ** len(idx_b)
+        layout, rows_pad, pitch = self.geometry(R, Cc)
+        s0, G, ws = self._buffers(layout, rows_pad, pitch)
+        call("spb_flatten_u8", _p(t.keys), _p(t.counts), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch,
+             layout, SPB_U8_NO_MEMSET, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num), self.hi_cap, _st())
+        run = lambda: call("spb_gram_u8", _p(s0), rows_pad, pitch, layout, _p(G), _p(ws), _st())  # noqa: E731
+        run() if self.gram_hook is None else self.gram_hook(run)
+        call("spb_gram_hi_correction", _p(s0), rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num),
+             self.hi_cap, _p(G), _st())
+        call("spb_flatten_u8_clear", _p(t.keys), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch, layout, _st())
+        return G, R
+
+    def score(self, idx_a, idx_b, reduced=False):
+        G, k = self.gram(idx_a, idx_b, reduced)
+        if k == 0:
+            return torch.full((1,), float("nan"), dtype=torch.float64, device=G.device)
+        return score_gram(G, k)
+
+    def check_hi(self):
+        n = int(self.hi_num.item())
+        if n > self.hi_cap:
+            raise MemoryError(f"splitp_b200: {n} counts >= 256 exceed the high-part capacity {self.hi_cap}")
+
+
+def score_splits_counts(table, splits_idx, reduced=False):
+    """Scores of many splits [(idx_a, idx_b), ...] of a count table, exact-integer Gram path."""
+    scorer = CountScorer(table)
+    out = _empty(len(splits_idx), torch.float64)
+    for s, (ia, ib) in enumerate(splits_idx):
+        out[s:s + 1] = scorer.score(ia, ib, reduced)
+    scorer.check_hi()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# subflattenings (kernel 3)
+# --------------------------------------------------------------------------------------------
+class PairTables:
+    def __init__(self, n, N_tab, T, total):
+        self.n, self.N, self.T, self.total = n, N_tab, T, total
+
+
+def pair_raw(aln, word_begin=0, word_end=None):
+    """Raw pair statistics of a range of 32-site words (sum-reducible across GPUs)."""
+    if aln.planes is None:
+        raise ValueError("pair tables need the taxon-major bit planes (pack(want_planes=True))")
+    word_end = (aln.N + 31) // 32 if word_end is None else word_end
+    raw = _zeros(int(lib.spb_pair_raw_words(aln.n)), torch.int64)
+    call("spb_pair_tables", _p(aln.planes), _p(aln.valid), aln.n, aln.plane_words, word_begin, word_end, _p(raw), _st())
+    return raw
+
+
+def pair_finalize(raw, n, divisor=0.0):
+    N_tab, T, total = _empty((n, n, 4, 4), torch.float64), _empty((n, n, 4, 4), torch.float64), _empty(1, torch.float64)
+    call("spb_pair_finalize", _p(raw), n, float(divisor), _p(N_tab), _p(T), _p(total), _st())
+    return PairTables(n, N_tab, T, total)
+
+
+def pair_tables_from_alignment(aln, as_counts=False):
+    raw = pair_raw(aln)
+    usable = 0.0 if as_counts else float(int(raw[-1].item()))
+    return pair_finalize(raw, aln.n, usable)
+
+
+def pair_tables_from_table(table, as_counts=False):
+    n = table.n
+    N_tab = _zeros((n, n, 4, 4), torch.float64)
+    vals = table.counts.to(torch.float64) if (as_counts and table.counts is not None) else table.values_f64()
+    call("spb_pair_tables_weighted", _p(table.keys), _p(vals.contiguous()), table.num, n, _p(N_tab), _st())
+    T, total = _empty((n, n, 4, 4), torch.float64), _empty(1, torch.float64)
+    call("spb_pair_transform", _p(N_tab), n, _p(T), _p(total), _st())
+    return PairTables(n, N_tab, T, total)
+
+
+def subflatten(pt, idx_a, idx_b):
+    sp = make_split(pt.n, idx_a, idx_b)
+    out = _empty((3 * len(idx_a) + 1, 3 * len(idx_b) + 1), torch.float64)
+    call("spb_subflatten", _p(pt.T), _p(pt.total), pt.n, C.byref(sp), _p(out), _st())
+    return out
+
+
+def masks_from_splits(splits_idx):
+    ma = np.zeros(len(splits_idx), dtype=np.uint64)
+    mb = np.zeros(len(splits_idx), dtype=np.uint64)
+    for s, (ia, ib) in enumerate(splits_idx):
+        ma[s] = sum(1 << t for t in ia)
+        mb[s] = sum(1 << t for t in ib)
+    return ma, mb
+
+
+def subflatten_scores(pt, masks_a, masks_b=None):
+    """Batched subflattening scores.  masks: uint64 bit masks over taxon positions (torch int64 tensors on
+    the device, or numpy uint64 arrays).  Side taxa are taken in ascending position order."""
+    def up(m):
+        if m is None or isinstance(m, torch.Tensor):
+            return m
+        return torch.from_numpy(np.ascontiguousarray(m).view(np.int64)).to(device())
+    ma, mb = up(masks_a), up(masks_b)
+    out = _empty(int(ma.shape[0]), torch.float64)
+    call("spb_subflatten_score", _p(pt.T), _p(pt.total), pt.n, _p(ma), _p(mb), int(ma.shape[0]), _p(out), _st())
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# Alignment.sub_alignment support (splitp/alignment.py:10-31)
+# --------------------------------------------------------------------------------------------
+def marginalise(table, idx):
+    """Pattern table over the taxa positions `idx` (ascending): values of collapsing patterns are added."""
+    idx = sorted(idx)
+    rows, _ = flatten_coo(table, idx, [])
+    uniq, inv = torch.unique(rows, return_inverse=True)
+    if table.counts is not None:
+        acc = torch.zeros(len(uniq), dtype=torch.int64, device=rows.device).index_add_(0, inv, table.counts.to(torch.int64))
+        return PatternTable(len(idx), uniq, counts=acc.to(torch.int32), divisor=table.divisor)
+    acc = torch.zeros(len(uniq), dtype=torch.float64, device=rows.device).index_add_(0, inv, table.values)
+    return PatternTable(len(idx), uniq, values=acc)

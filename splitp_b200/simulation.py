@@ -1,0 +1,75 @@
+"""Alignment generation (reference: splitp/simulation.py:9-56, splitp/model.py:14-75).
+
+The reference evolves one site at a time through networkx (about 830 sites/s), which
+cannot produce the 10^6..10^8-site benchmark inputs.  `simulate_codes` draws all sites at once with torch
+on whatever device it is given: uniform root state (simulation.py:28), then for every edge the child
+state is drawn from column `parent state` of expm(t Q) (simulation.py:18-19).  It is statistically
+equivalent to the reference simulator, not bit-identical; parity is always checked on the SAME
+alignment fed to both sides.  `generate_alignment` keeps the reference's signature and return type
+(a plain dict of sorted patterns -> count / float(sequence_length), simulation.py:42-56) with the
+counting done on the device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from scipy.linalg import expm
+
+from . import engine
+
+
+class GTR:
+    """General time-reversible rate matrix, normalised to one expected substitution per unit time
+    (model.py:24-61)."""
+
+    def __init__(self, equilibrium=(0.25, 0.25, 0.25, 0.25), rates=(1, 1, 1, 1, 1, 1), name="GTR"):
+        pi = np.asarray(equilibrium, dtype=np.float64)
+        if len(pi) != 4 or len(rates) != 6:
+            raise ValueError("Incorrect number of parameters for GTR model.")
+        if any(x < 0 for x in list(pi) + list(rates)):
+            raise ValueError("All parameters must be positive.")
+        Q = np.zeros((4, 4))
+        Q[np.triu_indices(4, 1)] = rates
+        Q = (Q + Q.T) * (np.tile(pi, (4, 1)) - np.diag(pi))
+        Q -= np.diag(Q.sum(axis=1))
+        self.rate_matrix = Q / -(pi @ np.diag(Q))
+        self.init_dist = pi
+        self.name = name
+
+    @classmethod
+    def JukesCantor(cls, rate=1):
+        return cls(rates=[rate] * 6, name="Jukes-Cantor model")
+
+    def transition_matrix(self, t):
+        return expm(t * self.rate_matrix)
+
+
+def simulate_codes(tree, model, sequence_length, seed=0, device=None):
+    """uint8 [n_taxa, sequence_length] of codes 0..3, rows in `tree.taxa` order."""
+    device = torch.device(device) if device is not None else engine.device()
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    N = int(sequence_length)
+    states = {0: torch.randint(0, 4, (N,), generator=gen, device=device, dtype=torch.int64)}
+    cache = {}
+    for node in range(1, len(tree.parent)):
+        t = tree.branch_length[node]
+        if t not in cache:
+            M = np.asarray(model.transition_matrix(t), dtype=np.float64)  # column = parent state
+            cache[t] = torch.from_numpy(np.cumsum(M, axis=0).T.copy()).to(device)  # [parent, cumulative child]
+        cdf = cache[t]
+        parent = states[tree.parent[node]]
+        u = torch.rand(N, generator=gen, device=device, dtype=torch.float64)
+        c = cdf[parent]  # [N, 4]
+        states[node] = ((u >= c[:, 0]).to(torch.int64) + (u >= c[:, 1]).to(torch.int64) + (u >= c[:, 2]).to(torch.int64))
+    row = {name: node for node, name in tree.names.items()}
+    return torch.stack([states[row[t]] for t in tree.taxa]).to(torch.uint8)
+
+
+def generate_alignment(tree, model, sequence_length, seed=0):
+    """{pattern: count / float(sequence_length)} in lexicographic A<C<G<T order (simulation.py:42-56)."""
+    codes = simulate_codes(tree, model, sequence_length, seed)
+    aln = engine.pack(codes, is_ascii=False, want_planes=False)
+    table = engine.count_patterns(aln)
+    table.divisor = float(sequence_length)
+    return engine.table_to_dict(table)

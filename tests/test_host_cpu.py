@@ -1,0 +1,174 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/splitp_b200.h declares, the
+host logic (split enumeration, tree topology, pattern encoding, sharding) and the N>1 plumbing over gloo.
+No compute calls are made here (there is no GPU in the build container)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from splitp_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "splitp_b200.h")).read()
+    declared = set(re.findall(r"\b(spb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.PROTOTYPES), (declared ^ set(_lib.PROTOTYPES))
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert _lib.lib.spb_version() == 100
+    assert _lib.lib.spb_plane_words(33) == 4 and _lib.lib.spb_sm_words(12, 32) >= 24
+    assert _lib.lib.spb_pair_raw_words(20) == 20 * 20 * 9 + 60 + 1
+    # argument errors are reported through the status code + message, never abort(): NULL buffers
+    assert _lib.lib.spb_pack(None, 4, 10, 10, 0, None, None, None, None) == 1
+    assert b"spb_pack" in _lib.lib.spb_last_error()
+    with pytest.raises(ValueError):
+        _lib.call("spb_count_direct", None, None, 20, 0, 10, None, None, None, None)
+
+
+def test_no_cpu_fallback_in_product():
+    """The product path must fail loudly without a device; nothing under splitp_b200/ imports the oracle."""
+    import torch
+    import splitp_b200 as sp
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            sp.flattening("01|23", {"ACGT": 1.0})
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            sp.split_score(np.eye(6))
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "splitp_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_all_splits_matches_golden(golden_small):
+    from splitp_b200.splits import all_splits
+
+    class T:
+        def __init__(self, taxa):
+            self.taxa = list(taxa)
+
+        def get_taxa(self):
+            return self.taxa
+    g = golden_small["all_splits"]
+    for taxa, d in g.items():
+        if taxa == "named5":
+            assert [[list(a), list(b)] for a, b in all_splits(T([f"t{i}" for i in range(5)]))] == d
+            with pytest.raises(ValueError):
+                list(all_splits(T([f"t{i}" for i in range(5)]), string_format=True))
+            continue
+        t = T(taxa)
+        assert [[list(a), list(b)] for a, b in all_splits(t)] == d["default"]
+        assert [[list(a), list(b)] for a, b in all_splits(t, trivial=True)] == d["trivial"]
+        assert [[list(a), list(b)] for a, b in all_splits(t, size=2)] == d["size2"]
+        assert list(all_splits(t, string_format=True)) == d["strings"]
+    r = list(all_splits(T("012345"), randomise=True))
+    assert sorted(r) == sorted(all_splits(T("012345")))
+    with pytest.raises(ValueError):
+        next(all_splits(T([str(i) for i in range(40)]), string_format=True))
+
+
+def test_balanced_tree(golden_readme):
+    from splitp_b200.trees import balanced_tree
+    t = balanced_tree(10, 0.05)
+    assert t.taxa == [str(x) for x in golden_readme["taxa"]]
+    assert sorted(t.splits(as_strings=True)) == sorted(str(s) for s in golden_readme["true_splits"])
+    assert len(list(balanced_tree(12, 0.05).splits())) == 9
+    assert balanced_tree(38).taxa[:3] == ["t0", "t1", "t10"]
+    with pytest.raises(ValueError):
+        balanced_tree(7)
+
+
+def test_encode_decode_and_simulator():
+    import torch
+    from splitp_b200 import engine, simulation, trees
+    pats = ["ACGT", "TTTT", "AAAA", "GATC"]
+    keys, n = engine.encode_patterns(pats)
+    assert n == 4 and keys.tolist() == [0b00011011, 255, 0, 0b10001101]
+    assert engine.decode_keys(keys, 4) == pats
+    with pytest.raises(KeyError):
+        engine.encode_patterns(["ACGU"])
+    with pytest.raises(KeyError):
+        engine.encode_patterns(["acgt"])  # the reference's __index_of only knows upper case
+    tree = trees.balanced_tree(6, 0.1)
+    m = simulation.GTR((0.1, 0.2, 0.3, 0.4), (1, 2, 3, 4, 5, 6))
+    Q = m.rate_matrix
+    assert abs(-(m.init_dist @ np.diag(Q)) - 1) < 1e-12 and np.allclose(Q.sum(axis=1), 0)
+    c = simulation.simulate_codes(tree, m, 20000, seed=1, device="cpu")
+    assert c.shape == (6, 20000) and c.dtype == torch.uint8 and int(c.max()) <= 3
+    c2 = simulation.simulate_codes(tree, m, 20000, seed=1, device="cpu")
+    assert torch.equal(c, c2)
+    # siblings agree more often than taxa across the root
+    same = lambda i, j: float((c[i] == c[j]).float().mean())  # noqa: E731
+    assert same(0, 1) > same(0, 5)
+
+
+def test_count_scorer_geometry():
+    from splitp_b200 import engine
+    g = engine.CountScorer.geometry
+    assert g(16, 1 << 20) == (0, 16, 1 << 20)
+    assert g(64, 262144) == (0, 64, 262144)
+    assert g(256, 65536) == (1, 256, 65536)
+    assert g(4096, 4096) == (1, 4096, 4096)
+    assert g(100, 1000) == (1, 128, 1024)
+    assert g(1810, 1814) == (1, 2048, 1920)
+
+
+def test_shard_range():
+    from splitp_b200.distributed import shard_range
+    for total, world, align in [(1_000_000, 8, 32), (33, 4, 32), (2035, 8, 1), (5, 8, 1), (0, 2, 32)]:
+        cover = []
+        for r in range(world):
+            b, e = shard_range(total, r, world, align)
+            assert 0 <= b <= e <= total and (b % align == 0 or b == total)
+            cover += list(range(b, e))
+        assert cover == list(range(total))
+
+
+def test_gloo_world2_plumbing(tmp_path):
+    """world_size=2 over gloo on CPU tensors: integer table allreduce, u32 min-reduce of first-site indices,
+    variable-length gathers and the score gather are rank-order exact."""
+    script = tmp_path / "w2.py"
+    script.write_text(f'''
+import os, sys
+sys.path.insert(0, {ROOT!r})
+import torch, torch.distributed as dist
+from splitp_b200 import distributed as spd
+rank, local, world = spd.init_from_env()
+assert world == 2 and dist.get_backend() == "gloo"
+fn = spd.make_reduce_fn()
+t = torch.arange(10, dtype=torch.int32) * (rank + 1)
+fn(t, "sum"); assert t.tolist() == [3 * i for i in range(10)]
+f = torch.tensor([-1, 5 + rank, -1 if rank == 0 else 7, -2147483648 + rank], dtype=torch.int32)  # -1 = 0xFFFFFFFF = "unset"
+fn(f, "min_u32"); assert f.tolist() == [-1, 5, 7, -2147483648], f.tolist()
+v = torch.arange(3 + 4 * rank, dtype=torch.int64) + 100 * rank
+g = spd.all_gather_varlen(v); assert g.tolist() == [0, 1, 2] + [100 + i for i in range(7)]
+S = 11
+b, e = spd.shard_range(S, rank, world)
+sc = spd.gather_scores(torch.arange(b, e, dtype=torch.float64), S, rank, world)
+assert sc.tolist() == [float(i) for i in range(S)]
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+''')
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29517", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
+
+
+def test_bench_reference_arm_runs():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--sites", "20000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    import json
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
