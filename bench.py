@@ -228,14 +228,7 @@ def main():
             if scorer is None:
                 scorer = state["scorer"] = eng.CountScorer(table)
             scorer.table = table
-            out = torch.empty(len(idx_mine), dtype=torch.float64, device=dev)
-            for s, (ia, ib) in enumerate(idx_mine):
-                big = min(len(ia), len(ib)) == 6
-                if big and state.get("profile"):
-                    scorer.gram_hook = lambda f: timed("gram", f)
-                else:
-                    scorer.gram_hook = None
-                out[s:s + 1] = scorer.score(ia, ib)
+            out = scorer.score_many(idx_mine, big_hook=(lambda f: timed("gram", f)) if state.get("profile") else None)
             scorer.check_hi()
         else:
             aln = eng.pack(codes, want_sm=False)

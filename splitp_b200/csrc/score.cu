@@ -9,6 +9,7 @@
 // total is trace(G) = ||F||_F^2.
 #include "common.cuh"
 #include "jacobi.cuh"
+#include <vector>
 
 using namespace spb;
 
@@ -173,11 +174,20 @@ __global__ void __launch_bounds__(256) score_small_kernel(const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-// large path: block Krylov + Rayleigh-Ritz
+// large path: restarted block Krylov + Rayleigh-Ritz (all kernels batched over matrices)
+//
+// One cycle: Q_0 (8 x k, orthonormal) -> for j < nb: AQ_j = Q_j G (symv_block_kernel, HBM-bound: G is read once
+// per block), next block = AQ_j orthogonalised twice against all previous blocks (classical Gram-Schmidt x2) and
+// orthonormalised by SVQB; T = Q AQ^T (dim x dim, dim = 8 nb <= 96) is diagonalised by the shared-memory Jacobi
+// solver WITH eigenvectors; the top-8 Ritz vectors (in place of Q_0) restart the next cycle and the residuals
+// ||G y - theta y|| / theta_0 of the top 4 measure convergence.  The host loop (spb_score_gram_large) runs cycles
+// until every matrix of the batch has converged: one cycle of dim 32 is enough for flattenings of alignments
+// (their spectrum decays by 10^-3 .. 10^-7 after the 4th eigenvalue); flat spectra take a few dim-96 cycles.
 // ------------------------------------------------------------------------------------------
-constexpr int kKB = 16;       // block size
-constexpr int kKBlocks = 6;   // Krylov blocks
-constexpr int kKDim = kKB * kKBlocks;  // 96
+constexpr int kKB = 8;        // block size
+constexpr int kKMaxBlocks = 12;
+constexpr int kKDim = kKB * kKMaxBlocks;  // 96
+constexpr int kInfo = 8;      // per-matrix status: top4, trace, residual, dim, cycles, delta_top, -, -
 
 __global__ void krylov_init_kernel(double* W, int64_t strideW, int k) {
   int64_t bt = blockIdx.y;
@@ -185,6 +195,55 @@ __global__ void krylov_init_kernel(double* W, int64_t strideW, int k) {
   if (i >= (int64_t)kKB * k) return;
   uint64_t h = mix64((uint64_t)i * 0x9E3779B97F4A7C15ull + 0x1234567ull + (uint64_t)bt * 0xD1B54A32D192ED03ull);
   W[bt * strideW + i] = (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+// AQ[c][i] = sum_j G[i][j] Q[c][j], c < 8.  CTA = 32 rows of G; warp = 4 rows processed together; lanes stride j.
+// The Q chunk (8 x 1024 doubles, 64 KB) is staged in shared memory and reused by all 32 rows.
+constexpr int kSymvRows = 32;
+constexpr int kSymvChunk = 1024;
+__global__ void __launch_bounds__(256) symv_block_kernel(const double* __restrict__ G, int64_t ld, int64_t strideG,
+                                                         const double* __restrict__ Q, int64_t strideQ, double* __restrict__ AQ,
+                                                         int k) {
+  extern __shared__ __align__(16) double s_q[];  // [kKB][kSymvChunk]
+  const int bt = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kSymvRows + warp * 4;
+  const double* Gb = G + (int64_t)bt * strideG;
+  const double* Qb = Q + (int64_t)bt * strideQ;
+  double acc[4][kKB];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < kKB; ++c) acc[r][c] = 0.0;
+  for (int j0 = 0; j0 < k; j0 += kSymvChunk) {
+    const int len = min(kSymvChunk, k - j0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kKB * kSymvChunk; idx += 256) {
+      int c = idx / kSymvChunk, j = idx - c * kSymvChunk;
+      s_q[idx] = (j < len) ? Qb[(int64_t)c * k + j0 + j] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int j = lane; j < len; j += 32) {
+      double g[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) g[r] = (row0 + r < k) ? __ldg(Gb + (int64_t)(row0 + r) * ld + j0 + j) : 0.0;
+#pragma unroll
+      for (int c = 0; c < kKB; ++c) {
+        double q = s_q[c * kSymvChunk + j];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r][c] = fma(g[r], q, acc[r][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < kKB; ++c) {
+      double v = acc[r][c];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      if (lane == 0 && row0 + r < k) AQ[(int64_t)bt * strideQ + (int64_t)c * k + row0 + r] = v;
+    }
 }
 
 __global__ void copy_block_kernel(const double* src, int64_t strideS, double* dst, int64_t strideD, int64_t elems) {
@@ -216,7 +275,7 @@ __global__ void __launch_bounds__(256) krylov_subtract_kernel(double* W, int64_t
   for (int c = 0; c < kKB; ++c) Wb[(int64_t)c * k + pos] = w[c];
 }
 
-// SVQB orthonormalisation of a block: S = W W^T (16x16, given), eigen-decompose the diagonally scaled S,
+// SVQB orthonormalisation of a block: S = W W^T (8 x 8, given), eigen-decompose the diagonally scaled S,
 // W <- Lambda^{-1/2} V^T D W.  Directions with lambda <= 1e-13 * lambda_max are dropped (zero vectors).
 __global__ void __launch_bounds__(256) krylov_svqb_kernel(double* W, int64_t strideW, const double* __restrict__ S,
                                                           int64_t strideS, int k) {
@@ -265,16 +324,21 @@ __global__ void __launch_bounds__(256) krylov_svqb_kernel(double* W, int64_t str
   }
 }
 
-// Rayleigh-Ritz: eigenvalues of T (dim x dim) and of its leading (dim - 16) block; trace of G.
+// Rayleigh-Ritz of T (dim x dim): Jacobi with eigenvectors in shared memory; writes the coefficients of the top-8
+// Ritz vectors (Vtop [dim][8]), their Ritz values (theta [8]), zeroes the residual accumulators and updates
+// info = {top4, trace(G), residual (filled by ritz_kernel), dim, cycles, |top4 - previous top4| / trace}.
 __global__ void __launch_bounds__(256) krylov_rr_kernel(const double* __restrict__ T, int64_t strideT, int dim,
-                                                        const double* __restrict__ G, int k, int64_t ld, double* scores,
-                                                        double* info) {
-  extern __shared__ __align__(16) double s_A[];
+                                                        const double* __restrict__ G, int k, int64_t ld, double* Vtop, double* theta,
+                                                        double* res2, double* info) {
+  extern __shared__ __align__(16) double s_A[];  // A [dim][dim|1], V [dim][dim|1]
   __shared__ JacobiScratch js;
   __shared__ double lam[kJacobiMaxK], tmp[kJacobiMaxK];
+  __shared__ int order[kKB];
   __shared__ double red[256];
   const int64_t bt = blockIdx.x;
   const int tid = threadIdx.x;
+  const int lda = dim | 1;
+  double* s_V = s_A + dim * lda;
   const double* Tb = T + bt * strideT;
   const double* Gb = G + bt * ld * ld;
   double tr = 0.0;
@@ -283,36 +347,94 @@ __global__ void __launch_bounds__(256) krylov_rr_kernel(const double* __restrict
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
   tr = red[0];
-  double top[2] = {0.0, 0.0};
-  for (int pass = 0; pass < 2; ++pass) {
-    int d = pass == 0 ? dim - kKB : dim;
-    if (d < 4) { top[pass] = 0.0; continue; }
-    int lda = d | 1;
-    __syncthreads();
-    for (int idx = tid; idx < d * d; idx += blockDim.x) {
-      int r = idx / d, c = idx - r * d;
-      s_A[r * lda + c] = 0.5 * (Tb[r * dim + c] + Tb[c * dim + r]);
-    }
-    __syncthreads();
-    jacobi_eig_smem(s_A, lda, d, nullptr, 0, &js);
-    sort_diag_desc(s_A, lda, d, tmp, lam);
-    top[pass] = lam[0] + lam[1] + lam[2] + lam[3];
-    __syncthreads();
+  for (int idx = tid; idx < dim * dim; idx += blockDim.x) {
+    int r = idx / dim, c = idx - r * dim;
+    s_A[r * lda + c] = 0.5 * (Tb[r * kKDim + c] + Tb[c * kKDim + r]);
+    s_V[r * lda + c] = (r == c) ? 1.0 : 0.0;
   }
+  __syncthreads();
+  jacobi_eig_smem(s_A, lda, dim, s_V, lda, &js);
+  sort_diag_desc(s_A, lda, dim, tmp, lam);
+  // column index of the i-th largest eigenvalue, i < 8 (same rank rule as sort_diag_desc)
+  for (int i = tid; i < dim; i += blockDim.x) {
+    double v = tmp[i];
+    int rank = 0;
+    for (int j = 0; j < dim; ++j) rank += (tmp[j] > v || (tmp[j] == v && j < i)) ? 1 : 0;
+    if (rank < kKB) order[rank] = i;
+  }
+  __syncthreads();
+  double* Vb = Vtop + bt * kKDim * kKB;
+  for (int idx = tid; idx < dim * kKB; idx += blockDim.x) {
+    int d = idx / kKB, c = idx - d * kKB;
+    Vb[idx] = s_V[d * lda + order[c]];
+  }
+  if (tid < kKB) theta[bt * kKB + tid] = lam[tid];
+  if (tid < 4) res2[bt * 4 + tid] = 0.0;
   if (tid == 0) {
-    double rad = 1.0 - top[1] / tr;
-    scores[bt] = tr > 0.0 ? sqrt(fmax(rad, 0.0)) : nan("");
-    if (info) {
-      info[bt * 4 + 0] = top[1];
-      info[bt * 4 + 1] = tr;
-      info[bt * 4 + 2] = tr > 0.0 ? fabs(top[1] - top[0]) / tr : 0.0;
-      info[bt * 4 + 3] = (double)dim;
-    }
+    double top = lam[0] + lam[1] + lam[2] + lam[3];
+    double* inf = info + bt * kInfo;
+    double prev = inf[0];
+    inf[5] = tr > 0.0 ? fabs(top - prev) / tr : 0.0;
+    inf[0] = top;
+    inf[1] = tr;
+    inf[3] = (double)dim;
+    inf[4] += 1.0;
   }
 }
 
+// Ritz vectors Y = Vtop^T Q written in place of Q_0 (every thread owns one column `pos`), and the squared
+// residual norms of the top 4: || Vtop_i^T AQ - theta_i Y_i ||^2 accumulated with one atomic per warp.
+__global__ void __launch_bounds__(256) krylov_ritz_kernel(double* Q, const double* __restrict__ AQ, int64_t strideQ,
+                                                          const double* __restrict__ Vtop, const double* __restrict__ theta,
+                                                          double* res2, int dim, int k) {
+  __shared__ double sV[kKDim * kKB], sT[kKB];
+  const int64_t bt = blockIdx.y;
+  for (int i = threadIdx.x; i < dim * kKB; i += blockDim.x) sV[i] = Vtop[bt * kKDim * kKB + i];
+  if (threadIdx.x < kKB) sT[threadIdx.x] = theta[bt * kKB + threadIdx.x];
+  __syncthreads();
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  double y[kKB], gy[4];
+#pragma unroll
+  for (int c = 0; c < kKB; ++c) y[c] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) gy[c] = 0.0;
+  if (pos < k) {
+    double* Qb = Q + bt * strideQ;
+    const double* Ab = AQ + bt * strideQ;
+    for (int d = 0; d < dim; ++d) {
+      double q = Qb[(int64_t)d * k + pos], a = Ab[(int64_t)d * k + pos];
+#pragma unroll
+      for (int c = 0; c < kKB; ++c) y[c] = fma(sV[d * kKB + c], q, y[c]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) gy[c] = fma(sV[d * kKB + c], a, gy[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < kKB; ++c) Qb[(int64_t)c * k + pos] = y[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    double r = gy[c] - sT[c] * y[c];
+    double v = r * r;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(res2 + bt * 4 + c, v);
+  }
+}
+
+__global__ void krylov_finish_kernel(const double* __restrict__ theta, const double* __restrict__ res2, double* info, double* scores,
+                                     int64_t batch) {
+  int64_t bt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bt >= batch) return;
+  double* inf = info + bt * kInfo;
+  double t0 = theta[bt * kKB];
+  double r = 0.0;
+  for (int c = 0; c < 4; ++c) r = fmax(r, res2[bt * 4 + c]);
+  inf[2] = t0 > 0.0 ? sqrt(r) / t0 : 0.0;
+  double tr = inf[1];
+  scores[bt] = tr > 0.0 ? sqrt(fmax(1.0 - inf[0] / tr, 0.0)) : nan("");
+}
+
 struct KrylovWs {
-  double *Q, *AQ, *C, *S, *T, *part;
+  double *Q, *AQ, *C, *S, *T, *Vtop, *theta, *res2, *info, *part;
   int64_t sQ, sC, sS, sT, part_elems;
 };
 
@@ -328,6 +450,10 @@ static int64_t krylov_layout(int64_t k, int64_t batch, double* base, KrylovWs* w
   w->S = take(batch * w->sS);
   w->sT = (int64_t)kKDim * kKDim;
   w->T = take(batch * w->sT);
+  w->Vtop = take(batch * kKDim * kKB);
+  w->theta = take(batch * kKB);
+  w->res2 = take(batch * 4);
+  w->info = take(batch * kInfo);
   w->part_elems = batch * 64 * (int64_t)kKDim * kKDim;  // up to 64 k-splits of the largest product
   w->part = take(w->part_elems);
   return off;
@@ -371,18 +497,14 @@ extern "C" int64_t spb_score_gram_large_ws(int64_t k, int64_t batch) {
   return krylov_layout(k, batch, nullptr, &w);
 }
 
-extern "C" int spb_score_gram_large(const double* d_G, int64_t k64, int64_t ld, int64_t batch64, double* d_scores, double* d_info,
-                                    double* d_ws, void* stream) {
-  SPB_REQUIRE(d_G && d_scores && d_ws && k64 > kJacobiMaxK && ld >= k64 && batch64 >= 1 && k64 < (1 << 24),
-              "spb_score_gram_large: need k > %d and a workspace", kJacobiMaxK);
-  const int k = (int)k64, batch = (int)batch64;
-  cudaStream_t st = (cudaStream_t)stream;
-  KrylovWs w;
-  krylov_layout(k, batch, d_ws, &w);
+// One Krylov cycle with `nb` blocks (dim = 8 nb).  first = 1 starts from pseudo-random vectors, otherwise from the
+// Ritz vectors the previous cycle left in Q_0.
+static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb, bool first, const KrylovWs& w, cudaStream_t st) {
   const int64_t blk = (int64_t)kKB * k;
+  const int dim = nb * kKB;
   int rc;
-  auto ortho_block = [&](double* W) -> int {  // SVQB twice
-    for (int pass = 0; pass < 2; ++pass) {
+  auto ortho_block = [&](double* W, int passes) -> int {  // SVQB
+    for (int pass = 0; pass < passes; ++pass) {
       GemmArgs g{W, k, w.sQ, W, k, w.sQ, w.S, kKB, w.sS, kKB, kKB, k, batch};
       int ks = choose_ksplit(kKB, kKB, k, batch, false);
       int r = gemm_nt(g, false, ks, w.part, st);
@@ -393,20 +515,25 @@ extern "C" int spb_score_gram_large(const double* d_G, int64_t k64, int64_t ld, 
     }
     return SPB_OK;
   };
-  {
+  if (first) {
     dim3 grid((unsigned)((blk + 255) / 256), batch);
     krylov_init_kernel<<<grid, 256, 0, st>>>(w.Q, w.sQ, k);
     SPB_LAUNCH_CHECK();
+    if ((rc = ortho_block(w.Q, 2))) return rc;
+  } else {
+    if ((rc = ortho_block(w.Q, 1))) return rc;  // Ritz vectors are orthonormal up to rounding: one clean-up pass
   }
-  if ((rc = ortho_block(w.Q))) return rc;
-  for (int j = 0; j < kKBlocks; ++j) {
+  const size_t symv_smem = (size_t)kKB * kSymvChunk * sizeof(double);
+  SPB_CUDA(cudaFuncSetAttribute(symv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
+  for (int j = 0; j < nb; ++j) {
     double* Qj = w.Q + (int64_t)j * blk;
     double* AQj = w.AQ + (int64_t)j * blk;
     {
-      GemmArgs g{Qj, k, w.sQ, d_G, ld, ld * ld, AQj, k, w.sQ, kKB, k, k, batch};
-      if ((rc = gemm_nt(g, true, 1, nullptr, st))) return rc;
+      dim3 grid((k + kSymvRows - 1) / kSymvRows, batch);
+      symv_block_kernel<<<grid, 256, symv_smem, st>>>(d_G, ld, ld * ld, Qj, w.sQ, AQj, k);
+      SPB_LAUNCH_CHECK();
     }
-    if (j == kKBlocks - 1) break;
+    if (j == nb - 1) break;
     double* Wn = w.Q + (int64_t)(j + 1) * blk;
     {
       dim3 grid((unsigned)((blk + 255) / 256), batch);
@@ -422,16 +549,54 @@ extern "C" int spb_score_gram_large(const double* d_G, int64_t k64, int64_t ld, 
       krylov_subtract_kernel<<<grid, 256, 0, st>>>(Wn, w.sQ, w.Q, w.sQ, w.C, w.sC, rows, k);
       SPB_LAUNCH_CHECK();
     }
-    if ((rc = ortho_block(Wn))) return rc;
+    if ((rc = ortho_block(Wn, 2))) return rc;
   }
   {
-    GemmArgs g{w.Q, k, w.sQ, w.AQ, k, w.sQ, w.T, kKDim, w.sT, kKDim, kKDim, k, batch};
-    int ks = choose_ksplit(kKDim, kKDim, k, batch, false);
+    GemmArgs g{w.Q, k, w.sQ, w.AQ, k, w.sQ, w.T, kKDim, w.sT, dim, dim, k, batch};
+    int ks = choose_ksplit(dim, dim, k, batch, false);
     if ((rc = gemm_nt(g, false, ks, w.part, st))) return rc;
   }
-  size_t smem = (size_t)kKDim * (kKDim | 1) * sizeof(double);
+  size_t smem = (size_t)2 * dim * (dim | 1) * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(krylov_rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  krylov_rr_kernel<<<batch, 256, smem, st>>>(w.T, w.sT, kKDim, d_G, k, ld, d_scores, d_info);
+  krylov_rr_kernel<<<batch, 256, smem, st>>>(w.T, w.sT, dim, d_G, k, ld, w.Vtop, w.theta, w.res2, w.info);
   SPB_LAUNCH_CHECK();
+  {
+    dim3 grid((k + 255) / 256, batch);
+    krylov_ritz_kernel<<<grid, 256, 0, st>>>(w.Q, w.AQ, w.sQ, w.Vtop, w.theta, w.res2, dim, k);
+    SPB_LAUNCH_CHECK();
+  }
+  return SPB_OK;
+}
+
+extern "C" int spb_score_gram_large(const double* d_G, int64_t k64, int64_t ld, int64_t batch64, double* d_scores, double* d_info,
+                                    double* d_ws, void* stream) {
+  SPB_REQUIRE(d_G && d_scores && d_ws && k64 > kJacobiMaxK && ld >= k64 && batch64 >= 1 && k64 < (1 << 24),
+              "spb_score_gram_large: need k > %d and a workspace", kJacobiMaxK);
+  const int k = (int)k64, batch = (int)batch64;
+  cudaStream_t st = (cudaStream_t)stream;
+  KrylovWs w;
+  krylov_layout(k, batch, d_ws, &w);
+  SPB_CUDA(cudaMemsetAsync(w.info, 0, (size_t)batch * kInfo * sizeof(double), st));
+  static thread_local std::vector<double> h_info;
+  h_info.resize((size_t)batch * kInfo);
+  const int kMaxCycles = 40;
+  const double kResTol = 2e-9;  // relative residual of the top-4 Ritz pairs; the eigenvalue error is its square
+  int rc;
+  for (int cycle = 0; cycle < kMaxCycles; ++cycle) {
+    const int nb = cycle < 2 ? 4 : kKMaxBlocks;
+    if ((rc = krylov_cycle(d_G, k, ld, batch, nb, cycle == 0, w, st))) return rc;
+    krylov_finish_kernel<<<(batch + 127) / 128, 128, 0, st>>>(w.theta, w.res2, w.info, d_scores, batch);
+    SPB_LAUNCH_CHECK();
+    SPB_CUDA(cudaMemcpyAsync(h_info.data(), w.info, (size_t)batch * kInfo * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    bool done = true;
+    for (int b = 0; b < batch; ++b) {
+      const double res = h_info[(size_t)b * kInfo + 2], delta = h_info[(size_t)b * kInfo + 5];
+      const bool ok = res <= kResTol || (cycle > 0 && delta <= 1e-16 && res <= 1e-6) || !(h_info[(size_t)b * kInfo + 1] > 0.0);
+      if (!ok) { done = false; break; }
+    }
+    if (done) break;
+  }
+  if (d_info) SPB_CUDA(cudaMemcpyAsync(d_info, w.info, (size_t)batch * kInfo * sizeof(double), cudaMemcpyDeviceToDevice, st));
   return SPB_OK;
 }

@@ -133,6 +133,9 @@ def count_patterns(aln, site_begin=0, site_end=None, want_first=False, force_has
         raise NotImplementedError("pattern counting uses uint64 keys: at most 31 taxa")
     site_end = aln.N if site_end is None else site_end
     nsites = max(0, site_end - site_begin)
+    if aln.N == 0 and reduce_fn is None:  # nothing to count (and no buffers to hand to the kernels)
+        return PatternTable(n, _empty(0, torch.int64), counts=_empty(0, torch.int32), divisor=0.0,
+                            first=_empty(0, torch.int32) if want_first else None, taxa=aln.taxa)
     usable = _zeros(1, torch.int64)
     num = _zeros(1, torch.int64)
     if n <= DIRECT_MAX_TAXA and not force_hash:
@@ -363,6 +366,17 @@ def gram_f64(A):
     return G
 
 
+_KRYLOV_WS = {}
+
+
+def _krylov_ws(k, batch):
+    need = int(lib.spb_score_gram_large_ws(k, batch))
+    ws = _KRYLOV_WS.get("ws")
+    if ws is None or ws.numel() < need or ws.device != device():
+        ws = _KRYLOV_WS["ws"] = _empty(need, torch.float64)
+    return ws
+
+
 def score_gram(G, k=None, want_info=False):
     """Scores from symmetric PSD Gram matrices G [batch, ld, ld] using the leading k x k block.
     k <= 4 -> 0.0 (at most 4 singular values: 1 - top4/total vanishes, phylogenetics.py:293-300)."""
@@ -373,12 +387,15 @@ def score_gram(G, k=None, want_info=False):
     k = ld if k is None else int(k)
     scores = _empty(batch, torch.float64)
     info = None
+    if k <= 4:
+        scores.zero_()
+        return (scores, None) if want_info else scores
     if k <= JACOBI_MAX_K:
         info = _empty((batch, k), torch.float64) if want_info else None
         call("spb_score_gram_small", _p(G), k, ld, batch, _p(scores), _p(info), _st())
     else:
-        ws = _empty(int(lib.spb_score_gram_large_ws(k, batch)), torch.float64)
-        info = _empty((batch, 4), torch.float64) if want_info else None
+        ws = _krylov_ws(k, batch)
+        info = _empty((batch, 8), torch.float64) if want_info else None
         call("spb_score_gram_large", _p(G), k, ld, batch, _p(scores), _p(info), _p(ws), _st())
     return (scores, info) if want_info else scores
 
@@ -420,20 +437,20 @@ class CountScorer:
         rp = 128 if rows <= 128 else (rows + 255) // 256 * 256
         return SPB_S0_TILED, rp, (cols + 127) // 128 * 128
 
-    def _buffers(self, layout, rows_pad, pitch):
+    def _buffers(self, layout, rows_pad, pitch, batch=1):
         key = (layout, rows_pad, pitch)
         if key not in self._s0:
             self._s0[key] = _zeros(rows_pad * pitch, torch.uint8)
-        if rows_pad not in self._G:
-            self._G[rows_pad] = _empty((rows_pad, rows_pad), torch.float64)
-        wkey = (layout, rows_pad, pitch)
-        if wkey not in self._ws:
+        g = self._G.get(rows_pad)
+        if g is None or g.shape[0] < batch:
+            g = self._G[rows_pad] = _empty((batch, rows_pad, rows_pad), torch.float64)
+        if key not in self._ws:
             n = int(lib.spb_gram_u8_ws(rows_pad, pitch, layout))
-            self._ws[wkey] = _empty(n, torch.int64) if n else None
-        return self._s0[key], self._G[rows_pad], self._ws[wkey]
+            self._ws[key] = _empty(n, torch.int64) if n else None
+        return self._s0[key], g, self._ws[key]
 
-    def gram(self, idx_a, idx_b, reduced=False):
-        """Exact F F^T (short side) of the count flattening of one split.  Returns (G, k)."""
+    def _plan(self, idx_a, idx_b, reduced):
+        """Orient the split so that the Gram is taken on the short side; returns the launch geometry."""
         t = self.table
         if not covers_all(t.n, idx_a, idx_b):
             raise ValueError("CountScorer: the split must cover all taxa")
@@ -448,8 +465,12 @@ class CountScorer:
                 idx_a, idx_b = idx_b, idx_a
             sp = make_split(t.n, idx_a, idx_b)
             R, Cc = 4 ** len(idx_a), 4 ** len(idx_b)
-        layout, rows_pad, pitch = self.geometry(R, Cc)
-        s0, G, ws = self._buffers(layout, rows_pad, pitch)
+        return sp, rank_r, rank_c, R, Cc
+
+    def _gram_into(self, plan, s0, G, ws, layout, rows_pad, pitch):
+        """flatten (u8 scatter) -> exact Gram -> high-part correction -> un-scatter, all on the current stream."""
+        t = self.table
+        sp, rank_r, rank_c, R, Cc = plan
         call("spb_flatten_u8", _p(t.keys), _p(t.counts), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch,
              layout, SPB_U8_NO_MEMSET, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num), self.hi_cap, _st())
         run = lambda: call("spb_gram_u8", _p(s0), rows_pad, pitch, layout, _p(G), _p(ws), _st())  # noqa: E731
@@ -457,13 +478,52 @@ class CountScorer:
         call("spb_gram_hi_correction", _p(s0), rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num),
              self.hi_cap, _p(G), _st())
         call("spb_flatten_u8_clear", _p(t.keys), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch, layout, _st())
-        return G, R
+
+    def gram(self, idx_a, idx_b, reduced=False):
+        """Exact F F^T (short side) of the count flattening of one split.  Returns (G [rows_pad, rows_pad], k)."""
+        plan = self._plan(idx_a, idx_b, reduced)
+        R, Cc = plan[3], plan[4]
+        layout, rows_pad, pitch = self.geometry(R, Cc)
+        s0, G, ws = self._buffers(layout, rows_pad, pitch)
+        self._gram_into(plan, s0, G[0], ws, layout, rows_pad, pitch)
+        return G[0], R
 
     def score(self, idx_a, idx_b, reduced=False):
         G, k = self.gram(idx_a, idx_b, reduced)
         if k == 0:
             return torch.full((1,), float("nan"), dtype=torch.float64, device=G.device)
         return score_gram(G, k)
+
+    def score_many(self, splits_idx, reduced=False, max_batch=64, max_batch_bytes=2 << 30, big_hook=None):
+        """Scores of many splits.  Dense count flattenings of equal shape are batched: their Gram matrices are
+        built one after the other into G[b] and ONE batched eigen-solver call scores the whole batch (the Jacobi /
+        Krylov kernels are latency-bound per matrix, so batching is what keeps all SMs busy)."""
+        out = _empty(len(splits_idx), torch.float64)
+        if reduced:
+            for s, (ia, ib) in enumerate(splits_idx):
+                out[s:s + 1] = self.score(ia, ib, True)
+            return out
+        groups = {}
+        for s, (ia, ib) in enumerate(splits_idx):
+            groups.setdefault(min(len(ia), len(ib)), []).append(s)
+        n = self.table.n
+        for a, members in groups.items():
+            R, Cc = 4 ** a, 4 ** (n - a)
+            layout, rows_pad, pitch = self.geometry(R, Cc)
+            B = int(max(1, min(len(members), max_batch, max_batch_bytes // (rows_pad * rows_pad * 8))))
+            s0, G, ws = self._buffers(layout, rows_pad, pitch, B)
+            for c0 in range(0, len(members), B):
+                chunk = members[c0:c0 + B]
+                for b, s in enumerate(chunk):
+                    self.gram_hook = big_hook if (big_hook is not None and R >= 4096) else None
+                    self._gram_into(self._plan(*splits_idx[s], False), s0, G[b], ws, layout, rows_pad, pitch)
+                self.gram_hook = None
+                sc = score_gram(G[:len(chunk)], R)
+                if chunk == list(range(chunk[0], chunk[0] + len(chunk))):
+                    out[chunk[0]:chunk[0] + len(chunk)] = sc
+                else:
+                    out.index_copy_(0, torch.tensor(chunk, dtype=torch.int64, device=out.device), sc)
+        return out
 
     def check_hi(self):
         n = int(self.hi_num.item())
@@ -474,9 +534,7 @@ class CountScorer:
 def score_splits_counts(table, splits_idx, reduced=False):
     """Scores of many splits [(idx_a, idx_b), ...] of a count table, exact-integer Gram path."""
     scorer = CountScorer(table)
-    out = _empty(len(splits_idx), torch.float64)
-    for s, (ia, ib) in enumerate(splits_idx):
-        out[s:s + 1] = scorer.score(ia, ib, reduced)
+    out = scorer.score_many(splits_idx, reduced)
     scorer.check_hi()
     return out
 
