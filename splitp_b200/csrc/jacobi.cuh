@@ -18,12 +18,25 @@ struct JacobiScratch {  // lives in shared memory
   double trace0;
 };
 
-// All threads of the CTA call this.  A: k x k symmetric, row stride lda (odd lda avoids bank
-// conflicts).  If V != nullptr it must hold the identity on entry and receives the eigenvectors as
-// columns (A_in = V diag V^T).  On return the eigenvalues are on the diagonal of A (unsorted).
+// Storage contract: the solver works on an even dimension m = jacobi_dim(k) (one zero row/column of padding when
+// k is odd), row stride lda >= m (jacobi_ld(k) = m | 1 is odd, which keeps the 2x2-block accesses spread over the
+// banks).  The CALLER zero-fills row/column k when k is odd.
+__host__ __device__ constexpr int jacobi_dim(int k) { return (k + 1) & ~1; }
+__host__ __device__ constexpr int jacobi_ld(int k) { return jacobi_dim(k) | 1; }
+
+// All threads of the CTA call this.  A: k x k symmetric in the storage described above.  If V != nullptr it must
+// hold the identity (jacobi_dim(k) rows) on entry and receives the eigenvectors as columns (A_in = V diag V^T).
+// On return the eigenvalues are on the diagonal of A (unsorted).
+//
+// One round = the m/2 disjoint pairs of a round-robin tournament rotated at once:
+//   (1) m/2 threads compute the rotation (c, s) of their pair from the current 2x2 diagonal block,
+//   (2) every 2x2 block B(t1, t2) = A[{p1,q1}][{p2,q2}], t1 <= t2, is replaced by J1^T B J2 in ONE pass (the block
+//       and its mirror image are written by the same thread, so the update is in place with a single barrier);
+//       the diagonal blocks are written in closed form (npp, 0; 0, nqq).
 __device__ inline void jacobi_eig_smem(double* A, int lda, int k, double* V, int ldv, JacobiScratch* js) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int m = (k + 1) & ~1;  // players in the round-robin (one dummy when k is odd)
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  const int m = jacobi_dim(k);
   const int np = m >> 1;
   if (tid == 0) {
     double tr = 0.0;
@@ -37,67 +50,60 @@ __device__ inline void jacobi_eig_smem(double* A, int lda, int k, double* V, int
     if (tid == 0) js->rotated = 0;
     __syncthreads();
     for (int r = 0; r < m - 1; ++r) {
-      // 1. rotation parameters for the np disjoint pairs of this round
+      // (1) rotation parameters of the np disjoint pairs of this round
       if (tid < np) {
         int p, q;
         if (tid == 0) { p = r; q = m - 1; }
         else { p = (r + tid) % (m - 1); q = (r - tid + m - 1) % (m - 1); }
         if (p > q) { int t = p; p = q; q = t; }
-        double c = 1.0, s = 0.0, npp = 0.0, nqq = 0.0;
-        if (q < k) {
-          double app = A[p * lda + p], aqq = A[q * lda + q], apq = A[p * lda + q];
-          npp = app; nqq = aqq;
-          double thr = fmax(2.0e-16 * sqrt(fabs(app * aqq)), abs_floor);
-          if (fabs(apq) > thr) {
-            double tau = (aqq - app) / (2.0 * apq);
-            double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + t * t);
-            s = t * c;
-            npp = app - t * apq;
-            nqq = aqq + t * apq;
-            js->rotated = 1;
-          } else if (apq != 0.0) {
-            // below threshold: drop the entry so it cannot accumulate
-            A[p * lda + q] = 0.0; A[q * lda + p] = 0.0;
-          }
-        } else {
-          q = -1;  // dummy pair
+        double app = A[p * lda + p], aqq = A[q * lda + q], apq = A[p * lda + q];
+        double c = 1.0, s = 0.0, npp = app, nqq = aqq;
+        double thr = fmax(2.0e-16 * sqrt(fabs(app * aqq)), abs_floor);
+        if (fabs(apq) > thr) {
+          double tau = (aqq - app) / (2.0 * apq);
+          double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = rsqrt(1.0 + t * t);
+          s = t * c;
+          npp = app - t * apq;
+          nqq = aqq + t * apq;
+          js->rotated = 1;
+        } else if (apq != 0.0) {
+          // below threshold: drop the entry so it cannot accumulate
+          A[p * lda + q] = 0.0; A[q * lda + p] = 0.0;
         }
         js->p[tid] = p; js->q[tid] = q; js->c[tid] = c; js->s[tid] = s; js->npp[tid] = npp; js->nqq[tid] = nqq;
       }
       __syncthreads();
-      // 2. columns: A <- A J  (and V <- V J)
-      for (int idx = tid; idx < np * k; idx += nt) {
-        int t = idx / k, row = idx - t * k;
-        int q = js->q[t];
-        double s = js->s[t];
-        if (q < 0 || s == 0.0) continue;
-        int p = js->p[t];
-        double c = js->c[t];
-        double x = A[row * lda + p], y = A[row * lda + q];
-        A[row * lda + p] = c * x - s * y;
-        A[row * lda + q] = s * x + c * y;
-        if (V) {
-          double vx = V[row * ldv + p], vy = V[row * ldv + q];
-          V[row * ldv + p] = c * vx - s * vy;
-          V[row * ldv + q] = s * vx + c * vy;
+      // (2) fused two-sided update, one 2x2 block per thread iteration
+      for (int t1 = warp; t1 < np; t1 += nwarps) {
+        const int p1 = js->p[t1], q1 = js->q[t1];
+        const double c1 = js->c[t1], s1 = js->s[t1];
+        for (int t2 = t1 + lane; t2 < np; t2 += 32) {
+          const double c2 = js->c[t2], s2 = js->s[t2];
+          if (s1 == 0.0 && s2 == 0.0) continue;
+          const int p2 = js->p[t2], q2 = js->q[t2];
+          if (t1 == t2) {
+            A[p1 * lda + p1] = js->npp[t1]; A[q1 * lda + q1] = js->nqq[t1];
+            A[p1 * lda + q1] = 0.0; A[q1 * lda + p1] = 0.0;
+            continue;
+          }
+          double a = A[p1 * lda + p2], b = A[p1 * lda + q2], cc = A[q1 * lda + p2], d = A[q1 * lda + q2];
+          double a1 = c1 * a - s1 * cc, b1 = c1 * b - s1 * d, cc1 = s1 * a + c1 * cc, d1 = s1 * b + c1 * d;
+          double a2 = c2 * a1 - s2 * b1, b2 = s2 * a1 + c2 * b1, cc2 = c2 * cc1 - s2 * d1, d2 = s2 * cc1 + c2 * d1;
+          A[p1 * lda + p2] = a2; A[p1 * lda + q2] = b2; A[q1 * lda + p2] = cc2; A[q1 * lda + q2] = d2;
+          A[p2 * lda + p1] = a2; A[q2 * lda + p1] = b2; A[p2 * lda + q1] = cc2; A[q2 * lda + q1] = d2;
         }
       }
-      __syncthreads();
-      // 3. rows: A <- J^T A, with the rotated 2x2 block written in closed form
-      for (int idx = tid; idx < np * k; idx += nt) {
-        int t = idx / k, col = idx - t * k;
-        int q = js->q[t];
-        double s = js->s[t];
-        if (q < 0 || s == 0.0) continue;
-        int p = js->p[t];
-        double c = js->c[t];
-        if (col == p) { A[p * lda + p] = js->npp[t]; A[q * lda + p] = 0.0; }
-        else if (col == q) { A[p * lda + q] = 0.0; A[q * lda + q] = js->nqq[t]; }
-        else {
-          double x = A[p * lda + col], y = A[q * lda + col];
-          A[p * lda + col] = c * x - s * y;
-          A[q * lda + col] = s * x + c * y;
+      if (V) {
+        for (int t = warp; t < np; t += nwarps) {
+          const double c = js->c[t], s = js->s[t];
+          if (s == 0.0) continue;
+          const int p = js->p[t], q = js->q[t];
+          for (int row = lane; row < m; row += 32) {
+            double vx = V[row * ldv + p], vy = V[row * ldv + q];
+            V[row * ldv + p] = c * vx - s * vy;
+            V[row * ldv + q] = s * vx + c * vy;
+          }
         }
       }
       __syncthreads();

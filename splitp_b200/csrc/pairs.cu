@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kSThreads) subflatten_score_kernel(const doubl
     const int rows = 3 * a + 1, cols = 3 * b + 1;
     const bool tr = rows > cols;          // orient so that k = smaller dimension
     const int k = tr ? cols : rows, L = tr ? rows : cols;
-    const int ldm = L + 1, ldg = k | 1;
+    const int ldm = L + 1, ldg = jacobi_ld(k);
     for (int idx = tid; idx < k * L; idx += kSThreads) {
       int r = idx / L, c = idx - r * L;
       M[r * ldm + c] = tr ? subflat_entry(T, tot, n, la, a, lb, b, c, r) : subflat_entry(T, tot, n, la, a, lb, b, r, c);
@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(kSThreads) subflatten_score_kernel(const doubl
       G[r1 * ldg + r2] = acc;
       G[r2 * ldg + r1] = acc;
     }
+    if ((k & 1) && tid <= k) { G[k * ldg + tid] = 0.0; G[tid * ldg + k] = 0.0; }  // zero padding of the odd dimension
     __syncthreads();
     jacobi_eig_smem(G, ldg, k, nullptr, 0, &js);
     sort_diag_desc(G, ldg, k, tmp, lam);
@@ -279,8 +280,7 @@ inline size_t subflat_smem(int n, int* m_elems) {
   int m1 = k * (L + 1);
   int m2 = 4 * (3 * (n - 1) + 2);
   *m_elems = m1 > m2 ? m1 : m2;
-  int ldg = k | 1;
-  return ((size_t)*m_elems + (size_t)k * ldg) * sizeof(double);
+  return ((size_t)*m_elems + (size_t)jacobi_dim(k) * jacobi_ld(k)) * sizeof(double);
 }
 
 }  // namespace

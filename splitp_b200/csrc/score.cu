@@ -156,14 +156,14 @@ __global__ void __launch_bounds__(256) score_small_kernel(const double* __restri
   extern __shared__ __align__(16) double s_A[];
   __shared__ JacobiScratch js;
   __shared__ double lam[kJacobiMaxK], tmp[kJacobiMaxK];
-  const int lda = k | 1;
+  const int m = jacobi_dim(k), lda = jacobi_ld(k);
   for (int64_t bt = blockIdx.x; bt < batch; bt += gridDim.x) {
     __syncthreads();
     const double* Gb = G + bt * ld * ld;
-    for (int idx = threadIdx.x; idx < k * k; idx += blockDim.x) {
-      int r = idx / k, c = idx - r * k;
-      // symmetrise on load: the callers' Gram matrices are symmetric up to rounding
-      s_A[r * lda + c] = 0.5 * (Gb[(int64_t)r * ld + c] + Gb[(int64_t)c * ld + r]);
+    for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+      int r = idx / m, c = idx - r * m;
+      // symmetrise on load: the callers' Gram matrices are symmetric up to rounding; zero padding when k is odd
+      s_A[r * lda + c] = (r < k && c < k) ? 0.5 * (Gb[(int64_t)r * ld + c] + Gb[(int64_t)c * ld + r]) : 0.0;
     }
     __syncthreads();
     jacobi_eig_smem(s_A, lda, k, nullptr, 0, &js);
@@ -479,7 +479,7 @@ extern "C" int spb_score_gram_small(const double* d_G, int64_t k, int64_t ld, in
   SPB_REQUIRE(d_G && d_scores && k >= 1 && k <= kJacobiMaxK && ld >= k && batch >= 0,
               "spb_score_gram_small: need 1 <= k <= %d (got %lld)", kJacobiMaxK, (long long)k);
   if (batch == 0) return SPB_OK;
-  size_t smem = (size_t)k * (k | 1) * sizeof(double);
+  size_t smem = (size_t)jacobi_dim((int)k) * jacobi_ld((int)k) * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(score_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int threads = k <= 32 ? 128 : 256;
   int occ = 1;
