@@ -1,0 +1,6 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=300 -k "score or scorer or config2 or smoke or flat" > gpurun_out/t_quick.log 2>&1; echo "pytest rc=$?"
+timeout 600 python scripts/phase_profile.py > gpurun_out/phase.log 2>&1; echo "phase rc=$?"
+timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"
+tail -5 gpurun_out/t_quick.log; cat gpurun_out/phase.log; cat gpurun_out/bench_quick.json; tail -5 gpurun_out/bench_quick.err

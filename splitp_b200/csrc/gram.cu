@@ -413,16 +413,17 @@ __global__ void __launch_bounds__(256) hi_cross_kernel(const uint8_t* __restrict
   }
 }
 
+// one thread per ordered pair (e1, e2) of high entries; pairs in the same column contribute v1 * v2 to G[r1][r2]
 __global__ void __launch_bounds__(256) hi_self_kernel(const int32_t* __restrict__ hi_rc, const uint32_t* __restrict__ hi_val,
                                                       const uint32_t* __restrict__ hi_num, int64_t hi_cap, int64_t ldg,
                                                       double* __restrict__ G) {
   int64_t n = *hi_num;
   if (n > hi_cap) n = hi_cap;
-  for (int64_t e1 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e1 < n; e1 += (int64_t)gridDim.x * blockDim.x) {
-    const int r1 = hi_rc[2 * e1], c1 = hi_rc[2 * e1 + 1];
-    const double v1 = (double)hi_val[e1];
-    for (int64_t e2 = 0; e2 < n; ++e2)
-      if (hi_rc[2 * e2 + 1] == c1) atomicAdd(G + (int64_t)r1 * ldg + hi_rc[2 * e2], v1 * (double)hi_val[e2]);  // (H H^T)[r1][r2]
+  const int64_t pairs = n * n;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e1 = t / n, e2 = t - e1 * n;
+    if (hi_rc[2 * e1 + 1] == hi_rc[2 * e2 + 1])
+      atomicAdd(G + (int64_t)hi_rc[2 * e1] * ldg + hi_rc[2 * e2], (double)hi_val[e1] * (double)hi_val[e2]);  // (H H^T)[r1][r2]
   }
 }
 
@@ -536,8 +537,7 @@ extern "C" int spb_gram_hi_correction(const uint8_t* d_s0, int64_t rows_pad, int
   dim3 grid((unsigned)((rows_pad + 255) / 256 > 16 ? 16 : (rows_pad + 255) / 256), (unsigned)gy);
   hi_cross_kernel<<<grid, 256, 0, st>>>(d_s0, layout, rows_pad, pitch, d_hi_rc, d_hi_val, d_hi_num, hi_cap, rows_pad, d_G);
   SPB_LAUNCH_CHECK();
-  int64_t gx = (hi_cap + 255) / 256;
-  if (gx > 1024) gx = 1024;
+  int64_t gx = 4 * (int64_t)sm_count();  // grid-stride over the n^2 pairs (n is only known on the device)
   hi_self_kernel<<<(unsigned)gx, 256, 0, st>>>(d_hi_rc, d_hi_val, d_hi_num, hi_cap, rows_pad, d_G);
   SPB_LAUNCH_CHECK();
   return SPB_OK;

@@ -96,6 +96,61 @@ __global__ void reduce_kernel(const double* __restrict__ part, int64_t elems, in
   C[(int64_t)bt * strideC + (int64_t)r * ldc + c] = s;
 }
 
+// Tall-skinny inner products of the Krylov solver: C[m][n] = sum_pos A[m][pos] * B[n][pos], M, N <= 96, K = k long.
+// One CTA = one chunk of kDotChunk positions of one matrix: both operand panels are staged in shared memory with
+// coalesced loads and every thread owns the outputs (ti + 16 a, tj + 16 b).  Partials go to part[(bt, chunk)][M][N]
+// and are summed in chunk order by reduce_kernel (deterministic).
+constexpr int kDotChunk = 128;
+constexpr int kDotMax = 6;  // 96 / 16
+__global__ void __launch_bounds__(256) dot_kernel(const double* __restrict__ A, int64_t strideA, const double* __restrict__ B,
+                                                  int64_t strideB, int M, int N, int k, int nchunks, double* __restrict__ part) {
+  extern __shared__ __align__(16) double s_dot[];  // A panel [M][kDotChunk + 1], B panel [N][kDotChunk + 1]
+  const int ldp = kDotChunk + 1;
+  double* sA = s_dot;
+  double* sB = s_dot + M * ldp;
+  const int bt = blockIdx.y, ch = blockIdx.x;
+  const int pos0 = ch * kDotChunk;
+  const int len = min(kDotChunk, k - pos0);
+  const double* Ab = A + (int64_t)bt * strideA;
+  const double* Bb = B + (int64_t)bt * strideB;
+  for (int idx = threadIdx.x; idx < M * kDotChunk; idx += 256) {
+    int r = idx / kDotChunk, p = idx - r * kDotChunk;
+    sA[r * ldp + p] = p < len ? Ab[(int64_t)r * k + pos0 + p] : 0.0;
+  }
+  for (int idx = threadIdx.x; idx < N * kDotChunk; idx += 256) {
+    int r = idx / kDotChunk, p = idx - r * kDotChunk;
+    sB[r * ldp + p] = p < len ? Bb[(int64_t)r * k + pos0 + p] : 0.0;
+  }
+  __syncthreads();
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  const int ma = (M + 15) >> 4, nb = (N + 15) >> 4;
+  double acc[kDotMax][kDotMax];
+#pragma unroll
+  for (int a = 0; a < kDotMax; ++a)
+#pragma unroll
+    for (int b = 0; b < kDotMax; ++b) acc[a][b] = 0.0;
+  for (int p = 0; p < kDotChunk; ++p) {
+    double x[kDotMax], y[kDotMax];
+#pragma unroll
+    for (int a = 0; a < kDotMax; ++a) x[a] = (a < ma && ti + 16 * a < M) ? sA[(ti + 16 * a) * ldp + p] : 0.0;
+#pragma unroll
+    for (int b = 0; b < kDotMax; ++b) y[b] = (b < nb && tj + 16 * b < N) ? sB[(tj + 16 * b) * ldp + p] : 0.0;
+#pragma unroll
+    for (int a = 0; a < kDotMax; ++a)
+#pragma unroll
+      for (int b = 0; b < kDotMax; ++b)
+        if (a < ma && b < nb) acc[a][b] = fma(x[a], y[b], acc[a][b]);
+  }
+  double* out = part + ((int64_t)bt * nchunks + ch) * M * N;
+#pragma unroll
+  for (int a = 0; a < kDotMax; ++a)
+#pragma unroll
+    for (int b = 0; b < kDotMax; ++b) {
+      int i = ti + 16 * a, j = tj + 16 * b;
+      if (a < ma && b < nb && i < M && j < N) out[i * N + j] = acc[a][b];
+    }
+}
+
 struct GemmArgs {
   const double* A; int64_t lda, strideA;
   const double* B; int64_t ldb, strideB;
@@ -146,6 +201,22 @@ static int choose_ksplit(int M, int N, int K, int batch, bool skinny) {
   if (ks > maxks) ks = maxks;
   if (ks > 64) ks = 64;
   return ks;
+}
+
+// C (ldc, strideC) = A B^T for the tall-skinny Krylov operands; part must hold batch * ceil(k/128) * M * N doubles
+static int dot_product(const double* A, int64_t strideA, const double* B, int64_t strideB, int M, int N, int k, int batch,
+                       double* C, int64_t ldc, int64_t strideC, double* part, cudaStream_t st) {
+  const int nchunks = (k + kDotChunk - 1) / kDotChunk;
+  const size_t smem = (size_t)(M + N) * (kDotChunk + 1) * sizeof(double);
+  SPB_CUDA(cudaFuncSetAttribute(dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(nchunks, batch);
+  dot_kernel<<<grid, 256, smem, st>>>(A, strideA, B, strideB, M, N, k, nchunks, part);
+  SPB_LAUNCH_CHECK();
+  const int64_t elems = (int64_t)M * N;
+  dim3 rg((unsigned)((elems + 255) / 256), batch);
+  reduce_kernel<<<rg, 256, 0, st>>>(part, elems, nchunks, C, strideC, M, N, ldc);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -454,7 +525,8 @@ static int64_t krylov_layout(int64_t k, int64_t batch, double* base, KrylovWs* w
   w->theta = take(batch * kKB);
   w->res2 = take(batch * 4);
   w->info = take(batch * kInfo);
-  w->part_elems = batch * 64 * (int64_t)kKDim * kKDim;  // up to 64 k-splits of the largest product
+  // partial sums of the inner-product kernel: ceil(k / 128) chunks of the largest (96 x 96) product
+  w->part_elems = batch * ((k + kDotChunk - 1) / kDotChunk) * (int64_t)kKDim * kKDim;
   w->part = take(w->part_elems);
   return off;
 }
@@ -505,9 +577,7 @@ static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb,
   int rc;
   auto ortho_block = [&](double* W, int passes) -> int {  // SVQB
     for (int pass = 0; pass < passes; ++pass) {
-      GemmArgs g{W, k, w.sQ, W, k, w.sQ, w.S, kKB, w.sS, kKB, kKB, k, batch};
-      int ks = choose_ksplit(kKB, kKB, k, batch, false);
-      int r = gemm_nt(g, false, ks, w.part, st);
+      int r = dot_product(W, w.sQ, W, w.sQ, kKB, kKB, k, batch, w.S, kKB, w.sS, w.part, st);
       if (r) return r;
       dim3 grid((k + 255) / 256 > 32 ? 32 : (k + 255) / 256, batch);
       krylov_svqb_kernel<<<grid, 256, 0, st>>>(W, w.sQ, w.S, w.sS, k);
@@ -542,9 +612,7 @@ static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb,
     }
     const int rows = (j + 1) * kKB;
     for (int pass = 0; pass < 2; ++pass) {
-      GemmArgs g{w.Q, k, w.sQ, Wn, k, w.sQ, w.C, kKB, w.sC, rows, kKB, k, batch};
-      int ks = choose_ksplit(rows, kKB, k, batch, false);
-      if ((rc = gemm_nt(g, false, ks, w.part, st))) return rc;
+      if ((rc = dot_product(w.Q, w.sQ, Wn, w.sQ, rows, kKB, k, batch, w.C, kKB, w.sC, w.part, st))) return rc;
       dim3 grid((k + 255) / 256, batch);
       krylov_subtract_kernel<<<grid, 256, 0, st>>>(Wn, w.sQ, w.Q, w.sQ, w.C, w.sC, rows, k);
       SPB_LAUNCH_CHECK();
@@ -552,9 +620,7 @@ static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb,
     if ((rc = ortho_block(Wn, 2))) return rc;
   }
   {
-    GemmArgs g{w.Q, k, w.sQ, w.AQ, k, w.sQ, w.T, kKDim, w.sT, dim, dim, k, batch};
-    int ks = choose_ksplit(dim, dim, k, batch, false);
-    if ((rc = gemm_nt(g, false, ks, w.part, st))) return rc;
+    if ((rc = dot_product(w.Q, w.sQ, w.AQ, w.sQ, dim, dim, k, batch, w.T, kKDim, w.sT, w.part, st))) return rc;
   }
   size_t smem = (size_t)2 * dim * (dim | 1) * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(krylov_rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

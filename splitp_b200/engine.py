@@ -494,7 +494,7 @@ class CountScorer:
             return torch.full((1,), float("nan"), dtype=torch.float64, device=G.device)
         return score_gram(G, k)
 
-    def score_many(self, splits_idx, reduced=False, max_batch=64, max_batch_bytes=2 << 30, big_hook=None):
+    def score_many(self, splits_idx, reduced=False, max_batch=256, max_batch_bytes=16 << 30, big_hook=None):
         """Scores of many splits.  Dense count flattenings of equal shape are batched: their Gram matrices are
         built one after the other into G[b] and ONE batched eigen-solver call scores the whole batch (the Jacobi /
         Krylov kernels are latency-bound per matrix, so batching is what keeps all SMs busy)."""
