@@ -123,13 +123,16 @@ int spb_flatten_reduced_fill_w(const uint64_t* d_keys, const void* d_vals, int v
 /* Scoring layout of a count flattening: low byte of every count into d_s0 (uint8, rows_pad x pitch cells;
  * rows_pad >= R, pitch >= C) and the remainder (count - (count & 255)) of counts >= 256 as COO triplets
  * (d_hi_rc int32 [cap][2], d_hi_val uint32 [cap]), *d_hi_num (uint32, zeroed by the call) = number of
- * triplets (may exceed cap -> caller must check).  layout: SPB_S0_ROWMAJOR = [rows_pad][pitch], pitch % 16 == 0;
+ * triplets (may exceed cap -> caller must check).  layout: SPB_S0_ROWMAJOR = [rows_pad][pitch], pitch % 16 == 0
+ * (plain layout, accepted by spb_gram_u8_simt and the correction kernels only); SPB_S0_K4MAJOR = 32-bit words of 4
+ * consecutive k stored at word (k/4) * rows_pad + r (the dp4a operand layout, rows_pad % 4 == 0, pitch % 16 == 0);
  * SPB_S0_TILED = 128 x 128-byte tiles in the tensor-core operand layout (see csrc/gram.cu), rows_pad % 128 ==
  * 0 and pitch % 128 == 0.  flags & SPB_U8_NO_MEMSET: d_s0 is known to be all zero (see spb_flatten_u8_clear),
  * skip the memset.  If d_rank_r/d_rank_c are non-NULL the reduced row/col ranks are used instead of the raw
  * base-4 indices.  Requires the split to cover all n taxa (otherwise cells would collide). */
 #define SPB_S0_ROWMAJOR 0
 #define SPB_S0_TILED 1
+#define SPB_S0_K4MAJOR 2
 #define SPB_U8_NO_MEMSET 1
 int spb_flatten_u8(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* split,
                    const uint32_t* d_rank_r, const uint32_t* d_rank_c, uint8_t* d_s0, int64_t rows_pad,
@@ -170,7 +173,7 @@ int spb_subflatten_score(const double* d_T, const double* d_total, int n_taxa, c
 int64_t spb_gram_f64_ws(int64_t R, int64_t C, int64_t batch);
 int spb_gram_f64(const double* d_A, int64_t R, int64_t C, int64_t batch, double* d_G, double* d_ws, void* stream);
 /* Exact integer Gram of a u8 matrix (see spb_flatten_u8): d_G double [rows_pad][rows_pad] is OVERWRITTEN with
- * S0 S0^T.  SPB_S0_ROWMAJOR: rows_pad <= 64, dp4a kernel.  SPB_S0_TILED: rows_pad == 128 or rows_pad % 256 == 0,
+ * S0 S0^T.  SPB_S0_K4MAJOR: rows_pad <= 64, dp4a kernel.  SPB_S0_TILED: rows_pad == 128 or rows_pad % 256 == 0,
  * tcgen05 (tensor core, kind::i8) kernel.  K = pitch.  d_ws: uint64 [spb_gram_u8_ws(...)] (NULL when that is 0);
  * it holds exact 64-bit partial sums when K is split across CTAs. */
 int64_t spb_s0_bytes(int64_t rows_pad, int64_t pitch);

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libsplitp_b200.so")
 
 SPB_MAX_TAXA = 64
 SPB_VAL_U32, SPB_VAL_F64 = 0, 1
-SPB_S0_ROWMAJOR, SPB_S0_TILED = 0, 1
+SPB_S0_ROWMAJOR, SPB_S0_TILED, SPB_S0_K4MAJOR = 0, 1, 2
 SPB_U8_NO_MEMSET = 1
 EMPTY_KEY = 0xFFFFFFFFFFFFFFFF
 

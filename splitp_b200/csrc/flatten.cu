@@ -61,8 +61,9 @@ __global__ void mark_kernel(const uint64_t* __restrict__ keys, int64_t num, Spli
   flag_c[side_index(k, sp.sh_b, sp.b)] = 1u;
 }
 
-__device__ __forceinline__ int64_t s0_cell(int layout, int64_t pitch, uint64_t r, uint64_t c) {
+__device__ __forceinline__ int64_t s0_cell(int layout, int64_t rows_pad, int64_t pitch, uint64_t r, uint64_t c) {
   if (layout == SPB_S0_ROWMAJOR) return (int64_t)(r * (uint64_t)pitch + c);
+  if (layout == SPB_S0_K4MAJOR) return (int64_t)(((c >> 2) * (uint64_t)rows_pad + r) * 4ull + (c & 3ull));  // csrc/gram.cu
   // 128 x 128-byte tiles, K-major SWIZZLE_128B inside the tile (the tcgen05 operand layout, csrc/gram.cu)
   uint64_t KT = (uint64_t)pitch >> 7;
   uint64_t rt = r >> 7, kt = c >> 7;
@@ -71,7 +72,7 @@ __device__ __forceinline__ int64_t s0_cell(int layout, int64_t pitch, uint64_t r
 }
 
 __global__ void u8_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t num, SplitDev sp,
-                          const uint32_t* rank_r, const uint32_t* rank_c, uint8_t* s0, int64_t pitch, int layout, int32_t* hi_rc,
+                          const uint32_t* rank_r, const uint32_t* rank_c, uint8_t* s0, int64_t rows_pad, int64_t pitch, int layout, int32_t* hi_rc,
                           uint32_t* hi_val, uint32_t* hi_num, int64_t hi_cap) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= num) return;
@@ -79,7 +80,7 @@ __global__ void u8_kernel(const uint64_t* __restrict__ keys, const uint32_t* __r
   uint32_t cnt = counts ? counts[i] : 0u;  // counts == NULL: clear pass
   uint64_t r = side_index(k, sp.sh_a, sp.a), c = side_index(k, sp.sh_b, sp.b);
   if (rank_r) { r = rank_r[r]; c = rank_c[c]; }
-  s0[s0_cell(layout, pitch, r, c)] = (uint8_t)(cnt & 255u);
+  s0[s0_cell(layout, rows_pad, pitch, r, c)] = (uint8_t)(cnt & 255u);
   if (cnt >= 256u) {
     uint32_t slot = atomicAdd(hi_num, 1u);
     if ((int64_t)slot < hi_cap) {
@@ -211,8 +212,11 @@ static int u8_check(const spb_split* split, SplitDev* sp, const uint32_t* d_rank
   if (rc) return rc;
   SPB_REQUIRE(covers_all(split), "spb_flatten_u8: the split must cover all %d taxa", sp->n);
   SPB_REQUIRE(d_s0 && rows_pad >= 1 && pitch >= 1, "spb_flatten_u8: bad buffers");
-  SPB_REQUIRE(layout == SPB_S0_ROWMAJOR || layout == SPB_S0_TILED, "spb_flatten_u8: unknown layout %d", layout);
+  SPB_REQUIRE(layout == SPB_S0_ROWMAJOR || layout == SPB_S0_TILED || layout == SPB_S0_K4MAJOR, "spb_flatten_u8: unknown layout %d",
+              layout);
   if (layout == SPB_S0_ROWMAJOR) SPB_REQUIRE(pitch % 16 == 0, "spb_flatten_u8: row-major pitch must be a multiple of 16");
+  else if (layout == SPB_S0_K4MAJOR)
+    SPB_REQUIRE(pitch % 16 == 0 && rows_pad % 4 == 0, "spb_flatten_u8: k4-major layout needs pitch %% 16 == 0 and rows_pad %% 4 == 0");
   else SPB_REQUIRE(pitch % 128 == 0 && rows_pad % 128 == 0, "spb_flatten_u8: tiled layout needs rows_pad, pitch multiples of 128");
   SPB_REQUIRE((d_rank_r == nullptr) == (d_rank_c == nullptr), "spb_flatten_u8: give both rank arrays or neither");
   if (!d_rank_r) {
@@ -235,7 +239,7 @@ extern "C" int spb_flatten_u8(const uint64_t* d_keys, const uint32_t* d_counts, 
   SPB_CUDA(cudaMemsetAsync(d_hi_num, 0, 4, st));
   if (num <= 0) return SPB_OK;
   SPB_REQUIRE(d_keys && d_counts, "spb_flatten_u8: NULL pattern table");
-  u8_kernel<<<nblk(num, 256), 256, 0, st>>>(d_keys, d_counts, num, sp, d_rank_r, d_rank_c, d_s0, pitch, layout, d_hi_rc, d_hi_val,
+  u8_kernel<<<nblk(num, 256), 256, 0, st>>>(d_keys, d_counts, num, sp, d_rank_r, d_rank_c, d_s0, rows_pad, pitch, layout, d_hi_rc, d_hi_val,
                                             d_hi_num, hi_cap);
   SPB_LAUNCH_CHECK();
   return SPB_OK;
@@ -249,8 +253,8 @@ extern "C" int spb_flatten_u8_clear(const uint64_t* d_keys, int64_t num, const s
   if (rc) return rc;
   if (num <= 0) return SPB_OK;
   SPB_REQUIRE(d_keys, "spb_flatten_u8_clear: NULL pattern table");
-  u8_kernel<<<nblk(num, 256), 256, 0, (cudaStream_t)stream>>>(d_keys, nullptr, num, sp, d_rank_r, d_rank_c, d_s0, pitch, layout,
-                                                              nullptr, nullptr, nullptr, 0);
+  u8_kernel<<<nblk(num, 256), 256, 0, (cudaStream_t)stream>>>(d_keys, nullptr, num, sp, d_rank_r, d_rank_c, d_s0, rows_pad, pitch,
+                                                              layout, nullptr, nullptr, nullptr, 0);
   SPB_LAUNCH_CHECK();
   return SPB_OK;
 }

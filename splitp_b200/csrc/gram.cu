@@ -320,60 +320,77 @@ __global__ void gram_finalize_kernel(const unsigned long long* __restrict__ acc6
 }
 
 // ---------------------------------------------------------------------------------------------------
-// small row counts (rows_pad <= 64, row-major layout): dp4a over K chunks, 64-bit integer atomics
+// small row counts (rows_pad <= 64): dp4a on the "k4-major" layout.
+//   SPB_S0_K4MAJOR: the 4 bytes k = 4w .. 4w+3 of row r form one 32-bit word stored at word index w * rows_pad + r,
+//   so (a) a K chunk of all rows is one contiguous piece of memory (straight 128-bit copies, no transpose) and
+//   (b) the four rows 4t .. 4t+3 of one word column are ONE conflict-free LDS.128.
+// Thread (ty, tx) of a group owns the 4 x 4 outputs rows 4ty.. x rows 4tx..; per word column it issues 2 LDS.128 and
+// 16 dp4a.  256 / (rows_pad/4)^2 groups share the word columns of a chunk; accumulators stay in registers (u32 per
+// chunk: 255^2 * 4 * 256 < 2^32, u64 across chunks) for the whole persistent CTA, then one 64-bit atomic per output.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kSmallChunk = 2048;  // K bytes per CTA iteration (255^2 * 2048 < 2^32: u32 partials are exact)
+constexpr int kSmallWords = 256;  // word columns (= 1024 k) per chunk
 
-__global__ void __launch_bounds__(256) gram_u8_small_kernel(const uint8_t* __restrict__ s0, int R, int64_t pitch,
+__global__ void __launch_bounds__(256) gram_u8_small_kernel(const uint32_t* __restrict__ s0w, int Rp, int64_t words,
                                                             unsigned long long* __restrict__ acc64) {
-  extern __shared__ uint32_t s_rows[];  // [R][kSmallChunk/4 + 1]
-  const int ldw = kSmallChunk / 4 + 1;
+  extern __shared__ __align__(16) uint32_t s_chunk[];  // [kSmallWords][Rp]
   const int tid = threadIdx.x;
-  const int64_t nchunks = (pitch + kSmallChunk - 1) / kSmallChunk;
-  const int nb = (R + 15) / 16;          // 16 x 16 output blocks
-  const int tr = tid >> 4, tc = tid & 15;
+  const int q = Rp >> 2;                 // 4-row blocks per side
+  const int per_group = q * q;           // threads of one group
+  const int groups = 256 / per_group;    // >= 1 for Rp <= 64
+  const int grp = tid / per_group, t = tid - grp * per_group;
+  const int ty = t / q, tx = t - ty * q;
+  const bool active = grp < groups;
+  unsigned long long tot[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) tot[e] = 0ull;
+  const int64_t nchunks = (words + kSmallWords - 1) / kSmallWords;
   for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const int64_t k0 = ch * kSmallChunk;
+    const int64_t w0 = ch * kSmallWords;
+    const int nw = (int)min((int64_t)kSmallWords, words - w0);
     __syncthreads();
-    // coalesced 128-bit loads of R rows x chunk (pitch % 16 == 0)
-    for (int idx = tid; idx < R * (kSmallChunk / 16); idx += 256) {
-      int r = idx / (kSmallChunk / 16), v = idx - r * (kSmallChunk / 16);
-      int64_t k = k0 + (int64_t)v * 16;
-      uint4 x = make_uint4(0, 0, 0, 0);
-      if (k < pitch) x = __ldg(reinterpret_cast<const uint4*>(s0 + (int64_t)r * pitch + k));
-      uint32_t* d = s_rows + r * ldw + v * 4;
-      d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
-    }
+    const uint4* src = reinterpret_cast<const uint4*>(s0w + w0 * Rp);  // Rp % 4 == 0: 16-byte aligned
+    for (int v = tid; v < nw * Rp / 4; v += 256) reinterpret_cast<uint4*>(s_chunk)[v] = __ldg(src + v);
     __syncthreads();
-    for (int bi = 0; bi < nb; ++bi)
-      for (int bj = bi; bj < nb; ++bj) {
-        int r1 = bi * 16 + tr, r2 = bj * 16 + tc;
-        if (r1 < R && r2 < R) {
-          const uint32_t* x = s_rows + r1 * ldw;
-          const uint32_t* y = s_rows + r2 * ldw;
-          uint32_t s = 0;
-#pragma unroll 8
-          for (int w = 0; w < kSmallChunk / 4; ++w) s = __dp4a(x[w], y[w], s);
-          if (s) atomicAdd(acc64 + (int64_t)r1 * R + r2, (unsigned long long)s);
-        }
+    if (active) {
+      uint32_t part[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) part[e] = 0u;
+      for (int w = grp; w < nw; w += groups) {
+        const uint4 x = *reinterpret_cast<const uint4*>(s_chunk + w * Rp + 4 * ty);
+        const uint4 y = *reinterpret_cast<const uint4*>(s_chunk + w * Rp + 4 * tx);
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) part[i * 4 + j] = __dp4a(xs[i], ys[j], part[i * 4 + j]);
       }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) tot[e] += part[e];
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (tot[i * 4 + j]) atomicAdd(acc64 + (int64_t)(4 * ty + i) * Rp + 4 * tx + j, tot[i * 4 + j]);
   }
 }
 
-// acc64 [R][R] (upper 16-block triangle valid) -> symmetric fp64 G [ld][ld] leading R x R block
+// acc64 [Rp][Rp] -> fp64 G [ld][ld] leading Rp x Rp block
 __global__ void gram_small_finalize_kernel(const unsigned long long* __restrict__ acc64, int R, int64_t ld, double* __restrict__ G) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * R) return;
   int r = idx / R, c = idx - r * R;
-  unsigned long long v = ((c >> 4) >= (r >> 4)) ? acc64[(int64_t)r * R + c] : acc64[(int64_t)c * R + r];
-  G[(int64_t)r * ld + c] = (double)(long long)v;
+  G[(int64_t)r * ld + c] = (double)(long long)acc64[idx];
 }
 
 // ---------------------------------------------------------------------------------------------------
 // generic SIMT Gram for any layout / size: the on-device cross-check of the tensor-core kernel (tests)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int64_t s0_offset(int layout, int64_t pitch, int64_t r, int64_t k) {
+__device__ __forceinline__ int64_t s0_offset(int layout, int64_t rows_pad, int64_t pitch, int64_t r, int64_t k) {
   if (layout == SPB_S0_ROWMAJOR) return r * pitch + k;
+  if (layout == SPB_S0_K4MAJOR) return ((k >> 2) * rows_pad + r) * 4 + (k & 3);
   int64_t KT = pitch / kTile;
   int64_t rt = r / kTile, kt = k / kTile;
   int rr = (int)(r - rt * kTile), kk = (int)(k - kt * kTile);
@@ -386,7 +403,7 @@ __global__ void gram_u8_simt_kernel(const uint8_t* __restrict__ s0, int layout, 
   if (r2 >= R) return;
   unsigned long long s = 0;
   for (int64_t k = 0; k < pitch; ++k)
-    s += (unsigned long long)s0[s0_offset(layout, pitch, r1, k)] * (unsigned long long)s0[s0_offset(layout, pitch, r2, k)];
+    s += (unsigned long long)s0[s0_offset(layout, R, pitch, r1, k)] * (unsigned long long)s0[s0_offset(layout, R, pitch, r2, k)];
   G[r1 * ldg + r2] = (double)s;
 }
 
@@ -403,7 +420,7 @@ __global__ void __launch_bounds__(256) hi_cross_kernel(const uint8_t* __restrict
     const int64_t r = hi_rc[2 * e], c = hi_rc[2 * e + 1];
     const double v = (double)hi_val[e];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.x * blockDim.x) {
-      uint32_t s = s0[s0_offset(layout, pitch, i, c)];
+      uint32_t s = s0[s0_offset(layout, R, pitch, i, c)];
       if (s) {
         double t = v * (double)s;
         atomicAdd(G + i * ldg + r, t);  // (S0 H^T)[i][r]
@@ -459,8 +476,8 @@ UmmaPlan plan_umma(int64_t rows_pad, int64_t pitch) {
 extern "C" int64_t spb_s0_bytes(int64_t rows_pad, int64_t pitch) { return rows_pad * pitch; }
 
 extern "C" int64_t spb_gram_u8_ws(int64_t rows_pad, int64_t pitch, int layout) {
-  if (layout == SPB_S0_ROWMAJOR) return rows_pad * rows_pad;
-  if (rows_pad % kTile || pitch % kTile) return 0;
+  if (layout == SPB_S0_K4MAJOR) return rows_pad * rows_pad;
+  if (layout != SPB_S0_TILED || rows_pad % kTile || pitch % kTile) return 0;
   UmmaPlan p = plan_umma(rows_pad, pitch);
   return p.ksplit > 1 ? rows_pad * rows_pad : 0;
 }
@@ -469,18 +486,20 @@ extern "C" int spb_gram_u8(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch,
                            void* stream) {
   SPB_REQUIRE(d_s0 && d_G && rows_pad >= 1 && pitch >= 16 && pitch % 16 == 0, "spb_gram_u8: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  if (layout == SPB_S0_ROWMAJOR) {
-    SPB_REQUIRE(rows_pad <= 64, "spb_gram_u8: the row-major (dp4a) path handles rows_pad <= 64, got %lld; use the tiled layout",
-                (long long)rows_pad);
+  if (layout == SPB_S0_K4MAJOR) {
+    SPB_REQUIRE(rows_pad <= 64 && rows_pad % 4 == 0, "spb_gram_u8: the k4-major (dp4a) path handles rows_pad <= 64, rows_pad %% 4 == 0 "
+                "(got %lld); use the tiled layout", (long long)rows_pad);
     SPB_REQUIRE(d_ws, "spb_gram_u8: workspace required (spb_gram_u8_ws)");
     int R = (int)rows_pad;
     SPB_CUDA(cudaMemsetAsync(d_ws, 0, (size_t)R * R * 8, st));
-    size_t smem = (size_t)R * (kSmallChunk / 4 + 1) * 4;
+    size_t smem = (size_t)kSmallWords * R * 4;
     SPB_CUDA(cudaFuncSetAttribute(gram_u8_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t nchunks = (pitch + kSmallChunk - 1) / kSmallChunk;
-    int64_t grid = (int64_t)sm_count() * (smem > 110 * 1024 ? 1 : 2);
+    int64_t words = pitch / 4;
+    int64_t nchunks = (words + kSmallWords - 1) / kSmallWords;
+    int64_t grid = (int64_t)sm_count() * 2;
     if (grid > nchunks) grid = nchunks;
-    gram_u8_small_kernel<<<(unsigned)grid, 256, smem, st>>>(d_s0, R, pitch, (unsigned long long*)d_ws);
+    gram_u8_small_kernel<<<(unsigned)grid, 256, smem, st>>>(reinterpret_cast<const uint32_t*>(d_s0), R, words,
+                                                          (unsigned long long*)d_ws);
     SPB_LAUNCH_CHECK();
     gram_small_finalize_kernel<<<(R * R + 255) / 256, 256, 0, st>>>((const unsigned long long*)d_ws, R, rows_pad, d_G);
     SPB_LAUNCH_CHECK();
@@ -520,7 +539,8 @@ extern "C" int spb_gram_u8(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch,
 // Test / cross-check entry: same result as spb_gram_u8 from a plain SIMT loop (any layout, any size).
 extern "C" int spb_gram_u8_simt(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, double* d_G, void* stream) {
   SPB_REQUIRE(d_s0 && d_G && rows_pad >= 1 && pitch >= 1, "spb_gram_u8_simt: bad arguments");
-  SPB_REQUIRE(layout == SPB_S0_ROWMAJOR || (rows_pad % kTile == 0 && pitch % kTile == 0), "spb_gram_u8_simt: bad tiled shape");
+  SPB_REQUIRE(layout == SPB_S0_ROWMAJOR || layout == SPB_S0_K4MAJOR || (rows_pad % kTile == 0 && pitch % kTile == 0),
+              "spb_gram_u8_simt: bad tiled shape");
   dim3 grid((unsigned)((rows_pad + 127) / 128), (unsigned)rows_pad);
   gram_u8_simt_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_s0, layout, rows_pad, pitch, rows_pad, d_G);
   SPB_LAUNCH_CHECK();

@@ -101,7 +101,7 @@ __global__ void reduce_kernel(const double* __restrict__ part, int64_t elems, in
 // coalesced loads and every thread owns the outputs (ti + 16 a, tj + 16 b).  Partials go to part[(bt, chunk)][M][N]
 // and are summed in chunk order by reduce_kernel (deterministic).
 constexpr int kDotChunk = 128;
-constexpr int kDotMax = 6;  // 96 / 16
+template <int MA, int NB>  // output register block per thread: rows ti + 16 a (a < MA), columns tj + 16 b (b < NB)
 __global__ void __launch_bounds__(256) dot_kernel(const double* __restrict__ A, int64_t strideA, const double* __restrict__ B,
                                                   int64_t strideB, int M, int N, int k, int nchunks, double* __restrict__ part) {
   extern __shared__ __align__(16) double s_dot[];  // A panel [M][kDotChunk + 1], B panel [N][kDotChunk + 1]
@@ -123,31 +123,36 @@ __global__ void __launch_bounds__(256) dot_kernel(const double* __restrict__ A, 
   }
   __syncthreads();
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
-  const int ma = (M + 15) >> 4, nb = (N + 15) >> 4;
-  double acc[kDotMax][kDotMax];
+  double acc[MA][NB];
+  const double* xa[MA];
+  const double* yb[NB];
 #pragma unroll
-  for (int a = 0; a < kDotMax; ++a)
+  for (int a = 0; a < MA; ++a) {
+    xa[a] = sA + min(ti + 16 * a, M - 1) * ldp;  // clamped rows are computed but never stored
 #pragma unroll
-    for (int b = 0; b < kDotMax; ++b) acc[a][b] = 0.0;
+    for (int b = 0; b < NB; ++b) acc[a][b] = 0.0;
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) yb[b] = sB + min(tj + 16 * b, N - 1) * ldp;
+#pragma unroll 4
   for (int p = 0; p < kDotChunk; ++p) {
-    double x[kDotMax], y[kDotMax];
+    double x[MA], y[NB];
 #pragma unroll
-    for (int a = 0; a < kDotMax; ++a) x[a] = (a < ma && ti + 16 * a < M) ? sA[(ti + 16 * a) * ldp + p] : 0.0;
+    for (int a = 0; a < MA; ++a) x[a] = xa[a][p];
 #pragma unroll
-    for (int b = 0; b < kDotMax; ++b) y[b] = (b < nb && tj + 16 * b < N) ? sB[(tj + 16 * b) * ldp + p] : 0.0;
+    for (int b = 0; b < NB; ++b) y[b] = yb[b][p];
 #pragma unroll
-    for (int a = 0; a < kDotMax; ++a)
+    for (int a = 0; a < MA; ++a)
 #pragma unroll
-      for (int b = 0; b < kDotMax; ++b)
-        if (a < ma && b < nb) acc[a][b] = fma(x[a], y[b], acc[a][b]);
+      for (int b = 0; b < NB; ++b) acc[a][b] = fma(x[a], y[b], acc[a][b]);
   }
   double* out = part + ((int64_t)bt * nchunks + ch) * M * N;
 #pragma unroll
-  for (int a = 0; a < kDotMax; ++a)
+  for (int a = 0; a < MA; ++a)
 #pragma unroll
-    for (int b = 0; b < kDotMax; ++b) {
+    for (int b = 0; b < NB; ++b) {
       int i = ti + 16 * a, j = tj + 16 * b;
-      if (a < ma && b < nb && i < M && j < N) out[i * N + j] = acc[a][b];
+      if (i < M && j < N) out[i * N + j] = acc[a][b];
     }
 }
 
@@ -208,9 +213,19 @@ static int dot_product(const double* A, int64_t strideA, const double* B, int64_
                        double* C, int64_t ldc, int64_t strideC, double* part, cudaStream_t st) {
   const int nchunks = (k + kDotChunk - 1) / kDotChunk;
   const size_t smem = (size_t)(M + N) * (kDotChunk + 1) * sizeof(double);
-  SPB_CUDA(cudaFuncSetAttribute(dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(nchunks, batch);
-  dot_kernel<<<grid, 256, smem, st>>>(A, strideA, B, strideB, M, N, k, nchunks, part);
+  const int ma = (M + 15) >> 4, nb = (N + 15) >> 4;
+#define SPB_DOT(MA_, NB_)                                                                                           \
+  do {                                                                                                              \
+    SPB_CUDA(cudaFuncSetAttribute(dot_kernel<MA_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    dot_kernel<MA_, NB_><<<grid, 256, smem, st>>>(A, strideA, B, strideB, M, N, k, nchunks, part);                  \
+  } while (0)
+  if (ma <= 1 && nb <= 1) SPB_DOT(1, 1);
+  else if (ma <= 2 && nb <= 1) SPB_DOT(2, 1);
+  else if (nb <= 1) SPB_DOT(6, 1);
+  else if (ma <= 2 && nb <= 2) SPB_DOT(2, 2);
+  else SPB_DOT(6, 6);
+#undef SPB_DOT
   SPB_LAUNCH_CHECK();
   const int64_t elems = (int64_t)M * N;
   dim3 rg((unsigned)((elems + 255) / 256), batch);

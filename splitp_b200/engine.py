@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import SPB_S0_ROWMAJOR, SPB_S0_TILED, SPB_U8_NO_MEMSET, SPB_VAL_F64, SPB_VAL_U32, call, lib, make_split
+from ._lib import SPB_S0_K4MAJOR, SPB_S0_ROWMAJOR, SPB_S0_TILED, SPB_U8_NO_MEMSET, SPB_VAL_F64, SPB_VAL_U32, call, lib, make_split
 
 STATES = "ACGT"
 _UPPER_LUT = np.full(256, 255, dtype=np.uint8)
@@ -433,7 +433,7 @@ class CountScorer:
     def geometry(rows, cols):
         """(layout, rows_pad, pitch) for a rows x cols count matrix with rows <= cols."""
         if rows <= 64:
-            return SPB_S0_ROWMAJOR, max(rows, 1), (cols + 15) // 16 * 16
+            return SPB_S0_K4MAJOR, max((rows + 3) // 4 * 4, 4), (cols + 15) // 16 * 16
         rp = 128 if rows <= 128 else (rows + 255) // 256 * 256
         return SPB_S0_TILED, rp, (cols + 127) // 128 * 128
 

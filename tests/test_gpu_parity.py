@@ -325,17 +325,21 @@ def test_gram_u8_tensor_core_exact(eng, R, K, density):
     np.testing.assert_array_equal(G2.cpu().numpy(), ref.astype(np.float64))
 
 
-@pytest.mark.parametrize("R,K", [(16, 4096), (16, 1 << 20), (64, 262144), (40, 1000 * 16), (1, 16)])
+@pytest.mark.parametrize("R,K", [(16, 4096), (16, 1 << 20), (64, 262144), (40, 1000 * 16), (4, 16), (32, 48)])
 def test_gram_u8_small_exact(eng, R, K):
     rng = np.random.default_rng(R * 7 + K)
     M = (rng.integers(0, 256, size=(R, K)) * (rng.random((R, K)) < 0.05)).astype(np.uint8)
     M[0, :] = 255
     ref = M.astype(np.int64) @ M.astype(np.int64).T
-    s0 = torch.from_numpy(M).cuda()
+    k4 = np.ascontiguousarray(M.reshape(R, K // 4, 4).transpose(1, 0, 2))  # [k/4][r][4]: the k4-major layout
+    s0 = torch.from_numpy(k4.reshape(-1)).cuda()
     G = torch.empty((R, R), dtype=torch.float64, device="cuda")
-    ws = torch.empty(int(eng.lib.spb_gram_u8_ws(R, K, 0)), dtype=torch.int64, device="cuda")
-    eng.call("spb_gram_u8", eng._p(s0), R, K, 0, eng._p(G), eng._p(ws), eng._st())
+    ws = torch.empty(int(eng.lib.spb_gram_u8_ws(R, K, 2)), dtype=torch.int64, device="cuda")
+    eng.call("spb_gram_u8", eng._p(s0), R, K, 2, eng._p(G), eng._p(ws), eng._st())
     np.testing.assert_array_equal(G.cpu().numpy(), ref.astype(np.float64))
+    G2 = torch.empty_like(G)
+    eng.call("spb_gram_u8_simt", eng._p(s0), R, K, 2, eng._p(G2), eng._st())
+    np.testing.assert_array_equal(G2.cpu().numpy(), ref.astype(np.float64))
 
 
 def _count_table(sp, eng, n, N, seed, bl=0.05):

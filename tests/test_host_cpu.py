@@ -114,8 +114,9 @@ def test_encode_decode_and_simulator():
 def test_count_scorer_geometry():
     from splitp_b200 import engine
     g = engine.CountScorer.geometry
-    assert g(16, 1 << 20) == (0, 16, 1 << 20)
-    assert g(64, 262144) == (0, 64, 262144)
+    assert g(16, 1 << 20) == (2, 16, 1 << 20)
+    assert g(64, 262144) == (2, 64, 262144)
+    assert g(7, 55) == (2, 8, 64)
     assert g(256, 65536) == (1, 256, 65536)
     assert g(4096, 4096) == (1, 4096, 4096)
     assert g(100, 1000) == (1, 128, 1024)
