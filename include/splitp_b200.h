@@ -37,6 +37,7 @@ typedef enum {
 } spb_status;
 
 #define SPB_MAX_TAXA 64
+#define SPB_MAX_BATCH 16 /* splits per batched flatten launch */
 #define SPB_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 
 typedef struct {
@@ -143,6 +144,14 @@ int spb_flatten_u8(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num
 int spb_flatten_u8_clear(const uint64_t* d_keys, int64_t num, const spb_split* split, const uint32_t* d_rank_r,
                          const uint32_t* d_rank_c, uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout,
                          void* stream);
+/* Batched forms (one launch for nb <= SPB_MAX_BATCH splits of equal shape, raw base-4 indices only): entry b uses
+ * h_splits[b] (HOST array), the S0 buffer d_s0 + b * s0_stride (bytes) and the high-part buffers
+ * d_hi_rc + b * 2 * hi_cap, d_hi_val + b * hi_cap, d_hi_num + b. */
+int spb_flatten_u8_batch(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* h_splits, int nb,
+                         uint8_t* d_s0, int64_t s0_stride, int64_t rows_pad, int64_t pitch, int layout, int flags,
+                         int32_t* d_hi_rc, uint32_t* d_hi_val, uint32_t* d_hi_num, int64_t hi_cap, void* stream);
+int spb_flatten_u8_clear_batch(const uint64_t* d_keys, int64_t num, const spb_split* h_splits, int nb, uint8_t* d_s0,
+                               int64_t s0_stride, int64_t rows_pad, int64_t pitch, int layout, void* stream);
 
 /* ---- a11: subflattening (constructions.py:108-198) ---- */
 /* Raw pair statistics of sites [32*word_begin, 32*word_end) accumulated (atomicAdd) into d_raw
@@ -177,15 +186,23 @@ int spb_gram_f64(const double* d_A, int64_t R, int64_t C, int64_t batch, double*
  * tcgen05 (tensor core, kind::i8) kernel.  K = pitch.  d_ws: uint64 [spb_gram_u8_ws(...)] (NULL when that is 0);
  * it holds exact 64-bit partial sums when K is split across CTAs. */
 int64_t spb_s0_bytes(int64_t rows_pad, int64_t pitch);
-int64_t spb_gram_u8_ws(int64_t rows_pad, int64_t pitch, int layout);
+int64_t spb_gram_u8_ws(int64_t rows_pad, int64_t pitch, int layout, int nb);
 int spb_gram_u8(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, double* d_G, uint64_t* d_ws,
                 void* stream);
+/* nb matrices in one launch: S0 of entry b at d_s0 + b * s0_stride (bytes), its Gram at d_G + b * g_stride (doubles).
+ * The tensor-core kernel schedules the tiles of all matrices over the SMs and splits K only when nb * tiles < #SMs.
+ * d_ws: uint64 [spb_gram_u8_ws(rows_pad, pitch, layout, nb)]. */
+int spb_gram_u8_batch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int layout,
+                      double* d_G, int64_t g_stride, uint64_t* d_ws, void* stream);
 /* Same result from a plain SIMT loop, any layout and size: the on-device cross-check used by the tests. */
 int spb_gram_u8_simt(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, double* d_G, void* stream);
 /* Adds the terms of the sparse high part H (F = S0 + H): G += S0 H^T + H S0^T + H H^T, so that G = F F^T. */
 int spb_gram_hi_correction(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, const int32_t* d_hi_rc,
                            const uint32_t* d_hi_val, const uint32_t* d_hi_num, int64_t hi_cap, double* d_G,
                            void* stream);
+int spb_gram_hi_correction_batch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch,
+                                 int layout, const int32_t* d_hi_rc, const uint32_t* d_hi_val, const uint32_t* d_hi_num,
+                                 int64_t hi_cap, double* d_G, int64_t g_stride, void* stream);
 /* Scores from symmetric PSD Gram matrices d_G double [batch][ld][ld] using the leading k x k block
  * (k <= 128): cyclic Jacobi in shared memory, score = sqrt(sum_{i>=4} lambda_i / sum_i lambda_i).
  * d_eig (optional) double [batch][k] receives the eigenvalues in descending order. */

@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsplitp_b200.so")
 
 SPB_MAX_TAXA = 64
+SPB_MAX_BATCH = 16
 SPB_VAL_U32, SPB_VAL_F64 = 0, 1
 SPB_S0_ROWMAJOR, SPB_S0_TILED, SPB_S0_K4MAJOR = 0, 1, 2
 SPB_U8_NO_MEMSET = 1
@@ -80,7 +81,11 @@ PROTOTYPES = {
     "spb_gram_f64_ws": (_l, [_l, _l, _l]),
     "spb_gram_f64": (_i, [_p, _l, _l, _l, _p, _p, _p]),
     "spb_s0_bytes": (_l, [_l, _l]),
-    "spb_gram_u8_ws": (_l, [_l, _l, _i]),
+    "spb_gram_u8_ws": (_l, [_l, _l, _i, _i]),
+    "spb_gram_u8_batch": (_i, [_p, _l, _i, _l, _l, _i, _p, _l, _p, _p]),
+    "spb_gram_hi_correction_batch": (_i, [_p, _l, _i, _l, _l, _i, _p, _p, _p, _l, _p, _l, _p]),
+    "spb_flatten_u8_batch": (_i, [_p, _p, _l, _sp, _i, _p, _l, _l, _l, _i, _i, _p, _p, _p, _l, _p]),
+    "spb_flatten_u8_clear_batch": (_i, [_p, _l, _sp, _i, _p, _l, _l, _l, _i, _p]),
     "spb_gram_u8": (_i, [_p, _l, _l, _i, _p, _p, _p]),
     "spb_gram_u8_simt": (_i, [_p, _l, _l, _i, _p, _p]),
     "spb_gram_hi_correction": (_i, [_p, _l, _l, _i, _p, _p, _p, _l, _p, _p]),

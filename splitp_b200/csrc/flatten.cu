@@ -71,22 +71,33 @@ __device__ __forceinline__ int64_t s0_cell(int layout, int64_t rows_pad, int64_t
   return (int64_t)((rt * KT + kt) * 16384ull + rr * 128u + ((((kk >> 4) ^ (rr & 7u))) << 4) + (kk & 15u));
 }
 
-__global__ void u8_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t num, SplitDev sp,
-                          const uint32_t* rank_r, const uint32_t* rank_c, uint8_t* s0, int64_t rows_pad, int64_t pitch, int layout, int32_t* hi_rc,
-                          uint32_t* hi_val, uint32_t* hi_num, int64_t hi_cap) {
+struct SplitBatch {  // passed by value as a kernel parameter (16 x 140 bytes)
+  SplitDev s[SPB_MAX_BATCH];
+};
+
+// blockIdx.y = batch entry: split sb.s[b], S0 buffer s0 + b * s0_stride, high-part buffers offset by b * hi_cap.
+// counts == NULL: clear pass (writes zeros to the cells the scatter touched).
+__global__ void u8_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t num,
+                          const __grid_constant__ SplitBatch sb, const uint32_t* rank_r, const uint32_t* rank_c, uint8_t* s0_base,
+                          int64_t s0_stride, int64_t rows_pad, int64_t pitch, int layout, int32_t* hi_rc_base, uint32_t* hi_val_base,
+                          uint32_t* hi_num_base, int64_t hi_cap) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= num) return;
+  const int b = blockIdx.y;
+  const SplitDev& sp = sb.s[b];
+  uint8_t* s0 = s0_base + (size_t)b * s0_stride;
   uint64_t k = keys[i];
-  uint32_t cnt = counts ? counts[i] : 0u;  // counts == NULL: clear pass
+  uint32_t cnt = counts ? counts[i] : 0u;
   uint64_t r = side_index(k, sp.sh_a, sp.a), c = side_index(k, sp.sh_b, sp.b);
   if (rank_r) { r = rank_r[r]; c = rank_c[c]; }
   s0[s0_cell(layout, rows_pad, pitch, r, c)] = (uint8_t)(cnt & 255u);
   if (cnt >= 256u) {
-    uint32_t slot = atomicAdd(hi_num, 1u);
+    uint32_t slot = atomicAdd(hi_num_base + b, 1u);
     if ((int64_t)slot < hi_cap) {
+      int32_t* hi_rc = hi_rc_base + (size_t)b * 2 * hi_cap;
       hi_rc[2 * (int64_t)slot] = (int32_t)r;
       hi_rc[2 * (int64_t)slot + 1] = (int32_t)c;
-      hi_val[slot] = cnt - (cnt & 255u);
+      hi_val_base[(size_t)b * hi_cap + slot] = cnt - (cnt & 255u);
     }
   }
 }
@@ -226,35 +237,57 @@ static int u8_check(const spb_split* split, SplitDev* sp, const uint32_t* d_rank
   return SPB_OK;
 }
 
+static int u8_batch_common(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* h_splits, int nb,
+                           const uint32_t* d_rank_r, const uint32_t* d_rank_c, uint8_t* d_s0, int64_t s0_stride, int64_t rows_pad,
+                           int64_t pitch, int layout, int flags, int32_t* d_hi_rc, uint32_t* d_hi_val, uint32_t* d_hi_num,
+                           int64_t hi_cap, bool clear, cudaStream_t st) {
+  SPB_REQUIRE(h_splits && nb >= 1 && nb <= SPB_MAX_BATCH, "spb_flatten_u8: batch size must be 1..%d (got %d)", SPB_MAX_BATCH, nb);
+  SPB_REQUIRE(nb == 1 || (s0_stride >= rows_pad * pitch && !d_rank_r), "spb_flatten_u8: bad batch stride / rank arrays in a batch");
+  SplitBatch sb;
+  for (int b = 0; b < nb; ++b) {
+    int rc = u8_check(h_splits + b, &sb.s[b], d_rank_r, d_rank_c, d_s0, rows_pad, pitch, layout);
+    if (rc) return rc;
+  }
+  if (!clear) {
+    SPB_REQUIRE(d_hi_rc && d_hi_val && d_hi_num, "spb_flatten_u8: NULL high-part buffers");
+    if (!(flags & SPB_U8_NO_MEMSET)) {
+      for (int b = 0; b < nb; ++b) SPB_CUDA(cudaMemsetAsync(d_s0 + (size_t)b * s0_stride, 0, (size_t)rows_pad * (size_t)pitch, st));
+    }
+    SPB_CUDA(cudaMemsetAsync(d_hi_num, 0, 4 * (size_t)nb, st));
+  }
+  if (num <= 0) return SPB_OK;
+  SPB_REQUIRE(d_keys && (clear || d_counts), "spb_flatten_u8: NULL pattern table");
+  dim3 grid(nblk(num, 256), (unsigned)nb);
+  u8_kernel<<<grid, 256, 0, st>>>(d_keys, clear ? nullptr : d_counts, num, sb, d_rank_r, d_rank_c, d_s0, s0_stride, rows_pad, pitch,
+                                  layout, d_hi_rc, d_hi_val, d_hi_num, hi_cap);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int spb_flatten_u8_batch(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* h_splits, int nb,
+                                    uint8_t* d_s0, int64_t s0_stride, int64_t rows_pad, int64_t pitch, int layout, int flags,
+                                    int32_t* d_hi_rc, uint32_t* d_hi_val, uint32_t* d_hi_num, int64_t hi_cap, void* stream) {
+  return u8_batch_common(d_keys, d_counts, num, h_splits, nb, nullptr, nullptr, d_s0, s0_stride, rows_pad, pitch, layout, flags,
+                         d_hi_rc, d_hi_val, d_hi_num, hi_cap, false, (cudaStream_t)stream);
+}
+
+extern "C" int spb_flatten_u8_clear_batch(const uint64_t* d_keys, int64_t num, const spb_split* h_splits, int nb, uint8_t* d_s0,
+                                          int64_t s0_stride, int64_t rows_pad, int64_t pitch, int layout, void* stream) {
+  return u8_batch_common(d_keys, nullptr, num, h_splits, nb, nullptr, nullptr, d_s0, s0_stride, rows_pad, pitch, layout, 0, nullptr,
+                         nullptr, nullptr, 0, true, (cudaStream_t)stream);
+}
+
 extern "C" int spb_flatten_u8(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* split,
                               const uint32_t* d_rank_r, const uint32_t* d_rank_c, uint8_t* d_s0, int64_t rows_pad,
                               int64_t pitch, int layout, int flags, int32_t* d_hi_rc, uint32_t* d_hi_val, uint32_t* d_hi_num,
                               int64_t hi_cap, void* stream) {
-  SplitDev sp;
-  int rc = u8_check(split, &sp, d_rank_r, d_rank_c, d_s0, rows_pad, pitch, layout);
-  if (rc) return rc;
-  SPB_REQUIRE(d_hi_rc && d_hi_val && d_hi_num, "spb_flatten_u8: NULL high-part buffers");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (!(flags & SPB_U8_NO_MEMSET)) SPB_CUDA(cudaMemsetAsync(d_s0, 0, (size_t)rows_pad * (size_t)pitch, st));
-  SPB_CUDA(cudaMemsetAsync(d_hi_num, 0, 4, st));
-  if (num <= 0) return SPB_OK;
-  SPB_REQUIRE(d_keys && d_counts, "spb_flatten_u8: NULL pattern table");
-  u8_kernel<<<nblk(num, 256), 256, 0, st>>>(d_keys, d_counts, num, sp, d_rank_r, d_rank_c, d_s0, rows_pad, pitch, layout, d_hi_rc, d_hi_val,
-                                            d_hi_num, hi_cap);
-  SPB_LAUNCH_CHECK();
-  return SPB_OK;
+  return u8_batch_common(d_keys, d_counts, num, split, 1, d_rank_r, d_rank_c, d_s0, rows_pad * pitch, rows_pad, pitch, layout, flags,
+                         d_hi_rc, d_hi_val, d_hi_num, hi_cap, false, (cudaStream_t)stream);
 }
 
 extern "C" int spb_flatten_u8_clear(const uint64_t* d_keys, int64_t num, const spb_split* split, const uint32_t* d_rank_r,
                                     const uint32_t* d_rank_c, uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout,
                                     void* stream) {
-  SplitDev sp;
-  int rc = u8_check(split, &sp, d_rank_r, d_rank_c, d_s0, rows_pad, pitch, layout);
-  if (rc) return rc;
-  if (num <= 0) return SPB_OK;
-  SPB_REQUIRE(d_keys, "spb_flatten_u8_clear: NULL pattern table");
-  u8_kernel<<<nblk(num, 256), 256, 0, (cudaStream_t)stream>>>(d_keys, nullptr, num, sp, d_rank_r, d_rank_c, d_s0, rows_pad, pitch,
-                                                              layout, nullptr, nullptr, nullptr, 0);
-  SPB_LAUNCH_CHECK();
-  return SPB_OK;
+  return u8_batch_common(d_keys, nullptr, num, split, 1, d_rank_r, d_rank_c, d_s0, rows_pad * pitch, rows_pad, pitch, layout, 0,
+                         nullptr, nullptr, nullptr, 0, true, (cudaStream_t)stream);
 }

@@ -134,7 +134,7 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
 // only if the tile's 256-block column index >= its 256-block row index.  Work item = (tile, k-split).
 // ---------------------------------------------------------------------------------------------------
 struct Work {
-  int i, j, ks;
+  int b, i, j, ks;  // batch entry, row tile, column tile, k-split
 };
 
 template <int BN>
@@ -146,7 +146,10 @@ __device__ __forceinline__ bool tile_needed(int i, int j) {
 }
 
 template <int BN>
-__device__ __forceinline__ bool get_work(int w, int T, int TN, int ksplit, Work* out) {
+__device__ __forceinline__ bool get_work(int w, int T, int TN, int tiles, int ksplit, Work* out) {
+  const int per = tiles * ksplit;
+  out->b = w / per;
+  w -= out->b * per;
   int tile = w / ksplit;
   int ks = w - tile * ksplit;
   int seen = 0;
@@ -176,8 +179,9 @@ int count_tiles(int T, int TN) {
 // ---------------------------------------------------------------------------------------------------
 template <int BN>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
-gram_u8_umma_kernel(const uint8_t* __restrict__ s0t, int T, int KT, int ksplit, int kt_per_split, int num_work, int64_t ldg,
-                    double* __restrict__ G, unsigned long long* __restrict__ acc64) {
+gram_u8_umma_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int T, int KT, int tiles, int ksplit, int kt_per_split,
+                    int num_work, int64_t ldg, double* __restrict__ G_base, int64_t g_stride,
+                    unsigned long long* __restrict__ acc_base) {
   constexpr int kStageBytes = kTileBytes + BN * kTile;  // A tile + B tile(s)
   constexpr uint32_t kTmemCols = 2 * BN;                 // two accumulator stages (power of two >= 32)
   constexpr uint32_t kIdesc = make_idesc_i8(kTile, BN);
@@ -212,9 +216,10 @@ gram_u8_umma_kernel(const uint8_t* __restrict__ s0t, int T, int KT, int ksplit, 
       uint32_t stage = 0, phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         Work wk;
-        if (!get_work<BN>(w, T, TN, ksplit, &wk)) break;
+        if (!get_work<BN>(w, T, TN, tiles, ksplit, &wk)) break;
         const int kt0 = wk.ks * kt_per_split;
         const int kt1 = min(KT, kt0 + kt_per_split);
+        const uint8_t* s0t = s0_base + (size_t)wk.b * s0_stride;
         for (int kt = kt0; kt < kt1; ++kt) {
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
           const uint32_t fb = smem_u32(full_bar + stage);
@@ -237,7 +242,7 @@ gram_u8_umma_kernel(const uint8_t* __restrict__ s0t, int T, int KT, int ksplit, 
       uint32_t acc = 0, acc_phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         Work wk;
-        if (!get_work<BN>(w, T, TN, ksplit, &wk)) break;
+        if (!get_work<BN>(w, T, TN, tiles, ksplit, &wk)) break;
         const int kt0 = wk.ks * kt_per_split;
         const int kt1 = min(KT, kt0 + kt_per_split);
         mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -267,11 +272,13 @@ gram_u8_umma_kernel(const uint8_t* __restrict__ s0t, int T, int KT, int ksplit, 
     uint32_t acc = 0, acc_phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       Work wk;
-      if (!get_work<BN>(w, T, TN, ksplit, &wk)) break;
+      if (!get_work<BN>(w, T, TN, tiles, ksplit, &wk)) break;
       mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
       tc_fence_after();
       const int row = wk.i * kTile + q * 32 + lane;
       const int rb = row >> 8;
+      double* G = G_base + (size_t)wk.b * g_stride;
+      unsigned long long* acc64 = acc_base ? acc_base + (size_t)wk.b * ldg * ldg : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -311,9 +318,12 @@ gram_u8_umma_kernel(const uint8_t* __restrict__ s0t, int T, int KT, int ksplit, 
 }
 
 // split-K finalize: 64-bit integer accumulators (upper 256-block triangle valid) -> symmetric fp64 G
-__global__ void gram_finalize_kernel(const unsigned long long* __restrict__ acc64, int64_t R, int64_t ldg, double* __restrict__ G) {
+__global__ void gram_finalize_kernel(const unsigned long long* __restrict__ acc_base, int64_t R, int64_t ldg, double* __restrict__ G_base,
+                                     int64_t g_stride) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * R) return;
+  const unsigned long long* acc64 = acc_base + (size_t)blockIdx.y * R * R;
+  double* G = G_base + (size_t)blockIdx.y * g_stride;
   int64_t r = idx / R, c = idx - r * R;
   unsigned long long v = ((c >> 8) >= (r >> 8)) ? acc64[r * ldg + c] : acc64[c * ldg + r];
   G[r * ldg + c] = (double)(long long)v;
@@ -330,9 +340,11 @@ __global__ void gram_finalize_kernel(const unsigned long long* __restrict__ acc6
 // ---------------------------------------------------------------------------------------------------
 constexpr int kSmallWords = 256;  // word columns (= 1024 k) per chunk
 
-__global__ void __launch_bounds__(256) gram_u8_small_kernel(const uint32_t* __restrict__ s0w, int Rp, int64_t words,
-                                                            unsigned long long* __restrict__ acc64) {
+__global__ void __launch_bounds__(256) gram_u8_small_kernel(const uint32_t* __restrict__ s0w_base, int64_t s0_stride_words, int Rp,
+                                                            int64_t words, unsigned long long* __restrict__ acc_base) {
   extern __shared__ __align__(16) uint32_t s_chunk[];  // [kSmallWords][Rp]
+  const uint32_t* s0w = s0w_base + (size_t)blockIdx.y * s0_stride_words;
+  unsigned long long* acc64 = acc_base + (size_t)blockIdx.y * Rp * Rp;
   const int tid = threadIdx.x;
   const int q = Rp >> 2;                 // 4-row blocks per side
   const int per_group = q * q;           // threads of one group
@@ -378,11 +390,12 @@ __global__ void __launch_bounds__(256) gram_u8_small_kernel(const uint32_t* __re
 }
 
 // acc64 [Rp][Rp] -> fp64 G [ld][ld] leading Rp x Rp block
-__global__ void gram_small_finalize_kernel(const unsigned long long* __restrict__ acc64, int R, int64_t ld, double* __restrict__ G) {
+__global__ void gram_small_finalize_kernel(const unsigned long long* __restrict__ acc_base, int R, int64_t ld, double* __restrict__ G_base,
+                                           int64_t g_stride) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * R) return;
   int r = idx / R, c = idx - r * R;
-  G[(int64_t)r * ld + c] = (double)(long long)acc64[idx];
+  G_base[(size_t)blockIdx.y * g_stride + (int64_t)r * ld + c] = (double)(long long)acc_base[(size_t)blockIdx.y * R * R + idx];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -410,11 +423,16 @@ __global__ void gram_u8_simt_kernel(const uint8_t* __restrict__ s0, int layout, 
 // ---------------------------------------------------------------------------------------------------
 // sparse high-part corrections: G += S0 H^T + H S0^T + H H^T
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) hi_cross_kernel(const uint8_t* __restrict__ s0, int layout, int64_t R, int64_t pitch,
-                                                       const int32_t* __restrict__ hi_rc, const uint32_t* __restrict__ hi_val,
-                                                       const uint32_t* __restrict__ hi_num, int64_t hi_cap, int64_t ldg,
-                                                       double* __restrict__ G) {
-  int64_t n = *hi_num;
+__global__ void __launch_bounds__(256) hi_cross_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int layout, int64_t R,
+                                                       int64_t pitch, const int32_t* __restrict__ hi_rc_base,
+                                                       const uint32_t* __restrict__ hi_val_base, const uint32_t* __restrict__ hi_num_base,
+                                                       int64_t hi_cap, int64_t ldg, double* __restrict__ G_base, int64_t g_stride) {
+  const int b = blockIdx.z;
+  const uint8_t* s0 = s0_base + (size_t)b * s0_stride;
+  const int32_t* hi_rc = hi_rc_base + (size_t)b * 2 * hi_cap;
+  const uint32_t* hi_val = hi_val_base + (size_t)b * hi_cap;
+  double* G = G_base + (size_t)b * g_stride;
+  int64_t n = hi_num_base[b];
   if (n > hi_cap) n = hi_cap;
   for (int64_t e = blockIdx.y; e < n; e += gridDim.y) {
     const int64_t r = hi_rc[2 * e], c = hi_rc[2 * e + 1];
@@ -431,10 +449,14 @@ __global__ void __launch_bounds__(256) hi_cross_kernel(const uint8_t* __restrict
 }
 
 // one thread per ordered pair (e1, e2) of high entries; pairs in the same column contribute v1 * v2 to G[r1][r2]
-__global__ void __launch_bounds__(256) hi_self_kernel(const int32_t* __restrict__ hi_rc, const uint32_t* __restrict__ hi_val,
-                                                      const uint32_t* __restrict__ hi_num, int64_t hi_cap, int64_t ldg,
-                                                      double* __restrict__ G) {
-  int64_t n = *hi_num;
+__global__ void __launch_bounds__(256) hi_self_kernel(const int32_t* __restrict__ hi_rc_base, const uint32_t* __restrict__ hi_val_base,
+                                                      const uint32_t* __restrict__ hi_num_base, int64_t hi_cap, int64_t ldg,
+                                                      double* __restrict__ G_base, int64_t g_stride) {
+  const int b = blockIdx.y;
+  const int32_t* hi_rc = hi_rc_base + (size_t)b * 2 * hi_cap;
+  const uint32_t* hi_val = hi_val_base + (size_t)b * hi_cap;
+  double* G = G_base + (size_t)b * g_stride;
+  int64_t n = hi_num_base[b];
   if (n > hi_cap) n = hi_cap;
   const int64_t pairs = n * n;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += (int64_t)gridDim.x * blockDim.x) {
@@ -449,24 +471,26 @@ struct UmmaPlan {
   size_t smem;
 };
 
-UmmaPlan plan_umma(int64_t rows_pad, int64_t pitch) {
+UmmaPlan plan_umma(int64_t rows_pad, int64_t pitch, int nb) {
   UmmaPlan p;
   p.BN = rows_pad >= 256 ? 256 : 128;
   p.T = (int)(rows_pad / kTile);
   p.KT = (int)(pitch / kTile);
   int TN = (int)(rows_pad / p.BN);
   p.tiles = p.BN == 256 ? count_tiles<256>(p.T, TN) : count_tiles<128>(p.T, TN);
-  // split K so that every SM has work; one s32 accumulation must stay below 2^31: 255^2 * 128 * kt <= 2^31 -> kt <= 258
+  // split K only when the batch does not give every SM a tile; one s32 accumulation must stay below 2^31:
+  // 255^2 * 128 * kt <= 2^31 -> kt <= 258
   int sms = sm_count();
+  int total = p.tiles * nb;
   int ks = 1;
-  if (p.tiles < sms) ks = (sms + p.tiles - 1) / p.tiles;
+  if (total < sms) ks = (sms + total - 1) / total;
   if (ks > p.KT) ks = p.KT;
   int per = (p.KT + ks - 1) / ks;
   if (per > 256) per = 256;
   ks = (p.KT + per - 1) / per;
   p.ksplit = ks;
   p.kt_per_split = per;
-  p.num_work = p.tiles * ks;
+  p.num_work = total * ks;
   p.smem = (size_t)kStages * (kTileBytes + p.BN * kTile) + 16 * 8 + 1024;
   return p;
 }
@@ -475,65 +499,78 @@ UmmaPlan plan_umma(int64_t rows_pad, int64_t pitch) {
 
 extern "C" int64_t spb_s0_bytes(int64_t rows_pad, int64_t pitch) { return rows_pad * pitch; }
 
-extern "C" int64_t spb_gram_u8_ws(int64_t rows_pad, int64_t pitch, int layout) {
-  if (layout == SPB_S0_K4MAJOR) return rows_pad * rows_pad;
+extern "C" int64_t spb_gram_u8_ws(int64_t rows_pad, int64_t pitch, int layout, int nb) {
+  if (nb < 1) nb = 1;
+  if (layout == SPB_S0_K4MAJOR) return nb * rows_pad * rows_pad;
   if (layout != SPB_S0_TILED || rows_pad % kTile || pitch % kTile) return 0;
-  UmmaPlan p = plan_umma(rows_pad, pitch);
-  return p.ksplit > 1 ? rows_pad * rows_pad : 0;
+  UmmaPlan p = plan_umma(rows_pad, pitch, nb);
+  return p.ksplit > 1 ? nb * rows_pad * rows_pad : 0;
 }
 
-extern "C" int spb_gram_u8(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, double* d_G, uint64_t* d_ws,
-                           void* stream) {
-  SPB_REQUIRE(d_s0 && d_G && rows_pad >= 1 && pitch >= 16 && pitch % 16 == 0, "spb_gram_u8: bad arguments");
+extern "C" int spb_gram_u8_batch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int layout,
+                                 double* d_G, int64_t g_stride, uint64_t* d_ws, void* stream) {
+  SPB_REQUIRE(d_s0 && d_G && rows_pad >= 1 && pitch >= 16 && pitch % 16 == 0 && nb >= 1 && nb <= 65535,
+              "spb_gram_u8: bad arguments");
+  SPB_REQUIRE(nb == 1 || (s0_stride >= rows_pad * pitch && s0_stride % 16 == 0 && g_stride >= rows_pad * rows_pad),
+              "spb_gram_u8: bad batch strides");
   cudaStream_t st = (cudaStream_t)stream;
   if (layout == SPB_S0_K4MAJOR) {
     SPB_REQUIRE(rows_pad <= 64 && rows_pad % 4 == 0, "spb_gram_u8: the k4-major (dp4a) path handles rows_pad <= 64, rows_pad %% 4 == 0 "
                 "(got %lld); use the tiled layout", (long long)rows_pad);
     SPB_REQUIRE(d_ws, "spb_gram_u8: workspace required (spb_gram_u8_ws)");
     int R = (int)rows_pad;
-    SPB_CUDA(cudaMemsetAsync(d_ws, 0, (size_t)R * R * 8, st));
+    SPB_CUDA(cudaMemsetAsync(d_ws, 0, (size_t)nb * R * R * 8, st));
     size_t smem = (size_t)kSmallWords * R * 4;
     SPB_CUDA(cudaFuncSetAttribute(gram_u8_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t words = pitch / 4;
     int64_t nchunks = (words + kSmallWords - 1) / kSmallWords;
-    int64_t grid = (int64_t)sm_count() * 2;
-    if (grid > nchunks) grid = nchunks;
-    gram_u8_small_kernel<<<(unsigned)grid, 256, smem, st>>>(reinterpret_cast<const uint32_t*>(d_s0), R, words,
-                                                          (unsigned long long*)d_ws);
+    int64_t gx = ((int64_t)sm_count() * 2 + nb - 1) / nb;
+    if (gx > nchunks) gx = nchunks;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)nb);
+    gram_u8_small_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const uint32_t*>(d_s0), s0_stride / 4, R, words,
+                                                  (unsigned long long*)d_ws);
     SPB_LAUNCH_CHECK();
-    gram_small_finalize_kernel<<<(R * R + 255) / 256, 256, 0, st>>>((const unsigned long long*)d_ws, R, rows_pad, d_G);
+    dim3 fg((R * R + 255) / 256, (unsigned)nb);
+    gram_small_finalize_kernel<<<fg, 256, 0, st>>>((const unsigned long long*)d_ws, R, rows_pad, d_G, g_stride);
     SPB_LAUNCH_CHECK();
     return SPB_OK;
   }
-  SPB_REQUIRE(layout == SPB_S0_TILED, "spb_gram_u8: unknown layout %d", layout);
+  SPB_REQUIRE(layout == SPB_S0_TILED, "spb_gram_u8: layout %d has no Gram kernel (use SPB_S0_K4MAJOR or SPB_S0_TILED)", layout);
   SPB_REQUIRE(rows_pad % kTile == 0 && pitch % kTile == 0 && (rows_pad == kTile || rows_pad % 256 == 0),
               "spb_gram_u8: the tiled (tcgen05) path needs pitch %% 128 == 0 and rows_pad == 128 or a multiple of 256 "
               "(got rows_pad=%lld pitch=%lld)", (long long)rows_pad, (long long)pitch);
   SPB_REQUIRE(rows_pad <= 32768, "spb_gram_u8: rows_pad too large");
-  UmmaPlan p = plan_umma(rows_pad, pitch);
+  UmmaPlan p = plan_umma(rows_pad, pitch, nb);
   unsigned long long* acc = nullptr;
   if (p.ksplit > 1) {
     SPB_REQUIRE(d_ws, "spb_gram_u8: workspace required (spb_gram_u8_ws)");
     acc = (unsigned long long*)d_ws;
-    SPB_CUDA(cudaMemsetAsync(acc, 0, (size_t)rows_pad * rows_pad * 8, st));
+    SPB_CUDA(cudaMemsetAsync(acc, 0, (size_t)nb * rows_pad * rows_pad * 8, st));
   }
   int grid = p.num_work < sm_count() ? p.num_work : sm_count();
   if (p.BN == 256) {
     SPB_CUDA(cudaFuncSetAttribute(gram_u8_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    gram_u8_umma_kernel<256><<<grid, kUmmaThreads, p.smem, st>>>(d_s0, p.T, p.KT, p.ksplit, p.kt_per_split, p.num_work, rows_pad,
-                                                               d_G, acc);
+    gram_u8_umma_kernel<256><<<grid, kUmmaThreads, p.smem, st>>>(d_s0, s0_stride, p.T, p.KT, p.tiles, p.ksplit, p.kt_per_split,
+                                                               p.num_work, rows_pad, d_G, g_stride, acc);
   } else {
     SPB_CUDA(cudaFuncSetAttribute(gram_u8_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    gram_u8_umma_kernel<128><<<grid, kUmmaThreads, p.smem, st>>>(d_s0, p.T, p.KT, p.ksplit, p.kt_per_split, p.num_work, rows_pad,
-                                                               d_G, acc);
+    gram_u8_umma_kernel<128><<<grid, kUmmaThreads, p.smem, st>>>(d_s0, s0_stride, p.T, p.KT, p.tiles, p.ksplit, p.kt_per_split,
+                                                               p.num_work, rows_pad, d_G, g_stride, acc);
   }
   SPB_LAUNCH_CHECK();
   if (acc) {
     int64_t cells = rows_pad * rows_pad;
-    gram_finalize_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(acc, rows_pad, rows_pad, d_G);
+    dim3 fg((unsigned)((cells + 255) / 256), (unsigned)nb);
+    gram_finalize_kernel<<<fg, 256, 0, st>>>(acc, rows_pad, rows_pad, d_G, g_stride);
     SPB_LAUNCH_CHECK();
   }
   return SPB_OK;
+}
+
+extern "C" int spb_gram_u8(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, double* d_G, uint64_t* d_ws,
+                           void* stream) {
+  return spb_gram_u8_batch(d_s0, rows_pad * pitch, 1, rows_pad, pitch, layout, d_G, rows_pad * rows_pad, d_ws, stream);
 }
 
 // Test / cross-check entry: same result as spb_gram_u8 from a plain SIMT loop (any layout, any size).
@@ -547,18 +584,28 @@ extern "C" int spb_gram_u8_simt(const uint8_t* d_s0, int64_t rows_pad, int64_t p
   return SPB_OK;
 }
 
+extern "C" int spb_gram_hi_correction_batch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch,
+                                            int layout, const int32_t* d_hi_rc, const uint32_t* d_hi_val, const uint32_t* d_hi_num,
+                                            int64_t hi_cap, double* d_G, int64_t g_stride, void* stream) {
+  SPB_REQUIRE(d_s0 && d_hi_rc && d_hi_val && d_hi_num && d_G && hi_cap >= 0 && nb >= 1 && nb <= 65535,
+              "spb_gram_hi_correction: bad arguments");
+  if (hi_cap == 0) return SPB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t gy = hi_cap < 64 ? hi_cap : 64;  // the entry loop strides over gridDim.y
+  dim3 grid((unsigned)((rows_pad + 255) / 256 > 16 ? 16 : (rows_pad + 255) / 256), (unsigned)gy, (unsigned)nb);
+  hi_cross_kernel<<<grid, 256, 0, st>>>(d_s0, s0_stride, layout, rows_pad, pitch, d_hi_rc, d_hi_val, d_hi_num, hi_cap, rows_pad, d_G,
+                                        g_stride);
+  SPB_LAUNCH_CHECK();
+  int64_t gx = (4 * (int64_t)sm_count() + nb - 1) / nb;  // grid-stride over the n^2 pairs (n is only known on the device)
+  dim3 sg((unsigned)gx, (unsigned)nb);
+  hi_self_kernel<<<sg, 256, 0, st>>>(d_hi_rc, d_hi_val, d_hi_num, hi_cap, rows_pad, d_G, g_stride);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
 extern "C" int spb_gram_hi_correction(const uint8_t* d_s0, int64_t rows_pad, int64_t pitch, int layout, const int32_t* d_hi_rc,
                                       const uint32_t* d_hi_val, const uint32_t* d_hi_num, int64_t hi_cap, double* d_G,
                                       void* stream) {
-  SPB_REQUIRE(d_s0 && d_hi_rc && d_hi_val && d_hi_num && d_G && hi_cap >= 0, "spb_gram_hi_correction: bad arguments");
-  if (hi_cap == 0) return SPB_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  int64_t gy = hi_cap < 1024 ? hi_cap : 1024;
-  dim3 grid((unsigned)((rows_pad + 255) / 256 > 16 ? 16 : (rows_pad + 255) / 256), (unsigned)gy);
-  hi_cross_kernel<<<grid, 256, 0, st>>>(d_s0, layout, rows_pad, pitch, d_hi_rc, d_hi_val, d_hi_num, hi_cap, rows_pad, d_G);
-  SPB_LAUNCH_CHECK();
-  int64_t gx = 4 * (int64_t)sm_count();  // grid-stride over the n^2 pairs (n is only known on the device)
-  hi_self_kernel<<<(unsigned)gx, 256, 0, st>>>(d_hi_rc, d_hi_val, d_hi_num, hi_cap, rows_pad, d_G);
-  SPB_LAUNCH_CHECK();
-  return SPB_OK;
+  return spb_gram_hi_correction_batch(d_s0, rows_pad * pitch, 1, rows_pad, pitch, layout, d_hi_rc, d_hi_val, d_hi_num, hi_cap, d_G,
+                                      rows_pad * rows_pad, stream);
 }

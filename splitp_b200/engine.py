@@ -414,20 +414,25 @@ def score_matrix(A):
 class CountScorer:
     """Exact-integer scoring of count flattenings: u8 low-byte matrix -> Gram on the tensor cores
     (tcgen05 kind::i8) or dp4a for <= 64 rows -> sparse high-part correction -> eigen-solver.
-    Buffers are allocated once and reused across splits."""
+    Buffers are allocated once and reused across splits; up to SPB_MAX_BATCH splits share one launch of
+    every stage (the scatter / correction kernels are a few microseconds each, so batching them is what
+    keeps the GPU busy)."""
+
+    NB = _lib.SPB_MAX_BATCH
 
     def __init__(self, table, hi_cap=None):
         if table.counts is None:
             raise ValueError("CountScorer needs a PatternTable with integer counts")
         self.table = table
-        self.hi_cap = int(hi_cap if hi_cap is not None else max(1024, min(table.num, 1 << 20)))
-        self.hi_rc = _empty((self.hi_cap, 2), torch.int32)
-        self.hi_val = _empty(self.hi_cap, torch.int32)
-        self.hi_num = _zeros(1, torch.int32)
+        self.hi_cap = int(hi_cap if hi_cap is not None else max(1024, min(table.num, 1 << 16)))
+        self.hi_rc = _empty((self.NB, self.hi_cap, 2), torch.int32)
+        self.hi_val = _empty((self.NB, self.hi_cap), torch.int32)
+        self.hi_num = _zeros(self.NB, torch.int32)
+        self.hi_max = _zeros(1, torch.int32)  # running maximum of hi_num (checked once by check_hi)
         self._s0 = {}
         self._G = {}
         self._ws = {}
-        self.gram_hook = None  # optional wrapper around the Gram launch (bench.py times it with CUDA events)
+        self.gram_hook = None  # optional wrapper (fn, nb) around the Gram launch (bench.py times it with CUDA events)
 
     @staticmethod
     def geometry(rows, cols):
@@ -440,13 +445,13 @@ class CountScorer:
     def _buffers(self, layout, rows_pad, pitch, batch=1):
         key = (layout, rows_pad, pitch)
         if key not in self._s0:
-            self._s0[key] = _zeros(rows_pad * pitch, torch.uint8)
+            self._s0[key] = _zeros((self.NB, rows_pad * pitch), torch.uint8)
         g = self._G.get(rows_pad)
         if g is None or g.shape[0] < batch:
             g = self._G[rows_pad] = _empty((batch, rows_pad, rows_pad), torch.float64)
         if key not in self._ws:
-            n = int(lib.spb_gram_u8_ws(rows_pad, pitch, layout))
-            self._ws[key] = _empty(n, torch.int64) if n else None
+            n = int(lib.spb_gram_u8_ws(rows_pad, pitch, layout, 1))
+            self._ws[key] = _empty(self.NB * rows_pad * rows_pad, torch.int64) if n else None
         return self._s0[key], g, self._ws[key]
 
     def _plan(self, idx_a, idx_b, reduced):
@@ -468,16 +473,32 @@ class CountScorer:
         return sp, rank_r, rank_c, R, Cc
 
     def _gram_into(self, plan, s0, G, ws, layout, rows_pad, pitch):
-        """flatten (u8 scatter) -> exact Gram -> high-part correction -> un-scatter, all on the current stream."""
+        """One split (supports the reduced-format rank arrays): flatten -> Gram -> correction -> un-scatter."""
         t = self.table
         sp, rank_r, rank_c, R, Cc = plan
         call("spb_flatten_u8", _p(t.keys), _p(t.counts), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch,
              layout, SPB_U8_NO_MEMSET, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num), self.hi_cap, _st())
         run = lambda: call("spb_gram_u8", _p(s0), rows_pad, pitch, layout, _p(G), _p(ws), _st())  # noqa: E731
-        run() if self.gram_hook is None else self.gram_hook(run)
+        run() if self.gram_hook is None else self.gram_hook(run, 1)
         call("spb_gram_hi_correction", _p(s0), rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num),
              self.hi_cap, _p(G), _st())
         call("spb_flatten_u8_clear", _p(t.keys), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch, layout, _st())
+        torch.maximum(self.hi_max, self.hi_num[:1], out=self.hi_max)
+
+    def _gram_batch(self, splits, s0, G, ws, layout, rows_pad, pitch):
+        """nb <= SPB_MAX_BATCH dense splits of equal shape, one launch per stage.  G: [nb, rows_pad, rows_pad] view."""
+        t = self.table
+        nb = len(splits)
+        arr = (_lib.SpbSplit * nb)(*splits)
+        s0_stride, g_stride = rows_pad * pitch, rows_pad * rows_pad
+        call("spb_flatten_u8_batch", _p(t.keys), _p(t.counts), t.num, arr, nb, _p(s0), s0_stride, rows_pad, pitch, layout,
+             SPB_U8_NO_MEMSET, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num), self.hi_cap, _st())
+        run = lambda: call("spb_gram_u8_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(G), g_stride, _p(ws), _st())  # noqa: E731
+        run() if self.gram_hook is None else self.gram_hook(run, nb)
+        call("spb_gram_hi_correction_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
+             _p(self.hi_num), self.hi_cap, _p(G), g_stride, _st())
+        call("spb_flatten_u8_clear_batch", _p(t.keys), t.num, arr, nb, _p(s0), s0_stride, rows_pad, pitch, layout, _st())
+        torch.maximum(self.hi_max, self.hi_num[:nb].max().reshape(1), out=self.hi_max)
 
     def gram(self, idx_a, idx_b, reduced=False):
         """Exact F F^T (short side) of the count flattening of one split.  Returns (G [rows_pad, rows_pad], k)."""
@@ -485,7 +506,7 @@ class CountScorer:
         R, Cc = plan[3], plan[4]
         layout, rows_pad, pitch = self.geometry(R, Cc)
         s0, G, ws = self._buffers(layout, rows_pad, pitch)
-        self._gram_into(plan, s0, G[0], ws, layout, rows_pad, pitch)
+        self._gram_into(plan, s0[0], G[0], ws, layout, rows_pad, pitch)
         return G[0], R
 
     def score(self, idx_a, idx_b, reduced=False):
@@ -496,8 +517,8 @@ class CountScorer:
 
     def score_many(self, splits_idx, reduced=False, max_batch=256, max_batch_bytes=16 << 30, big_hook=None):
         """Scores of many splits.  Dense count flattenings of equal shape are batched: their Gram matrices are
-        built one after the other into G[b] and ONE batched eigen-solver call scores the whole batch (the Jacobi /
-        Krylov kernels are latency-bound per matrix, so batching is what keeps all SMs busy)."""
+        built SPB_MAX_BATCH at a time into G[b] and ONE batched eigen-solver call scores up to `max_batch` of them
+        (the Jacobi / Krylov kernels are latency-bound per matrix, so batching is what keeps all SMs busy)."""
         out = _empty(len(splits_idx), torch.float64)
         if reduced:
             for s, (ia, ib) in enumerate(splits_idx):
@@ -512,21 +533,23 @@ class CountScorer:
             layout, rows_pad, pitch = self.geometry(R, Cc)
             B = int(max(1, min(len(members), max_batch, max_batch_bytes // (rows_pad * rows_pad * 8))))
             s0, G, ws = self._buffers(layout, rows_pad, pitch, B)
+            self.gram_hook = big_hook if (big_hook is not None and R >= 4096) else None
             for c0 in range(0, len(members), B):
                 chunk = members[c0:c0 + B]
-                for b, s in enumerate(chunk):
-                    self.gram_hook = big_hook if (big_hook is not None and R >= 4096) else None
-                    self._gram_into(self._plan(*splits_idx[s], False), s0, G[b], ws, layout, rows_pad, pitch)
-                self.gram_hook = None
+                for b0 in range(0, len(chunk), self.NB):
+                    sub = chunk[b0:b0 + self.NB]
+                    self._gram_batch([self._plan(*splits_idx[s], False)[0] for s in sub], s0, G[b0:b0 + len(sub)], ws, layout,
+                                     rows_pad, pitch)
                 sc = score_gram(G[:len(chunk)], R)
                 if chunk == list(range(chunk[0], chunk[0] + len(chunk))):
                     out[chunk[0]:chunk[0] + len(chunk)] = sc
                 else:
                     out.index_copy_(0, torch.tensor(chunk, dtype=torch.int64, device=out.device), sc)
+            self.gram_hook = None
         return out
 
     def check_hi(self):
-        n = int(self.hi_num.item())
+        n = int(self.hi_max.item())
         if n > self.hi_cap:
             raise MemoryError(f"splitp_b200: {n} counts >= 256 exceed the high-part capacity {self.hi_cap}")
 

@@ -315,7 +315,7 @@ def test_gram_u8_tensor_core_exact(eng, R, K, density):
     ref = M.astype(np.int64) @ M.astype(np.int64).T
     s0 = torch.from_numpy(_tiled_from_rowmajor(M)).cuda()
     G = torch.empty((R, R), dtype=torch.float64, device="cuda")
-    n_ws = int(eng.lib.spb_gram_u8_ws(R, K, 1))
+    n_ws = int(eng.lib.spb_gram_u8_ws(R, K, 1, 1))
     ws = torch.empty(max(n_ws, 1), dtype=torch.int64, device="cuda")
     eng.call("spb_gram_u8", eng._p(s0), R, K, 1, eng._p(G), eng._p(ws), eng._st())
     torch.cuda.synchronize()
@@ -334,7 +334,7 @@ def test_gram_u8_small_exact(eng, R, K):
     k4 = np.ascontiguousarray(M.reshape(R, K // 4, 4).transpose(1, 0, 2))  # [k/4][r][4]: the k4-major layout
     s0 = torch.from_numpy(k4.reshape(-1)).cuda()
     G = torch.empty((R, R), dtype=torch.float64, device="cuda")
-    ws = torch.empty(int(eng.lib.spb_gram_u8_ws(R, K, 2)), dtype=torch.int64, device="cuda")
+    ws = torch.empty(int(eng.lib.spb_gram_u8_ws(R, K, 2, 1)), dtype=torch.int64, device="cuda")
     eng.call("spb_gram_u8", eng._p(s0), R, K, 2, eng._p(G), eng._p(ws), eng._st())
     np.testing.assert_array_equal(G.cpu().numpy(), ref.astype(np.float64))
     G2 = torch.empty_like(G)
