@@ -83,11 +83,14 @@ def gather_scores(local_scores, total, rank, world, group=None):
     return out
 
 
-def count_patterns_sharded(aln, rank, world, group=None, want_first=False):
-    """Pattern table of the WHOLE alignment when every rank holds (at least) its site range of `aln`:
-    rank r counts sites shard_range(N, r, world, 32) and the tables are combined."""
+def count_patterns_sharded(aln, rank, world, group=None, want_first=False, local=False):
+    """Pattern table of the WHOLE alignment.  local=False: every rank holds the full alignment and counts the
+    site range shard_range(N, r, world, 32) of it.  local=True: `aln` IS this rank's site shard (then `first`
+    indices are shard-relative and not supported).  The per-rank tables are combined on every rank."""
     from . import engine
-    b, e = shard_range(aln.N, rank, world, 32)
+    b, e = (0, aln.N) if local else shard_range(aln.N, rank, world, 32)
+    if local and want_first:
+        raise NotImplementedError("first-site indices need the full alignment on every rank (local=False)")
     if world == 1:
         return engine.count_patterns(aln, want_first=want_first)
     if aln.n <= engine.DIRECT_MAX_TAXA:

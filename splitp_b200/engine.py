@@ -177,7 +177,7 @@ def count_patterns(aln, site_begin=0, site_end=None, want_first=False, force_has
         keys, counts = keys[:P], counts[:P]
         fo = fo[:P] if fo is not None else None
         if reduce_fn is not None:
-            reduce_fn(usable, "sum")
+            raise NotImplementedError("hashed tables are merged by distributed.count_patterns_sharded, not by an allreduce")
         if sort and P > 1:
             keys, perm = torch.sort(keys)  # keys < 2^62: signed order = unsigned order
             counts = counts[perm]
