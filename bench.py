@@ -198,8 +198,7 @@ def main():
     splits = list(sp.all_splits(tree))[: args.max_splits]
     S = len(splits)
     idx_all = [eng.split_positions(s, tree.taxa) for s in splits]
-    pb, pe = spd.shard_range(S, rank, world)
-    idx_mine = idx_all[pb:pe]
+    idx_mine = spd.shard_strided(idx_all, rank, world)  # round-robin: balances the steeply size-dependent split cost
     reduce_fn = spd.make_reduce_fn() if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     prof = {"gram": [], "pairs": [], "count": []}
@@ -237,7 +236,7 @@ def main():
                 dist.all_reduce(raw)
             pt = eng.pair_finalize(raw, n, float(N))
             out = eng.subflatten_scores(pt, ma, mb)
-        return spd.gather_scores(out, S, rank, world)
+        return spd.gather_strided(out, S, rank, world)
 
     def barrier():
         if world > 1:

@@ -2,12 +2,16 @@
 // Replaces splitp/parsers/fasta.py:48-63 (get_pattern_counts) and the counting half of
 // splitp/simulation.py:43-54.  Bit-exact integer work.
 //
-// Data flow per CTA (256 threads, tile = 8192 sites):
+// Data flow per CTA (256 threads, tile = 8192 sites, persistent over tiles):
 //   coalesced 128-bit loads of the tile's bit stream -> shared memory
-//   -> per-site key extraction (funnel shifts) -> warp-level aggregation (__match_any_sync)
-//   -> shared-memory hash of (key, count, first site), kept across the tiles of a persistent CTA
-//   -> flush: one global atomic per distinct key per CTA (direct-indexed table for n <= 14,
-//      open-addressing global hash otherwise).
+//   -> per-site key extraction (funnel shifts), 32 consecutive sites per warp iteration
+//   -> warp-level aggregation: __match_any_sync groups equal keys, the lowest lane (= earliest site) leads
+//   -> WARP-PRIVATE direct-mapped cache in shared memory (256 entries per warp, plain loads/stores, no
+//      atomics): a hit adds the group size, a miss evicts the resident entry to the global table.  Alignments
+//      are dominated by a few very frequent patterns; the cache absorbs them on chip, so the global table sees
+//      one update per (warp, pattern) residency instead of one per site
+//   -> global sink: direct-indexed table (n <= 14, one RED per eviction) or open-addressing hash table.
+// Leaders whose cache slot is claimed by another leader of the same iteration bypass the cache.
 #include "common.cuh"
 
 using namespace spb;
@@ -15,9 +19,9 @@ using namespace spb;
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
 constexpr int kTileSites = 32 * kThreads;  // 8192
-constexpr int kHashSlots = 4096;           // shared-memory staging table
-constexpr int kMaxProbe = 16;
+constexpr int kCacheSlots = 256;           // per warp
 
 struct DirectSink {
   uint32_t* table;
@@ -54,69 +58,36 @@ struct HashSink {
 };
 
 template <class Sink>
-__device__ __forceinline__ void stage_add(unsigned long long* s_keys, uint32_t* s_cnt, uint32_t* s_first, uint32_t* s_fill,
-                                          const Sink& sink, uint64_t key, uint32_t c, uint32_t f) {
-  uint32_t h = (uint32_t)mix64(key) & (kHashSlots - 1);
-#pragma unroll 1
-  for (int probe = 0; probe < kMaxProbe; ++probe) {
-    unsigned long long k = *((volatile unsigned long long*)(s_keys + h));
-    if (k == SPB_EMPTY_KEY) {
-      unsigned long long old = atomicCAS(s_keys + h, (unsigned long long)SPB_EMPTY_KEY, (unsigned long long)key);
-      if (old == SPB_EMPTY_KEY) { atomicAdd(s_fill, 1u); k = key; } else k = old;
-    }
-    if (k == key) {
-      atomicAdd(s_cnt + h, c);
-      atomicMin(s_first + h, f);
-      return;
-    }
-    h = (h + 1) & (kHashSlots - 1);
-  }
-  sink.add(key, c, f);
-}
-
-template <class Sink>
-__device__ __forceinline__ void stage_flush(unsigned long long* s_keys, uint32_t* s_cnt, uint32_t* s_first, uint32_t* s_fill,
-                                            const Sink& sink) {
-  __syncthreads();
-  for (int i = threadIdx.x; i < kHashSlots; i += kThreads) {
-    unsigned long long k = s_keys[i];
-    if (k != SPB_EMPTY_KEY) {
-      sink.add(k, s_cnt[i], s_first[i]);
-      s_keys[i] = SPB_EMPTY_KEY;
-      s_cnt[i] = 0;
-      s_first[i] = 0xFFFFFFFFu;
-    }
-  }
-  if (threadIdx.x == 0) *s_fill = 0;
-  __syncthreads();
-}
-
-template <class Sink>
 __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restrict__ sm, int64_t sm_words,
                                                          const uint32_t* __restrict__ valid, int64_t valid_words, int n,
                                                          int64_t site_begin, int64_t site_end, int64_t tile_begin,
                                                          int64_t tile_end, Sink sink, unsigned long long* usable) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);
-  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_keys + kHashSlots);
-  uint32_t* s_first = s_cnt + kHashSlots;
-  uint32_t* s_tile = s_first + kHashSlots;  // 512*n words + 4 pad
-  __shared__ uint32_t s_fill;
+  unsigned long long* c_keys = reinterpret_cast<unsigned long long*>(smem_raw);  // [kWarps][kCacheSlots]
+  uint32_t* c_cnt = reinterpret_cast<uint32_t*>(c_keys + kWarps * kCacheSlots);    // [kWarps][kCacheSlots]
+  uint32_t* c_first = c_cnt + kWarps * kCacheSlots;                                // [kWarps][kCacheSlots]
+  uint32_t* c_claim = c_first + kWarps * kCacheSlots;                              // [kWarps][kCacheSlots]
+  uint32_t* s_tile = c_claim + kWarps * kCacheSlots;                               // 512*n words + 4 pad
   __shared__ uint32_t s_usable;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int bits = 2 * n;
   const int tile_words = (kTileSites / 32) * bits;  // 512 n
   const uint64_t kmask = (bits == 64) ? ~0ull : ((1ull << bits) - 1ull);
+  unsigned long long* wk = c_keys + wid * kCacheSlots;
+  uint32_t* wc = c_cnt + wid * kCacheSlots;
+  uint32_t* wf = c_first + wid * kCacheSlots;
+  uint32_t* wclaim = c_claim + wid * kCacheSlots;
 
-  for (int i = tid; i < kHashSlots; i += kThreads) { s_keys[i] = SPB_EMPTY_KEY; s_cnt[i] = 0; s_first[i] = 0xFFFFFFFFu; }
-  if (tid == 0) { s_fill = 0; s_usable = 0; }
+  for (int i = lane; i < kCacheSlots; i += 32) { wk[i] = SPB_EMPTY_KEY; wc[i] = 0; wf[i] = 0xFFFFFFFFu; }
+  if (tid == 0) s_usable = 0;
   __syncthreads();
 
   uint32_t my_usable = 0;
   for (int64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
     const int64_t base_site = tile * kTileSites;
     const int64_t base_word = tile * (int64_t)tile_words;
+    __syncthreads();  // every warp is done reading the previous tile
     // coalesced 128-bit loads of the tile (tile_words is a multiple of 4, base_word of 4)
     for (int v = tid; v < tile_words / 4; v += kThreads) {
       int64_t gw = base_word + (int64_t)v * 4;
@@ -126,30 +97,52 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restr
     }
     if (tid < 4) s_tile[tile_words + tid] = 0;
     __syncthreads();
-#pragma unroll 4
+    // warp `wid` owns the 1024 consecutive sites [wid * 1024, wid * 1024 + 1024) of the tile
+    const int64_t vw0 = (base_site >> 5) + wid * 32;
+    const uint32_t vmine = (vw0 + lane < valid_words) ? __ldg(valid + vw0 + lane) : 0u;  // lane l: validity word of iteration l
+#pragma unroll 2
     for (int it = 0; it < 32; ++it) {
-      const int sl = it * kThreads + tid;  // consecutive lanes = consecutive sites
+      const int sl = wid * 1024 + it * 32 + lane;  // consecutive lanes = consecutive sites
       const int64_t site = base_site + sl;
-      const int64_t vw = (base_site + it * kThreads + wid * 32) >> 5;
-      uint32_t vbits = (vw < valid_words) ? __ldg(valid + vw) : 0u;
-      bool ok = ((vbits >> lane) & 1u) && site >= site_begin && site < site_end;
+      const uint32_t vbits = __shfl_sync(0xFFFFFFFFu, vmine, it);
+      const bool ok = ((vbits >> lane) & 1u) && site >= site_begin && site < site_end;
       const uint32_t bp = (uint32_t)sl * (uint32_t)bits;
       const uint32_t w = bp >> 5, sh = bp & 31;
-      uint32_t w0 = s_tile[w], w1 = s_tile[w + 1], w2 = s_tile[w + 2];
+      const uint32_t w0 = s_tile[w], w1 = s_tile[w + 1], w2 = s_tile[w + 2];
       uint64_t key = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | (uint64_t)__funnelshift_r(w0, w1, sh);
       key &= kmask;
       my_usable += ok ? 1u : 0u;
+      if (__ballot_sync(0xFFFFFFFFu, ok) == 0u) continue;
       // warp-level aggregation: lanes with equal keys elect the lowest lane (= earliest site)
       unsigned long long mk = ok ? (unsigned long long)key : (0xFFFFFFFF00000000ull | (unsigned)lane);
       if (!ok && bits > 32) mk = SPB_EMPTY_KEY - 1 - lane;  // never equals a valid (<2^62) key
-      unsigned peers = __match_any_sync(0xFFFFFFFFu, mk);
-      if (ok && lane == (__ffs(peers) - 1))
-        stage_add(s_keys, s_cnt, s_first, &s_fill, sink, key, (uint32_t)__popc(peers), (uint32_t)site);
+      const unsigned peers = __match_any_sync(0xFFFFFFFFu, mk);
+      const bool leader = ok && lane == (__ffs(peers) - 1);
+      const uint32_t c = (uint32_t)__popc(peers);
+      const uint32_t slot = (uint32_t)mix64(key) & (kCacheSlots - 1);
+      // claim the cache slot: when several leaders of this iteration hash to one slot, one of them wins it
+      if (leader) wclaim[slot] = (uint32_t)lane;
+      __syncwarp();
+      if (leader) {
+        if (wclaim[slot] == (uint32_t)lane) {
+          const unsigned long long k0 = wk[slot];
+          if (k0 == key) {
+            wc[slot] += c;
+          } else {
+            if (k0 != SPB_EMPTY_KEY) sink.add(k0, wc[slot], wf[slot]);  // evict
+            wk[slot] = key; wc[slot] = c; wf[slot] = (uint32_t)site;
+          }
+        } else {
+          sink.add(key, c, (uint32_t)site);  // slot taken by another leader of this iteration: bypass the cache
+        }
+      }
+      __syncwarp();
     }
-    __syncthreads();
-    if (s_fill > (kHashSlots * 3) / 4) stage_flush(s_keys, s_cnt, s_first, &s_fill, sink);
   }
-  stage_flush(s_keys, s_cnt, s_first, &s_fill, sink);
+  // flush the warp caches
+  __syncwarp();
+  for (int i = lane; i < kCacheSlots; i += 32)
+    if (wk[i] != SPB_EMPTY_KEY) sink.add(wk[i], wc[i], wf[i]);
   // usable-site count: warp reduce, one atomic per CTA
   for (int o = 16; o > 0; o >>= 1) my_usable += __shfl_xor_sync(0xFFFFFFFFu, my_usable, o);
   if (lane == 0 && my_usable) atomicAdd(&s_usable, my_usable);
@@ -161,7 +154,7 @@ template <class Sink>
 int launch_count(const uint32_t* d_sm, const uint32_t* d_valid, int n, int64_t site_begin, int64_t site_end, Sink sink,
                  uint64_t* d_usable, cudaStream_t st) {
   if (site_end <= site_begin) return SPB_OK;
-  size_t smem = (size_t)kHashSlots * 16 + ((size_t)(kTileSites / 32) * 2 * n + 4) * 4;
+  size_t smem = (size_t)kWarps * kCacheSlots * 20 + ((size_t)(kTileSites / 32) * 2 * n + 4) * 4;
   SPB_CUDA(cudaFuncSetAttribute(count_kernel<Sink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_kernel<Sink>, kThreads, smem));

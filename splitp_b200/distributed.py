@@ -83,6 +83,28 @@ def gather_scores(local_scores, total, rank, world, group=None):
     return out
 
 
+def shard_strided(items, rank, world):
+    """Round-robin share of a list: items[rank::world].  all_splits lists splits by ascending size and the cost
+    of a split grows steeply with its size, so a strided deal balances the ranks where contiguous ranges do not."""
+    return items[rank::world]
+
+
+def gather_strided(local_scores, total, rank, world, group=None):
+    """Inverse of shard_strided for the score vector: out[r::world] = scores of rank r."""
+    if world == 1:
+        return local_scores
+    m = (total + world - 1) // world
+    pad = torch.zeros(m, dtype=local_scores.dtype, device=local_scores.device)
+    pad[:local_scores.shape[0]] = local_scores
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    out = torch.empty(total, dtype=local_scores.dtype, device=local_scores.device)
+    for r in range(world):
+        cnt = len(range(r, total, world))
+        out[r::world] = bufs[r][:cnt]
+    return out
+
+
 def count_patterns_sharded(aln, rank, world, group=None, want_first=False, local=False):
     """Pattern table of the WHOLE alignment.  local=False: every rank holds the full alignment and counts the
     site range shard_range(N, r, world, 32) of it.  local=True: `aln` IS this rank's site shard (then `first`

@@ -156,6 +156,9 @@ S = 11
 b, e = spd.shard_range(S, rank, world)
 sc = spd.gather_scores(torch.arange(b, e, dtype=torch.float64), S, rank, world)
 assert sc.tolist() == [float(i) for i in range(S)]
+mine = spd.shard_strided(list(range(S)), rank, world)
+sc = spd.gather_strided(torch.tensor(mine, dtype=torch.float64), S, rank, world)
+assert sc.tolist() == [float(i) for i in range(S)]
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 ''')
