@@ -5,13 +5,17 @@
 // Data flow per CTA (256 threads, tile = 8192 sites, persistent over tiles):
 //   coalesced 128-bit loads of the tile's bit stream -> shared memory
 //   -> per-site key extraction (funnel shifts), 32 consecutive sites per warp iteration
-//   -> warp-level aggregation: __match_any_sync groups equal keys, the lowest lane (= earliest site) leads
-//   -> WARP-PRIVATE direct-mapped cache in shared memory (256 entries per warp, plain loads/stores, no
-//      atomics): a hit adds the group size, a miss evicts the resident entry to the global table.  Alignments
-//      are dominated by a few very frequent patterns; the cache absorbs them on chip, so the global table sees
-//      one update per (warp, pattern) residency instead of one per site
+//   -> WARP-PRIVATE direct-mapped cache in shared memory (256 entries per warp):
+//        hit  : one shared-memory atomicAdd on the entry's counter (lanes that carry the same key as lane 0 -- the
+//               usual case, alignments are dominated by a few very frequent patterns -- are first aggregated with
+//               one ballot, so the hot pattern costs one atomic per warp iteration);
+//        miss : the missing lanes claim their slot, the winner evicts the resident entry to the global table and
+//               installs its key, lanes with the same key then add to it, lanes that lost the slot to a different
+//               key bypass the cache.
+//      The cache absorbs the frequent patterns on chip: the global table sees one update per (warp, pattern)
+//      residency instead of one per site.  No __match_any_sync: its cost grows with the number of distinct keys
+//      in the warp and made the first two versions of this kernel issue-bound (profiles/r1_kernel_roofline_*).
 //   -> global sink: direct-indexed table (n <= 14, one RED per eviction) or open-addressing hash table.
-// Leaders whose cache slot is claimed by another leader of the same iteration bypass the cache.
 #include "common.cuh"
 
 using namespace spb;
@@ -57,6 +61,13 @@ struct HashSink {
   }
 };
 
+__device__ __forceinline__ uint32_t cache_slot(uint64_t key) {
+  uint32_t x = (uint32_t)key ^ (uint32_t)(key >> 32) * 0x9E3779B1u;
+  x ^= x >> 15;
+  x *= 0x2C1B3C6Du;
+  return (x >> 24) & (kCacheSlots - 1);
+}
+
 template <class Sink>
 __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restrict__ sm, int64_t sm_words,
                                                          const uint32_t* __restrict__ valid, int64_t valid_words, int n,
@@ -74,6 +85,7 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restr
   const int bits = 2 * n;
   const int tile_words = (kTileSites / 32) * bits;  // 512 n
   const uint64_t kmask = (bits == 64) ? ~0ull : ((1ull << bits) - 1ull);
+  const bool want_first = sink.first != nullptr;
   unsigned long long* wk = c_keys + wid * kCacheSlots;
   uint32_t* wc = c_cnt + wid * kCacheSlots;
   uint32_t* wf = c_first + wid * kCacheSlots;
@@ -100,7 +112,7 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restr
     // warp `wid` owns the 1024 consecutive sites [wid * 1024, wid * 1024 + 1024) of the tile
     const int64_t vw0 = (base_site >> 5) + wid * 32;
     const uint32_t vmine = (vw0 + lane < valid_words) ? __ldg(valid + vw0 + lane) : 0u;  // lane l: validity word of iteration l
-#pragma unroll 2
+#pragma unroll 1
     for (int it = 0; it < 32; ++it) {
       const int sl = wid * 1024 + it * 32 + lane;  // consecutive lanes = consecutive sites
       const int64_t site = base_site + sl;
@@ -112,31 +124,38 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restr
       uint64_t key = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | (uint64_t)__funnelshift_r(w0, w1, sh);
       key &= kmask;
       my_usable += ok ? 1u : 0u;
-      if (__ballot_sync(0xFFFFFFFFu, ok) == 0u) continue;
-      // warp-level aggregation: lanes with equal keys elect the lowest lane (= earliest site)
-      unsigned long long mk = ok ? (unsigned long long)key : (0xFFFFFFFF00000000ull | (unsigned)lane);
-      if (!ok && bits > 32) mk = SPB_EMPTY_KEY - 1 - lane;  // never equals a valid (<2^62) key
-      const unsigned peers = __match_any_sync(0xFFFFFFFFu, mk);
-      const bool leader = ok && lane == (__ffs(peers) - 1);
-      const uint32_t c = (uint32_t)__popc(peers);
-      const uint32_t slot = (uint32_t)mix64(key) & (kCacheSlots - 1);
-      // claim the cache slot: when several leaders of this iteration hash to one slot, one of them wins it
-      if (leader) wclaim[slot] = (uint32_t)lane;
-      __syncwarp();
-      if (leader) {
-        if (wclaim[slot] == (uint32_t)lane) {
-          const unsigned long long k0 = wk[slot];
-          if (k0 == key) {
-            wc[slot] += c;
-          } else {
-            if (k0 != SPB_EMPTY_KEY) sink.add(k0, wc[slot], wf[slot]);  // evict
-            wk[slot] = key; wc[slot] = c; wf[slot] = (uint32_t)site;
-          }
-        } else {
-          sink.add(key, c, (uint32_t)site);  // slot taken by another leader of this iteration: bypass the cache
+      const unsigned okmask = __ballot_sync(0xFFFFFFFFu, ok);
+      if (okmask == 0u) continue;
+      // aggregate the lanes that carry the key of the first usable lane (the frequent-pattern fast path)
+      const int lead = __ffs(okmask) - 1;
+      const uint32_t k_lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)key, lead), k_hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(key >> 32), lead);
+      const bool same = ok && key == (((uint64_t)k_hi << 32) | k_lo);
+      const unsigned samemask = __ballot_sync(0xFFFFFFFFu, same);
+      const bool active = ok && (!same || lane == lead);       // one representative for the aggregated group
+      const uint32_t c = (lane == lead) ? (uint32_t)__popc(samemask) : 1u;
+      const uint32_t slot = cache_slot(key);
+      const unsigned long long k0 = wk[slot];
+      const bool hit = active && k0 == key;
+      if (hit) atomicAdd(wc + slot, c);
+      const bool miss = active && !hit;
+      if (__ballot_sync(0xFFFFFFFFu, miss) != 0u) {
+        if (miss) wclaim[slot] = (uint32_t)lane;
+        __syncwarp();
+        if (miss && wclaim[slot] == (uint32_t)lane) {  // installer: evict the resident entry, install this key
+          if (k0 != SPB_EMPTY_KEY) sink.add(k0, wc[slot], wf[slot]);
+          wk[slot] = key; wc[slot] = 0u; wf[slot] = 0xFFFFFFFFu;
         }
+        __syncwarp();
+        if (miss) {
+          if (wk[slot] == key) {
+            atomicAdd(wc + slot, c);
+            if (want_first) atomicMin(wf + slot, (uint32_t)site);
+          } else {
+            sink.add(key, c, (uint32_t)site);  // lost the slot to a different key: bypass the cache
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   // flush the warp caches
