@@ -332,119 +332,6 @@ __global__ void __launch_bounds__(256) symv_block_kernel(const double* __restric
     }
 }
 
-// Symmetric variant for large k: reads only the upper 128 x 128 blocks of G (half the HBM traffic of
-// symv_block_kernel).  CTA = block-row I, loops over the blocks J >= I.  For every block both products are formed
-// from ONE read:  out1[c][i] += sum_j G[i][j] Q[c][j]  (rows of I; accumulated in registers over all J) and, for
-// J > I,  out2[c][j] = sum_i G[i][j] Q[c][i]  (the mirrored block G[J][I] = G[I][J]^T), written as a partial to
-// P2[I][c][j].  symv_half_reduce_kernel then adds the partials of the blocks above the diagonal in fixed order, so
-// the result is deterministic.  Warp (cg, rh) owns columns 32 cg.. and rows 64 rh.. of the block: it loads 32 x 32
-// sub-blocks with lanes along columns (coalesced; out2 FMAs straight from the registers), transposes them through
-// shared memory and re-reads them with lanes along rows for the out1 FMAs.
-constexpr int kHB = 128;
-struct SymvHalfSmem {
-  double qi[kKB][kHB];
-  double qj[kKB][kHB];
-  double red2[2][kKB][kHB];
-  double t[8][32][33];
-};
-
-__global__ void __launch_bounds__(256) symv_half_kernel(const double* __restrict__ G, int64_t ld, int64_t strideG,
-                                                        const double* __restrict__ Q, int64_t strideQ, double* __restrict__ AQ,
-                                                        double* __restrict__ P2, int64_t strideP2, int k, int nblk) {
-  extern __shared__ __align__(16) unsigned char smem_raw_sh[];
-  SymvHalfSmem& s = *reinterpret_cast<SymvHalfSmem*>(smem_raw_sh);
-  const int bt = blockIdx.y, I = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int cg = warp & 3, rh = warp >> 2;
-  const int i0 = I * kHB;
-  const double* Gb = G + (int64_t)bt * strideG;
-  const double* Qb = Q + (int64_t)bt * strideQ;
-  double* P2b = P2 + (int64_t)bt * strideP2 + (int64_t)I * kKB * k;
-  for (int idx = tid; idx < kKB * kHB; idx += 256) {
-    int c = idx / kHB, x = idx - c * kHB;
-    s.qi[c][x] = (i0 + x < k) ? Qb[(int64_t)c * k + i0 + x] : 0.0;
-  }
-  double acc1[2][kKB];
-#pragma unroll
-  for (int g = 0; g < 2; ++g)
-#pragma unroll
-    for (int c = 0; c < kKB; ++c) acc1[g][c] = 0.0;
-  for (int J = I; J < nblk; ++J) {
-    const int j0 = J * kHB;
-    __syncthreads();  // previous block: qj and red2 are free again (also orders the qi fill on the first pass)
-    for (int idx = tid; idx < kKB * kHB; idx += 256) {
-      int c = idx / kHB, x = idx - c * kHB;
-      s.qj[c][x] = (j0 + x < k) ? Qb[(int64_t)c * k + j0 + x] : 0.0;
-    }
-    __syncthreads();
-    double acc2[kKB];
-#pragma unroll
-    for (int c = 0; c < kKB; ++c) acc2[c] = 0.0;
-    const int col = j0 + 32 * cg + lane;
-    const bool diag = (J == I);
-#pragma unroll
-    for (int rg = 0; rg < 2; ++rg) {
-      const int rl = 64 * rh + 32 * rg;  // first local row of this 32 x 32 sub-block
-      // phase A: lanes along columns
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int row = i0 + rl + r;
-        const double g = (row < k && col < k) ? __ldg(Gb + (int64_t)row * ld + col) : 0.0;
-        s.t[warp][r][lane] = g;
-        if (!diag) {
-#pragma unroll
-          for (int c = 0; c < kKB; ++c) acc2[c] = fma(g, s.qi[c][rl + r], acc2[c]);
-        }
-      }
-      __syncwarp();
-      // phase B: lanes along rows
-#pragma unroll 8
-      for (int cc = 0; cc < 32; ++cc) {
-        const double g = s.t[warp][lane][cc];
-#pragma unroll
-        for (int c = 0; c < kKB; ++c) acc1[rg][c] = fma(g, s.qj[c][32 * cg + cc], acc1[rg][c]);
-      }
-      __syncwarp();
-    }
-    if (!diag) {  // out2 partial of this block: the two row halves are added in fixed order
-#pragma unroll
-      for (int c = 0; c < kKB; ++c) s.red2[rh][c][32 * cg + lane] = acc2[c];
-      __syncthreads();
-      for (int idx = tid; idx < kKB * kHB; idx += 256) {
-        int c = idx / kHB, x = idx - c * kHB;
-        if (j0 + x < k) P2b[(int64_t)c * k + j0 + x] = s.red2[0][c][x] + s.red2[1][c][x];
-      }
-    }
-  }
-  // out1: add the four column groups in fixed order (reuse the transposition buffers: 4 x 8 x 128 doubles)
-  __syncthreads();
-  double* red1 = &s.t[0][0][0];  // [4][kKB][kHB]
-#pragma unroll
-  for (int g = 0; g < 2; ++g)
-#pragma unroll
-    for (int c = 0; c < kKB; ++c) red1[(cg * kKB + c) * kHB + 64 * rh + 32 * g + lane] = acc1[g][c];
-  __syncthreads();
-  for (int idx = tid; idx < kKB * kHB; idx += 256) {
-    int c = idx / kHB, x = idx - c * kHB;
-    if (i0 + x < k)
-      AQ[(int64_t)bt * strideQ + (int64_t)c * k + i0 + x] =
-          ((red1[(0 * kKB + c) * kHB + x] + red1[(1 * kKB + c) * kHB + x]) + red1[(2 * kKB + c) * kHB + x]) + red1[(3 * kKB + c) * kHB + x];
-  }
-}
-
-// AQ[c][x] += sum_{I < X} P2[I][c][x], X = x / 128, in ascending I
-__global__ void symv_half_reduce_kernel(double* __restrict__ AQ, int64_t strideQ, const double* __restrict__ P2, int64_t strideP2, int k) {
-  const int bt = blockIdx.y;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= kKB * k) return;
-  const int x = idx % k;
-  const int X = x / kHB;
-  const double* p = P2 + (int64_t)bt * strideP2 + idx;
-  double sum = AQ[(int64_t)bt * strideQ + idx];
-  for (int I = 0; I < X; ++I) sum += p[(int64_t)I * kKB * k];
-  AQ[(int64_t)bt * strideQ + idx] = sum;
-}
-
 __global__ void copy_block_kernel(const double* src, int64_t strideS, double* dst, int64_t strideD, int64_t elems) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < elems) dst[blockIdx.y * strideD + i] = src[blockIdx.y * strideS + i];
@@ -632,11 +519,9 @@ __global__ void krylov_finish_kernel(const double* __restrict__ theta, const dou
   scores[bt] = tr > 0.0 ? sqrt(fmax(1.0 - inf[0] / tr, 0.0)) : nan("");
 }
 
-constexpr int kSymvHalfMin = 512;  // below this the plain kernel is launch-latency bound anyway
-
 struct KrylovWs {
-  double *Q, *AQ, *C, *S, *T, *Vtop, *theta, *res2, *info, *part, *P2;
-  int64_t sQ, sC, sS, sT, part_elems, sP2;
+  double *Q, *AQ, *C, *S, *T, *Vtop, *theta, *res2, *info, *part;
+  int64_t sQ, sC, sS, sT, part_elems;
 };
 
 static int64_t krylov_layout(int64_t k, int64_t batch, double* base, KrylovWs* w) {
@@ -658,9 +543,6 @@ static int64_t krylov_layout(int64_t k, int64_t batch, double* base, KrylovWs* w
   // partial sums of the inner-product kernel: ceil(k / 128) chunks of the largest (96 x 96) product
   w->part_elems = batch * ((k + kDotChunk - 1) / kDotChunk) * (int64_t)kKDim * kKDim;
   w->part = take(w->part_elems);
-  // partial products of the mirrored blocks of symv_half_kernel (only for k >= kSymvHalfMin)
-  w->sP2 = k >= kSymvHalfMin ? ((k + kHB - 1) / kHB) * (int64_t)kKB * k : 0;
-  w->P2 = take(batch * w->sP2);
   return off;
 }
 
@@ -728,19 +610,10 @@ static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb,
   }
   const size_t symv_smem = (size_t)kKB * kSymvChunk * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(symv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
-  SPB_CUDA(cudaFuncSetAttribute(symv_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymvHalfSmem)));
   for (int j = 0; j < nb; ++j) {
     double* Qj = w.Q + (int64_t)j * blk;
     double* AQj = w.AQ + (int64_t)j * blk;
-    if (k >= kSymvHalfMin) {
-      const int nblk = (k + kHB - 1) / kHB;
-      dim3 grid(nblk, batch);
-      symv_half_kernel<<<grid, 256, sizeof(SymvHalfSmem), st>>>(d_G, ld, ld * ld, Qj, w.sQ, AQj, w.P2, w.sP2, k, nblk);
-      SPB_LAUNCH_CHECK();
-      dim3 rg((kKB * k + 255) / 256, batch);
-      symv_half_reduce_kernel<<<rg, 256, 0, st>>>(AQj, w.sQ, w.P2, w.sP2, k);
-      SPB_LAUNCH_CHECK();
-    } else {
+    {
       dim3 grid((k + kSymvRows - 1) / kSymvRows, batch);
       symv_block_kernel<<<grid, 256, symv_smem, st>>>(d_G, ld, ld * ld, Qj, w.sQ, AQj, k);
       SPB_LAUNCH_CHECK();
