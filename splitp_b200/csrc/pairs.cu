@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kSThreads) subflatten_score_kernel(const doubl
     const int rows = 3 * a + 1, cols = 3 * b + 1;
     const bool tr = rows > cols;          // orient so that k = smaller dimension
     const int k = tr ? cols : rows, L = tr ? rows : cols;
-    const int ldm = L + 1, ldg = jacobi_ld(k);
+    const int ldm = (L + 1) | 1, ldg = jacobi_ld(k);  // odd strides: rows of M / G start on different banks
     for (int idx = tid; idx < k * L; idx += kSThreads) {
       int r = idx / L, c = idx - r * L;
       M[r * ldm + c] = tr ? subflat_entry(T, tot, n, la, a, lb, b, c, r) : subflat_entry(T, tot, n, la, a, lb, b, r, c);
@@ -275,10 +275,10 @@ __global__ void __launch_bounds__(kSThreads) subflatten_score_kernel(const doubl
 inline size_t subflat_smem(int n, int* m_elems) {
   int h = n / 2;
   int k = 3 * h + 1, L = 3 * (n - h) + 1;
-  // the widest staging matrix over all splits: k x (L+1) is maximised at the balanced split, but a
+  // the widest staging matrix over all splits: k x ((L+1)|1) is maximised at the balanced split, but a
   // 1|n-1 split has k=4, L=3(n-1)+1; cover both
-  int m1 = k * (L + 1);
-  int m2 = 4 * (3 * (n - 1) + 2);
+  int m1 = k * ((L + 1) | 1);
+  int m2 = 4 * ((3 * (n - 1) + 2) | 1);
   *m_elems = m1 > m2 ? m1 : m2;
   return ((size_t)*m_elems + (size_t)jacobi_dim(k) * jacobi_ld(k)) * sizeof(double);
 }

@@ -283,22 +283,26 @@ __global__ void krylov_init_kernel(double* W, int64_t strideW, int k) {
   W[bt * strideW + i] = (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
 }
 
-// AQ[c][i] = sum_j G[i][j] Q[c][j], c < 8.  CTA = 32 rows of G; warp = 4 rows processed together; lanes stride j.
-// The Q chunk (8 x 1024 doubles, 64 KB) is staged in shared memory and reused by all 32 rows.
-constexpr int kSymvRows = 32;
-constexpr int kSymvChunk = 1024;
-__global__ void __launch_bounds__(256) symv_block_kernel(const double* __restrict__ G, int64_t ld, int64_t strideG,
-                                                         const double* __restrict__ Q, int64_t strideQ, double* __restrict__ AQ,
-                                                         int k) {
+// AQ[c][i] = sum_j G[i][j] Q[c][j], c < 8.  CTA = 16 rows of G; warp = 2 rows processed together; lanes stride j.
+// The Q chunk (8 x 512 doubles, 32 KB) is staged in shared memory and reused by all 16 rows.  The kernel is bound
+// by HBM latency (ncu: long-scoreboard stalls), so it is shaped for occupancy: <= 85 registers and 32 KB of shared
+// memory per CTA (3 CTAs = 24 warps per SM) with 8 independent 8-byte loads in flight per lane.
+constexpr int kSymvRows = 16;
+constexpr int kSymvChunk = 512;
+__global__ void __launch_bounds__(256, 3) symv_block_kernel(const double* __restrict__ G, int64_t ld, int64_t strideG,
+                                                            const double* __restrict__ Q, int64_t strideQ, double* __restrict__ AQ,
+                                                            int k) {
   extern __shared__ __align__(16) double s_q[];  // [kKB][kSymvChunk]
   const int bt = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * kSymvRows + warp * 4;
+  const int row0 = blockIdx.x * kSymvRows + warp * 2;
   const double* Gb = G + (int64_t)bt * strideG;
   const double* Qb = Q + (int64_t)bt * strideQ;
-  double acc[4][kKB];
+  const double* g0 = Gb + (int64_t)min(row0, k - 1) * ld;      // clamped rows are computed but never stored
+  const double* g1 = Gb + (int64_t)min(row0 + 1, k - 1) * ld;
+  double acc[2][kKB];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int c = 0; c < kKB; ++c) acc[r][c] = 0.0;
   for (int j0 = 0; j0 < k; j0 += kSymvChunk) {
@@ -309,21 +313,19 @@ __global__ void __launch_bounds__(256) symv_block_kernel(const double* __restric
       s_q[idx] = (j < len) ? Qb[(int64_t)c * k + j0 + j] : 0.0;
     }
     __syncthreads();
-#pragma unroll 2
+#pragma unroll 4
     for (int j = lane; j < len; j += 32) {
-      double g[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) g[r] = (row0 + r < k) ? __ldg(Gb + (int64_t)(row0 + r) * ld + j0 + j) : 0.0;
+      const double a = __ldg(g0 + j0 + j), b = __ldg(g1 + j0 + j);
 #pragma unroll
       for (int c = 0; c < kKB; ++c) {
-        double q = s_q[c * kSymvChunk + j];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r][c] = fma(g[r], q, acc[r][c]);
+        const double q = s_q[c * kSymvChunk + j];
+        acc[0][c] = fma(a, q, acc[0][c]);
+        acc[1][c] = fma(b, q, acc[1][c]);
       }
     }
   }
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int c = 0; c < kKB; ++c) {
       double v = acc[r][c];
