@@ -78,13 +78,12 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restr
   uint32_t* c_cnt = reinterpret_cast<uint32_t*>(c_keys + kWarps * kCacheSlots);    // [kWarps][kCacheSlots]
   uint32_t* c_first = c_cnt + kWarps * kCacheSlots;                                // [kWarps][kCacheSlots]
   uint32_t* c_claim = c_first + kWarps * kCacheSlots;                              // [kWarps][kCacheSlots]
-  uint32_t* s_tile = c_claim + kWarps * kCacheSlots;                               // 2 x (512*n words + 4 pad)
+  uint32_t* s_tile = c_claim + kWarps * kCacheSlots;                               // 512*n words + 4 pad
   __shared__ uint32_t s_usable;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int bits = 2 * n;
   const int tile_words = (kTileSites / 32) * bits;  // 512 n
-  const int tile_stride = tile_words + 4;
   const uint64_t kmask = (bits == 64) ? ~0ull : ((1ull << bits) - 1ull);
   const bool want_first = sink.first != nullptr;
   unsigned long long* wk = c_keys + wid * kCacheSlots;
@@ -96,36 +95,23 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restr
   if (tid == 0) s_usable = 0;
   __syncthreads();
 
-  // double-buffered tile pipeline: the cp.async copies of tile t+1 are in flight while tile t is processed
-  auto issue_tile = [&](int64_t tile, uint32_t* dst) {
-    const int64_t base_word = tile * (int64_t)tile_words;
-    for (int v = tid; v < tile_words / 4; v += kThreads) {
-      const int64_t gw = base_word + (int64_t)v * 4;
-      const uint32_t src_bytes = (gw + 4 <= sm_words) ? 16u : 0u;  // 0 = zero fill
-      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + v * 4);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(sm + (src_bytes ? gw : 0)), "r"(src_bytes) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
   uint32_t my_usable = 0;
-  int cur = 0;
-  const int64_t tile_first = tile_begin + blockIdx.x;
-  if (tile_first < tile_end) issue_tile(tile_first, s_tile);
-  for (int64_t tile = tile_first; tile < tile_end; tile += gridDim.x) {
+  for (int64_t tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
     const int64_t base_site = tile * kTileSites;
-    uint32_t* tile_buf = s_tile + cur * tile_stride;
-    const int64_t next = tile + gridDim.x;
-    if (next < tile_end) {
-      issue_tile(next, s_tile + (cur ^ 1) * tile_stride);  // that buffer was released by the barrier ending the previous tile
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int64_t base_word = tile * (int64_t)tile_words;
+    __syncthreads();  // every warp is done reading the previous tile
+    // coalesced 128-bit loads of the tile (tile_words is a multiple of 4, base_word of 4)
+    for (int v = tid; v < tile_words / 4; v += kThreads) {
+      int64_t gw = base_word + (int64_t)v * 4;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (gw + 4 <= sm_words) x = __ldg(reinterpret_cast<const uint4*>(sm + gw));
+      reinterpret_cast<uint4*>(s_tile)[v] = x;
     }
+    if (tid < 4) s_tile[tile_words + tid] = 0;
+    __syncthreads();
     // warp `wid` owns the 1024 consecutive sites [wid * 1024, wid * 1024 + 1024) of the tile
     const int64_t vw0 = (base_site >> 5) + wid * 32;
     const uint32_t vmine = (vw0 + lane < valid_words) ? __ldg(valid + vw0 + lane) : 0u;  // lane l: validity word of iteration l
-    if (tid < 4) tile_buf[tile_words + tid] = 0;
-    __syncthreads();  // the tile is complete and visible to every warp
 #pragma unroll 1
     for (int it = 0; it < 32; ++it) {
       const int sl = wid * 1024 + it * 32 + lane;  // consecutive lanes = consecutive sites
@@ -134,7 +120,7 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restr
       const bool ok = ((vbits >> lane) & 1u) && site >= site_begin && site < site_end;
       const uint32_t bp = (uint32_t)sl * (uint32_t)bits;
       const uint32_t w = bp >> 5, sh = bp & 31;
-      const uint32_t w0 = tile_buf[w], w1 = tile_buf[w + 1], w2 = tile_buf[w + 2];
+      const uint32_t w0 = s_tile[w], w1 = s_tile[w + 1], w2 = s_tile[w + 2];
       uint64_t key = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | (uint64_t)__funnelshift_r(w0, w1, sh);
       key &= kmask;
       my_usable += ok ? 1u : 0u;
@@ -171,8 +157,6 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restr
         __syncwarp();
       }
     }
-    __syncthreads();  // every warp is done with this buffer: the next iteration may refill it
-    cur ^= 1;
   }
   // flush the warp caches
   __syncwarp();
@@ -189,7 +173,7 @@ template <class Sink>
 int launch_count(const uint32_t* d_sm, const uint32_t* d_valid, int n, int64_t site_begin, int64_t site_end, Sink sink,
                  uint64_t* d_usable, cudaStream_t st) {
   if (site_end <= site_begin) return SPB_OK;
-  size_t smem = (size_t)kWarps * kCacheSlots * 20 + 2 * ((size_t)(kTileSites / 32) * 2 * n + 4) * 4;
+  size_t smem = (size_t)kWarps * kCacheSlots * 20 + ((size_t)(kTileSites / 32) * 2 * n + 4) * 4;
   SPB_CUDA(cudaFuncSetAttribute(count_kernel<Sink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_kernel<Sink>, kThreads, smem));

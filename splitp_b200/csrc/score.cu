@@ -283,26 +283,24 @@ __global__ void krylov_init_kernel(double* W, int64_t strideW, int k) {
   W[bt * strideW + i] = (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
 }
 
-// AQ[c][i] = sum_j G[i][j] Q[c][j], c < 8.  CTA = 16 rows of G; warp = 2 rows processed together; lanes stride j.
-// The Q chunk (8 x 512 doubles, 32 KB) is staged in shared memory and reused by all 16 rows.  The kernel is bound
-// by HBM latency (ncu: long-scoreboard stalls), so it is shaped for occupancy: <= 85 registers and 32 KB of shared
-// memory per CTA (3 CTAs = 24 warps per SM) with 8 independent 8-byte loads in flight per lane.
-constexpr int kSymvRows = 16;
-constexpr int kSymvChunk = 512;
-__global__ void __launch_bounds__(256, 3) symv_block_kernel(const double* __restrict__ G, int64_t ld, int64_t strideG,
-                                                            const double* __restrict__ Q, int64_t strideQ, double* __restrict__ AQ,
-                                                            int k) {
+// AQ[c][i] = sum_j G[i][j] Q[c][j], c < 8.  CTA = 32 rows of G; warp = 4 rows processed together; every lane owns two
+// adjacent columns (128-bit loads of G and of the staged Q chunk: 8 x 16 bytes in flight per lane and iteration).
+// The Q chunk (8 x 1024 doubles, 64 KB) is staged in shared memory and reused by all 32 rows.
+constexpr int kSymvRows = 32;
+constexpr int kSymvChunk = 1024;
+__global__ void __launch_bounds__(256, 2) symv_block_kernel(const double* __restrict__ G, int64_t ld, int64_t strideG,
+                                                         const double* __restrict__ Q, int64_t strideQ, double* __restrict__ AQ,
+                                                         int k) {
   extern __shared__ __align__(16) double s_q[];  // [kKB][kSymvChunk]
   const int bt = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * kSymvRows + warp * 2;
+  const int row0 = blockIdx.x * kSymvRows + warp * 4;
   const double* Gb = G + (int64_t)bt * strideG;
   const double* Qb = Q + (int64_t)bt * strideQ;
-  const double* g0 = Gb + (int64_t)min(row0, k - 1) * ld;      // clamped rows are computed but never stored
-  const double* g1 = Gb + (int64_t)min(row0 + 1, k - 1) * ld;
-  double acc[2][kKB];
+  const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(Gb) & 15) == 0);  // 16-byte aligned row starts
+  double acc[4][kKB];
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < kKB; ++c) acc[r][c] = 0.0;
   for (int j0 = 0; j0 < k; j0 += kSymvChunk) {
@@ -313,19 +311,26 @@ __global__ void __launch_bounds__(256, 3) symv_block_kernel(const double* __rest
       s_q[idx] = (j < len) ? Qb[(int64_t)c * k + j0 + j] : 0.0;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int j = lane; j < len; j += 32) {
-      const double a = __ldg(g0 + j0 + j), b = __ldg(g1 + j0 + j);
+#pragma unroll 2
+    for (int j = 2 * lane; j < len; j += 64) {
+      double2 g[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double* p = Gb + (int64_t)(row0 + r) * ld + j0 + j;
+        if (row0 + r >= k) g[r] = make_double2(0.0, 0.0);
+        else if (vec_ok && j + 1 < len) g[r] = __ldg(reinterpret_cast<const double2*>(p));
+        else g[r] = make_double2(__ldg(p), (j + 1 < len) ? __ldg(p + 1) : 0.0);
+      }
 #pragma unroll
       for (int c = 0; c < kKB; ++c) {
-        const double q = s_q[c * kSymvChunk + j];
-        acc[0][c] = fma(a, q, acc[0][c]);
-        acc[1][c] = fma(b, q, acc[1][c]);
+        const double2 q = *reinterpret_cast<const double2*>(s_q + c * kSymvChunk + j);  // padded with zeros beyond len
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r][c] = fma(g[r].y, q.y, fma(g[r].x, q.x, acc[r][c]));
       }
     }
   }
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < kKB; ++c) {
       double v = acc[r][c];
