@@ -2,12 +2,10 @@
 // Replaces splitp/parsers/fasta.py:48-63 (get_pattern_counts) and the counting half of
 // splitp/simulation.py:43-54.  Bit-exact integer work.
 //
-// Data flow per CTA (256 threads, tile = 4096 sites, persistent over tiles; 32 KB of shared memory at 12 taxa so
-// that 7 CTAs = 56 warps per SM hide the shared-memory dependency chain of an iteration -- ncu shows the kernel
-// stalled on the short scoreboard, i.e. latency- not bandwidth-bound):
+// Data flow per CTA (256 threads, tile = 8192 sites, persistent over tiles):
 //   coalesced 128-bit loads of the tile's bit stream -> shared memory
 //   -> per-site key extraction (funnel shifts), 32 consecutive sites per warp iteration
-//   -> WARP-PRIVATE direct-mapped cache in shared memory (128 entries per warp):
+//   -> WARP-PRIVATE direct-mapped cache in shared memory (256 entries per warp):
 //        hit  : one shared-memory atomicAdd on the entry's counter (lanes that carry the same key as lane 0 -- the
 //               usual case, alignments are dominated by a few very frequent patterns -- are first aggregated with
 //               one ballot, so the hot pattern costs one atomic per warp iteration);
@@ -26,9 +24,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kIters = 16;                  // warp iterations (of 32 sites) per tile
-constexpr int kTileSites = kIters * kThreads;  // 4096
-constexpr int kCacheSlots = 128;           // per warp
+constexpr int kTileSites = 32 * kThreads;  // 8192
+constexpr int kCacheSlots = 256;           // per warp
 
 struct DirectSink {
   uint32_t* table;
@@ -68,7 +65,7 @@ __device__ __forceinline__ uint32_t cache_slot(uint64_t key) {
   uint32_t x = (uint32_t)key ^ (uint32_t)(key >> 32) * 0x9E3779B1u;
   x ^= x >> 15;
   x *= 0x2C1B3C6Du;
-  return (x >> 25) & (kCacheSlots - 1);
+  return (x >> 24) & (kCacheSlots - 1);
 }
 
 template <class Sink>
@@ -81,12 +78,12 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restr
   uint32_t* c_cnt = reinterpret_cast<uint32_t*>(c_keys + kWarps * kCacheSlots);    // [kWarps][kCacheSlots]
   uint32_t* c_first = c_cnt + kWarps * kCacheSlots;                                // [kWarps][kCacheSlots]
   uint32_t* c_claim = c_first + kWarps * kCacheSlots;                              // [kWarps][kCacheSlots]
-  uint32_t* s_tile = c_claim + kWarps * kCacheSlots;                               // 256*n words + 4 pad
+  uint32_t* s_tile = c_claim + kWarps * kCacheSlots;                               // 512*n words + 4 pad
   __shared__ uint32_t s_usable;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int bits = 2 * n;
-  const int tile_words = (kTileSites / 32) * bits;  // 256 n
+  const int tile_words = (kTileSites / 32) * bits;  // 512 n
   const uint64_t kmask = (bits == 64) ? ~0ull : ((1ull << bits) - 1ull);
   const bool want_first = sink.first != nullptr;
   unsigned long long* wk = c_keys + wid * kCacheSlots;
@@ -112,12 +109,12 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const uint32_t* __restr
     }
     if (tid < 4) s_tile[tile_words + tid] = 0;
     __syncthreads();
-    // warp `wid` owns the 512 consecutive sites [wid * 512, wid * 512 + 512) of the tile
-    const int64_t vw0 = (base_site >> 5) + wid * kIters;
-    const uint32_t vmine = (lane < kIters && vw0 + lane < valid_words) ? __ldg(valid + vw0 + lane) : 0u;  // lane l: word of iteration l
+    // warp `wid` owns the 1024 consecutive sites [wid * 1024, wid * 1024 + 1024) of the tile
+    const int64_t vw0 = (base_site >> 5) + wid * 32;
+    const uint32_t vmine = (vw0 + lane < valid_words) ? __ldg(valid + vw0 + lane) : 0u;  // lane l: validity word of iteration l
 #pragma unroll 1
-    for (int it = 0; it < kIters; ++it) {
-      const int sl = wid * (32 * kIters) + it * 32 + lane;  // consecutive lanes = consecutive sites
+    for (int it = 0; it < 32; ++it) {
+      const int sl = wid * 1024 + it * 32 + lane;  // consecutive lanes = consecutive sites
       const int64_t site = base_site + sl;
       const uint32_t vbits = __shfl_sync(0xFFFFFFFFu, vmine, it);
       const bool ok = ((vbits >> lane) & 1u) && site >= site_begin && site < site_end;
