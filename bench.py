@@ -34,6 +34,9 @@ WORKLOADS = {
     "c2": dict(n=12, sites=1_000_000, bl=0.05, model="JC", seed=2,
                desc="BASELINE configs[1]: balanced 12-taxon JC tree bl=0.05, 1M sites, all 2035 splits, dense count "
                     "flattenings (6|6 = 4096x4096), exact u8 tensor-core Gram + eigen score"),
+    "c5": dict(n=32, sites=1_000_000, bl=0.05, model="JC", seed=5, random_splits=100_000,
+               desc="BASELINE configs[4]: 10^5 random splits (side sizes 2..16, numpy default_rng(5)) of a balanced 32-taxon JC "
+                    "tree bl=0.05, 1M sites, subflattening scores"),
     "c3": dict(n=20, sites=10_000_000, bl=0.05, model="GTR", seed=3,
                desc="BASELINE configs[2]: balanced 20-taxon GTR tree bl=0.05, 10M sites, subflattening scores of all "
                     "524267 splits"),
@@ -51,6 +54,19 @@ def parse():
     ap.add_argument("--max-splits", type=int, default=None, help="score only the first M splits (debug runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
+
+
+def make_splits(splits_mod, tree, wl):
+    """All splits of the tree (all_splits order), or `random_splits` random ones for the sweep workload."""
+    if not wl.get("random_splits"):
+        return list(splits_mod.all_splits(tree))
+    rng = np.random.default_rng(5)
+    taxa, n, out = list(tree.taxa), len(tree.taxa), []
+    for _ in range(wl["random_splits"]):
+        a = int(rng.integers(2, n // 2 + 1))
+        left = set(rng.choice(n, size=a, replace=False).tolist())
+        out.append((tuple(t for i, t in enumerate(taxa) if i in left), tuple(t for i, t in enumerate(taxa) if i not in left)))
+    return out
 
 
 def make_model(sim, name):
@@ -103,15 +119,16 @@ def cpu_reference_sample(workload, codes_np, tree, splits, budget_s=25.0):
     from oracle import splitp_oracle as O
     cores = os.cpu_count() or 1
     n = codes_np.shape[0]
-    t0 = time.perf_counter()
-    keys, counts, usable = O.get_pattern_counts_arrays(codes_np)
-    t_count = time.perf_counter() - t0
-    vals = counts / float(usable)
     pos = {t: i for i, t in enumerate(tree.taxa)}
     by_size = {}
     for s in splits:
         by_size.setdefault(min(len(s[0]), len(s[1])), []).append(s)
     per_size, spent = {}, 0.0
+    if workload == "c2" or n <= 31:
+        t0 = time.perf_counter()
+        keys, counts, usable = O.get_pattern_counts_arrays(codes_np)
+        t_count = time.perf_counter() - t0
+        vals = counts / float(usable)
     if workload == "c2":
         for a in sorted(by_size):
             s = by_size[a][len(by_size[a]) // 2]
@@ -128,19 +145,24 @@ def cpu_reference_sample(workload, codes_np, tree, splits, budget_s=25.0):
                   + f"); value = {len(splits)} / (t_count + sum_a n_a t_a)")
     else:
         t1 = time.perf_counter()
-        tables = O.pair_tables(keys, vals, n)
+        if n <= 31:
+            tables = O.pair_tables(keys, vals, n)
+            tot, how = vals.sum(), f"pattern count of all {codes_np.shape[1]} sites ({t_count:.2f} s) + numpy pair tables from the pattern table"
+        else:  # pattern keys are uint64 in the oracle: above 31 taxa the tables come straight from the code matrix
+            t_count = 0.0
+            tables, _ = O.pair_tables_from_codes(codes_np)
+            tot, how = 1.0, f"numpy pair tables straight from the {codes_np.shape[1]}-site code matrix"
         t_pairs = time.perf_counter() - t1
         done, t2 = 0, time.perf_counter()
-        tot = vals.sum()
         while done < len(splits) and time.perf_counter() - t2 < budget_s:
             s = splits[(done * 7919) % len(splits)]
             O.split_score(O.subflattening_from_tables(tables, tot, [pos[x] for x in s[0]], [pos[x] for x in s[1]]))
             done += 1
         t_split = (time.perf_counter() - t2) / max(done, 1)
         value = len(splits) / (t_count + t_pairs + len(splits) * t_split)
-        sample = (f"oracle port: pattern count of all {codes_np.shape[1]} sites ({t_count:.2f} s) + numpy pair tables "
-                  f"({t_pairs:.2f} s) + {done} splits ({t_split * 1e3:.3f} ms each, subflattening from tables + LAPACK "
-                  f"score); value = {len(splits)} / (t_count + t_pairs + S * t_split)")
+        sample = (f"oracle port: {how} ({t_pairs:.2f} s) + {done} splits ({t_split * 1e3:.3f} ms each, subflattening from "
+                  f"tables + LAPACK score); value = {len(splits)} / (t_count + t_pairs + S * t_split)")
+        t_count = max(t_count + t_pairs, 1e-9)
     return {"value": value, "unit": "split-scores/s", "cores": cores, "kind": "port", "sample": sample,
             "sites_per_s": codes_np.shape[1] / t_count}
 
@@ -160,8 +182,10 @@ def main():
         import torch
         from splitp_b200 import simulation, splits as splits_mod, trees
         tree = trees.balanced_tree(wl["n"], wl["bl"])
-        codes = simulation.simulate_codes(tree, make_model(simulation, wl["model"]), wl["sites"], wl["seed"], device="cpu").numpy()
-        splits = list(splits_mod.all_splits(tree))[: args.max_splits]
+        # same generator as the GPU arm when a device is present (identical alignment), CPU generator otherwise
+        gen_dev = "cuda" if torch.cuda.is_available() else "cpu"
+        codes = simulation.simulate_codes(tree, make_model(simulation, wl["model"]), wl["sites"], wl["seed"], device=gen_dev).cpu().numpy()
+        splits = make_splits(splits_mod, tree, wl)[: args.max_splits]
         vals = []
         for _ in range(args.warmup):
             cpu_reference_sample(args.workload, codes, tree, splits, budget_s=3.0)
@@ -195,7 +219,7 @@ def main():
     sb, se = spd.shard_range(N, rank, world, 32)
     codes_dev = codes_full[:, sb:se].contiguous()          # this rank's site shard, resident in HBM
     codes_pin = codes_dev.cpu().pin_memory()               # e2e: host buffer
-    splits = list(sp.all_splits(tree))[: args.max_splits]
+    splits = make_splits(sp.splits, tree, wl)[: args.max_splits]
     S = len(splits)
     idx_all = [eng.split_positions(s, tree.taxa) for s in splits]
     idx_mine = spd.shard_strided(idx_all, rank, world)  # round-robin: balances the steeply size-dependent split cost
@@ -203,7 +227,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     prof = {"gram": [], "pairs": [], "count": []}
     state = {}
-    if args.workload == "c3":
+    if args.workload != "c2":
         ma_np, mb_np = eng.masks_from_splits(idx_mine)
         ma = torch.from_numpy(ma_np.view(np.int64)).to(dev)
         mb = torch.from_numpy(mb_np.view(np.int64)).to(dev)
@@ -320,7 +344,7 @@ def main():
                 "executed_frac_of_algorithmic": tiles_done / tiles_all,
                 "note": "algorithmic flops = full 2*R^2*C; the kernel computes only the 272 of 512 tiles touching the upper "
                         "triangle and mirrors the rest"}
-    elif args.workload == "c3" and prof["pairs"]:
+    elif args.workload != "c2" and prof["pairs"]:
         ms = float(np.mean([a.elapsed_time(b) for a, b, _ in prof["pairs"]]))
         nbytes = (se - sb) * n / 4.0 + (se - sb) / 8.0  # N n / 4 (+ N / 8 validity mask)
         hbm = peaks.get("hbm_gbs", 6650.0)

@@ -219,6 +219,19 @@ def pair_tables(keys, vals, n):
     return out
 
 
+def pair_tables_from_codes(codes, as_counts=False):
+    """Same tables as `pair_tables` straight from a code matrix uint8 [n, N] (no pattern keys: works above 31
+    taxa).  Only usable sites count (fasta.py:55-57); values are count / usable (fasta.py:66-70) unless as_counts."""
+    valid = (codes <= 3).all(axis=0)
+    c = codes[:, valid].astype(np.int64)
+    n, usable = c.shape
+    out = np.zeros((n, n, 4, 4), dtype=np.int64)
+    for i in range(n):
+        for j in range(n):
+            out[i, j] = np.bincount(c[i] * 4 + c[j], minlength=16).reshape(4, 4)
+    return (out, usable) if as_counts else (out / float(usable), usable)
+
+
 def subflattening_from_tables(tables, total, idx_a, idx_b):
     """Entry (3i+c, 3j+d) = (H N_{A_i B_j} H^T)[c, d]; last row/col use the marginals; corner = total
     (derivation: SURVEY.md section 8 row a11; labels from constructions.py:174-189)."""

@@ -443,6 +443,37 @@ def test_config2_properties(sp, eng, oracle):
     assert_score(scores["true"], ref)
 
 
+
+def test_config5_random_splits_32_taxa(sp, eng, oracle):
+    """BASELINE configs[4] shape: random splits of a 32-taxon tree, subflattening scores (side sizes 2..16), with an
+    oracle check on a sample; plus invariance of the score under swapping the two sides."""
+    n, N = 32, 400_000
+    tree = sp.trees.balanced_tree(n, 0.05)
+    codes = sp.simulation.simulate_codes(tree, sp.simulation.GTR.JukesCantor(0.5), N, seed=5)
+    aln = eng.pack(codes, want_sm=False)
+    pt = eng.pair_tables_from_alignment(aln)
+    rng = np.random.default_rng(5)
+    splits = []
+    for _ in range(3000):
+        a = int(rng.integers(2, 17))
+        left = sorted(rng.choice(n, size=a, replace=False).tolist())
+        right = [t for t in range(n) if t not in left]
+        splits.append((left, right))
+    ma, mb = eng.masks_from_splits(splits)
+    sc = eng.subflatten_scores(pt, ma, mb).cpu().numpy()
+    sc_swapped = eng.subflatten_scores(pt, mb, ma).cpu().numpy()
+    assert np.isfinite(sc).all() and (sc >= 0).all() and (sc <= 1).all()
+    np.testing.assert_allclose(sc, sc_swapped, rtol=1e-9)
+    c = codes.cpu().numpy().astype(np.int64)
+    tables = np.zeros((n, n, 4, 4))
+    for i in range(n):
+        for j in range(n):
+            np.add.at(tables[i, j], (c[i], c[j]), 1.0 / N)
+    for s in range(0, 3000, 250):
+        ref = oracle.split_score(oracle.subflattening_from_tables(tables, 1.0, splits[s][0], splits[s][1]))
+        assert_score(sc[s], ref)
+
+
 def test_config3_properties(sp, eng, oracle):
     """20 taxa GTR: pair tables from the bit planes equal pair tables from the hashed pattern table; every
     table sums to the number of sites; subflattening scores of true splits are the smallest of their size."""

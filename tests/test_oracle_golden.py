@@ -157,3 +157,18 @@ def test_readme_config(oracle, golden_readme):
         ia, ib = [taxa.index(x) for x in a], [taxa.index(x) for x in b]
         S = oracle.subflattening(keys, vals, n, ia, ib)
         assert oracle.split_score(S) == pytest.approx(float(g["sub_scores"][k]), rel=1e-9)
+
+
+def test_pair_tables_from_codes_matches_pattern_route(oracle):
+    """The code-matrix route to the pair tables (used above 31 taxa) equals the pattern-table route."""
+    rng = np.random.default_rng(8)
+    codes = rng.integers(0, 4, size=(7, 5000)).astype(np.uint8)
+    codes[rng.random(codes.shape) < 0.01] = 255
+    keys, counts, usable = oracle.get_pattern_counts_arrays(codes)
+    ref = oracle.pair_tables(keys, counts, 7)
+    got, us = oracle.pair_tables_from_codes(codes, as_counts=True)
+    assert us == usable
+    np.testing.assert_array_equal(got, ref)
+    S1 = oracle.subflattening(keys, counts / usable, 7, [0, 3, 5], [1, 2, 4, 6])
+    S2 = oracle.subflattening_from_tables(oracle.pair_tables_from_codes(codes)[0], 1.0, [0, 3, 5], [1, 2, 4, 6])
+    np.testing.assert_allclose(S1, S2, rtol=1e-12, atol=1e-14)
