@@ -6,9 +6,9 @@ from . import alignment, constants, constructions, engine, phylogenetics, simula
 from .alignment import Alignment  # noqa: F401
 from .constructions import flattening, subflattening  # noqa: F401
 from .enums import FlatFormat, Method  # noqa: F401
-from .phylogenetics import split_score  # noqa: F401
+from .phylogenetics import erickson_SVD, split_score  # noqa: F401
 from .simulation import generate_alignment  # noqa: F401
 from .splits import all_splits  # noqa: F401
 
 __all__ = ["flattening", "subflattening", "split_score", "all_splits", "FlatFormat", "Method", "Alignment",
-           "generate_alignment", "engine", "trees", "simulation", "splits", "constructions", "phylogenetics"]
+           "generate_alignment", "erickson_SVD", "engine", "trees", "simulation", "splits", "constructions", "phylogenetics"]

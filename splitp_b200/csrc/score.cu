@@ -368,13 +368,13 @@ __global__ void __launch_bounds__(256) krylov_subtract_kernel(double* W, int64_t
   for (int c = 0; c < kKB; ++c) Wb[(int64_t)c * k + pos] = w[c];
 }
 
-// SVQB orthonormalisation of a block: S = W W^T (8 x 8, given), eigen-decompose the diagonally scaled S,
-// W <- Lambda^{-1/2} V^T D W.  Directions with lambda <= 1e-13 * lambda_max are dropped (zero vectors).
-__global__ void __launch_bounds__(256) krylov_svqb_kernel(double* W, int64_t strideW, const double* __restrict__ S,
-                                                          int64_t strideS, int k) {
-  __shared__ double sS[kKB * (kKB + 1)], sV[kKB * (kKB + 1)], sU[kKB * kKB], sD[kKB];
+// SVQB orthonormalisation of a block, in two kernels.  factor: S = W W^T (8 x 8, given) is scaled to unit diagonal
+// and eigen-decomposed ONCE per matrix; U = Lambda^{-1/2} V^T D (8 x 8) goes to global memory.  Directions with
+// lambda <= 1e-13 * lambda_max are dropped (zero vectors).  apply: W <- U W, one thread per column of W.
+__global__ void __launch_bounds__(64) krylov_svqb_factor_kernel(const double* __restrict__ S, int64_t strideS, double* __restrict__ U) {
+  __shared__ double sS[kKB * (kKB + 1)], sV[kKB * (kKB + 1)], sD[kKB];
   __shared__ JacobiScratch js;
-  const int64_t bt = blockIdx.y;
+  const int64_t bt = blockIdx.x;
   const int tid = threadIdx.x;
   const int ld = kKB + 1;
   const double* Sb = S + bt * strideS;
@@ -397,24 +397,30 @@ __global__ void __launch_bounds__(256) krylov_svqb_kernel(double* W, int64_t str
     double lam = sS[tid * ld + tid];
     double sc = (lam > 1e-13 * lmax && lam > 0.0) ? rsqrt(lam) : 0.0;
     // new vector `tid` = sum_c U[tid][c] W_c, U[tid][c] = sc * V[c][tid] * D[c]
-    for (int c = 0; c < kKB; ++c) sU[tid * kKB + c] = sc * sV[c * ld + tid] * sD[c];
+    for (int c = 0; c < kKB; ++c) U[bt * kKB * kKB + tid * kKB + c] = sc * sV[c * ld + tid] * sD[c];
   }
+}
+
+__global__ void __launch_bounds__(256) krylov_svqb_apply_kernel(double* W, int64_t strideW, const double* __restrict__ U, int k) {
+  __shared__ double sU[kKB * kKB];
+  const int64_t bt = blockIdx.y;
+  if (threadIdx.x < kKB * kKB) sU[threadIdx.x] = U[bt * kKB * kKB + threadIdx.x];
   __syncthreads();
   double* Wb = W + bt * strideW;
-  for (int pos = blockIdx.x * blockDim.x + tid; pos < k; pos += gridDim.x * blockDim.x) {
-    double w[kKB], o[kKB];
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= k) return;
+  double w[kKB], o[kKB];
 #pragma unroll
-    for (int c = 0; c < kKB; ++c) w[c] = Wb[(int64_t)c * k + pos];
+  for (int c = 0; c < kKB; ++c) w[c] = Wb[(int64_t)c * k + pos];
 #pragma unroll
-    for (int v = 0; v < kKB; ++v) {
-      double s = 0.0;
+  for (int v = 0; v < kKB; ++v) {
+    double s = 0.0;
 #pragma unroll
-      for (int c = 0; c < kKB; ++c) s = fma(sU[v * kKB + c], w[c], s);
-      o[v] = s;
-    }
-#pragma unroll
-    for (int v = 0; v < kKB; ++v) Wb[(int64_t)v * k + pos] = o[v];
+    for (int c = 0; c < kKB; ++c) s = fma(sU[v * kKB + c], w[c], s);
+    o[v] = s;
   }
+#pragma unroll
+  for (int v = 0; v < kKB; ++v) Wb[(int64_t)v * k + pos] = o[v];
 }
 
 // Rayleigh-Ritz of T (dim x dim): Jacobi with eigenvectors in shared memory; writes the coefficients of the top-8
@@ -527,7 +533,7 @@ __global__ void krylov_finish_kernel(const double* __restrict__ theta, const dou
 }
 
 struct KrylovWs {
-  double *Q, *AQ, *C, *S, *T, *Vtop, *theta, *res2, *info, *part;
+  double *Q, *AQ, *C, *S, *U, *T, *Vtop, *theta, *res2, *info, *part;
   int64_t sQ, sC, sS, sT, part_elems;
 };
 
@@ -541,6 +547,7 @@ static int64_t krylov_layout(int64_t k, int64_t batch, double* base, KrylovWs* w
   w->C = take(batch * w->sC);
   w->sS = (int64_t)kKB * kKB;
   w->S = take(batch * w->sS);
+  w->U = take(batch * w->sS);
   w->sT = (int64_t)kKDim * kKDim;
   w->T = take(batch * w->sT);
   w->Vtop = take(batch * kKDim * kKB);
@@ -601,8 +608,10 @@ static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb,
     for (int pass = 0; pass < passes; ++pass) {
       int r = dot_product(W, w.sQ, W, w.sQ, kKB, kKB, k, batch, w.S, kKB, w.sS, w.part, st);
       if (r) return r;
-      dim3 grid((k + 255) / 256 > 32 ? 32 : (k + 255) / 256, batch);
-      krylov_svqb_kernel<<<grid, 256, 0, st>>>(W, w.sQ, w.S, w.sS, k);
+      krylov_svqb_factor_kernel<<<batch, 64, 0, st>>>(w.S, w.sS, w.U);
+      SPB_LAUNCH_CHECK();
+      dim3 grid((k + 255) / 256, batch);
+      krylov_svqb_apply_kernel<<<grid, 256, 0, st>>>(W, w.sQ, w.U, k);
       SPB_LAUNCH_CHECK();
     }
     return SPB_OK;

@@ -423,16 +423,30 @@ class CountScorer:
     def __init__(self, table, hi_cap=None):
         if table.counts is None:
             raise ValueError("CountScorer needs a PatternTable with integer counts")
-        self.table = table
-        self.hi_cap = int(hi_cap if hi_cap is not None else max(1024, min(table.num, 1 << 16)))
-        self.hi_rc = _empty((self.NB, self.hi_cap, 2), torch.int32)
-        self.hi_val = _empty((self.NB, self.hi_cap), torch.int32)
+        self._table = None
+        self.hi_cap = int(hi_cap) if hi_cap is not None else 0
+        self.hi_rc = self.hi_val = None
         self.hi_num = _zeros(self.NB, torch.int32)
-        self.hi_max = _zeros(1, torch.int32)  # running maximum of hi_num (checked once by check_hi)
+        self.table = table
         self._s0 = {}
         self._G = {}
         self._ws = {}
         self.gram_hook = None  # optional wrapper (fn, nb) around the Gram launch (bench.py times it with CUDA events)
+
+    @property
+    def table(self):
+        return self._table
+
+    @table.setter
+    def table(self, table):
+        """The number of counts >= 256 is a property of the table (every split scatters the same patterns), so the
+        high-part buffers are sized once per table: no per-split overflow tracking is needed."""
+        self._table = table
+        self.n_hi = int((table.counts.to(torch.int64) & 0xFFFFFFFF).ge(256).sum().item()) if table.num else 0
+        if self.hi_rc is None or self.n_hi > self.hi_cap:
+            self.hi_cap = max(self.hi_cap, 1024, 2 * self.n_hi)
+            self.hi_rc = _empty((self.NB, self.hi_cap, 2), torch.int32)
+            self.hi_val = _empty((self.NB, self.hi_cap), torch.int32)
 
     @staticmethod
     def geometry(rows, cols):
@@ -483,7 +497,6 @@ class CountScorer:
         call("spb_gram_hi_correction", _p(s0), rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num),
              self.hi_cap, _p(G), _st())
         call("spb_flatten_u8_clear", _p(t.keys), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch, layout, _st())
-        torch.maximum(self.hi_max, self.hi_num[:1], out=self.hi_max)
 
     def _gram_batch(self, splits, s0, G, ws, layout, rows_pad, pitch):
         """nb <= SPB_MAX_BATCH dense splits of equal shape, one launch per stage.  G: [nb, rows_pad, rows_pad] view."""
@@ -498,7 +511,6 @@ class CountScorer:
         call("spb_gram_hi_correction_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
              _p(self.hi_num), self.hi_cap, _p(G), g_stride, _st())
         call("spb_flatten_u8_clear_batch", _p(t.keys), t.num, arr, nb, _p(s0), s0_stride, rows_pad, pitch, layout, _st())
-        torch.maximum(self.hi_max, self.hi_num[:nb].max().reshape(1), out=self.hi_max)
 
     def gram(self, idx_a, idx_b, reduced=False):
         """Exact F F^T (short side) of the count flattening of one split.  Returns (G [rows_pad, rows_pad], k)."""
@@ -549,9 +561,9 @@ class CountScorer:
         return out
 
     def check_hi(self):
-        n = int(self.hi_max.item())
-        if n > self.hi_cap:
-            raise MemoryError(f"splitp_b200: {n} counts >= 256 exceed the high-part capacity {self.hi_cap}")
+        """Kept for API stability: the capacity is guaranteed by construction (see the `table` setter)."""
+        if self.n_hi > self.hi_cap:
+            raise MemoryError(f"splitp_b200: {self.n_hi} counts >= 256 exceed the high-part capacity {self.hi_cap}")
 
 
 def score_splits_counts(table, splits_idx, reduced=False):

@@ -9,11 +9,14 @@ conditioning floor c*eps/score^2 when that is larger ("score conditio
 """
 from __future__ import annotations
 
+from itertools import combinations
+
 import numpy as np
 import scipy.sparse
 import torch
 
 from . import engine
+from .enums import Method
 
 
 def is_sparse(matrix):
@@ -48,3 +51,75 @@ def split_score(matrix, return_singular_values=False, force_frob_norm_on_dense=F
         return np.float64("nan")
     dev = engine.device()
     return np.float64(engine.score_matrix(torch.from_numpy(np.ascontiguousarray(m)).to(dev))[0].item())
+
+
+def _leaves(cluster):
+    return (cluster,) if isinstance(cluster, str) else tuple(cluster)
+
+
+def erickson_SVD(alignment, taxa=None, method=Method.flattening, show_work=False):
+    """Agglomerative tree inference from split scores (reference: splitp/phylogenetics.py:99-171).
+
+    At every step each pair of current clusters is joined tentatively, the split (joined leaves | all other leaves)
+    is scored -- reduced flattening + split score (`Method.flattening`) or subflattening + split score
+    (`Method.subflattening`) -- and the best-scoring pair is merged; scores are memoised per split.  Returns the
+    n - 2 chosen splits as sorted 2-tuples of leaf tuples, like the reference.  The candidate splits of a step are
+    scored as ONE batch on the device: the batched subflattening kernel for `Method.subflattening`, device-resident
+    reduced flattenings for `Method.flattening`.  `Method.mutual_information` (rank-1 KL divergence,
+    phylogenetics.py:331-373) is outside the hot path and not implemented.
+    """
+    table = engine.table_from_mapping(alignment)
+    num_taxa = table.n
+    if taxa is None:
+        taxa = [str(np.base_repr(i, base=max(i + 1, 2))) if num_taxa <= 36 else f"t{i}" for i in range(num_taxa)]
+    if method not in (Method.flattening, Method.subflattening):
+        if method == Method.mutual_information:
+            raise NotImplementedError("erickson_SVD: Method.mutual_information is not part of the B200 hot path")
+    known = {}
+    pair_tables = None
+
+    def positions(split):
+        # same taxa order as flattening(): the mapping's .taxa, else the sorted union of both sides (constructions.py:21-24)
+        order = alignment.taxa if hasattr(alignment, "taxa") else sorted(set(split[0]) | set(split[1]))
+        return engine.split_positions(split, order)
+
+    def score_new(splits):
+        nonlocal pair_tables
+        if method == Method.subflattening:
+            if pair_tables is None:
+                pair_tables = engine.pair_tables_from_table(table)
+            idx = [positions(s) for s in splits]
+            for ia, ib in idx:
+                if not engine.covers_all(table.n, ia, ib):
+                    raise KeyError(min(set(range(table.n)) - set(ia) - set(ib)))  # as subflattening() would
+            ma, mb = engine.masks_from_splits(idx)
+            return [np.float64(v) for v in engine.subflatten_scores(pair_tables, ma, mb).cpu().numpy()]
+        if method == Method.flattening:
+            out = []
+            for s in splits:
+                ia, ib = positions(s)
+                F = engine.flatten_reduced(table, ia, ib)
+                out.append(np.float64(0.0) if min(F.shape) <= 4 else np.float64(engine.score_matrix(F)[0].item()))
+            return out
+        return [np.inf] * len(splits)  # the reference leaves the score at infinity for the other methods
+
+    chosen = []
+    while len(chosen) < num_taxa - 2:
+        candidates = []
+        for pair in combinations(taxa, 2):
+            joined = tuple(sorted(leaf for cluster in pair for leaf in _leaves(cluster)))
+            rest = tuple(sorted(leaf for cluster in taxa for leaf in _leaves(cluster) if leaf not in joined))
+            candidates.append((pair, (joined, rest)))
+        fresh = []
+        for _, split in candidates:
+            if split not in known and split not in fresh:
+                fresh.append(split)
+        if fresh:
+            known.update(zip(fresh, score_new(fresh)))
+        if show_work:
+            print(f"Scores: { {pair: (pair, split, known[split]) for pair, split in candidates} }")
+        best_pair, best_split = min(candidates, key=lambda c: known[c[1]])  # first minimum, like min() in the reference
+        chosen.append(tuple(sorted(best_split)))
+        merged = best_split[0]
+        taxa = tuple([c for c in taxa if c not in merged and not set(c).issubset(merged)] + [merged])
+    return chosen

@@ -200,8 +200,30 @@ def rand():
     np.savez_compressed(os.path.join(HERE, "golden_random.npz"), **store)
 
 
+def erickson():
+    """erickson_SVD (phylogenetics.py:99-171) on simulated 6- and 8-taxon alignments, both scoring methods."""
+    out = []
+    for n, N, seed in ((6, 3000, 1), (8, 4000, 2)):
+        random.seed(seed)
+        np.random.seed(seed)
+        tree = splitp.trees.balanced_newick_tree(n, 0.1)
+        aln = splitp.generate_alignment(tree, splitp.model.GTR.JukesCantor(1 / 2), N)
+        rec = {"n": n, "patterns": list(aln.keys()), "values": list(aln.values()),
+               "true_splits": sorted([list(map(list, s)) for s in tree.splits()])}
+        for method in (splitp.Method.flattening, splitp.Method.subflattening):
+            res = splitp.phylogenetics.erickson_SVD(aln, method=method)
+            rec[method.name] = [list(map(list, s)) for s in res]
+        out.append(rec)
+    with open(os.path.join(HERE, "golden_erickson.json"), "w") as f:
+        json.dump(out, f)
+
+
 if __name__ == "__main__":
-    small()
-    rand()
-    readme()
+    if len(sys.argv) > 1 and sys.argv[1] == "erickson":
+        erickson()
+    else:
+        small()
+        rand()
+        readme()
+        erickson()
     print("golden fixtures written")

@@ -246,6 +246,25 @@ def test_sparse_score_and_sub_alignment(sp, oracle, golden_small):
     assert_score(sp.split_score(F), oracle.split_score(Fd))
 
 
+
+def test_erickson_svd_golden(sp):
+    """The batched agglomeration reproduces the reference's erickson_SVD output (phylogenetics.py:99-171) on the
+    simulated alignments of tests/golden/golden_erickson.json, for both scoring methods."""
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_erickson.json")) as f:
+        cases = json.load(f)
+    for rec in cases:
+        aln = dict(zip(rec["patterns"], rec["values"]))
+        for method in (sp.Method.flattening, sp.Method.subflattening):
+            got = sp.erickson_SVD(aln, method=method)
+            assert [list(map(list, s)) for s in got] == rec[method.name], (rec["n"], method)
+        # every non-trivial split the reference found is a true split of the generating tree
+        nontrivial = [s for s in rec["flattening"] if min(len(s[0]), len(s[1])) > 1]
+        assert all(s in rec["true_splits"] for s in nontrivial)
+    with pytest.raises(NotImplementedError):
+        sp.erickson_SVD(aln, method=sp.Method.mutual_information)
+
+
 # ---------------------------------------------------------------------------------------------
 # kernel 3: pair tables / subflattening, batched
 # ---------------------------------------------------------------------------------------------
