@@ -256,8 +256,13 @@ def test_erickson_svd_golden(sp):
     for rec in cases:
         aln = dict(zip(rec["patterns"], rec["values"]))
         for method in (sp.Method.flattening, sp.Method.subflattening):
-            got = sp.erickson_SVD(aln, method=method)
-            assert [list(map(list, s)) for s in got] == rec[method.name], (rec["n"], method)
+            got = [list(map(list, s)) for s in sp.erickson_SVD(aln, method=method)]
+            ref = rec[method.name]
+            assert len(got) == len(ref) == rec["n"] - 2
+            # splits with a one-taxon side score exactly 0 here, while the reference's 1 - top4/total leaves rounding
+            # noise (0, 1e-8 or nan) that decides between them: only the informative picks are compared, in order
+            informative = lambda seq: [s for s in seq if min(len(s[0]), len(s[1])) > 1]  # noqa: E731
+            assert informative(got) == informative(ref), (rec["n"], method)
         # every non-trivial split the reference found is a true split of the generating tree
         nontrivial = [s for s in rec["flattening"] if min(len(s[0]), len(s[1])) > 1]
         assert all(s in rec["true_splits"] for s in nontrivial)
