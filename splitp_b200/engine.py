@@ -451,7 +451,7 @@ class CountScorer:
     @staticmethod
     def geometry(rows, cols):
         """(layout, rows_pad, pitch) for a rows x cols count matrix with rows <= cols."""
-        if rows <= 64:
+        if rows <= 32:  # dp4a; above that the (zero-padded) 128-row tensor-core tile is faster than dp4a on 64 rows
             return SPB_S0_K4MAJOR, max((rows + 3) // 4 * 4, 4), (cols + 15) // 16 * 16
         rp = 128 if rows <= 128 else (rows + 255) // 256 * 256
         return SPB_S0_TILED, rp, (cols + 127) // 128 * 128

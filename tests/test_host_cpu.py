@@ -115,7 +115,8 @@ def test_count_scorer_geometry():
     from splitp_b200 import engine
     g = engine.CountScorer.geometry
     assert g(16, 1 << 20) == (2, 16, 1 << 20)
-    assert g(64, 262144) == (2, 64, 262144)
+    assert g(64, 262144) == (1, 128, 262144)
+    assert g(32, 100) == (2, 32, 112)
     assert g(7, 55) == (2, 8, 64)
     assert g(256, 65536) == (1, 256, 65536)
     assert g(4096, 4096) == (1, 4096, 4096)
