@@ -16,10 +16,10 @@
 // tile is ONE 1-D bulk-TMA copy (cp.async.bulk, 16 KB) completing on an mbarrier: no tensor map, no swizzle
 // work on the load path, perfectly coalesced HBM/L2 reads.
 //
-// Kernel structure (persistent, one CTA per SM, 192 threads):
+// Kernel structure (persistent, one CTA per SM, 320 threads):
 //   warp 0   : TMA producer   (bulk copies into a 4-stage shared-memory ring)
 //   warp 1   : MMA issuer     (tcgen05.mma M=128, N=BN, K=32 x 4 per stage; accumulators in TMEM, 2 stages)
-//   warps 2-5: epilogue       (tcgen05.ld -> fp64 stores incl. the mirrored half, or 64-bit integer atomics
+//   warps 2-9: epilogue       (tcgen05.ld -> fp64 stores incl. the mirrored half, or 64-bit integer atomics
 //                              when K is split across CTAs)
 // Only tiles touching the upper triangle (in 256-wide blocks) are computed; the rest is mirrored.
 #include "common.cuh"
@@ -31,7 +31,7 @@ namespace {
 constexpr int kTile = 128;               // rows and K-bytes per operand tile
 constexpr int kTileBytes = kTile * kTile;  // 16 KB
 constexpr int kStages = 4;
-constexpr int kUmmaThreads = 192;
+constexpr int kUmmaThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr uint32_t kSpinLimit = 1u << 28;  // watchdog: a broken pipeline traps instead of hanging the GPU
 
 // ---------------------------------------------------------------------------------------------------
@@ -201,7 +201,7 @@ gram_u8_umma_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int 
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -267,8 +267,10 @@ gram_u8_umma_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int 
       }
     }
   } else {
-    // ===== epilogue: 4 warps, warp q = warp % 4 owns TMEM lanes [32q, 32q+32) =====
+    // ===== epilogue: 8 warps; warp q = warp % 4 may only touch TMEM lanes [32q, 32q+32), so two warps share each
+    // lane quarter and split the BN accumulator columns between them (half = 0 / 1) =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     uint32_t acc = 0, acc_phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       Work wk;
@@ -280,7 +282,7 @@ gram_u8_umma_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int 
       double* G = G_base + (size_t)wk.b * g_stride;
       unsigned long long* acc64 = acc_base ? acc_base + (size_t)wk.b * ldg * ldg : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
         const int col0 = wk.j * BN + c0;
