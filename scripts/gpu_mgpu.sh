@@ -2,8 +2,7 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 N=${1:-2}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
-timeout 600 $TR scripts/mgpu_check.py > gpurun_out/mgpu_check_$N.log 2>&1; echo "mgpu check rc=$?"; tail -4 gpurun_out/mgpu_check_$N.log
-timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench N=$N rc=$?"; cat gpurun_out/bench_n$N.json; tail -3 gpurun_out/bench_n$N.err
-timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 --workload c3 > gpurun_out/bench_c3_n$N.json 2> gpurun_out/bench_c3_n$N.err; echo "bench c3 N=$N rc=$?"; cat gpurun_out/bench_c3_n$N.json; tail -3 gpurun_out/bench_c3_n$N.err
-timeout 600 python bench.py --gpus 1 --steps 3 --warmup 3 --workload c3 --no-cpu-baseline > gpurun_out/bench_c3_n1.json 2>gpurun_out/bench_c3_n1.err; cat gpurun_out/bench_c3_n1.json
-timeout 900 python scripts/kernel_roofline.py > gpurun_out/kernel_roofline.log 2>&1; echo "roofline rc=$?"; cat gpurun_out/kernel_roofline.log
+timeout 600 $TR scripts/mgpu_check.py > gpurun_out/mgpu_check_$N.log 2>&1; echo "mgpu check rc=$?"; grep -c "parity ok" gpurun_out/mgpu_check_$N.log; tail -2 gpurun_out/mgpu_check_$N.log
+timeout 900 $TR bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench N=$N rc=$?"; cat gpurun_out/bench_n$N.json | cut -c1-330; tail -2 gpurun_out/bench_n$N.err
+timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 --workload c3 > gpurun_out/bench_c3_n$N.json 2> gpurun_out/bench_c3_n$N.err; echo "bench c3 N=$N rc=$?"; cat gpurun_out/bench_c3_n$N.json | cut -c1-330
+timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 --workload c5 > gpurun_out/bench_c5_n$N.json 2> gpurun_out/bench_c5_n$N.err; echo "bench c5 N=$N rc=$?"; cat gpurun_out/bench_c5_n$N.json | cut -c1-330
