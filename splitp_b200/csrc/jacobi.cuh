@@ -11,12 +11,17 @@ namespace spb {
 constexpr int kJacobiMaxK = 128;
 constexpr int kJacobiMaxSweeps = 40;
 
-struct JacobiScratch {  // lives in shared memory
-  double c[kJacobiMaxK / 2], s[kJacobiMaxK / 2], npp[kJacobiMaxK / 2], nqq[kJacobiMaxK / 2];
-  int p[kJacobiMaxK / 2], q[kJacobiMaxK / 2];
+template <int MAXK>
+struct JacobiScratchT {  // lives in shared memory; MAXK = largest matrix dimension the owner kernel solves
+  static constexpr int kPairs = (MAXK + 1) / 2;
+  static constexpr int kBlocks = kPairs * (kPairs + 1) / 2;
+  double c[kPairs], s[kPairs], npp[kPairs], nqq[kPairs];
+  int p[kPairs], q[kPairs];
   int rotated;
   double trace0;
+  uint8_t bt1[kBlocks], bt2[kBlocks];  // (t1 <= t2) of every 2x2 block: an even deal over the threads
 };
+using JacobiScratch = JacobiScratchT<kJacobiMaxK>;
 
 // Storage contract: the solver works on an even dimension m = jacobi_dim(k) (one zero row/column of padding when
 // k is odd), row stride lda >= m (jacobi_ld(k) = m | 1 is odd, which keeps the 2x2-block accesses spread over the
@@ -33,15 +38,21 @@ __host__ __device__ constexpr int jacobi_ld(int k) { return jacobi_dim(k) | 1; }
 //   (2) every 2x2 block B(t1, t2) = A[{p1,q1}][{p2,q2}], t1 <= t2, is replaced by J1^T B J2 in ONE pass (the block
 //       and its mirror image are written by the same thread, so the update is in place with a single barrier);
 //       the diagonal blocks are written in closed form (npp, 0; 0, nqq).
-__device__ inline void jacobi_eig_smem(double* A, int lda, int k, double* V, int ldv, JacobiScratch* js) {
+template <class Scratch>
+__device__ inline void jacobi_eig_smem(double* A, int lda, int k, double* V, int ldv, Scratch* js) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;  // used by the eigenvector update
   const int m = jacobi_dim(k);
   const int np = m >> 1;
+  const int nblocks = np * (np + 1) / 2;
   if (tid == 0) {
     double tr = 0.0;
     for (int i = 0; i < k; ++i) tr += fabs(A[i * lda + i]);
     js->trace0 = tr;
+  }
+  for (int t1 = tid; t1 < np; t1 += nt) {  // row t1 of the block triangle starts at t1 * np - t1 (t1 - 1) / 2
+    const int base = t1 * np - (t1 * (t1 - 1)) / 2;
+    for (int t2 = t1; t2 < np; ++t2) { js->bt1[base + t2 - t1] = (uint8_t)t1; js->bt2[base + t2 - t1] = (uint8_t)t2; }
   }
   __syncthreads();
   if (k < 2) return;
@@ -74,25 +85,23 @@ __device__ inline void jacobi_eig_smem(double* A, int lda, int k, double* V, int
         js->p[tid] = p; js->q[tid] = q; js->c[tid] = c; js->s[tid] = s; js->npp[tid] = npp; js->nqq[tid] = nqq;
       }
       __syncthreads();
-      // (2) fused two-sided update, one 2x2 block per thread iteration
-      for (int t1 = warp; t1 < np; t1 += nwarps) {
+      // (2) fused two-sided update, one 2x2 block per thread iteration (blocks dealt evenly over all threads)
+      for (int b = tid; b < nblocks; b += nt) {
+        const int t1 = js->bt1[b], t2 = js->bt2[b];
+        const double c1 = js->c[t1], s1 = js->s[t1], c2 = js->c[t2], s2 = js->s[t2];
+        if (s1 == 0.0 && s2 == 0.0) continue;
         const int p1 = js->p[t1], q1 = js->q[t1];
-        const double c1 = js->c[t1], s1 = js->s[t1];
-        for (int t2 = t1 + lane; t2 < np; t2 += 32) {
-          const double c2 = js->c[t2], s2 = js->s[t2];
-          if (s1 == 0.0 && s2 == 0.0) continue;
-          const int p2 = js->p[t2], q2 = js->q[t2];
-          if (t1 == t2) {
-            A[p1 * lda + p1] = js->npp[t1]; A[q1 * lda + q1] = js->nqq[t1];
-            A[p1 * lda + q1] = 0.0; A[q1 * lda + p1] = 0.0;
-            continue;
-          }
-          double a = A[p1 * lda + p2], b = A[p1 * lda + q2], cc = A[q1 * lda + p2], d = A[q1 * lda + q2];
-          double a1 = c1 * a - s1 * cc, b1 = c1 * b - s1 * d, cc1 = s1 * a + c1 * cc, d1 = s1 * b + c1 * d;
-          double a2 = c2 * a1 - s2 * b1, b2 = s2 * a1 + c2 * b1, cc2 = c2 * cc1 - s2 * d1, d2 = s2 * cc1 + c2 * d1;
-          A[p1 * lda + p2] = a2; A[p1 * lda + q2] = b2; A[q1 * lda + p2] = cc2; A[q1 * lda + q2] = d2;
-          A[p2 * lda + p1] = a2; A[q2 * lda + p1] = b2; A[p2 * lda + q1] = cc2; A[q2 * lda + q1] = d2;
+        if (t1 == t2) {
+          A[p1 * lda + p1] = js->npp[t1]; A[q1 * lda + q1] = js->nqq[t1];
+          A[p1 * lda + q1] = 0.0; A[q1 * lda + p1] = 0.0;
+          continue;
         }
+        const int p2 = js->p[t2], q2 = js->q[t2];
+        double a = A[p1 * lda + p2], bb = A[p1 * lda + q2], cc = A[q1 * lda + p2], d = A[q1 * lda + q2];
+        double a1 = c1 * a - s1 * cc, b1 = c1 * bb - s1 * d, cc1 = s1 * a + c1 * cc, d1 = s1 * bb + c1 * d;
+        double a2 = c2 * a1 - s2 * b1, b2 = s2 * a1 + c2 * b1, cc2 = c2 * cc1 - s2 * d1, d2 = s2 * cc1 + c2 * d1;
+        A[p1 * lda + p2] = a2; A[p1 * lda + q2] = b2; A[q1 * lda + p2] = cc2; A[q1 * lda + q2] = d2;
+        A[p2 * lda + p1] = a2; A[q2 * lda + p1] = b2; A[p2 * lda + q1] = cc2; A[q2 * lda + q1] = d2;
       }
       if (V) {
         for (int t = warp; t < np; t += nwarps) {

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kSThreads) subflatten_score_kernel(const doubl
   extern __shared__ __align__(16) double s_d[];
   double* M = s_d;                 // k x (L+1)
   double* G = M + m_elems;         // k x (k|1)
-  __shared__ JacobiScratch js;
+  __shared__ JacobiScratchT<3 * (SPB_MAX_TAXA / 2) + 2> js;  // k = min(3a, 3b) + 1 <= 97
   __shared__ double lam[kJacobiMaxK], tmp[kJacobiMaxK];
   __shared__ uint8_t la[SPB_MAX_TAXA], lb[SPB_MAX_TAXA];
   __shared__ int s_a, s_b;

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) krylov_subtract_kernel(double* W, int64_t
 // lambda <= 1e-13 * lambda_max are dropped (zero vectors).  apply: W <- U W, one thread per column of W.
 __global__ void __launch_bounds__(64) krylov_svqb_factor_kernel(const double* __restrict__ S, int64_t strideS, double* __restrict__ U) {
   __shared__ double sS[kKB * (kKB + 1)], sV[kKB * (kKB + 1)], sD[kKB];
-  __shared__ JacobiScratch js;
+  __shared__ JacobiScratchT<kKB> js;
   const int64_t bt = blockIdx.x;
   const int tid = threadIdx.x;
   const int ld = kKB + 1;
