@@ -163,8 +163,7 @@ struct GemmArgs {
   int M, N, K, batch;
 };
 
-// skinny = true: M <= 16 (block of Krylov vectors times the big symmetric matrix)
-static int gemm_nt(const GemmArgs& g, bool skinny, int ksplit, double* part, cudaStream_t st) {
+static int gemm_nt(const GemmArgs& g, int ksplit, double* part, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return SPB_OK;
   if (ksplit < 1) ksplit = 1;
   int kchunk = ((g.K + ksplit - 1) / ksplit + kBK - 1) / kBK * kBK;
@@ -173,15 +172,9 @@ static int gemm_nt(const GemmArgs& g, bool skinny, int ksplit, double* part, cud
   if (ksplit < 1) ksplit = 1;
   double* out = g.C; int64_t ldc = g.ldc, strideC = g.strideC;
   if (ksplit > 1) { out = part; ldc = g.N; strideC = (int64_t)g.M * g.N; }
-  if (skinny) {
-    dim3 grid((g.N + 255) / 256, (g.M + 15) / 16, g.batch * ksplit);
-    gemm_nt_kernel<16, 256, 4, 4><<<grid, 256, 0, st>>>(g.A, g.lda, g.strideA, g.B, g.ldb, g.strideB, out, ldc,
-                                                        ksplit > 1 ? strideC : g.strideC, g.M, g.N, g.K, ksplit, kchunk);
-  } else {
-    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.batch * ksplit);
-    gemm_nt_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(g.A, g.lda, g.strideA, g.B, g.ldb, g.strideB, out, ldc,
-                                                       ksplit > 1 ? strideC : g.strideC, g.M, g.N, g.K, ksplit, kchunk);
-  }
+  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.batch * ksplit);
+  gemm_nt_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(g.A, g.lda, g.strideA, g.B, g.ldb, g.strideB, out, ldc, strideC, g.M, g.N, g.K,
+                                                     ksplit, kchunk);
   SPB_LAUNCH_CHECK();
   if (ksplit > 1) {
     int64_t elems = (int64_t)g.M * g.N;
@@ -195,9 +188,8 @@ static int gemm_nt(const GemmArgs& g, bool skinny, int ksplit, double* part, cud
 // NOTE on strides with split-K: partial (bt, ks) lives at part[(bt*ksplit+ks)*M*N]; the kernel indexes C by
 // blockIdx.z = bt*ksplit+ks with strideC = M*N, which is exactly that layout.  Without split-K blockIdx.z = bt.
 
-static int choose_ksplit(int M, int N, int K, int batch, bool skinny) {
-  int64_t tiles = skinny ? (int64_t)((N + 255) / 256) * ((M + 15) / 16) : (int64_t)((N + 63) / 64) * ((M + 63) / 64);
-  tiles *= batch;
+static int choose_ksplit(int M, int N, int K, int batch) {
+  int64_t tiles = (int64_t)((N + 63) / 64) * ((M + 63) / 64) * batch;
   int target = 2 * sm_count();
   if (tiles >= target) return 1;
   int ks = (int)((target + tiles - 1) / tiles);
@@ -605,16 +597,16 @@ static int64_t krylov_layout(int64_t k, int64_t batch, double* base, KrylovWs* w
 }  // namespace
 
 extern "C" int64_t spb_gram_f64_ws(int64_t R, int64_t C, int64_t batch) {
-  int ks = choose_ksplit((int)R, (int)R, (int)C, (int)batch, false);
+  int ks = choose_ksplit((int)R, (int)R, (int)C, (int)batch);
   return ks > 1 ? batch * ks * R * R : 0;
 }
 
 extern "C" int spb_gram_f64(const double* d_A, int64_t R, int64_t C, int64_t batch, double* d_G, double* d_ws, void* stream) {
   SPB_REQUIRE(d_A && d_G && R >= 1 && C >= 1 && batch >= 1 && R < (1 << 30) && C < (1 << 30), "spb_gram_f64: bad arguments");
-  int ks = choose_ksplit((int)R, (int)R, (int)C, (int)batch, false);
+  int ks = choose_ksplit((int)R, (int)R, (int)C, (int)batch);
   SPB_REQUIRE(ks == 1 || d_ws, "spb_gram_f64: workspace required (spb_gram_f64_ws)");
   GemmArgs g{d_A, C, R * C, d_A, C, R * C, d_G, R, R * R, (int)R, (int)R, (int)C, (int)batch};
-  return gemm_nt(g, false, ks, d_ws, (cudaStream_t)stream);
+  return gemm_nt(g, ks, d_ws, (cudaStream_t)stream);
 }
 
 extern "C" int spb_score_gram_small(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores, double* d_eig,
