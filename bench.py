@@ -34,6 +34,9 @@ WORKLOADS = {
     "c2": dict(n=12, sites=1_000_000, bl=0.05, model="JC", seed=2,
                desc="BASELINE configs[1]: balanced 12-taxon JC tree bl=0.05, 1M sites, all 2035 splits, dense count "
                     "flattenings (6|6 = 4096x4096), exact u8 tensor-core Gram + eigen score"),
+    "c4": dict(n=64, sites=10_000_000, bl=0.05, model="JC", seed=4, pair_splits=True,
+               desc="BASELINE configs[3] (scaled: 10M sites by default, --sites 100000000 for the full size): balanced 64-taxon JC "
+                    "tree bl=0.05, 128-bit pattern compression + reduced flattening scores of all 2016 2|62 splits"),
     "c5": dict(n=32, sites=1_000_000, bl=0.05, model="JC", seed=5, random_splits=100_000,
                desc="BASELINE configs[4]: 10^5 random splits (side sizes 2..16, numpy default_rng(5)) of a balanced 32-taxon JC "
                     "tree bl=0.05, 1M sites, subflattening scores"),
@@ -58,6 +61,8 @@ def parse():
 
 def make_splits(splits_mod, tree, wl):
     """All splits of the tree (all_splits order), or `random_splits` random ones for the sweep workload."""
+    if wl.get("pair_splits"):
+        return list(splits_mod.all_splits(tree, size=2))
     if not wl.get("random_splits"):
         return list(splits_mod.all_splits(tree))
     rng = np.random.default_rng(5)
@@ -124,6 +129,25 @@ def cpu_reference_sample(workload, codes_np, tree, splits, budget_s=25.0):
     for s in splits:
         by_size.setdefault(min(len(s[0]), len(s[1])), []).append(s)
     per_size, spent = {}, 0.0
+    if workload == "c4":
+        sub = codes_np[:, : min(codes_np.shape[1], 200_000)]
+        t0 = time.perf_counter()
+        d, usable = O.get_pattern_counts_wide(sub)
+        t_count = time.perf_counter() - t0
+        done, t2 = 0, time.perf_counter()
+        while done < len(splits) and time.perf_counter() - t2 < budget_s:
+            s = splits[(done * 7919) % len(splits)]
+            ia = [pos[x] for x in s[0]]
+            O.split_score(O.flattening_reduced_from_dict(d, ia, [t for t in range(n) if t not in ia]))
+            done += 1
+        t_split = (time.perf_counter() - t2) / max(done, 1)
+        scale = codes_np.shape[1] / sub.shape[1]
+        value = len(splits) / (scale * (t_count + len(splits) * t_split))
+        return {"value": value, "unit": "split-scores/s", "cores": cores, "kind": "port",
+                "sample": f"oracle port on the first {sub.shape[1]} of {codes_np.shape[1]} sites: byte-row pattern count ({t_count:.2f} s) + "
+                          f"{done} 2|62 splits ({t_split:.3f} s each: dict-based reduced flattening + LAPACK score); both stages are "
+                          f"linear in the number of distinct patterns (= sites at 64 taxa), so value = S / (scale * (t_count + S * t_split)) "
+                          f"with scale = {scale:.0f}", "sites_per_s": sub.shape[1] / t_count}
     if workload == "c2" or n <= 31:
         t0 = time.perf_counter()
         keys, counts, usable = O.get_pattern_counts_arrays(codes_np)
@@ -227,7 +251,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     prof = {"gram": [], "pairs": [], "count": []}
     state = {}
-    if args.workload != "c2":
+    if args.workload not in ("c2", "c4"):
         ma_np, mb_np = eng.masks_from_splits(idx_mine)
         ma = torch.from_numpy(ma_np.view(np.int64)).to(dev)
         mb = torch.from_numpy(mb_np.view(np.int64)).to(dev)
@@ -253,6 +277,10 @@ def main():
             scorer.table = table
             out = scorer.score_many(idx_mine, big_hook=(lambda f, nb: timed("gram", f, nb)) if state.get("profile") else None)
             scorer.check_hi()
+        elif args.workload == "c4":
+            wide, valid, n_, N_ = eng.pack_wide(codes)
+            table = timed("count", lambda: spd.count_patterns_wide_sharded(wide, valid, n_, N_, rank, world, local=True))
+            out = eng.thin_split_scores(table, [min((ia, ib), key=len) for ia, ib in idx_mine])
         else:
             aln = eng.pack(codes, want_sm=False)
             raw = timed("pairs", lambda: eng.pair_raw(aln))
@@ -319,8 +347,9 @@ def main():
     e2e_ms = float(t2.item()) / args.steps
     e2e = {"value": S / (e2e_ms * 1e-3), "unit": "split-scores/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(codes_pin.numel()) * world, "d2h_bytes_per_step": S * 8,
-           "call": "engine.pack + count_patterns + CountScorer.score per split" if args.workload == "c2" else
-                   "engine.pack + pair_raw/pair_finalize + subflatten_scores"}
+           "call": {"c2": "engine.pack + count_patterns + CountScorer.score_many",
+                    "c4": "engine.pack_wide + count_patterns_wide + thin_split_scores"}.get(
+                        args.workload, "engine.pack + pair_raw/pair_finalize + subflatten_scores")}
 
     # ---- roofline of the dominant kernel, measured live with CUDA events on the launch stream ----
     peaks = {}
@@ -344,6 +373,14 @@ def main():
                 "executed_frac_of_algorithmic": tiles_done / tiles_all,
                 "note": "algorithmic flops = full 2*R^2*C; the kernel computes only the 272 of 512 tiles touching the upper "
                         "triangle and mirrors the rest"}
+    elif args.workload == "c4" and prof["count"]:
+        ms = float(np.mean([a.elapsed_time(b) for a, b, _ in prof["count"]]))
+        nbytes = (se - sb) * 16.0 + (se - sb) / 8.0  # one 128-bit key per site (= N n / 4 at 64 taxa) + validity mask
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        roof = {"kernel": "count_wide_kernel (+ table setup, compaction and merge when sharded)", "bound": "hbm",
+                "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s", "launch_ms": ms,
+                "note": "random 16-byte CAS + 4-byte atomic per distinct pattern: DRAM-transaction bound, not streaming bound"}
     elif args.workload != "c2" and prof["pairs"]:
         ms = float(np.mean([a.elapsed_time(b) for a, b, _ in prof["pairs"]]))
         nbytes = (se - sb) * n / 4.0 + (se - sb) / 8.0  # N n / 4 (+ N / 8 validity mask)
@@ -356,7 +393,7 @@ def main():
     if rank == 0:
         out = {"metric": "split_scores_per_sec", "value": value, "unit": "split-scores/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-               "vs_baseline": None, "dtype": "u8" if args.workload == "c2" else "f64", "data": "synthetic",
+               "vs_baseline": None, "dtype": {"c2": "u8", "c4": "u128"}.get(args.workload, "f64"), "data": "synthetic",
                "config": {"workload": wl["desc"], "taxa": n, "sites": N, "splits": S, "l2": "flushed between timed steps (256 MB fill)",
                           "parallelism": f"sites+splits sharded x{world}"},
                "sites_per_sec": (N / (count_ms * 1e-3)) if count_ms else N / (ms_per_step * 1e-3),

@@ -102,6 +102,38 @@ def get_pattern_counts(sequences):
     return {p: int(c) for p, c in zip(pats, counts)}, usable
 
 
+def get_pattern_counts_wide(codes):
+    """parsers/fasta.py:48-63 for any number of taxa (no uint64 key): {pattern: count} in first-occurrence order,
+    usable length.  Patterns are compared as byte rows."""
+    valid = (codes <= 3).all(axis=0)
+    rows = np.ascontiguousarray(codes[:, valid].T)
+    uniq, first, counts = np.unique(rows, axis=0, return_index=True, return_counts=True)
+    order = np.argsort(first, kind="stable")
+    lut = np.frombuffer(STATES.encode(), dtype=np.uint8)
+    pats = [lut[r].tobytes().decode("ascii") for r in uniq[order]]
+    return dict(zip(pats, counts[order].tolist())), int(valid.sum())
+
+
+def flattening_reduced_from_dict(pattern_values, idx_a, idx_b):
+    """constructions.py:31-55 on a {pattern: value} dict for any number of taxa (row / column indices as python ints:
+    the reference's own arithmetic, __index_of :166-171)."""
+    def index_of(pat, idx):
+        v = 0
+        for t in idx:
+            v = v * 4 + STATES.index(pat[t])
+        return v
+    cells = {}
+    for pat, val in pattern_values.items():
+        cells[(index_of(pat, idx_a), index_of(pat, idx_b))] = val  # assignment: the last pattern wins a cell (:43)
+    rows = sorted({r for r, _ in cells})
+    cols = sorted({c for _, c in cells})
+    ri, ci = {r: i for i, r in enumerate(rows)}, {c: i for i, c in enumerate(cols)}
+    out = np.zeros((len(rows), len(cols)))
+    for (r, c), v in cells.items():
+        out[ri[r], ci[c]] = v
+    return out
+
+
 def pattern_counts_to_probs(patterns, seq_len):
     """parsers/fasta.py:66-70 -- one IEEE division per pattern."""
     return {k: v / seq_len for k, v in patterns.items()}

@@ -139,3 +139,21 @@ def pair_tables_sharded(aln, rank, world, group=None, as_counts=False):
     if world > 1:
         dist.all_reduce(raw, group=group)
     return engine.pair_finalize(raw, aln.n, 0.0 if as_counts else float(int(raw[-1].item())))
+
+
+def count_patterns_wide_sharded(wide, valid, n, N, rank, world, group=None, local=False):
+    """128-bit-key pattern table of the whole alignment: every rank compresses its site range (or its local shard),
+    the per-rank (key, count) lists are all-gathered and merged into one table on every rank.  At 64 taxa nearly
+    every site is a distinct pattern, so this exchange moves about as many bytes as the packed input."""
+    from . import engine
+    b, e = (0, N) if local else shard_range(N, rank, world, 32)
+    mine = engine.count_patterns_wide(wide, valid, n, N, b, e)
+    if world == 1:
+        return mine
+    keys, counts = mine.compact(sort=False)
+    lo = all_gather_varlen(keys[:, 0].contiguous(), group)
+    hi = all_gather_varlen(keys[:, 1].contiguous(), group)
+    cnt = all_gather_varlen(counts, group)
+    usable = torch.tensor([int(mine.divisor)], dtype=torch.int64, device=lo.device)
+    dist.all_reduce(usable, group=group)
+    return engine.merge_wide_tables(n, torch.stack([lo, hi], dim=1), cnt, int(usable.item()))

@@ -656,3 +656,119 @@ def marginalise(table, idx):
         return PatternTable(len(idx), uniq, counts=acc.to(torch.int32), divisor=table.divisor)
     acc = torch.zeros(len(uniq), dtype=torch.float64, device=rows.device).index_add_(0, inv, table.values)
     return PatternTable(len(idx), uniq, values=acc)
+
+
+# --------------------------------------------------------------------------------------------
+# wide keys: up to 64 taxa (BASELINE config 4)
+# --------------------------------------------------------------------------------------------
+class WideTable:
+    """Hashed pattern table with 128-bit keys (two uint64 words {lo, hi} per key).  `hkeys` / `hcounts` are the
+    open-addressing table itself (kept because the thin-split Gram looks patterns up in it), `special` the count
+    of the all-ones key (the all-T pattern at exactly 64 taxa doubles as the EMPTY marker)."""
+
+    def __init__(self, n, hkeys, hcounts, cap, special, usable, taxa=None):
+        self.n, self.hkeys, self.hcounts, self.cap, self.special = n, hkeys, hcounts, cap, special
+        self.divisor = float(usable)
+        self.taxa = tuple(taxa) if taxa is not None else None
+
+    def compact(self, sort=True):
+        """(keys int64 [P, 2] = {lo, hi}, counts int32 [P]); sorted ascending as unsigned 128-bit numbers
+        (= lexicographic A<C<G<T pattern order) when sort=True."""
+        num = _zeros(1, torch.int64)
+        used = int((self.hcounts != 0).sum().item())
+        keys, counts = _empty((max(used, 1), 2), torch.int64), _empty(max(used, 1), torch.int32)
+        call("spb_compact_hash_wide", _p(self.hkeys), _p(self.hcounts), self.cap, _p(keys), _p(counts), max(used, 1), _p(num), _st())
+        P = int(num.item())
+        keys, counts = keys[:P], counts[:P]
+        sp = int(self.special.item())
+        if sp:  # the all-ones pattern lives outside the table
+            keys = torch.cat([keys, torch.full((1, 2), -1, dtype=torch.int64, device=keys.device)])
+            counts = torch.cat([counts, torch.tensor([sp], dtype=torch.int32, device=keys.device)])
+        if sort and keys.shape[0] > 1:
+            flip = torch.tensor(-(1 << 63), dtype=torch.int64, device=keys.device)  # unsigned order through signed sorts
+            o1 = torch.sort(keys[:, 0] ^ flip, stable=True).indices
+            o2 = torch.sort((keys[:, 1] ^ flip)[o1], stable=True).indices
+            order = o1[o2]
+            keys, counts = keys[order], counts[order]
+        return keys, counts
+
+    def to_dict(self, as_counts=True):
+        keys, counts = self.compact()
+        k = keys.cpu().numpy().view(np.uint64)
+        c = counts.cpu().numpy().view(np.uint32)
+        out = {}
+        for (lo, hi), cnt in zip(k, c):
+            v = (int(hi) << 64) | int(lo)
+            pat = "".join(STATES[(v >> (2 * (self.n - 1 - j))) & 3] for j in range(self.n))
+            out[pat] = int(cnt) if as_counts or self.divisor <= 0 else int(cnt) / self.divisor
+        return out
+
+
+def pack_wide(chars, is_ascii=False):
+    """chars uint8 [n, N] (device tensor or host array) -> (wide int64 [N, 2], valid int32 [Wp], n, N)."""
+    if not isinstance(chars, torch.Tensor):
+        chars = torch.from_numpy(np.ascontiguousarray(np.asarray(chars, dtype=np.uint8))).to(device())
+    chars = chars.contiguous()
+    n, N = int(chars.shape[0]), int(chars.shape[1])
+    wide = _empty((max(N, 1), 2), torch.int64)
+    valid = _zeros(int(lib.spb_plane_words(N)), torch.int32)
+    if N:
+        call("spb_pack_wide", _p(chars), n, N, N, int(bool(is_ascii)), _p(wide), _p(valid), _st())
+    return wide, valid, n, N
+
+
+def _new_wide_table(entries):
+    cap = 1024
+    while cap < 2 * max(int(entries), 1):
+        cap *= 2
+    hk = torch.full((cap, 2), -1, dtype=torch.int64, device=device())
+    return hk, _zeros(cap, torch.int32), cap
+
+
+def count_patterns_wide(wide, valid, n, N, site_begin=0, site_end=None, taxa=None):
+    """Pattern compression with 128-bit keys (n <= 64): one pass, open-addressing table."""
+    site_end = N if site_end is None else site_end
+    hk, hc, cap = _new_wide_table(site_end - site_begin)
+    special, usable, ovf = _zeros(1, torch.int64), _zeros(1, torch.int64), _zeros(1, torch.int32)
+    if site_end > site_begin:
+        call("spb_count_hash_wide", _p(wide), _p(valid), site_begin, site_end, _p(hk), _p(hc), cap, _p(special), _p(usable), _p(ovf), _st())
+    if int(ovf.item()):
+        raise MemoryError("splitp_b200: pattern hash table overflow")
+    return WideTable(n, hk, hc, cap, special, int(usable.item()), taxa)
+
+
+def merge_wide_tables(n, keys, counts, usable, taxa=None):
+    """One table from a concatenated (key, count) list (the multi-GPU merge of hashed wide tables)."""
+    hk, hc, cap = _new_wide_table(keys.shape[0])
+    special, ovf = _zeros(1, torch.int64), _zeros(1, torch.int32)
+    if keys.shape[0]:
+        call("spb_hash_merge_wide", _p(keys.contiguous()), _p(counts.contiguous()), int(keys.shape[0]), _p(hk), _p(hc), cap, _p(special),
+             _p(ovf), _st())
+    if int(ovf.item()):
+        raise MemoryError("splitp_b200: pattern hash table overflow")
+    return WideTable(n, hk, hc, cap, special, usable, taxa)
+
+
+def thin_split_scores(table, thin_sides):
+    """Scores of the splits {side} | {all other taxa} for sides of 1 or 2 taxon positions: exact Gram of the REDUCED
+    flattening (4^a rows, one column per distinct pattern of the other taxa) from hash lookups, then the Jacobi
+    scorer.  Sides of one taxon give a 4-row matrix, hence score 0 like the reference."""
+    out = _empty(len(thin_sides), torch.float64)
+    G = _empty((len(thin_sides), 16, 16), torch.float64)
+    by_a = {1: [], 2: []}
+    for s, side in enumerate(thin_sides):
+        side = list(side)
+        if len(side) not in (1, 2):
+            raise NotImplementedError("thin_split_scores: the thin side must have 1 or 2 taxa")
+        call("spb_thin_gram_wide", _p(table.hkeys), _p(table.hcounts), table.cap, _p(table.special), table.n, bytes(side), len(side),
+             _p(G[s]), _st())
+        by_a[len(side)].append(s)
+    for a, members in by_a.items():
+        if not members:
+            continue
+        idx = torch.tensor(members, dtype=torch.int64, device=out.device)
+        R = 4 ** a
+        # the Gram of entry s occupies the leading R*R doubles of G[s] with row stride R: repack to [R, R] matrices
+        Gs = G[idx].reshape(len(members), 256)[:, :R * R].reshape(len(members), R, R).contiguous()
+        out.index_copy_(0, idx, score_gram(Gs, R))
+    return out

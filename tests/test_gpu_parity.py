@@ -435,6 +435,58 @@ def test_split_score_flat_spectrum(sp, oracle, k, L, kind):
     assert_score(sp.split_score(A), oracle.split_score(A))
 
 
+
+# ---------------------------------------------------------------------------------------------
+# wide keys (up to 64 taxa, BASELINE config 4)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,N,seed,p_bad", [(64, 20_000, 71, 0.0005), (40, 50_001, 72, 0.0), (33, 777, 73, 0.01), (12, 30_000, 74, 0.0)])
+def test_wide_pattern_counts(eng, oracle, n, N, seed, p_bad):
+    codes = random_codes(n, N, seed, p_bad)
+    if n == 64:
+        codes[:, :37] = 3  # the all-T pattern: its key is all ones = the table's EMPTY marker
+    wide, valid, n_, N_ = eng.pack_wide(codes)
+    tab = eng.count_patterns_wide(wide, valid, n_, N_)
+    ref, usable = oracle.get_pattern_counts_wide(codes)
+    assert int(tab.divisor) == usable
+    got = tab.to_dict()
+    assert got == ref
+    assert list(got) == sorted(ref, key=lambda p: [oracle.STATES.index(c) for c in p])  # lexicographic A<C<G<T
+    # two site ranges merged = the whole alignment (the multi-GPU path on one device)
+    t1 = eng.count_patterns_wide(wide, valid, n_, N_, 0, (N // 64) * 32)
+    t2 = eng.count_patterns_wide(wide, valid, n_, N_, (N // 64) * 32, N)
+    k1, c1 = t1.compact(sort=False)
+    k2, c2 = t2.compact(sort=False)
+    merged = eng.merge_wide_tables(n_, torch.cat([k1, k2]), torch.cat([c1, c2]), usable)
+    assert merged.to_dict() == ref
+
+
+@pytest.mark.parametrize("n,N,seed", [(64, 30_000, 81), (36, 100_000, 82), (10, 50_000, 83)])
+def test_thin_split_scores(sp, eng, oracle, n, N, seed):
+    """Reduced flattenings of 2|n-2 (and 1|n-1) splits from the hashed wide table: exact Gram, scores vs LAPACK."""
+    tree = sp.trees.balanced_tree(n, 0.02)
+    codes = sp.simulation.simulate_codes(tree, sp.simulation.GTR.JukesCantor(0.5), N, seed=seed)
+    wide, valid, n_, N_ = eng.pack_wide(codes)
+    tab = eng.count_patterns_wide(wide, valid, n_, N_)
+    ref, usable = oracle.get_pattern_counts_wide(codes.cpu().numpy())
+    sides = [[0, 1], [2, 5], [n - 2, n - 1], [1, n // 2], [3]]
+    got = eng.thin_split_scores(tab, sides).cpu().numpy()
+    for s, ia in enumerate(sides):
+        ib = [t for t in range(n) if t not in ia]
+        F = oracle.flattening_reduced_from_dict(ref, ia, ib)
+        G = torch.empty((16, 16), dtype=torch.float64, device="cuda")
+        eng.call("spb_thin_gram_wide", eng._p(tab.hkeys), eng._p(tab.hcounts), tab.cap, eng._p(tab.special), n, bytes(ia), len(ia),
+                 eng._p(G), eng._st())
+        R = 4 ** len(ia)
+        Gd = G.cpu().numpy().reshape(-1)[:R * R].reshape(R, R)
+        # rows of the reduced matrix = the USED row patterns, in ascending order: compare on those
+        used = [r for r in range(R) if Gd[r, r] > 0]
+        assert len(used) == F.shape[0]
+        np.testing.assert_array_equal(Gd[np.ix_(used, used)], F @ F.T)
+        assert_score(got[s], oracle.split_score(F)) if len(ia) == 2 else None
+        if len(ia) == 1:
+            assert got[s] == 0.0
+
+
 # ---------------------------------------------------------------------------------------------
 # full-size properties (BASELINE.json configs 2 and 3): size-independent invariants
 # ---------------------------------------------------------------------------------------------

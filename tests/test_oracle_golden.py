@@ -172,3 +172,20 @@ def test_pair_tables_from_codes_matches_pattern_route(oracle):
     S1 = oracle.subflattening(keys, counts / usable, 7, [0, 3, 5], [1, 2, 4, 6])
     S2 = oracle.subflattening_from_tables(oracle.pair_tables_from_codes(codes)[0], 1.0, [0, 3, 5], [1, 2, 4, 6])
     np.testing.assert_allclose(S1, S2, rtol=1e-12, atol=1e-14)
+
+
+def test_wide_oracle_routes_agree(oracle):
+    """The any-number-of-taxa routes (byte-row counting, dict-based reduced flattening) equal the uint64-key routes."""
+    rng = np.random.default_rng(9)
+    base = rng.integers(0, 4, size=(9, 40))
+    codes = base[:, rng.integers(0, 40, size=3000)].astype(np.uint8)
+    codes[rng.random(codes.shape) < 0.03] = rng.integers(0, 4)
+    codes[rng.random(codes.shape) < 0.002] = 255
+    d, usable = oracle.get_pattern_counts_wide(codes)
+    keys, counts, us = oracle.get_pattern_counts_arrays(codes)
+    assert us == usable and d == dict(zip(oracle.keys_to_patterns(keys, 9), counts.tolist()))
+    assert list(d) == oracle.keys_to_patterns(keys, 9)  # first-occurrence order
+    for ia in ([0, 1], [7], [3, 8]):
+        ib = [t for t in range(9) if t not in ia]
+        np.testing.assert_array_equal(oracle.flattening_reduced_from_dict(d, ia, ib),
+                                      oracle.flattening_reduced(keys, counts.astype(float), 9, ia, ib))
