@@ -50,20 +50,32 @@ def simulate_codes(tree, model, sequence_length, seed=0, device=None):
     gen = torch.Generator(device=device)
     gen.manual_seed(int(seed))
     N = int(sequence_length)
-    states = {0: torch.randint(0, 4, (N,), generator=gen, device=device, dtype=torch.int64)}
-    cache = {}
+    states = {0: torch.randint(0, 4, (N,), generator=gen, device=device, dtype=torch.uint8)}
+    pending = {}  # node -> number of children still to be drawn (inner states are freed as soon as possible)
     for node in range(1, len(tree.parent)):
+        pending[tree.parent[node]] = pending.get(tree.parent[node], 0) + 1
+    cache = {}
+    chunk = 1 << 24  # bounds the float64 temporaries to a few hundred MB whatever the alignment length
+    for node in range(1, len(tree.parent)):  # parents precede their children in the node numbering
         t = tree.branch_length[node]
         if t not in cache:
             M = np.asarray(model.transition_matrix(t), dtype=np.float64)  # column = parent state
             cache[t] = torch.from_numpy(np.cumsum(M, axis=0).T.copy()).to(device)  # [parent, cumulative child]
         cdf = cache[t]
-        parent = states[tree.parent[node]]
-        u = torch.rand(N, generator=gen, device=device, dtype=torch.float64)
-        c = cdf[parent]  # [N, 4]
-        states[node] = ((u >= c[:, 0]).to(torch.int64) + (u >= c[:, 1]).to(torch.int64) + (u >= c[:, 2]).to(torch.int64))
+        par = tree.parent[node]
+        child = torch.empty(N, dtype=torch.uint8, device=device)
+        u = torch.rand(N, generator=gen, device=device, dtype=torch.float64) if N <= chunk else None
+        for b in range(0, N, chunk):
+            e = min(N, b + chunk)
+            uu = u[b:e] if u is not None else torch.rand(e - b, generator=gen, device=device, dtype=torch.float64)
+            c = cdf[states[par][b:e].to(torch.int64)]  # [len, 4]
+            child[b:e] = ((uu >= c[:, 0]).to(torch.uint8) + (uu >= c[:, 1]).to(torch.uint8) + (uu >= c[:, 2]).to(torch.uint8))
+        states[node] = child
+        pending[par] -= 1
+        if pending[par] == 0 and par not in tree.names:
+            del states[par]
     row = {name: node for node, name in tree.names.items()}
-    return torch.stack([states[row[t]] for t in tree.taxa]).to(torch.uint8)
+    return torch.stack([states[row[t]] for t in tree.taxa])
 
 
 def generate_alignment(tree, model, sequence_length, seed=0):
