@@ -208,15 +208,17 @@ __global__ void __launch_bounds__(256) thin_gram_wide_kernel(const unsigned long
     }
     uint32_t r1 = 0;
     for (int t = 0; t < sp.a; ++t) r1 = (r1 << 2) | get_digit(p, sp.shift[t]);
-    for (int r2 = 0; r2 < R; ++r2) {
-      uint32_t cq;
-      if ((uint32_t)r2 == r1) cq = cp;
-      else {
-        Key128 q = p;
-        for (int t = 0; t < sp.a; ++t) q = set_digit(q, sp.shift[t], ((uint32_t)r2 >> (2 * (sp.a - 1 - t))) & 3u);
-        cq = table_find(hkeys, hcounts, (uint64_t)cap - 1, spc, q);
+    // every unordered pair of patterns that differ only in their row part is found once, from its smaller row
+    atomicAdd(&sG[r1 * 16 + r1], (double)cp * (double)cp);
+    for (int r2 = (int)r1 + 1; r2 < R; ++r2) {
+      Key128 q = p;
+      for (int t = 0; t < sp.a; ++t) q = set_digit(q, sp.shift[t], ((uint32_t)r2 >> (2 * (sp.a - 1 - t))) & 3u);
+      const uint32_t cq = table_find(hkeys, hcounts, (uint64_t)cap - 1, spc, q);
+      if (cq) {
+        const double v = (double)cp * (double)cq;  // integers: exact and order independent below 2^53
+        atomicAdd(&sG[r1 * 16 + r2], v);
+        atomicAdd(&sG[r2 * 16 + r1], v);
       }
-      if (cq) atomicAdd(&sG[r1 * 16 + r2], (double)cp * (double)cq);  // integers: exact and order independent below 2^53
     }
   }
   __syncthreads();
