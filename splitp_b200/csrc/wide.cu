@@ -189,9 +189,11 @@ __device__ __forceinline__ Key128 set_digit(Key128 k, int shift, uint32_t d) {
 __global__ void __launch_bounds__(256) thin_gram_wide_kernel(const unsigned long long* __restrict__ hkeys, const uint32_t* __restrict__ hcounts,
                                                              int64_t cap, const unsigned long long* __restrict__ special, ThinSplit sp,
                                                              double* __restrict__ G) {
-  __shared__ double sG[16 * 16];
+  // per-CTA partial Gram in 64-bit integers: shared-memory integer atomics are native (a double atomicAdd in shared
+  // memory is a CAS loop, which collapses on the few row patterns that carry most sites); sum count^2 <= N^2 < 2^64
+  __shared__ unsigned long long sG[16 * 16];
   const int R = 1 << (2 * sp.a);
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) sG[i] = 0.0;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sG[i] = 0ull;
   __syncthreads();
   const unsigned long long spc = *special;
   // slot index cap stands for the all-ones pattern, which lives outside the table
@@ -209,13 +211,13 @@ __global__ void __launch_bounds__(256) thin_gram_wide_kernel(const unsigned long
     uint32_t r1 = 0;
     for (int t = 0; t < sp.a; ++t) r1 = (r1 << 2) | get_digit(p, sp.shift[t]);
     // every unordered pair of patterns that differ only in their row part is found once, from its smaller row
-    atomicAdd(&sG[r1 * 16 + r1], (double)cp * (double)cp);
+    atomicAdd(&sG[r1 * 16 + r1], (unsigned long long)cp * (unsigned long long)cp);
     for (int r2 = (int)r1 + 1; r2 < R; ++r2) {
       Key128 q = p;
       for (int t = 0; t < sp.a; ++t) q = set_digit(q, sp.shift[t], ((uint32_t)r2 >> (2 * (sp.a - 1 - t))) & 3u);
       const uint32_t cq = table_find(hkeys, hcounts, (uint64_t)cap - 1, spc, q);
       if (cq) {
-        const double v = (double)cp * (double)cq;  // integers: exact and order independent below 2^53
+        const unsigned long long v = (unsigned long long)cp * (unsigned long long)cq;
         atomicAdd(&sG[r1 * 16 + r2], v);
         atomicAdd(&sG[r2 * 16 + r1], v);
       }
@@ -224,8 +226,8 @@ __global__ void __launch_bounds__(256) thin_gram_wide_kernel(const unsigned long
   __syncthreads();
   for (int i = threadIdx.x; i < R * R; i += blockDim.x) {
     const int r1 = i / R, r2 = i - r1 * R;
-    const double v = sG[r1 * 16 + r2];
-    if (v != 0.0) atomicAdd(G + i, v);
+    const unsigned long long v = sG[r1 * 16 + r2];
+    if (v) atomicAdd(G + i, (double)v);  // integer-valued partial sums: exact and order independent below 2^53
   }
 }
 
