@@ -69,11 +69,15 @@ __device__ inline void jacobi_eig_smem(double* A, int lda, int k, double* V, int
         if (p > q) { int t = p; p = q; q = t; }
         double app = A[p * lda + p], aqq = A[q * lda + q], apq = A[p * lda + q];
         double c = 1.0, s = 0.0, npp = app, nqq = aqq;
-        double thr = fmax(2.0e-16 * sqrt(fabs(app * aqq)), abs_floor);
-        if (fabs(apq) > thr) {
-          double tau = (aqq - app) / (2.0 * apq);
-          double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = rsqrt(1.0 + t * t);
+        // rotate when |apq| > max(2e-16 sqrt|app aqq|, floor), compared on squares (no square root on this path)
+        const double apq2 = apq * apq;
+        if (apq2 > fmax(4.0e-32 * fabs(app * aqq), abs_floor * abs_floor)) {
+          // t = tan(theta) of the smaller rotation angle: 2 apq / (d + sign(d) sqrt(d^2 + 4 apq^2)), d = aqq - app
+          // (the usual sign(tau) / (|tau| + sqrt(1 + tau^2)) with one square root and one division)
+          const double d = aqq - app;
+          const double h = sqrt(fma(d, d, 4.0 * apq2));
+          const double t = (2.0 * apq) / (d >= 0.0 ? d + h : d - h);
+          c = rsqrt(fma(t, t, 1.0));
           s = t * c;
           npp = app - t * apq;
           nqq = aqq + t * apq;
