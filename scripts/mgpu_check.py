@@ -32,6 +32,24 @@ for n, N in ((10, 300_001), (16, 500_000)):
         full = eng.score_splits_counts(ref, idx[:40])
         mine = eng.score_splits_counts(got, idx[:40][spd.shard_range(40, rank, world)[0]:spd.shard_range(40, rank, world)[1]])
         assert torch.equal(spd.gather_scores(mine, 40, rank, world), full)
+# wide (128-bit) keys: sharded compression + merge equals the single-GPU table; thin-split scores agree
+n, N = 64, 200_001
+tree = sp.trees.balanced_tree(n, 0.02)
+codes = sp.simulation.simulate_codes(tree, sp.simulation.GTR.JukesCantor(0.5), N, seed=64)
+codes[:, :11] = 3  # the all-T pattern (EMPTY marker of the wide table)
+wide, valid, n_, N_ = eng.pack_wide(codes)
+ref = eng.count_patterns_wide(wide, valid, n_, N_)
+got = spd.count_patterns_wide_sharded(wide, valid, n_, N_, rank, world)
+kr, cr = ref.compact()
+kg, cg = got.compact()
+assert torch.equal(kr, kg) and torch.equal(cr, cg) and ref.divisor == got.divisor
+b, e = spd.shard_range(N, rank, world, 32)
+lw, lv, _, lN = eng.pack_wide(codes[:, b:e].contiguous())
+got2 = spd.count_patterns_wide_sharded(lw, lv, n_, lN, rank, world, local=True)
+kg2, cg2 = got2.compact()
+assert torch.equal(kr, kg2) and torch.equal(cr, cg2)
+sides = [[0, 1], [5, 40], [62, 63]]
+assert torch.equal(eng.thin_split_scores(ref, sides), eng.thin_split_scores(got2, sides))
 if world > 1:
     dist.barrier()
 print(f"rank {rank}/{world}: multi-GPU parity ok", flush=True)
