@@ -99,15 +99,19 @@ int spb_pack_wide(const uint8_t* d_chars, int n_taxa, int64_t n_sites, int64_t r
                   uint32_t* d_valid, void* stream);
 /* get_pattern_counts (parsers/fasta.py:48-63) with 128-bit keys: open addressing, d_hkeys uint64 [cap][2] filled with
  * 0xFF bytes (16-byte aligned), d_hcounts uint32 [cap] zeroed, cap = power of 2.  The all-ones key (all-T pattern at
- * 64 taxa) is the EMPTY marker, its count goes to *d_special (uint64, zeroed by the caller). */
+ * 64 taxa) is the EMPTY marker, its count goes to *d_special (uint64, zeroed by the caller).
+ * d_hfirst (optional, uint32 [cap + 1], 0xFF filled) receives the first site of every pattern (dict insertion order);
+ * its last cell belongs to the all-ones key. */
 int spb_count_hash_wide(const uint64_t* d_wide, const uint32_t* d_valid, int64_t site_begin, int64_t site_end,
-                        uint64_t* d_hkeys, uint32_t* d_hcounts, int64_t cap, uint64_t* d_special, uint64_t* d_usable,
+                        uint64_t* d_hkeys, uint32_t* d_hcounts, uint32_t* d_hfirst, int64_t cap, uint64_t* d_special,
+                        uint64_t* d_usable, uint32_t* d_overflow, void* stream);
+int spb_hash_merge_wide(const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_first, int64_t num,
+                        uint64_t* d_hkeys, uint32_t* d_hcounts, uint32_t* d_hfirst, int64_t cap, uint64_t* d_special,
                         uint32_t* d_overflow, void* stream);
-int spb_hash_merge_wide(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, uint64_t* d_hkeys, uint32_t* d_hcounts,
-                        int64_t cap, uint64_t* d_special, uint32_t* d_overflow, void* stream);
-/* Non-empty slots -> (keys uint64 [capacity][2], counts) in arbitrary order; *d_num (uint64) = their number. */
-int spb_compact_hash_wide(const uint64_t* d_hkeys, const uint32_t* d_hcounts, int64_t cap, uint64_t* d_keys, uint32_t* d_counts,
-                          int64_t capacity, uint64_t* d_num, void* stream);
+/* Non-empty slots -> (keys uint64 [capacity][2], counts, optional first) in arbitrary order; *d_num = their number. */
+int spb_compact_hash_wide(const uint64_t* d_hkeys, const uint32_t* d_hcounts, const uint32_t* d_hfirst, int64_t cap,
+                          uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first, int64_t capacity, uint64_t* d_num,
+                          void* stream);
 /* Exact Gram F F^T (double [4^a][4^a], a = 1 or 2) of the reduced flattening (constructions.py:31-55) of the split
  * {h_idx_a} | {all other taxa}, computed from the hashed table by one lookup per (pattern, row). */
 int spb_thin_gram_wide(const uint64_t* d_hkeys, const uint32_t* d_hcounts, int64_t cap, const uint64_t* d_special, int n_taxa,

@@ -64,9 +64,9 @@ PROTOTYPES = {
     "spb_compact_hash": (_i, [_p, _p, _p, _l, _p, _p, _p, _l, _p, _p, _p]),
     "spb_hash_merge": (_i, [_p, _p, _p, _l, _p, _p, _p, _l, _p, _p]),
     "spb_pack_wide": (_i, [_p, _i, _l, _l, _i, _p, _p, _p]),
-    "spb_count_hash_wide": (_i, [_p, _p, _l, _l, _p, _p, _l, _p, _p, _p, _p]),
-    "spb_hash_merge_wide": (_i, [_p, _p, _l, _p, _p, _l, _p, _p, _p]),
-    "spb_compact_hash_wide": (_i, [_p, _p, _l, _p, _p, _l, _p, _p]),
+    "spb_count_hash_wide": (_i, [_p, _p, _l, _l, _p, _p, _p, _l, _p, _p, _p, _p]),
+    "spb_hash_merge_wide": (_i, [_p, _p, _p, _l, _p, _p, _p, _l, _p, _p, _p]),
+    "spb_compact_hash_wide": (_i, [_p, _p, _p, _l, _p, _p, _p, _l, _p, _p]),
     "spb_thin_gram_wide": (_i, [_p, _p, _l, _p, _i, C.c_char_p, _i, _p, _p]),
     "spb_flatten_coo": (_i, [_p, _l, _sp, _p, _p, _p]),
     "spb_flatten_dense": (_i, [_p, _p, _i, _d, _l, _sp, _p, _p]),

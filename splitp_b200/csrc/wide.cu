@@ -54,19 +54,28 @@ __device__ __forceinline__ uint64_t hash128(Key128 k) { return mix64(k.lo ^ mix6
 struct WideTable {
   unsigned long long* keys;  // [cap][2] = {lo, hi}, EMPTY = all ones
   uint32_t* counts;          // [cap]
+  uint32_t* first;           // [cap + 1] first site of every pattern (optional; slot cap = the all-ones key)
   uint64_t mask;
   unsigned long long* special;  // count of the all-ones key
   uint32_t* overflow;
 };
 
-__device__ __forceinline__ void table_add(const WideTable& t, Key128 key, uint32_t c) {
-  if (is_empty(key)) { atomicAdd(t.special, (unsigned long long)c); return; }
+__device__ __forceinline__ void table_add(const WideTable& t, Key128 key, uint32_t c, uint32_t f) {
+  if (is_empty(key)) {
+    atomicAdd(t.special, (unsigned long long)c);
+    if (t.first) atomicMin(t.first + t.mask + 1, f);
+    return;
+  }
   uint64_t h = hash128(key) & t.mask;
   for (uint64_t probe = 0; probe <= t.mask; ++probe) {
     // One 128-bit CAS per probe: it returns the slot's previous content atomically (a 16-byte key cannot be read
     // torn this way while other threads are inserting).  EMPTY -> we inserted; equal -> the key is already there.
     const Key128 k = cas128(t.keys + 2 * h, Key128{kAll, kAll}, key);
-    if (is_empty(k) || same(k, key)) { atomicAdd(t.counts + h, c); return; }
+    if (is_empty(k) || same(k, key)) {
+      atomicAdd(t.counts + h, c);
+      if (t.first) atomicMin(t.first + h, f);
+      return;
+    }
     h = (h + 1) & t.mask;
   }
   atomicExch(t.overflow, 1u);
@@ -138,20 +147,22 @@ __global__ void __launch_bounds__(256) count_wide_kernel(const unsigned long lon
     lk.hi = __shfl_sync(0xFFFFFFFFu, key.hi, lead);
     const bool grp = ok && same(key, lk);
     const unsigned grpmask = __ballot_sync(0xFFFFFFFFu, grp);
-    if (ok && (!grp || lane == lead)) table_add(t, key, lane == lead ? (uint32_t)__popc(grpmask) : 1u);
+    if (ok && (!grp || lane == lead)) table_add(t, key, lane == lead ? (uint32_t)__popc(grpmask) : 1u, (uint32_t)s);  // lead = earliest site
   }
   for (int o = 16; o > 0; o >>= 1) my_usable += __shfl_xor_sync(0xFFFFFFFFu, my_usable, o);
   if (lane == 0 && my_usable && usable) atomicAdd(usable, my_usable);
 }
 
-__global__ void merge_wide_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t num, WideTable t) {
+__global__ void merge_wide_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ counts,
+                                  const uint32_t* __restrict__ first, int64_t num, WideTable t) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < num) table_add(t, Key128{keys[2 * i], keys[2 * i + 1]}, counts[i]);
+  if (i < num) table_add(t, Key128{keys[2 * i], keys[2 * i + 1]}, counts[i], first ? first[i] : 0xFFFFFFFFu);
 }
 
 // unordered compaction (the caller sorts): one atomic per warp
-__global__ void compact_wide_kernel(const unsigned long long* __restrict__ hkeys, const uint32_t* __restrict__ hcounts, int64_t cap,
-                                    unsigned long long* keys, uint32_t* counts, int64_t capacity, unsigned long long* num) {
+__global__ void compact_wide_kernel(const unsigned long long* __restrict__ hkeys, const uint32_t* __restrict__ hcounts,
+                                    const uint32_t* __restrict__ hfirst, int64_t cap, unsigned long long* keys, uint32_t* counts,
+                                    uint32_t* first, int64_t capacity, unsigned long long* num) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   Key128 k{kAll, kAll};
@@ -168,6 +179,7 @@ __global__ void compact_wide_kernel(const unsigned long long* __restrict__ hkeys
       keys[2 * o] = k.lo;
       keys[2 * o + 1] = k.hi;
       counts[o] = hcounts[i];
+      if (first) first[o] = hfirst ? hfirst[i] : 0xFFFFFFFFu;
     }
   }
 }
@@ -254,14 +266,14 @@ extern "C" int spb_pack_wide(const uint8_t* d_chars, int n_taxa, int64_t n_sites
 }
 
 extern "C" int spb_count_hash_wide(const uint64_t* d_wide, const uint32_t* d_valid, int64_t site_begin, int64_t site_end,
-                                   uint64_t* d_hkeys, uint32_t* d_hcounts, int64_t cap, uint64_t* d_special, uint64_t* d_usable,
-                                   uint32_t* d_overflow, void* stream) {
+                                   uint64_t* d_hkeys, uint32_t* d_hcounts, uint32_t* d_hfirst, int64_t cap, uint64_t* d_special,
+                                   uint64_t* d_usable, uint32_t* d_overflow, void* stream) {
   SPB_REQUIRE(d_wide && d_valid && d_special && d_overflow, "spb_count_hash_wide: NULL buffer");
   int rc = check_table(d_hkeys, d_hcounts, cap, "spb_count_hash_wide");
   if (rc) return rc;
-  SPB_REQUIRE(site_begin >= 0 && site_end >= site_begin, "spb_count_hash_wide: bad site range");
+  SPB_REQUIRE(site_begin >= 0 && site_end >= site_begin && site_end < (1ll << 32), "spb_count_hash_wide: bad site range");
   if (site_end == site_begin) return SPB_OK;
-  WideTable t{(unsigned long long*)d_hkeys, d_hcounts, (uint64_t)cap - 1, (unsigned long long*)d_special, d_overflow};
+  WideTable t{(unsigned long long*)d_hkeys, d_hcounts, d_hfirst, (uint64_t)cap - 1, (unsigned long long*)d_special, d_overflow};
   int64_t words = ((site_end + 31) >> 5) - (site_begin >> 5);
   int64_t grid = (int64_t)sm_count() * 8;
   if (grid > (words + 7) / 8) grid = (words + 7) / 8;
@@ -272,28 +284,32 @@ extern "C" int spb_count_hash_wide(const uint64_t* d_wide, const uint32_t* d_val
   return SPB_OK;
 }
 
-extern "C" int spb_hash_merge_wide(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, uint64_t* d_hkeys, uint32_t* d_hcounts,
-                                   int64_t cap, uint64_t* d_special, uint32_t* d_overflow, void* stream) {
+extern "C" int spb_hash_merge_wide(const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_first, int64_t num,
+                                   uint64_t* d_hkeys, uint32_t* d_hcounts, uint32_t* d_hfirst, int64_t cap, uint64_t* d_special,
+                                   uint32_t* d_overflow, void* stream) {
   SPB_REQUIRE(d_special && d_overflow, "spb_hash_merge_wide: NULL buffer");
   int rc = check_table(d_hkeys, d_hcounts, cap, "spb_hash_merge_wide");
   if (rc) return rc;
   if (num <= 0) return SPB_OK;
   SPB_REQUIRE(d_keys && d_counts, "spb_hash_merge_wide: NULL list");
-  WideTable t{(unsigned long long*)d_hkeys, d_hcounts, (uint64_t)cap - 1, (unsigned long long*)d_special, d_overflow};
-  merge_wide_kernel<<<(unsigned)((num + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)d_keys, d_counts, num, t);
+  WideTable t{(unsigned long long*)d_hkeys, d_hcounts, d_hfirst, (uint64_t)cap - 1, (unsigned long long*)d_special, d_overflow};
+  merge_wide_kernel<<<(unsigned)((num + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)d_keys, d_counts, d_first,
+                                                                                    num, t);
   SPB_LAUNCH_CHECK();
   return SPB_OK;
 }
 
-extern "C" int spb_compact_hash_wide(const uint64_t* d_hkeys, const uint32_t* d_hcounts, int64_t cap, uint64_t* d_keys, uint32_t* d_counts,
-                                     int64_t capacity, uint64_t* d_num, void* stream) {
+extern "C" int spb_compact_hash_wide(const uint64_t* d_hkeys, const uint32_t* d_hcounts, const uint32_t* d_hfirst, int64_t cap,
+                                     uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first, int64_t capacity, uint64_t* d_num,
+                                     void* stream) {
   int rc = check_table(d_hkeys, d_hcounts, cap, "spb_compact_hash_wide");
   if (rc) return rc;
   SPB_REQUIRE(d_keys && d_counts && d_num && capacity >= 0, "spb_compact_hash_wide: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   SPB_CUDA(cudaMemsetAsync(d_num, 0, 8, st));
-  compact_wide_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>((const unsigned long long*)d_hkeys, d_hcounts, cap,
-                                                                   (unsigned long long*)d_keys, d_counts, capacity, (unsigned long long*)d_num);
+  compact_wide_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>((const unsigned long long*)d_hkeys, d_hcounts, d_hfirst, cap,
+                                                                   (unsigned long long*)d_keys, d_counts, d_first, capacity,
+                                                                   (unsigned long long*)d_num);
   SPB_LAUNCH_CHECK();
   return SPB_OK;
 }

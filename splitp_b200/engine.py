@@ -664,44 +664,63 @@ def marginalise(table, idx):
 class WideTable:
     """Hashed pattern table with 128-bit keys (two uint64 words {lo, hi} per key).  `hkeys` / `hcounts` are the
     open-addressing table itself (kept because the thin-split Gram looks patterns up in it), `special` the count
-    of the all-ones key (the all-T pattern at exactly 64 taxa doubles as the EMPTY marker)."""
+    of the all-ones key (the all-T pattern at exactly 64 taxa doubles as the EMPTY marker), `hfirst` (optional,
+    cap + 1 cells) the first site of every pattern."""
 
-    def __init__(self, n, hkeys, hcounts, cap, special, usable, taxa=None):
+    def __init__(self, n, hkeys, hcounts, cap, special, usable, taxa=None, hfirst=None):
         self.n, self.hkeys, self.hcounts, self.cap, self.special = n, hkeys, hcounts, cap, special
+        self.hfirst = hfirst
         self.divisor = float(usable)
         self.taxa = tuple(taxa) if taxa is not None else None
 
-    def compact(self, sort=True):
-        """(keys int64 [P, 2] = {lo, hi}, counts int32 [P]); sorted ascending as unsigned 128-bit numbers
-        (= lexicographic A<C<G<T pattern order) when sort=True."""
+    def compact(self, sort=True, want_first=False):
+        """(keys int64 [P, 2] = {lo, hi}, counts int32 [P][, first int32 [P]]); sorted ascending as unsigned 128-bit
+        numbers (= lexicographic A<C<G<T pattern order) when sort=True."""
+        if want_first and self.hfirst is None:
+            raise ValueError("this table was built without first-site tracking")
         num = _zeros(1, torch.int64)
-        used = int((self.hcounts != 0).sum().item())
-        keys, counts = _empty((max(used, 1), 2), torch.int64), _empty(max(used, 1), torch.int32)
-        call("spb_compact_hash_wide", _p(self.hkeys), _p(self.hcounts), self.cap, _p(keys), _p(counts), max(used, 1), _p(num), _st())
+        used = max(int((self.hcounts != 0).sum().item()), 1)
+        keys, counts = _empty((used, 2), torch.int64), _empty(used, torch.int32)
+        first = _empty(used, torch.int32) if want_first else None
+        call("spb_compact_hash_wide", _p(self.hkeys), _p(self.hcounts), _p(self.hfirst) if want_first else None, self.cap, _p(keys),
+             _p(counts), _p(first), used, _p(num), _st())
         P = int(num.item())
         keys, counts = keys[:P], counts[:P]
+        first = first[:P] if want_first else None
         sp = int(self.special.item())
         if sp:  # the all-ones pattern lives outside the table
             keys = torch.cat([keys, torch.full((1, 2), -1, dtype=torch.int64, device=keys.device)])
             counts = torch.cat([counts, torch.tensor([sp], dtype=torch.int32, device=keys.device)])
+            if want_first:
+                first = torch.cat([first, self.hfirst[self.cap:self.cap + 1]])
         if sort and keys.shape[0] > 1:
             flip = torch.tensor(-(1 << 63), dtype=torch.int64, device=keys.device)  # unsigned order through signed sorts
             o1 = torch.sort(keys[:, 0] ^ flip, stable=True).indices
             o2 = torch.sort((keys[:, 1] ^ flip)[o1], stable=True).indices
             order = o1[o2]
             keys, counts = keys[order], counts[order]
-        return keys, counts
+            first = first[order] if want_first else None
+        return (keys, counts, first) if want_first else (keys, counts)
 
-    def to_dict(self, as_counts=True):
-        keys, counts = self.compact()
+    def _patterns(self, keys):
         k = keys.cpu().numpy().view(np.uint64)
-        c = counts.cpu().numpy().view(np.uint32)
-        out = {}
-        for (lo, hi), cnt in zip(k, c):
+        out = []
+        for lo, hi in k:
             v = (int(hi) << 64) | int(lo)
-            pat = "".join(STATES[(v >> (2 * (self.n - 1 - j))) & 3] for j in range(self.n))
-            out[pat] = int(cnt) if as_counts or self.divisor <= 0 else int(cnt) / self.divisor
+            out.append("".join(STATES[(v >> (2 * (self.n - 1 - j))) & 3] for j in range(self.n)))
         return out
+
+    def to_dict(self, as_counts=True, order="sorted"):
+        """{pattern: count (or count / usable)}; order = "sorted" (lexicographic, simulation.py:50-54) or "first"
+        (first occurrence along the alignment, the dict order of fasta.py:48-63)."""
+        if order == "first":
+            keys, counts, first = self.compact(sort=False, want_first=True)
+            perm = torch.argsort(first.to(torch.int64) & 0xFFFFFFFF)
+            keys, counts = keys[perm], counts[perm]
+        else:
+            keys, counts = self.compact()
+        c = counts.cpu().numpy().view(np.uint32)
+        return {p: (int(x) if as_counts or self.divisor <= 0 else int(x) / self.divisor) for p, x in zip(self._patterns(keys), c)}
 
 
 def pack_wide(chars, is_ascii=False):
@@ -725,16 +744,18 @@ def _new_wide_table(entries):
     return hk, _zeros(cap, torch.int32), cap
 
 
-def count_patterns_wide(wide, valid, n, N, site_begin=0, site_end=None, taxa=None):
+def count_patterns_wide(wide, valid, n, N, site_begin=0, site_end=None, taxa=None, want_first=False):
     """Pattern compression with 128-bit keys (n <= 64): one pass, open-addressing table."""
     site_end = N if site_end is None else site_end
     hk, hc, cap = _new_wide_table(site_end - site_begin)
+    hf = torch.full((cap + 1,), -1, dtype=torch.int32, device=device()) if want_first else None
     special, usable, ovf = _zeros(1, torch.int64), _zeros(1, torch.int64), _zeros(1, torch.int32)
     if site_end > site_begin:
-        call("spb_count_hash_wide", _p(wide), _p(valid), site_begin, site_end, _p(hk), _p(hc), cap, _p(special), _p(usable), _p(ovf), _st())
+        call("spb_count_hash_wide", _p(wide), _p(valid), site_begin, site_end, _p(hk), _p(hc), _p(hf), cap, _p(special), _p(usable),
+             _p(ovf), _st())
     if int(ovf.item()):
         raise MemoryError("splitp_b200: pattern hash table overflow")
-    return WideTable(n, hk, hc, cap, special, int(usable.item()), taxa)
+    return WideTable(n, hk, hc, cap, special, int(usable.item()), taxa, hf)
 
 
 def merge_wide_tables(n, keys, counts, usable, taxa=None):
@@ -742,8 +763,8 @@ def merge_wide_tables(n, keys, counts, usable, taxa=None):
     hk, hc, cap = _new_wide_table(keys.shape[0])
     special, ovf = _zeros(1, torch.int64), _zeros(1, torch.int32)
     if keys.shape[0]:
-        call("spb_hash_merge_wide", _p(keys.contiguous()), _p(counts.contiguous()), int(keys.shape[0]), _p(hk), _p(hc), cap, _p(special),
-             _p(ovf), _st())
+        call("spb_hash_merge_wide", _p(keys.contiguous()), _p(counts.contiguous()), None, int(keys.shape[0]), _p(hk), _p(hc), None, cap,
+             _p(special), _p(ovf), _st())
     if int(ovf.item()):
         raise MemoryError("splitp_b200: pattern hash table overflow")
     return WideTable(n, hk, hc, cap, special, usable, taxa)

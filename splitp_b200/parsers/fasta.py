@@ -49,7 +49,12 @@ def device_pattern_table(alignment, want_first=True):
 
 
 def get_pattern_counts(alignment):
-    """({pattern: count}, usable_length); dict order = first occurrence along the alignment (fasta.py:48-63)."""
+    """({pattern: count}, usable_length); dict order = first occurrence along the alignment (fasta.py:48-63).
+    Up to 31 taxa the keys are uint64 (csrc/count.cu); 32..64 taxa use the 128-bit table (csrc/wide.cu)."""
+    if len(alignment) > 31:
+        wide, valid, n, N = engine.pack_wide(_to_bytes_matrix(list(alignment.values())), is_ascii=True)
+        table = engine.count_patterns_wide(wide, valid, n, N, want_first=True)
+        return table.to_dict(order="first"), int(table.divisor)
     table = device_pattern_table(alignment, want_first=True)
     order = torch.argsort(table.first.to(torch.int64) & 0xFFFFFFFF)
     keys = table.keys[order].cpu().numpy().view(np.uint64)

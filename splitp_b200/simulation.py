@@ -81,6 +81,11 @@ def simulate_codes(tree, model, sequence_length, seed=0, device=None):
 def generate_alignment(tree, model, sequence_length, seed=0):
     """{pattern: count / float(sequence_length)} in lexicographic A<C<G<T order (simulation.py:42-56)."""
     codes = simulate_codes(tree, model, sequence_length, seed)
+    if codes.shape[0] > 31:  # 128-bit pattern keys
+        wide, valid, n, N = engine.pack_wide(codes)
+        wt = engine.count_patterns_wide(wide, valid, n, N)
+        wt.divisor = float(sequence_length)
+        return wt.to_dict(as_counts=False)
     aln = engine.pack(codes, is_ascii=False, want_planes=False)
     table = engine.count_patterns(aln)
     table.divisor = float(sequence_length)

@@ -458,6 +458,27 @@ def test_wide_pattern_counts(eng, oracle, n, N, seed, p_bad):
     k2, c2 = t2.compact(sort=False)
     merged = eng.merge_wide_tables(n_, torch.cat([k1, k2]), torch.cat([c1, c2]), usable)
     assert merged.to_dict() == ref
+    # first-occurrence order (the dict order of parsers/fasta.py:48-63)
+    tf = eng.count_patterns_wide(wide, valid, n_, N_, want_first=True)
+    assert list(tf.to_dict(order="first").items()) == list(ref.items())
+
+
+def test_fasta_64_taxa(sp, oracle):
+    """get_pattern_counts above 31 taxa goes through the 128-bit table and keeps the reference's dict order."""
+    from splitp_b200.parsers import fasta
+    import collections
+    rng = np.random.default_rng(64)
+    base = rng.integers(0, 4, size=(64, 30))
+    codes = base[:, rng.integers(0, 30, size=4000)]
+    codes = np.where(rng.random(codes.shape) < 0.01, rng.integers(0, 4, size=codes.shape), codes)
+    chars = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    chars[rng.random(chars.shape) < 0.0005] = ord("N")
+    low = rng.random(chars.shape) < 0.3
+    chars = np.where(low, chars | 0x20, chars).astype(np.uint8)  # mixed case, upper-cased by the reference (:54)
+    aln = collections.OrderedDict((f"t{i}", chars[i].tobytes().decode()) for i in range(64))
+    counts, L = fasta.get_pattern_counts(aln)
+    ref, usable = oracle.get_pattern_counts([aln[k] for k in aln]) if False else oracle.get_pattern_counts_wide(oracle.sequences_to_codes(list(aln.values())))
+    assert L == usable and list(counts.items()) == list(ref.items())
 
 
 @pytest.mark.parametrize("n,N,seed", [(64, 30_000, 81), (36, 100_000, 82), (10, 50_000, 83)])
