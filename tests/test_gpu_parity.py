@@ -477,7 +477,7 @@ def test_fasta_64_taxa(sp, oracle):
     chars = np.where(low, chars | 0x20, chars).astype(np.uint8)  # mixed case, upper-cased by the reference (:54)
     aln = collections.OrderedDict((f"t{i}", chars[i].tobytes().decode()) for i in range(64))
     counts, L = fasta.get_pattern_counts(aln)
-    ref, usable = oracle.get_pattern_counts([aln[k] for k in aln]) if False else oracle.get_pattern_counts_wide(oracle.sequences_to_codes(list(aln.values())))
+    ref, usable = oracle.get_pattern_counts_wide(oracle.sequences_to_codes(list(aln.values())))
     assert L == usable and list(counts.items()) == list(ref.items())
 
 
