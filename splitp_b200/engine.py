@@ -527,7 +527,7 @@ class CountScorer:
             return torch.full((1,), float("nan"), dtype=torch.float64, device=G.device)
         return score_gram(G, k)
 
-    def score_many(self, splits_idx, reduced=False, max_batch=256, max_batch_bytes=16 << 30, big_hook=None):
+    def score_many(self, splits_idx, reduced=False, max_batch=256, max_batch_bytes=None, big_hook=None):
         """Scores of many splits.  Dense count flattenings of equal shape are batched: their Gram matrices are
         built SPB_MAX_BATCH at a time into G[b] and ONE batched eigen-solver call scores up to `max_batch` of them
         (the Jacobi / Krylov kernels are latency-bound per matrix, so batching is what keeps all SMs busy)."""
@@ -536,6 +536,9 @@ class CountScorer:
             for s, (ia, ib) in enumerate(splits_idx):
                 out[s:s + 1] = self.score(ia, ib, True)
             return out
+        if max_batch_bytes is None:  # Gram batch buffer: at most 16 GB and at most a third of what is free right now
+            held = sum(g.numel() * 8 for g in self._G.values())
+            max_batch_bytes = min(16 << 30, (torch.cuda.mem_get_info()[0] + held) // 3)
         groups = {}
         for s, (ia, ib) in enumerate(splits_idx):
             groups.setdefault(min(len(ia), len(ib)), []).append(s)
