@@ -9,7 +9,6 @@
 // total is trace(G) = ||F||_F^2.
 #include "common.cuh"
 #include "jacobi.cuh"
-#include "ptx.cuh"
 #include <vector>
 
 using namespace spb;
@@ -371,97 +370,6 @@ __global__ void __launch_bounds__(256, 2) symv_block_kernel(const double* __rest
     }
 }
 
-// Streaming variant of the same product for k % 128 == 0 (the count-flattening sizes 256 / 1024 / 4096): a producer warp
-// feeds a 4-stage shared-memory ring with 1-D bulk-TMA copies (one 1 KB row segment per lane: 32 rows x 128 columns of G
-// plus the matching 8 x 128 chunk of Q per stage, 40 KB) and 8 consumer warps (4 rows each) take G and Q from shared
-// memory.  160 KB of copies are in flight per SM, which hides the HBM latency that limits symv_block_kernel (ncu: 24 %
-// of the warps active, long-scoreboard stalls, 0.6-0.7 of the HBM peak).
-constexpr int kTmaRows = 32;
-constexpr int kTmaCols = 128;
-constexpr int kTmaStages = 4;
-constexpr int kTmaStageDoubles = (kTmaRows + kKB) * kTmaCols;  // 5120 doubles = 40 KB
-constexpr int kTmaThreads = 32 + 8 * 32;
-
-__global__ void __launch_bounds__(kTmaThreads, 1) symv_tma_kernel(const double* __restrict__ G, int64_t ld, int64_t strideG,
-                                                                  const double* __restrict__ Q, int64_t strideQ,
-                                                                  double* __restrict__ AQ, int k, int batch) {
-  extern __shared__ __align__(128) double s_ring[];  // [stages][(32 G rows | 8 Q rows)][128]
-  __shared__ __align__(8) uint64_t bars[2 * kTmaStages];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nchunks = k / kTmaCols;
-  const int blocks_per_matrix = (k + kTmaRows - 1) / kTmaRows;
-  const int64_t items = (int64_t)batch * blocks_per_matrix;  // work item = 32 rows of one matrix
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kTmaStages; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + kTmaStages + s), 8); }
-    fence_barrier_init();
-  }
-  __syncthreads();
-  // persistent CTA: the producer streams straight through the item boundaries, so the ring never drains
-  if (warp == 0) {
-    // ===== producer =====
-    uint32_t stage = 0, phase = 0;
-    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
-      const int bt = (int)(it / blocks_per_matrix), row0 = (int)(it - (int64_t)bt * blocks_per_matrix) * kTmaRows;
-      const double* Gb = G + (int64_t)bt * strideG;
-      const double* Qb = Q + (int64_t)bt * strideQ;
-      const int grow = min(row0 + lane, k - 1);  // rows past the end are loaded (clamped) but never stored
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const uint32_t full = smem_u32(bars + stage);
-        if (lane == 0) {
-          mbar_wait(smem_u32(bars + kTmaStages + stage), phase ^ 1);
-          mbar_expect_tx(full, (uint32_t)(kTmaStageDoubles * sizeof(double)));
-        }
-        __syncwarp();
-        double* st = s_ring + (size_t)stage * kTmaStageDoubles;
-        bulk_g2s(smem_u32(st + lane * kTmaCols), Gb + (int64_t)grow * ld + (int64_t)ch * kTmaCols, kTmaCols * 8, full);
-        if (lane < kKB)
-          bulk_g2s(smem_u32(st + (kTmaRows + lane) * kTmaCols), Qb + (int64_t)lane * k + (int64_t)ch * kTmaCols, kTmaCols * 8, full);
-        if (++stage == kTmaStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else {
-    // ===== consumers: warp w owns rows 4 (w - 1) .. 4 (w - 1) + 3 of the item's 32 =====
-    const int r0 = (warp - 1) * 4;
-    uint32_t stage = 0, phase = 0;
-    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
-      const int bt = (int)(it / blocks_per_matrix), row0 = (int)(it - (int64_t)bt * blocks_per_matrix) * kTmaRows;
-      double acc[4][kKB];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < kKB; ++c) acc[r][c] = 0.0;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        mbar_wait(smem_u32(bars + stage), phase);
-        const double* st = s_ring + (size_t)stage * kTmaStageDoubles;
-#pragma unroll
-        for (int jj = 0; jj < kTmaCols / 32; ++jj) {
-          const int j = jj * 32 + lane;
-          double g[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) g[r] = st[(r0 + r) * kTmaCols + j];
-#pragma unroll
-          for (int c = 0; c < kKB; ++c) {
-            const double q = st[(kTmaRows + c) * kTmaCols + j];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r][c] = fma(g[r], q, acc[r][c]);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(bars + kTmaStages + stage));
-        if (++stage == kTmaStages) { stage = 0; phase ^= 1; }
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < kKB; ++c) {
-          double v = acc[r][c];
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-          if (lane == 0 && row0 + r0 + r < k) AQ[(int64_t)bt * strideQ + (int64_t)c * k + row0 + r0 + r] = v;
-        }
-    }
-  }
-}
-
 __global__ void copy_block_kernel(const double* src, int64_t strideS, double* dst, int64_t strideD, int64_t elems) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < elems) dst[blockIdx.y * strideD + i] = src[blockIdx.y * strideS + i];
@@ -754,20 +662,10 @@ static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb,
   }
   const size_t symv_smem = (size_t)kKB * kSymvChunk * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(symv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
-  // bulk copies need 16-byte aligned row segments: k % 128 == 0, even leading dimension, aligned bases
-  const size_t tma_smem = (size_t)kTmaStages * kTmaStageDoubles * sizeof(double);
-  const bool use_tma = (k % kTmaCols == 0) && (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(d_G) & 15) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(w.Q) & 15) == 0);
-  if (use_tma) SPB_CUDA(cudaFuncSetAttribute(symv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
   for (int j = 0; j < nb; ++j) {
     double* Qj = w.Q + (int64_t)j * blk;
     double* AQj = w.AQ + (int64_t)j * blk;
-    if (use_tma) {
-      const int64_t items = (int64_t)batch * ((k + kTmaRows - 1) / kTmaRows);
-      const int grid = (int)(items < sm_count() ? items : sm_count());
-      symv_tma_kernel<<<grid, kTmaThreads, tma_smem, st>>>(d_G, ld, ld * ld, Qj, w.sQ, AQj, k, batch);
-      SPB_LAUNCH_CHECK();
-    } else {
+    {
       dim3 grid((k + kSymvRows - 1) / kSymvRows, batch);
       symv_block_kernel<<<grid, 256, symv_smem, st>>>(d_G, ld, ld * ld, Qj, w.sQ, AQj, k);
       SPB_LAUNCH_CHECK();
