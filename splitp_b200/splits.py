@@ -1,48 +1,58 @@
-"""Split enumeration (reference: splitp/splits.py:7-59).  Host-side only: it defines the work-unit
-order and the split representation the engine accepts (2-tuple of taxon tuples, or "012|345")."""
-from itertools import combinations
-from math import floor
+"""Split enumeration, host side only (reference interface: splitp/splits.py:7-59).
 
-from numpy.random import shuffle
+`all_splits` fixes the work-unit order of the engine and the split representation it accepts: a pair of taxon
+tuples, or the "012|345" string form for single-character taxa.  Splits are enumerated on taxon POSITIONS and
+only mapped to names when they are yielded.
+"""
+import itertools
+import math
+
+import numpy.random
 
 
 def split_balance(s, asTuple=False):
-    left, right = s.split("|")
-    return (len(left), len(right)) if asTuple else f"{len(left)}|{len(right)}"
+    """'AB|CDE' -> '2|3' (or (2, 3))."""
+    sizes = tuple(len(part) for part in s.split("|"))
+    return sizes if asTuple else "|".join(str(x) for x in sizes)
 
 
 def format_split(tree, split):
+    """Pair of taxon tuples -> 'AB|CDE'; strings pass through.  Needs single-character taxa and at most 35 of them."""
     if isinstance(split, str):
         return split
-    if len(split[0]) + len(split[1]) > 35:
-        raise ValueError("Cannot produce string format for split with more than 35 taxa.")
-    if not all(len(taxon) == 1 for taxon in tree.get_taxa()):
-        raise ValueError("Cannot produce string format for split with taxa name of length > 1.")
-    return f'{"".join(split[0])}|{"".join(split[1])}'
+    left, right = split
+    if len(left) + len(right) > 35:
+        raise ValueError("string format is limited to splits of at most 35 taxa")
+    if any(len(name) != 1 for name in tree.get_taxa()):
+        raise ValueError("string format needs taxon names of length 1")
+    return "".join(left) + "|" + "".join(right)
 
 
 def all_splits(tree, trivial=False, size=None, randomise=False, string_format=False):
-    """Generator over the splits of `tree.taxa`: sizes 2..floor(n/2) ascending (1.. with `trivial`),
-    `itertools.combinations` order inside a size, balanced splits de-duplicated by pinning taxa[0] to
-    the left, taxa[0] always on the left side, both sides in `tree.taxa` order."""
-    taxa = tree.taxa
-    n = len(taxa)
+    """Generator over the splits of `tree.taxa`.
+
+    Order: left-side sizes 2..floor(n/2) ascending (from 1 with `trivial`; only `size` if given), and inside a size
+    the order of `itertools.combinations`.  A balanced split (size == n/2) is produced once, with taxon 0 pinned to
+    the left; in every split taxon 0 ends up on the left side and both sides keep the order of `tree.taxa`.
+    `randomise` shuffles the combinations of each size (numpy's global RNG, like the reference)."""
+    names = list(tree.taxa)
+    n = len(names)
     if string_format and n > 35:
-        raise ValueError("Cannot generate splits for more than 35 taxa in string format. Use string_format=False.")
-    sizes = [size] if size is not None else list(range(1 if trivial else 2, floor(n / 2) + 1))
-    position = {t: i for i, t in enumerate(taxa)}
-    for left_size in sizes:
-        balanced = left_size == n / 2
-        chosen = combinations(taxa[1:], left_size - 1) if balanced else combinations(taxa, left_size)
+        raise ValueError("string_format=True supports at most 35 taxa; use string_format=False")
+    wanted = [size] if size is not None else range(1 if trivial else 2, math.floor(n / 2) + 1)
+    everyone = range(n)
+    for k in wanted:
+        if 2 * k == n:  # balanced: choose the k - 1 companions of taxon 0
+            picks = ((0,) + rest for rest in itertools.combinations(range(1, n), k - 1))
+        else:
+            picks = itertools.combinations(everyone, k)
         if randomise:
-            chosen = list(chosen)
-            shuffle(chosen)
-        for pick in chosen:
-            if balanced:
-                pick = (taxa[0],) + tuple(pick)
-            inside = set(pick)
-            left = tuple(sorted(pick, key=position.__getitem__))
-            right = tuple(t for t in taxa if t not in inside)
-            if taxa[0] in right:
-                left, right = right, left
-            yield format_split(tree, (left, right)) if string_format else (left, right)
+            picks = list(picks)
+            numpy.random.shuffle(picks)
+        for chosen in picks:
+            inside = set(chosen)
+            side_a = tuple(names[i] for i in everyone if i in inside)
+            side_b = tuple(names[i] for i in everyone if i not in inside)
+            if 0 not in inside:
+                side_a, side_b = side_b, side_a
+            yield format_split(tree, (side_a, side_b)) if string_format else (side_a, side_b)

@@ -546,7 +546,7 @@ def test_config2_properties(sp, eng, oracle):
 def test_config5_random_splits_32_taxa(sp, eng, oracle):
     """BASELINE configs[4] shape: random splits of a 32-taxon tree, subflattening scores (side sizes 2..16), with an
     oracle check on a sample; plus invariance of the score under swapping the two sides."""
-    n, N = 32, 400_000
+    n, N = 32, 1_000_000  # BASELINE config 5 size
     tree = sp.trees.balanced_tree(n, 0.05)
     codes = sp.simulation.simulate_codes(tree, sp.simulation.GTR.JukesCantor(0.5), N, seed=5)
     aln = eng.pack(codes, want_sm=False)
@@ -571,6 +571,39 @@ def test_config5_random_splits_32_taxa(sp, eng, oracle):
     for s in range(0, 3000, 250):
         ref = oracle.split_score(oracle.subflattening_from_tables(tables, 1.0, splits[s][0], splits[s][1]))
         assert_score(sc[s], ref)
+
+
+
+def test_config3_full_size_properties(sp, eng):
+    """BASELINE config 3 at its full size (20 taxa, 10^7 sites): size-independent invariants of the counting side --
+    linearity of the pair statistics over site ranges, every joint table summing to N, marginals consistent -- and of
+    the scoring side -- all 190 two-taxon splits scored, the tree's cherries ranked first, scores independent of the
+    order in which the splits are submitted."""
+    n, N = 20, 10_000_000
+    tree = sp.trees.balanced_tree(n, 0.05)
+    codes = sp.simulation.simulate_codes(tree, sp.simulation.GTR((0.1, 0.2, 0.3, 0.4), (1, 2, 3, 4, 5, 6)), N, seed=3)
+    aln = eng.pack(codes, want_sm=False)
+    words = (N + 31) // 32
+    cut = (words // 3) | 1
+    whole = eng.pair_raw(aln)
+    parts = eng.pair_raw(aln, 0, cut) + eng.pair_raw(aln, cut, words)
+    assert torch.equal(whole, parts) and int(whole[-1].item()) == N
+    pt = eng.pair_finalize(whole, n, 0.0)
+    assert torch.all(pt.N.sum(dim=(2, 3)) == N)
+    for i in (0, 7, 19):  # row marginals of N[i][j] do not depend on j
+        m = pt.N[i].sum(dim=2)
+        assert torch.equal(m, m[0].expand_as(m))
+    twos = list(sp.all_splits(tree, size=2))
+    idx = [eng.split_positions(s, tree.taxa) for s in twos]
+    ma, mb = eng.masks_from_splits(idx)
+    ptp = eng.pair_finalize(whole, n, float(N))
+    sc = eng.subflatten_scores(ptp, ma, mb)
+    perm = torch.randperm(len(idx), generator=torch.Generator().manual_seed(0))
+    sc_perm = eng.subflatten_scores(ptp, ma[perm.numpy()], mb[perm.numpy()])
+    assert torch.equal(sc[perm.cuda()], sc_perm)
+    cherries = {s for s in tree.splits() if min(len(s[0]), len(s[1])) == 2}
+    best = {twos[i] for i in torch.argsort(sc)[:len(cherries)].tolist()}
+    assert best == cherries
 
 
 def test_config3_properties(sp, eng, oracle):
