@@ -272,6 +272,36 @@ def test_erickson_svd_golden(sp):
         sp.erickson_SVD(aln, method=sp.Method.mutual_information)
 
 
+
+def test_reduced_flattening_large_side(sp, eng, oracle):
+    """A side above 13 taxa cannot use the 4^side flag arrays: the rank computation goes through a sort-unique."""
+    n = 16
+    codes = random_codes(n, 30_000, 91, 0.0)
+    tab = eng.count_patterns(eng.pack(codes))
+    keys, counts, usable = oracle.get_pattern_counts_arrays(codes)
+    order = np.argsort(keys)
+    for ia, ib in (([0, 15], list(range(1, 15))), (list(range(2, 16)), [1, 0])):
+        got = eng.flatten_reduced(tab, ia, ib).cpu().numpy()
+        ref = oracle.flattening_reduced(keys[order], (counts[order] / usable), n, ia, ib)
+        np.testing.assert_array_equal(got, ref)
+        gotc = eng.flatten_reduced(tab, ia, ib, as_counts=True).cpu().numpy()
+        np.testing.assert_array_equal(gotc, oracle.flattening_reduced(keys[order], counts[order].astype(float), n, ia, ib))
+
+
+def test_generate_alignment_drop_in(sp, oracle):
+    """generate_alignment keeps the reference's return type: a plain dict, keys in lexicographic A<C<G<T order, values
+    count / float(sequence_length) (simulation.py:42-56); also above 31 taxa (128-bit keys)."""
+    for n, N in ((6, 5000), (40, 3000)):
+        tree = sp.trees.balanced_tree(n, 0.05)
+        model = sp.simulation.GTR.JukesCantor(0.5)
+        aln = sp.generate_alignment(tree, model, N, seed=3)
+        assert type(aln) is dict and all(len(p) == n for p in aln)
+        assert list(aln) == sorted(aln, key=lambda p: [oracle.STATES.index(c) for c in p])
+        codes = sp.simulation.simulate_codes(tree, model, N, seed=3).cpu().numpy()
+        ref, usable = oracle.get_pattern_counts_wide(codes)
+        assert usable == N and aln == {p: c / float(N) for p, c in ref.items()}
+
+
 # ---------------------------------------------------------------------------------------------
 # kernel 3: pair tables / subflattening, batched
 # ---------------------------------------------------------------------------------------------
