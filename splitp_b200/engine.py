@@ -117,7 +117,11 @@ class PatternTable:
         if self.values is not None:
             return self.values
         v = self.counts.to(torch.float64)
-        return v / self.divisor if self.divisor > 0 else v
+        if self.divisor <= 0:
+            return v
+        # tensor / tensor: one correctly rounded IEEE division per pattern, as fasta.py:66-70 (dividing by a python
+        # scalar would be turned into a multiplication by the reciprocal, which is 1 ulp off for some counts)
+        return torch.div(v, torch.full_like(v, self.divisor))
 
 
 def count_patterns(aln, site_begin=0, site_end=None, want_first=False, force_hash=False, sort=True, reduce_fn=None):
