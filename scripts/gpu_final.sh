@@ -6,6 +6,7 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "s
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench c2 rc=$?"; cat gpurun_out/bench_c2.json
 timeout 900 python bench.py --steps 3 --warmup 3 --workload c3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "bench c3 rc=$?"; cat gpurun_out/bench_c3.json
 timeout 900 python bench.py --steps 3 --warmup 3 --workload c5 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "bench c5 rc=$?"; cat gpurun_out/bench_c5.json
+timeout 900 python bench.py --steps 2 --warmup 3 --workload c4 --max-splits 256 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "bench c4 rc=$?"; cat gpurun_out/bench_c4.json
 timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref_c2.json 2> gpurun_out/bench_ref_c2.err; echo "ref rc=$?"; cat gpurun_out/bench_ref_c2.json
 python scripts/ncu_step.py > gpurun_out/ncu_plain_full.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_c2.csv python scripts/ncu_step.py > gpurun_out/ncu_full.log 2>&1; echo "ncu launches rc=$?"
