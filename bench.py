@@ -390,7 +390,10 @@ def main():
         hbm = peaks.get("hbm_gbs", 6650.0)
         roof = {"kernel": "pair_kernel (bit-plane AND + POPC pair statistics)", "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9,
                 "peak": hbm, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm, "traffic": None,
-                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s", "launch_ms": ms}
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s", "launch_ms": ms,
+                "note": "pair_kernel is the only HBM-streaming kernel of this workload (POPC-issue bound, see DESIGN.md) and a small "
+                        "share of the step; the step is dominated by subflatten_score_kernel (gather + shared-memory Jacobi per "
+                        "split, instruction-issue bound, no HBM roofline): its throughput is `value`"}
     count_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in prof["count"]])) if prof["count"] else None
 
     if rank == 0:
