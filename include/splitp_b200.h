@@ -239,6 +239,36 @@ int64_t spb_score_gram_large_ws(int64_t k, int64_t batch);
 int spb_score_gram_large(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores,
                          double* d_info, double* d_ws, void* stream);
 
+/* ---- marginals, rank-1 approximation and rank-1 divergence of a flattening ----
+ * reference: phylogenetics.py:331-341 (r = column sums, c = row sums, approximation = r^T c),
+ * phylogenetics.py:364-373 (divergence = sum over non-zero cells of F[x,y] log(F[x,y] / (r[y] c[x]))),
+ * constructions.py:94-101 (entries whose row / column pattern holds the banned state more than once are zeroed; used by
+ * phylogenetics.py:344-361).  States are 0..3 = A,C,G,T; -1 = nothing banned. */
+int64_t spb_mi_partials(void); /* doubles of d_partials below */
+/* matrix route: F is double [rows][ld] on the device */
+int spb_marginals_dense(const double* d_F, int64_t rows, int64_t cols, int64_t ld, double* d_rowsum, double* d_colsum,
+                        void* stream);
+int spb_mi_dense(const double* d_F, int64_t rows, int64_t cols, int64_t ld, const double* d_rowsum, const double* d_colsum,
+                 double* d_partials, double* d_out, void* stream);
+/* d_out[i][j] (+)= x[i] * y[j] */
+int spb_outer_f64(const double* d_x, int64_t nx, const double* d_y, int64_t ny, double* d_out, int accumulate, void* stream);
+/* rows / cols of every pattern as spb_flatten_coo, plus d_banned[i] = 1 where the banned-state rule zeroes the entry */
+int spb_flatten_coo_banned(const uint64_t* d_keys, int64_t num, const spb_split* split, int ban_row, int ban_col,
+                           int64_t* d_rows, int64_t* d_cols, uint8_t* d_banned, void* stream);
+/* pattern-table route, for a split that places every taxon on exactly one side (SPB_ERR_UNSUPPORTED otherwise).
+ * Side sums of the RAW values (counts or doubles) are ADDED into d_rowsum / d_colsum (caller zero-fills).  A side is
+ * either direct-indexed (d_?keys NULL, ?cap >= 4^side entries, side <= 15 taxa) or an open-addressing table
+ * (d_?keys uint64 [?cap] filled with 0xFF bytes, ?cap a power of two >= 2 x distinct side patterns; the sums then sit
+ * at the slots of their keys).  d_overflow (uint32, zeroed) is set when a table fills up. */
+int spb_table_marginals(const uint64_t* d_keys, const void* d_vals, int val_kind, int64_t num, const spb_split* split,
+                        int ban_row, int ban_col, double* d_rowsum, uint64_t* d_rkeys, int64_t rcap, double* d_colsum,
+                        uint64_t* d_ckeys, int64_t ccap, uint32_t* d_overflow, void* stream);
+/* divergence from the table and the side sums above; values and sums are divided by `divisor` when it is > 0 */
+int spb_mi_table(const uint64_t* d_keys, const void* d_vals, int val_kind, double divisor, int64_t num,
+                 const spb_split* split, const double* d_rowsum, const uint64_t* d_rkeys, int64_t rcap,
+                 const double* d_colsum, const uint64_t* d_ckeys, int64_t ccap, double* d_partials, double* d_out,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

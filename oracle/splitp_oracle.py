@@ -347,6 +347,83 @@ def split_score_gram(matrix):
 
 
 # ----------------------------------------------------------------------------------------------
+# banned-pattern flattening, rank-1 / rank-k approximations, rank-1 divergence
+# (splitp/constructions.py:94-101, splitp/phylogenetics.py:331-373)
+# ----------------------------------------------------------------------------------------------
+def digit_count(index, digits, code):
+    """How many of the `digits` base-4 digits of `index` equal `code` (str.count of constructions.py:95-98)."""
+    index = np.asarray(index, dtype=np.uint64)
+    out = np.zeros(index.shape, dtype=np.int64)
+    for d in range(digits):
+        out += ((index >> np.uint64(2 * d)) & np.uint64(3)) == np.uint64(code)
+    return out
+
+
+def flattening_coo_banned(keys, vals, n, idx_a, idx_b, ban_row=None, ban_col=None):
+    """constructions.py:86-102 with ban_row_patterns / ban_col_patterns: an entry whose row (col) pattern holds the
+    banned character more than once is assigned 0.  ban_* are state codes 0..3 or None.  Zero entries are dropped
+    (a DOK matrix stores nothing for an assigned zero)."""
+    rows = side_index(keys, n, idx_a)
+    cols = side_index(keys, n, idx_b)
+    v = np.array(vals, dtype=np.float64)
+    if ban_row is not None:
+        v[digit_count(rows, len(idx_a), ban_row) > 1] = 0.0
+    if ban_col is not None:
+        v[digit_count(cols, len(idx_b), ban_col) > 1] = 0.0
+    if len(set(idx_a) | set(idx_b)) < n:
+        rows, cols, v = _last_wins(rows, cols, v)
+    nz = v != 0
+    return rows[nz], cols[nz], v[nz]
+
+
+def rank_1_vectors(matrix):
+    """phylogenetics.py:334-335: r = sum(flattening) = column sums, c = sum(flattening.T) = row sums, both by
+    sequential addition of the rows (Python's builtin sum)."""
+    m = np.asarray(matrix, dtype=np.float64)
+    r = np.zeros(m.shape[1])
+    for row in m:
+        r = r + row
+    c = np.zeros(m.shape[0])
+    for col in m.T:
+        c = c + col
+    return r, c
+
+
+def rank_1_approximation(matrix):
+    """phylogenetics.py:336: r.T @ c -- note the orientation, (#cols x #rows)."""
+    r, c = rank_1_vectors(matrix)
+    return np.outer(r, c)
+
+
+def rank_1_divergence(matrix):
+    """phylogenetics.py:364-373: sum over non-zero cells of F[x,y] * log(F[x,y] / (r[y] * c[x])), row-major order."""
+    m = np.asarray(matrix, dtype=np.float64)
+    r, c = rank_1_vectors(m)
+    total = 0.0
+    for x in range(m.shape[0]):
+        nz = np.nonzero(m[x])[0]
+        for y in nz:
+            total += m[x, y] * np.log(m[x, y] / (r[y] * c[x]))
+    return total
+
+
+def rank_k_approximation(keys, vals, n, idx_a, idx_b):
+    """phylogenetics.py:344-361: sum over the four states of (column sums with that state banned on the rows)^T
+    times (row sums with that state banned on the columns): a (4^b x 4^a) matrix."""
+    R, C = 4 ** len(idx_a), 4 ** len(idx_b)
+    out = np.zeros((C, R))
+    for code in range(4):
+        rows, cols, v = flattening_coo_banned(keys, vals, n, idx_a, idx_b, ban_row=code)
+        colsum = np.zeros(C)
+        np.add.at(colsum, cols.astype(np.int64), v)
+        rows, cols, v = flattening_coo_banned(keys, vals, n, idx_a, idx_b, ban_col=code)
+        rowsum = np.zeros(R)
+        np.add.at(rowsum, rows.astype(np.int64), v)
+        out += np.outer(colsum, rowsum)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # Alignment.sub_alignment  (splitp/alignment.py:10-31)
 # ----------------------------------------------------------------------------------------------
 def sub_alignment(keys, vals, n, sub_idx):

@@ -97,6 +97,13 @@ PROTOTYPES = {
     "spb_score_gram_small": (_i, [_p, _l, _l, _l, _p, _p, _p]),
     "spb_score_gram_large_ws": (_l, [_l, _l]),
     "spb_score_gram_large": (_i, [_p, _l, _l, _l, _p, _p, _p, _p]),
+    "spb_mi_partials": (_l, []),
+    "spb_marginals_dense": (_i, [_p, _l, _l, _l, _p, _p, _p]),
+    "spb_mi_dense": (_i, [_p, _l, _l, _l, _p, _p, _p, _p, _p]),
+    "spb_outer_f64": (_i, [_p, _l, _p, _l, _p, _i, _p]),
+    "spb_flatten_coo_banned": (_i, [_p, _l, _sp, _i, _i, _p, _p, _p, _p]),
+    "spb_table_marginals": (_i, [_p, _p, _i, _l, _sp, _i, _i, _p, _p, _l, _p, _p, _l, _p, _p]),
+    "spb_mi_table": (_i, [_p, _p, _i, _d, _l, _sp, _p, _p, _l, _p, _p, _l, _p, _p, _p]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

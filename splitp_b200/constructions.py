@@ -44,12 +44,29 @@ def flattening(split, pattern_probabilities, flattening_format=FlatFormat.sparse
         return engine.flatten_reduced(table, idx_a, idx_b).cpu().numpy()
     if flattening_format is FlatFormat.dense:
         return engine.flatten_dense(table, idx_a, idx_b).cpu().numpy()
-    # sparse: rows / cols from the device, assembled into the DOK container the reference returns
+    return _sparse(table, idx_a, idx_b)
+
+
+def _ban_code(char):
+    if char is None:
+        return -1
+    if not isinstance(char, str) or len(char) != 1:
+        raise NotImplementedError("banned patterns: a single state character is supported (the only use in the reference)")
+    return constants.DNA_state_space.index(char) if char in constants.DNA_state_space else -1  # other chars never occur
+
+
+def _sparse(table, idx_a, idx_b, ban_row=-1, ban_col=-1):
+    # rows / cols (and the banned flags) from the device, assembled into the DOK container the reference returns
+    a, b = len(idx_a), len(idx_b)
     if a > 31 or b > 31:
         raise NotImplementedError("sparse flattening: sides are limited to 31 taxa (int64 indices)")
-    rows_t, cols_t = engine.flatten_coo(table, idx_a, idx_b)
-    rows, cols = rows_t.cpu().numpy(), cols_t.cpu().numpy()
     vals = table.values_f64().cpu().numpy()
+    if ban_row >= 0 or ban_col >= 0:
+        rows_t, cols_t, banned_t = engine.flatten_coo_banned(table, idx_a, idx_b, ban_row, ban_col)
+        vals = np.where(banned_t.cpu().numpy() != 0, 0.0, vals)  # constructions.py:94-99: the entry is assigned 0
+    else:
+        rows_t, cols_t = engine.flatten_coo(table, idx_a, idx_b)
+    rows, cols = rows_t.cpu().numpy(), cols_t.cpu().numpy()
     shape = (4 ** a, 4 ** b)
     if not engine.covers_all(table.n, idx_a, idx_b) and len(rows):
         # assignment semantics (constructions.py:101): the last pattern in table order wins a cell
@@ -62,6 +79,19 @@ def flattening(split, pattern_probabilities, flattening_format=FlatFormat.sparse
         nz = vals != 0  # assigning 0 to a DOK cell stores nothing
         out = coo_matrix((vals[nz], (rows[nz], cols[nz])), shape=shape).todok()
     return out
+
+
+def sparse_flattening_with_banned_patterns(split, pattern_probabilities, taxa, ban_row_patterns=None, ban_col_patterns=None):
+    """Sparse flattening in which an entry whose row (column) pattern contains the character `ban_row_patterns`
+    (`ban_col_patterns`) more than once is assigned 0 (reference: constructions.py:58-105; the only caller,
+    phylogenetics.py:344-361, passes single state characters).  `taxa` is the taxon order of the patterns."""
+    if isinstance(split, str):
+        split = split.split("|")
+    idx_a, idx_b = engine.split_positions((list(split[0]), list(split[1])), taxa)
+    table = engine.table_from_mapping(pattern_probabilities)
+    if table.num and max(idx_a + idx_b, default=-1) >= table.n:
+        raise IndexError("string index out of range")
+    return _sparse(table, idx_a, idx_b, _ban_code(ban_row_patterns), _ban_code(ban_col_patterns))
 
 
 def _labels(length):

@@ -666,6 +666,109 @@ def marginalise(table, idx):
 
 
 # --------------------------------------------------------------------------------------------
+# marginals, rank-1 approximation and rank-1 divergence of a flattening (SURVEY section 8 row f4;
+# splitp/phylogenetics.py:331-373, banned states: splitp/constructions.py:94-101)
+# --------------------------------------------------------------------------------------------
+MI_DIRECT_CELLS = 1 << 22  # a side of up to 11 taxa keeps its sums in a direct-indexed array, longer sides in a hash table
+
+
+class SideSums:
+    """Sums of the raw table values per row (or column) index of a flattening: `sums[index]` when `keys` is None,
+    else an open-addressing table (`keys[slot]` = index or -1, `sums[slot]`)."""
+
+    def __init__(self, side_len, distinct_bound):
+        cells = 4 ** side_len
+        cap = 1024
+        while cap < 2 * max(distinct_bound, 1):
+            cap *= 2
+        if cells <= MI_DIRECT_CELLS or (side_len <= 15 and cells <= cap):
+            self.keys, self.cap = None, cells
+        else:
+            self.keys, self.cap = torch.full((cap,), -1, dtype=torch.int64, device=device()), cap
+        self.sums = _zeros(self.cap, torch.float64)
+
+    def args(self):
+        return _p(self.sums), _p(self.keys), self.cap
+
+
+def table_marginals(table, idx_a, idx_b, ban_row=-1, ban_col=-1):
+    """(row sums, column sums) of the flattening of a split that places every taxon on one side, as SideSums of the RAW
+    table values (counts stay integers).  ban_row / ban_col: state code 0..3 whose repeated occurrence in the row /
+    column pattern zeroes the entry (constructions.py:94-99), -1 = none."""
+    sp = make_split(table.n, idx_a, idx_b)
+    rs, cs = SideSums(len(idx_a), table.num), SideSums(len(idx_b), table.num)
+    ovf = _zeros(1, torch.int32)
+    vp, kind, _ = table.val_args(True)
+    call("spb_table_marginals", _p(table.keys), vp, kind, table.num, C.byref(sp), int(ban_row), int(ban_col),
+         *rs.args(), *cs.args(), _p(ovf), _st())
+    if (rs.keys is not None or cs.keys is not None) and int(ovf.item()):
+        raise MemoryError("splitp_b200: side-sum hash table overflow")
+    return rs, cs
+
+
+def _partials():
+    return _empty(int(lib.spb_mi_partials()), torch.float64)
+
+
+def rank1_divergence_table(table, idx_a, idx_b):
+    """sum over patterns of v log(v / (r c)) without materialising the flattening (phylogenetics.py:364-373);
+    float64 tensor [1].  NotImplementedError (from the library) for a split that does not cover all taxa."""
+    rs, cs = table_marginals(table, idx_a, idx_b)
+    sp = make_split(table.n, idx_a, idx_b)
+    vp, kind, div = table.val_args()
+    out = _empty(1, torch.float64)
+    call("spb_mi_table", _p(table.keys), vp, kind, div, table.num, C.byref(sp), *rs.args(), *cs.args(), _p(_partials()),
+         _p(out), _st())
+    return out
+
+
+def marginals_dense(F):
+    """(row sums, column sums) of a device matrix."""
+    F = F.contiguous()
+    rows, cols = F.shape
+    rowsum, colsum = _empty(rows, torch.float64), _empty(cols, torch.float64)
+    call("spb_marginals_dense", _p(F), rows, cols, F.stride(0) if rows else cols, _p(rowsum), _p(colsum), _st())
+    return rowsum, colsum
+
+
+def rank1_divergence_dense(F):
+    F = F.contiguous()
+    rows, cols = F.shape
+    rowsum, colsum = marginals_dense(F)
+    out = _empty(1, torch.float64)
+    call("spb_mi_dense", _p(F), rows, cols, F.stride(0) if rows else cols, _p(rowsum), _p(colsum), _p(_partials()), _p(out), _st())
+    return out
+
+
+def rank1_divergence(table, idx_a, idx_b):
+    """Rank-1 divergence of the flattening of (idx_a | idx_b): from the table when the split covers all taxa, else
+    from the reduced flattening (dropping all-zero rows / columns does not change the sum)."""
+    if covers_all(table.n, idx_a, idx_b):
+        return rank1_divergence_table(table, idx_a, idx_b)
+    return rank1_divergence_dense(flatten_reduced(table, idx_a, idx_b))
+
+
+def outer(x, y, out=None, accumulate=False):
+    """out[i, j] (+)= x[i] * y[j] on the device."""
+    x, y = x.contiguous(), y.contiguous()
+    if out is None:
+        out = _empty((x.shape[0], y.shape[0]), torch.float64)
+        accumulate = False
+    call("spb_outer_f64", _p(x), x.shape[0], _p(y), y.shape[0], _p(out), int(bool(accumulate)), _st())
+    return out
+
+
+def flatten_coo_banned(table, idx_a, idx_b, ban_row=-1, ban_col=-1):
+    """(rows, cols, banned) of every pattern; banned[i] = 1 where the banned-state rule assigns 0."""
+    sp = make_split(table.n, idx_a, idx_b)
+    rows, cols = _empty(table.num, torch.int64), _empty(table.num, torch.int64)
+    banned = _empty(table.num, torch.uint8)
+    call("spb_flatten_coo_banned", _p(table.keys), table.num, C.byref(sp), int(ban_row), int(ban_col), _p(rows), _p(cols),
+         _p(banned), _st())
+    return rows, cols, banned
+
+
+# --------------------------------------------------------------------------------------------
 # wide keys: up to 64 taxa (BASELINE config 4)
 # --------------------------------------------------------------------------------------------
 class WideTable:

@@ -53,6 +53,51 @@ def split_score(matrix, return_singular_values=False, force_frob_norm_on_dense=F
     return np.float64(engine.score_matrix(torch.from_numpy(np.ascontiguousarray(m)).to(dev))[0].item())
 
 
+def _device_matrix(flattening):
+    m = np.asarray(flattening.todense() if is_sparse(flattening) else flattening, dtype=np.float64)
+    if m.ndim != 2:
+        raise ValueError("expected a matrix")
+    return torch.from_numpy(np.ascontiguousarray(m)).to(engine.device())
+
+
+def flattening_rank_1_approximation(flattening, return_vectors=False, dont_compute_matrix=False):
+    """r = column sums, c = row sums of the flattening; approximation = r^T c, a (#columns x #rows) array as in the
+    reference (phylogenetics.py:331-341).  Sums and outer product are computed on the device."""
+    F = _device_matrix(flattening)
+    c, r = engine.marginals_dense(F)
+    approximation = None if dont_compute_matrix else engine.outer(r, c).cpu().numpy()
+    if return_vectors:
+        return approximation, r.cpu().tolist(), c.cpu().tolist()
+    return approximation
+
+
+def flattening_rank_k_approximation(split, alignment):
+    """Sum over the four states of (column sums with the state banned on the rows)^T (row sums with the state banned
+    on the columns): a (4^|B| x 4^|A|) csr_matrix (phylogenetics.py:344-361).  The taxon order is the sorted union
+    of both sides, as in the reference."""
+    split = (list(split[0]), list(split[1]))
+    taxa = sorted(set(split[0]) | set(split[1]))
+    idx_a, idx_b = engine.split_positions(split, taxa)
+    table = engine.table_from_mapping(alignment)
+    R, Cn = 4 ** len(idx_a), 4 ** len(idx_b)
+    if R * Cn > 1 << 28 or R > engine.MI_DIRECT_CELLS or Cn > engine.MI_DIRECT_CELLS:
+        raise MemoryError(f"flattening_rank_k_approximation: a dense {Cn} x {R} result does not fit")
+    out = torch.zeros((Cn, R), dtype=torch.float64, device=engine.device())
+    div = table.divisor if (table.counts is not None and table.divisor > 0) else 1.0
+    for code in range(4):
+        _, cs = engine.table_marginals(table, idx_a, idx_b, ban_row=code)
+        rs, _ = engine.table_marginals(table, idx_a, idx_b, ban_col=code)
+        colsum = torch.div(cs.sums, torch.full_like(cs.sums, div))
+        rowsum = torch.div(rs.sums, torch.full_like(rs.sums, div))
+        engine.outer(colsum, rowsum, out, accumulate=True)
+    return scipy.sparse.csr_matrix(out.cpu().numpy())
+
+
+def flattening_rank_1_approximation_divergence(flattening):
+    """sum over the non-zero cells of F[x,y] log(F[x,y] / (r[y] c[x])) (phylogenetics.py:364-373), on the device."""
+    return np.float64(engine.rank1_divergence_dense(_device_matrix(flattening)).item())
+
+
 def _leaves(cluster):
     return (cluster,) if isinstance(cluster, str) else tuple(cluster)
 
@@ -65,16 +110,14 @@ def erickson_SVD(alignment, taxa=None, method=Method.flattening, show_work=False
     (`Method.subflattening`) -- and the best-scoring pair is merged; scores are memoised per split.  Returns the
     n - 2 chosen splits as sorted 2-tuples of leaf tuples, like the reference.  The candidate splits of a step are
     scored as ONE batch on the device: the batched subflattening kernel for `Method.subflattening`, device-resident
-    reduced flattenings for `Method.flattening`.  `Method.mutual_information` (rank-1 KL divergence,
-    phylogenetics.py:331-373) is outside the hot path and not implemented.
+    reduced flattenings for `Method.flattening`.  `Method.mutual_information` scores a split by the rank-1 divergence of
+    its flattening (phylogenetics.py:136-140, 364-373), computed straight from the pattern table.  `Method.distance`
+    leaves every score at infinity, as the reference does.
     """
     table = engine.table_from_mapping(alignment)
     num_taxa = table.n
     if taxa is None:
         taxa = [str(np.base_repr(i, base=max(i + 1, 2))) if num_taxa <= 36 else f"t{i}" for i in range(num_taxa)]
-    if method not in (Method.flattening, Method.subflattening):
-        if method == Method.mutual_information:
-            raise NotImplementedError("erickson_SVD: Method.mutual_information is not part of the B200 hot path")
     known = {}
     pair_tables = None
 
@@ -101,6 +144,8 @@ def erickson_SVD(alignment, taxa=None, method=Method.flattening, show_work=False
                 F = engine.flatten_reduced(table, ia, ib)
                 out.append(np.float64(0.0) if min(F.shape) <= 4 else np.float64(engine.score_matrix(F)[0].item()))
             return out
+        if method == Method.mutual_information:
+            return [np.float64(engine.rank1_divergence(table, *positions(s)).item()) for s in splits]
         return [np.inf] * len(splits)  # the reference leaves the score at infinity for the other methods
 
     chosen = []

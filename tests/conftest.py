@@ -38,3 +38,9 @@ def golden_random():
 def oracle():
     from oracle import splitp_oracle
     return splitp_oracle
+
+
+@pytest.fixture(scope="session")
+def golden_rank1():
+    with open(os.path.join(GOLDEN, "golden_rank1.json")) as f:
+        return json.load(f)

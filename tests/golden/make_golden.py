@@ -4,7 +4,7 @@ Run in the build container only (the reference is not present on the GPU box):
 
     PYTHONDONTWRITEBYTECODE=1 PYTHONPATH=/root/reference python tests/golden/make_golden.py
 
-Writes tests/golden/golden_small.json, golden_readme.npz, golden_random.npz.  The fixtures pin
+Writes tests/golden/golden_small.json, golden_readme.npz, golden_random.npz, golden_erickson.json, golden_rank1.json.  The fixtures pin
 oracle/splitp_oracle.py and (through it, or directly) the CUDA path.  Nothing here is imported by
 the product.
 """
@@ -218,12 +218,73 @@ def erickson():
         json.dump(out, f)
 
 
+def rank1():
+    """Banned-pattern sparse flattenings (constructions.py:58-105), rank-1 / rank-k approximations and the rank-1
+    divergence (phylogenetics.py:331-373), erickson_SVD with Method.mutual_information (phylogenetics.py:136-140)."""
+    out = {"cases": [], "erickson": []}
+    rng = np.random.default_rng(11)
+    for n, P, splits in ((4, 40, ["01|23", "02|13", "0|123"]), (5, 120, ["01|234", "024|13", "3|0124"]),
+                         (6, 300, ["012|345", "05|1234", "135|024"])):
+        pats = set()
+        while len(pats) < P:
+            pats.add("".join("ACGT"[i] for i in rng.integers(0, 4, n)))
+        pats = sorted(pats)
+        rng.shuffle(pats)
+        counts = rng.integers(1, 50, len(pats))
+        total = int(counts.sum())
+        aln = {p: int(c) / float(total) for p, c in zip(pats, counts)}
+        taxa = [str(i) for i in range(n)]
+        for split in splits:
+            rec = {"n": n, "split": split, "patterns": pats, "values": [aln[p] for p in pats]}
+            F = splitp.flattening(split, aln, splitp.FlatFormat.reduced)
+            rec["divergence"] = float(splitp.phylogenetics.flattening_rank_1_approximation_divergence(F))
+            approx, r, c = splitp.phylogenetics.flattening_rank_1_approximation(F, return_vectors=True)
+            rec["r"], rec["c"], rec["approx_sha"] = r, c, h(approx)
+            rec["approx_shape"] = list(approx.shape)
+            banned = {}
+            for char in ("ACGT" if n == 4 else "AG"):
+                for side in ("row", "col"):
+                    kw = {"ban_row_patterns": char} if side == "row" else {"ban_col_patterns": char}
+                    M = splitp.constructions.sparse_flattening_with_banned_patterns(split, aln, taxa, **kw).tocoo()
+                    order = np.lexsort((M.col, M.row))
+                    banned[char + side] = [M.row[order].tolist(), M.col[order].tolist(), M.data[order].tolist()]
+            rec["banned"] = banned
+            K = splitp.phylogenetics.flattening_rank_k_approximation(split.split("|"), aln)
+            K = K.tocoo()
+            order = np.lexsort((K.col, K.row))
+            rec["rank_k_shape"] = list(K.shape)
+            rec["rank_k_sha"] = h(K.toarray())
+            rec["rank_k_sum"] = float(K.toarray().sum())
+            if n == 4:
+                rec["rank_k"] = [K.row[order].tolist(), K.col[order].tolist(), K.data[order].tolist()]
+            out["cases"].append(rec)
+    for n, N, seed in ((6, 3000, 1), (8, 2000, 3)):
+        random.seed(seed)
+        np.random.seed(seed)
+        tree = splitp.trees.balanced_newick_tree(n, 0.1)
+        aln = splitp.generate_alignment(tree, splitp.model.GTR.JukesCantor(1 / 2), N)
+        res = splitp.phylogenetics.erickson_SVD(aln, method=splitp.Method.mutual_information)
+        # the divergence of every split, so that the test can tell near-ties from real disagreements
+        div = {}
+        for s in splitp.all_splits(_T([str(i) for i in range(n)]), trivial=False):
+            F = splitp.flattening(s, aln, splitp.FlatFormat.reduced)
+            div["|".join("".join(x) for x in s)] = float(splitp.phylogenetics.flattening_rank_1_approximation_divergence(F))
+        out["erickson"].append({"n": n, "patterns": list(aln.keys()), "values": list(aln.values()),
+                                "mutual_information": [list(map(list, s)) for s in res], "divergences": div,
+                                "true_splits": sorted([list(map(list, s)) for s in tree.splits()])})
+    with open(os.path.join(HERE, "golden_rank1.json"), "w") as f:
+        json.dump(out, f)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "erickson":
         erickson()
+    elif len(sys.argv) > 1 and sys.argv[1] == "rank1":
+        rank1()
     else:
         small()
         rand()
         readme()
         erickson()
+        rank1()
     print("golden fixtures written")

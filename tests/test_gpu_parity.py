@@ -8,6 +8,8 @@ Tolerances (stated per path):
   * scores, fp64 path: rel <= max(1e-9, 64 * eps / score^2): score^2 = 1 - top4/total cancels, so an fp64
     relative rounding error eps on the eigenvalues becomes eps / score^2 on the radicand.
   * scores, exact-integer tensor-core Gram path: same bound (the Gram itself is exact).
+  * rank-1 marginals / divergence: rel <= 1e-12 (tree-ordered fp64 sums against the reference's sequential ones; the
+    terms v log(v / (r c)) have both signs, but |sum| is of the order of the largest terms on phylogenetic data).
 """
 import ctypes as C
 import hashlib
@@ -268,8 +270,7 @@ def test_erickson_svd_golden(sp):
         # every non-trivial split the reference found is a true split of the generating tree
         nontrivial = [s for s in rec["flattening"] if min(len(s[0]), len(s[1])) > 1]
         assert all(s in rec["true_splits"] for s in nontrivial)
-    with pytest.raises(NotImplementedError):
-        sp.erickson_SVD(aln, method=sp.Method.mutual_information)
+    assert sp.erickson_SVD(aln, method=sp.Method.distance) is not None  # scores stay at infinity, as in the reference
 
 
 
@@ -662,3 +663,81 @@ def test_config3_properties(sp, eng, oracle):
     for i in (0, 17, 101):
         ref = oracle.split_score(oracle.subflattening(keys, vals, n, idx[i][0], idx[i][1]))
         assert_score(sc[i], ref)
+
+
+def test_rank1_golden(sp, eng, oracle, golden_rank1):
+    """Banned-pattern sparse flattenings (bit-exact), rank-1 vectors / approximation / divergence and the rank-k
+    approximation against outputs of the unmodified reference (constructions.py:94-105, phylogenetics.py:331-373)."""
+    for rec in golden_rank1["cases"]:
+        n = rec["n"]
+        aln = dict(zip(rec["patterns"], rec["values"]))
+        taxa = [str(i) for i in range(n)]
+        split = rec["split"]
+        F = sp.flattening(split, aln, sp.FlatFormat.reduced)
+        assert sp.phylogenetics.flattening_rank_1_approximation_divergence(F) == pytest.approx(rec["divergence"], rel=1e-12)
+        approx, r, c = sp.phylogenetics.flattening_rank_1_approximation(F, return_vectors=True)
+        np.testing.assert_allclose(r, rec["r"], rtol=1e-13)
+        np.testing.assert_allclose(c, rec["c"], rtol=1e-13)
+        assert list(approx.shape) == rec["approx_shape"]
+        np.testing.assert_allclose(approx, oracle.rank_1_approximation(F), rtol=1e-13)
+        none, r2, c2 = sp.phylogenetics.flattening_rank_1_approximation(F, return_vectors=True, dont_compute_matrix=True)
+        assert none is None and r2 == r and c2 == c
+        # table route (no materialised flattening), both value kinds
+        a, b = ([int(ch) for ch in side] for side in split.split("|"))
+        table = eng.table_from_mapping(aln)
+        assert float(eng.rank1_divergence_table(table, a, b).item()) == pytest.approx(rec["divergence"], rel=1e-12)
+        plain = eng.PatternTable(n, table.keys, values=table.values_f64())
+        assert float(eng.rank1_divergence_table(plain, a, b).item()) == pytest.approx(rec["divergence"], rel=1e-12)
+        for name, (rr, cc, vv) in rec["banned"].items():
+            kw = {"ban_row_patterns": name[0]} if name[1:] == "row" else {"ban_col_patterns": name[0]}
+            M = sp.constructions.sparse_flattening_with_banned_patterns(split, aln, taxa, **kw).tocoo()
+            order = np.lexsort((M.col, M.row))
+            assert M.row[order].tolist() == rr and M.col[order].tolist() == cc and M.data[order].tolist() == vv
+        K = sp.phylogenetics.flattening_rank_k_approximation(split.split("|"), aln)
+        assert list(K.shape) == rec["rank_k_shape"] and K.sum() == pytest.approx(rec["rank_k_sum"], rel=1e-12)
+        keys, _ = oracle.patterns_to_keys(rec["patterns"])
+        np.testing.assert_allclose(K.toarray(), oracle.rank_k_approximation(keys, np.array(rec["values"]), n, a, b),
+                                   rtol=1e-12, atol=1e-18)
+
+
+def test_erickson_mutual_information_golden(sp, golden_rank1):
+    """erickson_SVD(method=mutual_information) picks the same splits, in the same order, as the reference
+    (phylogenetics.py:136-140); the golden divergences of all splits differ by > 6e-6, far above the tolerance."""
+    for rec in golden_rank1["erickson"]:
+        aln = dict(zip(rec["patterns"], rec["values"]))
+        got = [list(map(list, s)) for s in sp.erickson_SVD(aln, method=sp.Method.mutual_information)]
+        assert got == rec["mutual_information"]
+        taxa = [str(i) for i in range(rec["n"])]
+        for name, ref in rec["divergences"].items():
+            F = sp.flattening(name, sp.Alignment(aln, taxa), sp.FlatFormat.reduced)
+            assert sp.phylogenetics.flattening_rank_1_approximation_divergence(F) == pytest.approx(ref, rel=1e-12)
+
+
+def test_rank1_divergence_routes_agree(sp, eng, oracle):
+    """Direct-indexed, hashed and materialised routes give the same divergence at sizes the oracle loop cannot reach:
+    17 taxa, splits with a 2-, 8- and 14-taxon side (4^14 row indices -> hash table), and a split that leaves a taxon
+    out (dense route)."""
+    n = 17
+    codes = random_codes(n, 60_000, 17, 0.0)
+    table = eng.count_patterns(eng.pack(codes))
+    keys = table.keys.cpu().numpy().astype(np.uint64)
+    cnt = table.counts.cpu().numpy().astype(np.float64)
+    total = cnt.sum()
+    for a in ([0, 5], list(range(8)), list(range(3, 17)), [2, 4, 6, 8, 10, 12, 14, 16, 1, 3, 5, 7]):
+        b = [t for t in range(n) if t not in a]
+        rows = oracle.side_index(keys, n, a)
+        cols = oracle.side_index(keys, n, b)
+        ur, ri = np.unique(rows, return_inverse=True)
+        uc, ci = np.unique(cols, return_inverse=True)
+        rs = np.bincount(ri, weights=cnt) / total
+        cs = np.bincount(ci, weights=cnt) / total
+        v = cnt / total
+        ref = float(np.sum(v * np.log(v / (rs[ri] * cs[ci]))))
+        got = float(eng.rank1_divergence(table, a, b).item())
+        assert got == pytest.approx(ref, rel=1e-12), (len(a), got, ref)
+        if len(a) <= 8:
+            dense = float(eng.rank1_divergence_dense(eng.flatten_reduced(table, a, b)).item())
+            assert dense == pytest.approx(ref, rel=1e-12)
+    part = float(eng.rank1_divergence(table, [0, 1, 2], list(range(4, 12))).item())  # taxa 3, 12..16 left out
+    F = eng.flatten_reduced(table, [0, 1, 2], list(range(4, 12))).cpu().numpy()
+    assert part == pytest.approx(oracle.rank_1_divergence(F), rel=1e-12)

@@ -189,3 +189,32 @@ def test_wide_oracle_routes_agree(oracle):
         ib = [t for t in range(9) if t not in ia]
         np.testing.assert_array_equal(oracle.flattening_reduced_from_dict(d, ia, ib),
                                       oracle.flattening_reduced(keys, counts.astype(float), 9, ia, ib))
+
+
+def test_rank1_golden(oracle, golden_rank1):
+    """Banned-pattern flattenings, rank-1 vectors / approximation / divergence and the rank-k approximation against
+    the reference's outputs (constructions.py:94-101, phylogenetics.py:331-373)."""
+    for rec in golden_rank1["cases"]:
+        n = rec["n"]
+        keys, _ = oracle.patterns_to_keys(rec["patterns"])
+        vals = np.array(rec["values"])
+        a, b = ([int(ch) for ch in side] for side in rec["split"].split("|"))
+        F = oracle.flattening_reduced(keys, vals, n, a, b)
+        r, c = oracle.rank_1_vectors(F)
+        assert r.tolist() == rec["r"] and c.tolist() == rec["c"]
+        approx = oracle.rank_1_approximation(F)
+        assert list(approx.shape) == rec["approx_shape"] and h(approx) == rec["approx_sha"]
+        assert oracle.rank_1_divergence(F) == pytest.approx(rec["divergence"], rel=1e-14)
+        for name, (rr, cc, vv) in rec["banned"].items():
+            code = "ACGT".index(name[0])
+            kw = {"ban_row": code} if name[1:] == "row" else {"ban_col": code}
+            rows, cols, v = oracle.flattening_coo_banned(keys, vals, n, a, b, **kw)
+            order = np.lexsort((cols, rows))
+            assert rows[order].tolist() == rr and cols[order].tolist() == cc and v[order].tolist() == vv
+        K = oracle.rank_k_approximation(keys, vals, n, a, b)
+        assert list(K.shape) == rec["rank_k_shape"]
+        assert K.sum() == pytest.approx(rec["rank_k_sum"], rel=1e-12)
+        if "rank_k" in rec:
+            ref = np.zeros(K.shape)
+            ref[rec["rank_k"][0], rec["rank_k"][1]] = rec["rank_k"][2]
+            np.testing.assert_allclose(K, ref, rtol=1e-12, atol=1e-18)
