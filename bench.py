@@ -82,15 +82,61 @@ def make_model(sim, name):
 # clocks (nvidia-smi sampled DURING the timed region)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed loops: an in-process NVML (nvidia_ml_py) thread polling
+    the two cheap per-field queries every 100 ms, initialised before the warm-up.  Measured on the c2 step
+    (scripts/step_jitter.py): this leaves the 86 ms steps within +3 ms, whereas a looping `nvidia-smi` child, a poll
+    from the launching thread, or cudaMemGetInfo inside the step each produced sporadic 100-170 ms steps.
+    Falls back to a looping nvidia-smi child when NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.handle, self.max_mhz = None, None, None
+        self.sm, self.reasons, self.active = [], set(), False
+        self.quit = threading.Event()
+
+    def _poll(self):
+        n = self.nvml
+        masks = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.quit.wait(0.1):
+            if not self.active:
+                continue
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:  # noqa: BLE001
+                continue
+            if self.active:
+                self.sm.append(mhz)
+                self.reasons.update(k for k, m in masks.items() if r & m)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            # torch device `index` of this process -> NVML handle via the PCI bus id (CUDA_VISIBLE_DEVICES-proof)
+            bus = getattr(torch.cuda.get_device_properties(self.index), "pci_bus_id", None)
+            if isinstance(bus, int):
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.handle = h
+                        break
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)  # the first query initialises (about 20 ms)
+            self.nvml = pynvml
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] NVML sampling unavailable ({type(exc).__name__}: {exc}); falling back to nvidia-smi", file=sys.stderr)
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -98,19 +144,43 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            if self.active:
+                self.rows.append([x.strip() for x in line.split(",")])
+
+    def reset(self):
+        """Start of a timed loop: forget earlier samples and record from now on."""
+        self.sm, self.reasons, self.rows = [], set(), []
+        self.active = True
+
+    def sample(self):
+        """One extra sample from the calling thread (used when a timed loop is shorter than the polling period)."""
+        if self.nvml is not None and not self.sm:
+            try:
+                self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+            except Exception:  # noqa: BLE001
+                pass
+
+    def close(self):
+        self.quit.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            self.proc = None
 
     def stop(self):
+        """End of a timed loop: summary of the samples taken since reset()."""
+        self.active = False
+        if self.nvml is not None:
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml thread, 100 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
-        self.proc.terminate()
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 250"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -266,8 +336,18 @@ def main():
         prof[key].append((a, b, units))
         return r
 
-    def step(codes):
-        """One pass of the hot path over this rank's shard.  Returns the scores of ALL splits (device)."""
+    def step(codes, probe=None):
+        """One pass of the hot path over this rank's shard.  Returns the scores of ALL splits (device).
+        probe() (clock sample) is called once, from this thread, at a point where the GPU has queued work."""
+        calls = [0]
+
+        def gram_hook(f, nb):
+            r = timed("gram", f, nb)
+            calls[0] += 1
+            if probe is not None and calls[0] == 8:
+                probe()
+            return r
+
         if args.workload == "c2":
             aln = eng.pack(codes, want_planes=False)
             table = timed("count", lambda: eng.count_patterns(aln, reduce_fn=reduce_fn))
@@ -275,12 +355,16 @@ def main():
             if scorer is None:
                 scorer = state["scorer"] = eng.CountScorer(table)
             scorer.table = table
-            out = scorer.score_many(idx_mine, big_hook=(lambda f, nb: timed("gram", f, nb)) if state.get("profile") else None)
+            out = scorer.score_many(idx_mine, big_hook=gram_hook if (state.get("profile") or probe is not None) else None)
+            if probe is not None and calls[0] < 8:
+                probe()
             scorer.check_hi()
         elif args.workload == "c4":
             wide, valid, n_, N_ = eng.pack_wide(codes)
             table = timed("count", lambda: spd.count_patterns_wide_sharded(wide, valid, n_, N_, rank, world, local=True))
             out = eng.thin_split_scores(table, [min((ia, ib), key=len) for ia, ib in idx_mine])
+            if probe is not None:
+                probe()
         else:
             aln = eng.pack(codes, want_sm=False)
             raw = timed("pairs", lambda: eng.pair_raw(aln))
@@ -288,6 +372,8 @@ def main():
                 dist.all_reduce(raw)
             pt = eng.pair_finalize(raw, n, float(N))
             out = eng.subflatten_scores(pt, ma, mb)
+            if probe is not None:
+                probe()
         return spd.gather_strided(out, S, rank, world)
 
     def barrier():
@@ -295,14 +381,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()  # NVML initialisation happens here, before the warm-up, so that it cannot disturb a timed step
+
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
         scores = step(codes_dev)
     barrier()
 
     # ---- timed: device-resident inputs ----
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.reset()
     launches0 = int(eng.lib.spb_launch_count())
     state["profile"] = True
     evs = []
@@ -315,12 +403,14 @@ def main():
         scores = step(codes_dev)
         b.record()
         evs.append((a, b))
+    sampler.sample()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     state["profile"] = False
     launches = int(eng.lib.spb_launch_count()) - launches0
     clocks = sampler.stop()
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = sum(step_ms)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -332,6 +422,7 @@ def main():
     for _ in range(2):
         step(codes_pin.to(dev, non_blocking=True)).cpu()
     barrier()
+    sampler.reset()
     evs2 = []
     for _ in range(args.steps):
         flush.fill_(1)
@@ -340,13 +431,18 @@ def main():
         host_scores = step(codes_pin.to(dev, non_blocking=True)).cpu()
         b.record()
         evs2.append((a, b))
+    sampler.sample()
     barrier()
-    t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in evs2)], dtype=torch.float64, device=dev)
+    clocks2 = sampler.stop()
+    sampler.close()
+    e2e_steps = [a.elapsed_time(b) for a, b in evs2]
+    t2 = torch.tensor([sum(e2e_steps)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_ms = float(t2.item()) / args.steps
     e2e = {"value": S / (e2e_ms * 1e-3), "unit": "split-scores/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(codes_pin.numel()) * world, "d2h_bytes_per_step": S * 8,
+           "ms_steps_rank0": [round(x, 3) for x in e2e_steps], "clocks": clocks2,
            "call": {"c2": "engine.pack + count_patterns + CountScorer.score_many",
                     "c4": "engine.pack_wide + count_patterns_wide + thin_split_scores"}.get(
                         args.workload, "engine.pack + pair_raw/pair_finalize + subflatten_scores")}
@@ -374,8 +470,10 @@ def main():
                 "16.8 MB S0 read + 134 MB G written (part of the writes is still in L2 when the kernel ends)",
                 "peak_source": which, "ms_per_matrix": ms, "launches_timed": len(prof["gram"]), "matrices_per_launch": 16,
                 "executed_frac_of_algorithmic": tiles_done / tiles_all,
-                "note": "algorithmic flops = full 2*R^2*C; the kernel computes only the 272 of 512 tiles touching the upper "
-                        "triangle and mirrors the rest"}
+                "achieved_executed": flops * tiles_done / tiles_all / (ms * 1e-3) / 1e12,
+                "frac_executed": flops * tiles_done / tiles_all / (ms * 1e-3) / 1e12 / (2 * bf16),
+                "note": "algorithmic flops = full 2*R^2*C (SURVEY 8d) while the kernel computes only the 272 of 512 tiles touching the "
+                        "upper triangle and mirrors the rest, so `frac` can exceed 1; `frac_executed` counts the executed MMAs only"}
     elif args.workload == "c4" and prof["count"]:
         ms = float(np.mean([a.elapsed_time(b) for a, b, _ in prof["count"]]))
         nbytes = (se - sb) * 16.0 + (se - sb) / 8.0  # one 128-bit key per site (= N n / 4 at 64 taxa) + validity mask
@@ -403,7 +501,7 @@ def main():
                "config": {"workload": wl["desc"], "taxa": n, "sites": N, "splits": S, "l2": "flushed between timed steps (256 MB fill)",
                           "parallelism": f"sites+splits sharded x{world}"},
                "sites_per_sec": (N / (count_ms * 1e-3)) if count_ms else N / (ms_per_step * 1e-3),
-               "count_stage_ms": count_ms, "wall_s_timed_region": t_wall,
+               "count_stage_ms": count_ms, "wall_s_timed_region": t_wall, "ms_steps_rank0": [round(x, 3) for x in step_ms],
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof}
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_reference_sample(args.workload, codes_full.cpu().numpy(), tree, splits, budget_s=15.0)

@@ -239,6 +239,23 @@ int64_t spb_score_gram_large_ws(int64_t k, int64_t batch);
 int spb_score_gram_large(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores,
                          double* d_info, double* d_ws, void* stream);
 
+/* ---- 32-bit integer form of the exact Gram (halves the HBM traffic of the eigen stage for large matrices) ----
+ * spb_gram_u8_batch_i32: G0 = S0 S0^T as int32 [nb][rows_pad][rows_pad] straight from the tensor-core accumulators
+ * (tiled layout, rows_pad % 256 == 0, pitch <= 32768 so that one accumulation stays below 2^31).
+ * spb_gram_hi_strip_batch: the correction C = S0 H^T + H S0^T + H H^T is non-zero only in the rows / columns of the m
+ * distinct rows that hold a high entry; it is returned as the strip d_Cs [nb][cs_rows][rows_pad] (fp64, exact
+ * integers, zero-filled here) of those rows, with d_pos [nb][rows_pad] = strip index of a row or -1, d_hr
+ * [nb][cs_rows] = the rows, d_hm [nb] = m.  cs_rows must be >= the number of high entries of the table.
+ * spb_score_gram_large_i32: spb_score_gram_large on G = G0 + C (same workspace size, same d_info). */
+int spb_gram_u8_batch_i32(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int32_t* d_Gi,
+                          int64_t g_stride, void* stream);
+int spb_gram_hi_strip_batch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int layout,
+                            const int32_t* d_hi_rc, const uint32_t* d_hi_val, const uint32_t* d_hi_num, int64_t hi_cap,
+                            double* d_Cs, int64_t cs_rows, int32_t* d_pos, int32_t* d_hr, int32_t* d_hm, void* stream);
+int spb_score_gram_large_i32(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Cs, int64_t cs_rows,
+                             const int32_t* d_pos, const int32_t* d_hr, const int32_t* d_hm, double* d_scores, double* d_info,
+                             double* d_ws, void* stream);
+
 /* ---- marginals, rank-1 approximation and rank-1 divergence of a flattening ----
  * reference: phylogenetics.py:331-341 (r = column sums, c = row sums, approximation = r^T c),
  * phylogenetics.py:364-373 (divergence = sum over non-zero cells of F[x,y] log(F[x,y] / (r[y] c[x]))),

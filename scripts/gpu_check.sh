@@ -1,12 +1,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-T="timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=300"
-$T > gpurun_out/t_all.log 2>&1; echo "pytest rc=$?"
-timeout 600 python scripts/phase_profile.py > gpurun_out/phase.log 2>&1; echo "phase rc=$?"
-timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench1.json 2> gpurun_out/bench1.err; echo "bench rc=$?"
-tail -5 gpurun_out/t_all.log; cat gpurun_out/phase.log; cat gpurun_out/bench1.json; tail -5 gpurun_out/bench1.err
-python scripts/ncu_step.py > gpurun_out/ncu_plain_full.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_c2.csv python scripts/ncu_step.py > gpurun_out/ncu_full.log 2>&1; echo "ncu launches rc=$?"
-python scripts/ncu_step.py --per-size 3 > gpurun_out/ncu_plain_small.log 2>&1 && \
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gram_u8_umma -o gpurun_out/prof_gram python scripts/ncu_step.py --per-size 3 > gpurun_out/ncu_small.log 2>&1; echo "ncu full rc=$?"
-ls -la gpurun_out | tail; tail -3 gpurun_out/ncu_full.log gpurun_out/ncu_small.log
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=600 -x > gpurun_out/t_gpu.log 2>&1; echo "pytest rc=$?"
+tail -6 gpurun_out/t_gpu.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench rc=$?"
+cut -c1-200 gpurun_out/bench_c2.json; tail -3 gpurun_out/bench_c2.err

@@ -139,7 +139,7 @@ template <int BN>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 gram_u8_umma_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int T, int KT, int tiles, int ksplit, int kt_per_split,
                     int num_work, int64_t ldg, double* __restrict__ G_base, int64_t g_stride,
-                    unsigned long long* __restrict__ acc_base) {
+                    unsigned long long* __restrict__ acc_base, int32_t* __restrict__ Gi_base) {
   constexpr int kStageBytes = kTileBytes + BN * kTile;  // A tile + B tile(s)
   constexpr uint32_t kTmemCols = 2 * BN;                 // two accumulator stages (power of two >= 32)
   constexpr uint32_t kIdesc = make_idesc_i8(kTile, BN);
@@ -250,6 +250,17 @@ gram_u8_umma_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int 
 #pragma unroll
           for (int e = 0; e < 32; ++e)
             if (v[e]) atomicAdd(dst + e, (unsigned long long)v[e]);
+        } else if (Gi_base) {
+          // 32-bit integer output (one K pass stays below 2^31): half the store traffic of the fp64 form
+          int32_t* Gi = Gi_base + (size_t)wk.b * g_stride;
+          int32_t* dst = Gi + (size_t)row * ldg + col0;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<int4*>(dst + e) = make_int4((int)v[e], (int)v[e + 1], (int)v[e + 2], (int)v[e + 3]);
+          if ((col0 >> 8) > rb) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) Gi[(size_t)(col0 + e) * ldg + row] = (int)v[e];
+          }
         } else {
           double* dst = G + (size_t)row * ldg + col0;
 #pragma unroll
@@ -426,12 +437,107 @@ __global__ void __launch_bounds__(256) hi_self_kernel(const int32_t* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same correction kept OUT of G (32-bit integer Gram): C = S0 H^T + H S0^T + H H^T is non-zero only in the rows
+// and columns that hold a high entry, so the rows C[hr[p]][:] of the m distinct high rows ("strip", fp64, exact
+// integers) describe all of it: C[i][j] = Cs[pos[i]][j] if pos[i] >= 0, else Cs[pos[j]][i] if pos[j] >= 0, else 0.
+// ---------------------------------------------------------------------------------------------------
+// one block per matrix: pos[i] = index of row i among the distinct high rows (ascending) or -1; hr = their list; hm = m
+__global__ void __launch_bounds__(1024) hi_rows_kernel(const int32_t* __restrict__ hi_rc_base, const uint32_t* __restrict__ hi_num_base,
+                                                       int64_t hi_cap, int64_t R, int32_t* __restrict__ pos_base,
+                                                       int32_t* __restrict__ hr_base, int64_t cs_rows, int32_t* __restrict__ hm) {
+  __shared__ int s_part[1024];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int32_t* hi_rc = hi_rc_base + (size_t)b * 2 * hi_cap;
+  int32_t* pos = pos_base + (size_t)b * R;
+  int32_t* hr = hr_base + (size_t)b * cs_rows;
+  int64_t n = hi_num_base[b];
+  if (n > hi_cap) n = hi_cap;
+  for (int64_t i = tid; i < R; i += 1024) pos[i] = 0;
+  __syncthreads();
+  for (int64_t e = tid; e < n; e += 1024) pos[hi_rc[2 * e]] = 1;
+  __syncthreads();
+  const int64_t per = (R + 1023) / 1024;
+  const int64_t i0 = tid * per, i1 = min(R, i0 + per);
+  int cnt = 0;
+  for (int64_t i = i0; i < i1; ++i) cnt += pos[i];
+  s_part[tid] = cnt;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // inclusive scan
+    int v = tid >= o ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = s_part[tid] - cnt;
+  for (int64_t i = i0; i < i1; ++i) {
+    if (pos[i]) {
+      if (run < cs_rows) { pos[i] = run; hr[run] = (int32_t)i; } else pos[i] = -1;
+      ++run;
+    } else {
+      pos[i] = -1;
+    }
+  }
+  if (tid == 1023) hm[b] = (int32_t)min((int64_t)s_part[1023], cs_rows);
+}
+
+__global__ void __launch_bounds__(256) hi_strip_cross_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int layout, int64_t R,
+                                                             int64_t pitch, const int32_t* __restrict__ hi_rc_base,
+                                                             const uint32_t* __restrict__ hi_val_base,
+                                                             const uint32_t* __restrict__ hi_num_base, int64_t hi_cap,
+                                                             const int32_t* __restrict__ pos_base, double* __restrict__ Cs_base,
+                                                             int64_t cs_rows) {
+  const int b = blockIdx.z;
+  const uint8_t* s0 = s0_base + (size_t)b * s0_stride;
+  const int32_t* hi_rc = hi_rc_base + (size_t)b * 2 * hi_cap;
+  const uint32_t* hi_val = hi_val_base + (size_t)b * hi_cap;
+  const int32_t* pos = pos_base + (size_t)b * R;
+  double* Cs = Cs_base + (size_t)b * cs_rows * R;
+  int64_t n = hi_num_base[b];
+  if (n > hi_cap) n = hi_cap;
+  for (int64_t e = blockIdx.y; e < n; e += gridDim.y) {
+    const int64_t r = hi_rc[2 * e], c = hi_rc[2 * e + 1];
+    const int pr = pos[r];
+    const double v = (double)hi_val[e];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.x * blockDim.x) {
+      uint32_t s = s0[s0_offset(layout, R, pitch, i, c)];
+      if (s) {
+        double t = v * (double)s;
+        if (pr >= 0) atomicAdd(Cs + (int64_t)pr * R + i, t);      // (H S0^T)[r][i]
+        const int pi = pos[i];
+        if (pi >= 0) atomicAdd(Cs + (int64_t)pi * R + r, t);      // (S0 H^T)[i][r], kept only for strip rows
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) hi_strip_self_kernel(const int32_t* __restrict__ hi_rc_base, const uint32_t* __restrict__ hi_val_base,
+                                                            const uint32_t* __restrict__ hi_num_base, int64_t hi_cap, int64_t R,
+                                                            const int32_t* __restrict__ pos_base, double* __restrict__ Cs_base,
+                                                            int64_t cs_rows) {
+  const int b = blockIdx.y;
+  const int32_t* hi_rc = hi_rc_base + (size_t)b * 2 * hi_cap;
+  const uint32_t* hi_val = hi_val_base + (size_t)b * hi_cap;
+  const int32_t* pos = pos_base + (size_t)b * R;
+  double* Cs = Cs_base + (size_t)b * cs_rows * R;
+  int64_t n = hi_num_base[b];
+  if (n > hi_cap) n = hi_cap;
+  const int64_t pairs = n * n;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e1 = t / n, e2 = t - e1 * n;
+    if (hi_rc[2 * e1 + 1] == hi_rc[2 * e2 + 1]) {
+      const int p1 = pos[hi_rc[2 * e1]];
+      if (p1 >= 0) atomicAdd(Cs + (int64_t)p1 * R + hi_rc[2 * e2], (double)hi_val[e1] * (double)hi_val[e2]);  // (H H^T)[r1][r2]
+    }
+  }
+}
+
 struct UmmaPlan {
   int BN, T, KT, tiles, ksplit, kt_per_split, num_work;
   size_t smem;
 };
 
-UmmaPlan plan_umma(int64_t rows_pad, int64_t pitch, int nb) {
+UmmaPlan plan_umma(int64_t rows_pad, int64_t pitch, int nb, bool single_pass = false) {
   UmmaPlan p;
   p.BN = rows_pad >= 256 ? 256 : 128;
   p.T = (int)(rows_pad / kTile);
@@ -443,7 +549,7 @@ UmmaPlan plan_umma(int64_t rows_pad, int64_t pitch, int nb) {
   int sms = sm_count();
   int total = p.tiles * nb;
   int ks = 1;
-  if (total < sms) ks = (sms + total - 1) / total;
+  if (total < sms && !single_pass) ks = (sms + total - 1) / total;
   if (ks > p.KT) ks = p.KT;
   int per = (p.KT + ks - 1) / ks;
   if (per > 256) per = 256;
@@ -512,11 +618,11 @@ extern "C" int spb_gram_u8_batch(const uint8_t* d_s0, int64_t s0_stride, int nb,
   if (p.BN == 256) {
     SPB_CUDA(cudaFuncSetAttribute(gram_u8_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     gram_u8_umma_kernel<256><<<grid, kUmmaThreads, p.smem, st>>>(d_s0, s0_stride, p.T, p.KT, p.tiles, p.ksplit, p.kt_per_split,
-                                                               p.num_work, rows_pad, d_G, g_stride, acc);
+                                                               p.num_work, rows_pad, d_G, g_stride, acc, nullptr);
   } else {
     SPB_CUDA(cudaFuncSetAttribute(gram_u8_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     gram_u8_umma_kernel<128><<<grid, kUmmaThreads, p.smem, st>>>(d_s0, s0_stride, p.T, p.KT, p.tiles, p.ksplit, p.kt_per_split,
-                                                               p.num_work, rows_pad, d_G, g_stride, acc);
+                                                               p.num_work, rows_pad, d_G, g_stride, acc, nullptr);
   }
   SPB_LAUNCH_CHECK();
   if (acc) {
@@ -525,6 +631,49 @@ extern "C" int spb_gram_u8_batch(const uint8_t* d_s0, int64_t s0_stride, int nb,
     gram_finalize_kernel<<<fg, 256, 0, st>>>(acc, rows_pad, rows_pad, d_G, g_stride);
     SPB_LAUNCH_CHECK();
   }
+  return SPB_OK;
+}
+
+extern "C" int spb_gram_u8_batch_i32(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch,
+                                     int32_t* d_Gi, int64_t g_stride, void* stream) {
+  SPB_REQUIRE(d_s0 && d_Gi && nb >= 1 && nb <= 65535, "spb_gram_u8_batch_i32: bad arguments");
+  SPB_REQUIRE(rows_pad % 256 == 0 && rows_pad >= 256 && rows_pad <= 32768 && pitch % kTile == 0 && pitch >= kTile,
+              "spb_gram_u8_batch_i32: needs the tiled layout with rows_pad %% 256 == 0 and pitch %% 128 == 0 (got %lld, %lld)",
+              (long long)rows_pad, (long long)pitch);
+  SPB_REQUIRE(pitch <= 256 * kTile, "spb_gram_u8_batch_i32: pitch %lld exceeds the %d columns one 32-bit accumulation can hold",
+              (long long)pitch, 256 * kTile);
+  SPB_REQUIRE(nb == 1 || (s0_stride >= rows_pad * pitch && s0_stride % 16 == 0 && g_stride >= rows_pad * rows_pad),
+              "spb_gram_u8_batch_i32: bad batch strides");
+  UmmaPlan p = plan_umma(rows_pad, pitch, nb, true);
+  if (p.ksplit != 1) { set_error("spb_gram_u8_batch_i32: internal: K split"); return SPB_ERR_ARG; }
+  int grid = p.num_work < sm_count() ? p.num_work : sm_count();
+  SPB_CUDA(cudaFuncSetAttribute(gram_u8_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  gram_u8_umma_kernel<256><<<grid, kUmmaThreads, p.smem, (cudaStream_t)stream>>>(d_s0, s0_stride, p.T, p.KT, p.tiles, 1, p.kt_per_split,
+                                                                              p.num_work, rows_pad, nullptr, g_stride, nullptr, d_Gi);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int spb_gram_hi_strip_batch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int layout,
+                                       const int32_t* d_hi_rc, const uint32_t* d_hi_val, const uint32_t* d_hi_num, int64_t hi_cap,
+                                       double* d_Cs, int64_t cs_rows, int32_t* d_pos, int32_t* d_hr, int32_t* d_hm, void* stream) {
+  SPB_REQUIRE(d_s0 && d_hi_rc && d_hi_val && d_hi_num && d_pos && d_hm && hi_cap >= 0 && nb >= 1 && nb <= 65535 && cs_rows >= 0,
+              "spb_gram_hi_strip: bad arguments");
+  SPB_REQUIRE(cs_rows == 0 || (d_Cs && d_hr), "spb_gram_hi_strip: NULL strip");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cs_rows) SPB_CUDA(cudaMemsetAsync(d_Cs, 0, (size_t)nb * cs_rows * rows_pad * sizeof(double), st));
+  hi_rows_kernel<<<nb, 1024, 0, st>>>(d_hi_rc, d_hi_num, hi_cap, rows_pad, d_pos, d_hr, cs_rows, d_hm);
+  SPB_LAUNCH_CHECK();
+  if (hi_cap == 0 || cs_rows == 0) return SPB_OK;
+  int64_t gy = hi_cap < 64 ? hi_cap : 64;
+  dim3 grid((unsigned)((rows_pad + 255) / 256 > 16 ? 16 : (rows_pad + 255) / 256), (unsigned)gy, (unsigned)nb);
+  hi_strip_cross_kernel<<<grid, 256, 0, st>>>(d_s0, s0_stride, layout, rows_pad, pitch, d_hi_rc, d_hi_val, d_hi_num, hi_cap, d_pos, d_Cs,
+                                              cs_rows);
+  SPB_LAUNCH_CHECK();
+  int64_t gx = (4 * (int64_t)sm_count() + nb - 1) / nb;
+  dim3 sg((unsigned)gx, (unsigned)nb);
+  hi_strip_self_kernel<<<sg, 256, 0, st>>>(d_hi_rc, d_hi_val, d_hi_num, hi_cap, rows_pad, d_pos, d_Cs, cs_rows);
+  SPB_LAUNCH_CHECK();
   return SPB_OK;
 }
 

@@ -269,16 +269,53 @@ constexpr int kKMaxBlocks = 12;
 constexpr int kKDim = kKB * kKMaxBlocks;  // 96
 constexpr int kInfo = 8;      // per-matrix status: top4, trace, residual, dim, cycles, delta_top, theta_4, theta_5 (1-based)
 
+// The matrix the Krylov solver works on: either fp64 G, or the exact 32-bit integer Gram G0 of the low bytes plus
+// the high-part correction C kept as a strip of its m non-zero rows (gram.cu, "hi_strip"):
+//   G = G0 + C,   C[i][j] = Cs[pos[i]][j] if pos[i] >= 0, else Cs[pos[j]][i] if pos[j] >= 0, else 0.
+// The integer form halves the bytes every G Q product streams from HBM.
+struct GramView {
+  const double* Gf;    // [batch][ld][ld] or nullptr
+  const int32_t* Gi;   // [batch][ld][ld] or nullptr
+  int64_t ld;
+  const double* Cs;    // [batch][cs_rows][ld]
+  int64_t cs_rows;
+  const int32_t* pos;  // [batch][ld]
+  const int32_t* hr;   // [batch][cs_rows]
+  const int32_t* hm;   // [batch]
+};
+
+__device__ __forceinline__ double view_entry(const GramView& g, int64_t bt, int64_t i, int64_t j) {
+  if (g.Gf) return g.Gf[bt * g.ld * g.ld + i * g.ld + j];
+  double v = (double)g.Gi[bt * g.ld * g.ld + i * g.ld + j];
+  if (g.cs_rows) {
+    const int32_t* pos = g.pos + bt * g.ld;
+    const double* Cs = g.Cs + bt * g.cs_rows * g.ld;
+    const int pi = pos[i];
+    if (pi >= 0) v += Cs[(int64_t)pi * g.ld + j];
+    else {
+      const int pj = pos[j];
+      if (pj >= 0) v += Cs[(int64_t)pj * g.ld + i];
+    }
+  }
+  return v;
+}
+
+__global__ void gram_diag_kernel(const GramView g, int k, double* __restrict__ diag) {
+  const int64_t bt = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) diag[bt * k + i] = view_entry(g, bt, i, i);
+}
+
 // Start block of the first cycle: the 8 rows of G with the largest diagonal entries, i.e. G e_j for the heaviest
 // indices j.  These are columns of G, so the start block already contains one application of G at no cost, and for
 // count flattenings the heavy rows carry most of the dominant eigenvectors: measured on 12-taxon / 10^6-site Gram
 // matrices, 2 Krylov blocks from this start reach the residual that 4 blocks reach from a random start.
-__global__ void __launch_bounds__(256) krylov_top8_kernel(const double* __restrict__ G, int64_t ld, int64_t strideG, int k, int* idx_out) {
+__global__ void __launch_bounds__(256) krylov_top8_kernel(const double* __restrict__ diag, int k, int* idx_out) {
   __shared__ double s_val[256];
   __shared__ int s_idx[256];
   __shared__ int chosen[kKB];
   const int64_t bt = blockIdx.x;
-  const double* Gb = G + bt * strideG;
+  const double* db = diag + bt * k;
   const int tid = threadIdx.x;
   for (int pick = 0; pick < kKB; ++pick) {
     double best = -1.0;
@@ -286,7 +323,7 @@ __global__ void __launch_bounds__(256) krylov_top8_kernel(const double* __restri
     for (int i = tid; i < k; i += 256) {
       bool taken = false;
       for (int p = 0; p < pick; ++p) taken |= (chosen[p] == i);
-      double v = taken ? -1.0 : fabs(Gb[(int64_t)i * ld + i]);
+      double v = taken ? -1.0 : fabs(db[i]);
       if (v > best) { best = v; bi = i; }
     }
     s_val[tid] = best; s_idx[tid] = bi;
@@ -305,13 +342,12 @@ __global__ void __launch_bounds__(256) krylov_top8_kernel(const double* __restri
   }
 }
 
-__global__ void krylov_start_rows_kernel(const double* __restrict__ G, int64_t ld, int64_t strideG, const int* __restrict__ idx, double* Q,
-                                         int64_t strideQ, int k) {
+__global__ void krylov_start_rows_kernel(const GramView g, const int* __restrict__ idx, double* Q, int64_t strideQ, int k) {
   const int64_t bt = blockIdx.y;
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= k) return;
 #pragma unroll
-  for (int c = 0; c < kKB; ++c) Q[bt * strideQ + (int64_t)c * k + pos] = G[bt * strideG + (int64_t)idx[bt * kKB + c] * ld + pos];
+  for (int c = 0; c < kKB; ++c) Q[bt * strideQ + (int64_t)c * k + pos] = view_entry(g, bt, idx[bt * kKB + c], pos);
 }
 
 // AQ[c][i] = sum_j G[i][j] Q[c][j], c < 8.  CTA = 32 rows of G; warp = 4 rows processed together; every lane owns two
@@ -368,6 +404,150 @@ __global__ void __launch_bounds__(256, 2) symv_block_kernel(const double* __rest
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
       if (lane == 0 && row0 + r < k) AQ[(int64_t)bt * strideQ + (int64_t)c * k + row0 + r] = v;
     }
+}
+
+// The same product on the 32-bit integer Gram G0.  Every lane owns FOUR adjacent columns (one 128-bit load per row, so
+// the bytes in flight per lane match the fp64 kernel while the bytes per element halve); the staged Q chunk is stored
+// permuted so that the two 16-byte halves of a lane's four columns come from two conflict-free arrays.  Entries of G0
+// are sums of products of bytes, 0 <= x < 2^31: (2^52 + x) - 2^52 converts exactly with one DADD (I2F.F64 is slow).
+__device__ __forceinline__ double u31_to_double(int x) { return __hiloint2double(0x43300000, x) - 4503599627370496.0; }
+
+__global__ void __launch_bounds__(256, 2) symv_block_i32_kernel(const int32_t* __restrict__ G, int64_t ld, int64_t strideG,
+                                                             const double* __restrict__ Q, int64_t strideQ,
+                                                             double* __restrict__ AQ, int k) {
+  extern __shared__ __align__(16) double s_q[];  // [kKB][kSymvChunk], permuted inside every group of 128 columns
+  const int bt = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kSymvRows + warp * 4;
+  const int32_t* Gb = G + (int64_t)bt * strideG;
+  const double* Qb = Q + (int64_t)bt * strideQ;
+  const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(Gb) & 15) == 0);
+  double acc[4][kKB];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < kKB; ++c) acc[r][c] = 0.0;
+  for (int j0 = 0; j0 < k; j0 += kSymvChunk) {
+    const int len = min(kSymvChunk, k - j0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kKB * kSymvChunk; idx += 256) {
+      const int c = idx / kSymvChunk, j = idx - c * kSymvChunk;
+      const int w = j & 127, e = w & 3;
+      const int pos = (j & ~127) + ((e >> 1) << 6) + ((w >> 2) << 1) + (e & 1);
+      s_q[c * kSymvChunk + pos] = (j < len) ? Qb[(int64_t)c * k + j0 + j] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int jb = 0; jb < len; jb += 128) {
+      const int j = jb + 4 * lane;
+      int4 g[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int32_t* p = Gb + (int64_t)(row0 + r) * ld + j0 + j;
+        if (row0 + r >= k || j >= len) g[r] = make_int4(0, 0, 0, 0);
+        else if (vec_ok && j + 3 < len) g[r] = __ldg(reinterpret_cast<const int4*>(p));
+        else g[r] = make_int4(__ldg(p), (j + 1 < len) ? __ldg(p + 1) : 0, (j + 2 < len) ? __ldg(p + 2) : 0, (j + 3 < len) ? __ldg(p + 3) : 0);
+      }
+      double gd[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        gd[r][0] = u31_to_double(g[r].x); gd[r][1] = u31_to_double(g[r].y);
+        gd[r][2] = u31_to_double(g[r].z); gd[r][3] = u31_to_double(g[r].w);
+      }
+#pragma unroll
+      for (int c = 0; c < kKB; ++c) {
+        const double2 qa = *reinterpret_cast<const double2*>(s_q + c * kSymvChunk + jb + 2 * lane);
+        const double2 qb = *reinterpret_cast<const double2*>(s_q + c * kSymvChunk + jb + 64 + 2 * lane);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          acc[r][c] = fma(gd[r][3], qb.y, fma(gd[r][2], qb.x, fma(gd[r][1], qa.y, fma(gd[r][0], qa.x, acc[r][c]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < kKB; ++c) {
+      double v = acc[r][c];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      if (lane == 0 && row0 + r < k) AQ[(int64_t)bt * strideQ + (int64_t)c * k + row0 + r] = v;
+    }
+}
+
+// AQ += C Q for the strip form of the correction (GramView).  Two deterministic passes, no atomics:
+//   rows i = hr[p]:      AQ[c][i] += sum_j Cs[p][j] Q[c][j]                 (one CTA per strip row, fixed-order reduction)
+//   rows i not in hr:    AQ[c][i] += sum_p Cs[p][i] Q[c][hr[p]]             (one thread per row, p ascending)
+__global__ void __launch_bounds__(256) strip_rows_kernel(const GramView g, const double* __restrict__ Q, int64_t strideQ,
+                                                         double* __restrict__ AQ, int k) {
+  __shared__ double red[kKB][8];
+  const int64_t bt = blockIdx.y;
+  const int p = blockIdx.x;
+  if (p >= g.hm[bt]) return;
+  const double* row = g.Cs + (bt * g.cs_rows + p) * g.ld;
+  const double* Qb = Q + bt * strideQ;
+  double acc[kKB];
+#pragma unroll
+  for (int c = 0; c < kKB; ++c) acc[c] = 0.0;
+  for (int j = threadIdx.x; j < k; j += 256) {
+    const double v = row[j];
+    if (v != 0.0) {
+#pragma unroll
+      for (int c = 0; c < kKB; ++c) acc[c] = fma(v, Qb[(int64_t)c * k + j], acc[c]);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < kKB; ++c) {
+    double v = acc[c];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) red[c][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kKB) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+    AQ[bt * strideQ + (int64_t)threadIdx.x * k + g.hr[bt * g.cs_rows + p]] += v;
+  }
+}
+
+constexpr int kStripChunk = 128;  // strip rows staged per pass
+__global__ void __launch_bounds__(256) strip_cols_kernel(const GramView g, const double* __restrict__ Q, int64_t strideQ,
+                                                         double* __restrict__ AQ, int k) {
+  __shared__ double s_q[kStripChunk][kKB];
+  const int64_t bt = blockIdx.y;
+  const int m = g.hm[bt];
+  if (m == 0) return;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const bool mine = i < k && g.pos[bt * g.ld + i] < 0;
+  const double* Cs = g.Cs + bt * g.cs_rows * g.ld;
+  const double* Qb = Q + bt * strideQ;
+  const int32_t* hr = g.hr + bt * g.cs_rows;
+  double acc[kKB];
+#pragma unroll
+  for (int c = 0; c < kKB; ++c) acc[c] = 0.0;
+  for (int p0 = 0; p0 < m; p0 += kStripChunk) {
+    const int len = min(kStripChunk, m - p0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < len * kKB; t += 256) {
+      const int pp = t / kKB, c = t - pp * kKB;
+      s_q[pp][c] = Qb[(int64_t)c * k + hr[p0 + pp]];
+    }
+    __syncthreads();
+    if (mine) {
+      for (int pp = 0; pp < len; ++pp) {
+        const double v = Cs[(int64_t)(p0 + pp) * g.ld + i];
+        if (v != 0.0) {
+#pragma unroll
+          for (int c = 0; c < kKB; ++c) acc[c] = fma(v, s_q[pp][c], acc[c]);
+        }
+      }
+    }
+  }
+  if (mine) {
+#pragma unroll
+    for (int c = 0; c < kKB; ++c) AQ[bt * strideQ + (int64_t)c * k + i] += acc[c];
+  }
 }
 
 __global__ void copy_block_kernel(const double* src, int64_t strideS, double* dst, int64_t strideD, int64_t elems) {
@@ -458,7 +638,7 @@ __global__ void __launch_bounds__(256) krylov_svqb_apply_kernel(double* W, int64
 // Ritz vectors (Vtop [dim][8]), their Ritz values (theta [8]), zeroes the residual accumulators and updates
 // info = {top4, trace(G), residual (filled by ritz_kernel), dim, cycles, |top4 - previous top4| / trace}.
 __global__ void __launch_bounds__(256) krylov_rr_kernel(const double* __restrict__ T, int64_t strideT, int dim,
-                                                        const double* __restrict__ G, int k, int64_t ld, double* Vtop, double* theta,
+                                                        const double* __restrict__ diag, int k, double* Vtop, double* theta,
                                                         double* res2, double* info) {
   extern __shared__ __align__(16) double s_A[];  // A [dim][dim|1], V [dim][dim|1]
   __shared__ JacobiScratch js;
@@ -470,9 +650,9 @@ __global__ void __launch_bounds__(256) krylov_rr_kernel(const double* __restrict
   const int lda = dim | 1;
   double* s_V = s_A + dim * lda;
   const double* Tb = T + bt * strideT;
-  const double* Gb = G + bt * ld * ld;
+  const double* db = diag + bt * k;
   double tr = 0.0;
-  for (int i = tid; i < k; i += blockDim.x) tr += Gb[(int64_t)i * ld + i];
+  for (int i = tid; i < k; i += blockDim.x) tr += db[i];
   red[tid] = tr;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
@@ -566,7 +746,7 @@ __global__ void krylov_finish_kernel(const double* __restrict__ theta, const dou
 }
 
 struct KrylovWs {
-  double *Q, *AQ, *C, *S, *U, *T, *Vtop, *theta, *res2, *info, *part, *idx;
+  double *Q, *AQ, *C, *S, *U, *T, *Vtop, *theta, *res2, *info, *part, *idx, *diag;
   int64_t sQ, sC, sS, sT, part_elems;
 };
 
@@ -588,6 +768,7 @@ static int64_t krylov_layout(int64_t k, int64_t batch, double* base, KrylovWs* w
   w->res2 = take(batch * 4);
   w->info = take(batch * kInfo);
   w->idx = take(batch * kKB);  // int[8] per matrix (start rows), stored in double-sized slots
+  w->diag = take(batch * k);   // diagonal of G (start-row choice, trace)
   // partial sums of the inner-product kernel: ceil(k / 128) chunks of the largest (96 x 96) product
   w->part_elems = batch * ((k + kDotChunk - 1) / kDotChunk) * (int64_t)kKDim * kKDim;
   w->part = take(w->part_elems);
@@ -634,7 +815,8 @@ extern "C" int64_t spb_score_gram_large_ws(int64_t k, int64_t batch) {
 
 // One Krylov cycle with `nb` blocks (dim = 8 nb).  first = 1 starts from pseudo-random vectors, otherwise from the
 // Ritz vectors the previous cycle left in Q_0.
-static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb, bool first, const KrylovWs& w, cudaStream_t st) {
+static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first, const KrylovWs& w, cudaStream_t st) {
+  const int64_t ld = gv.ld;
   const int64_t blk = (int64_t)kKB * k;
   const int dim = nb * kKB;
   int rc;
@@ -651,10 +833,12 @@ static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb,
     return SPB_OK;
   };
   if (first) {
-    krylov_top8_kernel<<<batch, 256, 0, st>>>(d_G, ld, ld * ld, k, reinterpret_cast<int*>(w.idx));
-    SPB_LAUNCH_CHECK();
     dim3 grid((k + 255) / 256, batch);
-    krylov_start_rows_kernel<<<grid, 256, 0, st>>>(d_G, ld, ld * ld, reinterpret_cast<const int*>(w.idx), w.Q, w.sQ, k);
+    gram_diag_kernel<<<grid, 256, 0, st>>>(gv, k, w.diag);
+    SPB_LAUNCH_CHECK();
+    krylov_top8_kernel<<<batch, 256, 0, st>>>(w.diag, k, reinterpret_cast<int*>(w.idx));
+    SPB_LAUNCH_CHECK();
+    krylov_start_rows_kernel<<<grid, 256, 0, st>>>(gv, reinterpret_cast<const int*>(w.idx), w.Q, w.sQ, k);
     SPB_LAUNCH_CHECK();
     if ((rc = ortho_block(w.Q, 2))) return rc;
   } else {
@@ -662,13 +846,23 @@ static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb,
   }
   const size_t symv_smem = (size_t)kKB * kSymvChunk * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(symv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
+  SPB_CUDA(cudaFuncSetAttribute(symv_block_i32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
   for (int j = 0; j < nb; ++j) {
     double* Qj = w.Q + (int64_t)j * blk;
     double* AQj = w.AQ + (int64_t)j * blk;
     {
       dim3 grid((k + kSymvRows - 1) / kSymvRows, batch);
-      symv_block_kernel<<<grid, 256, symv_smem, st>>>(d_G, ld, ld * ld, Qj, w.sQ, AQj, k);
+      if (gv.Gf) symv_block_kernel<<<grid, 256, symv_smem, st>>>(gv.Gf, ld, ld * ld, Qj, w.sQ, AQj, k);
+      else symv_block_i32_kernel<<<grid, 256, symv_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
       SPB_LAUNCH_CHECK();
+      if (!gv.Gf && gv.cs_rows) {
+        dim3 rg((unsigned)gv.cs_rows, batch);
+        strip_rows_kernel<<<rg, 256, 0, st>>>(gv, Qj, w.sQ, AQj, k);
+        SPB_LAUNCH_CHECK();
+        dim3 cg((k + 255) / 256, batch);
+        strip_cols_kernel<<<cg, 256, 0, st>>>(gv, Qj, w.sQ, AQj, k);
+        SPB_LAUNCH_CHECK();
+      }
     }
     if (j == nb - 1) break;
     double* Wn = w.Q + (int64_t)(j + 1) * blk;
@@ -691,7 +885,7 @@ static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb,
   }
   size_t smem = (size_t)2 * dim * (dim | 1) * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(krylov_rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  krylov_rr_kernel<<<batch, 256, smem, st>>>(w.T, w.sT, dim, d_G, k, ld, w.Vtop, w.theta, w.res2, w.info);
+  krylov_rr_kernel<<<batch, 256, smem, st>>>(w.T, w.sT, dim, w.diag, k, w.Vtop, w.theta, w.res2, w.info);
   SPB_LAUNCH_CHECK();
   {
     dim3 grid((k + 255) / 256, batch);
@@ -701,9 +895,10 @@ static int krylov_cycle(const double* d_G, int k, int64_t ld, int batch, int nb,
   return SPB_OK;
 }
 
-extern "C" int spb_score_gram_large(const double* d_G, int64_t k64, int64_t ld, int64_t batch64, double* d_scores, double* d_info,
-                                    double* d_ws, void* stream) {
-  SPB_REQUIRE(d_G && d_scores && d_ws && k64 > kJacobiMaxK && ld >= k64 && batch64 >= 1 && k64 < (1 << 24),
+static int score_gram_large(const GramView& gv, int64_t k64, int64_t batch64, double* d_scores, double* d_info, double* d_ws,
+                            void* stream) {
+  SPB_REQUIRE((gv.Gf || gv.Gi) && d_scores && d_ws && k64 > kJacobiMaxK && gv.ld >= k64 && batch64 >= 1 && k64 < (1 << 24) &&
+                  batch64 <= 65535,
               "spb_score_gram_large: need k > %d and a workspace", kJacobiMaxK);
   const int k = (int)k64, batch = (int)batch64;
   cudaStream_t st = (cudaStream_t)stream;
@@ -716,7 +911,7 @@ extern "C" int spb_score_gram_large(const double* d_G, int64_t k64, int64_t ld, 
   int rc;
   for (int cycle = 0; cycle < kMaxCycles; ++cycle) {
     const int nb = cycle < 2 ? 2 : (cycle < 4 ? 4 : kKMaxBlocks);
-    if ((rc = krylov_cycle(d_G, k, ld, batch, nb, cycle == 0, w, st))) return rc;
+    if ((rc = krylov_cycle(gv, k, batch, nb, cycle == 0, w, st))) return rc;
     krylov_finish_kernel<<<(batch + 127) / 128, 128, 0, st>>>(w.theta, w.res2, w.info, d_scores, batch);
     SPB_LAUNCH_CHECK();
     SPB_CUDA(cudaMemcpyAsync(h_info.data(), w.info, (size_t)batch * kInfo * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -741,4 +936,19 @@ extern "C" int spb_score_gram_large(const double* d_G, int64_t k64, int64_t ld, 
   }
   if (d_info) SPB_CUDA(cudaMemcpyAsync(d_info, w.info, (size_t)batch * kInfo * sizeof(double), cudaMemcpyDeviceToDevice, st));
   return SPB_OK;
+}
+
+extern "C" int spb_score_gram_large(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores, double* d_info,
+                                    double* d_ws, void* stream) {
+  GramView gv{d_G, nullptr, ld, nullptr, 0, nullptr, nullptr, nullptr};
+  return score_gram_large(gv, k, batch, d_scores, d_info, d_ws, stream);
+}
+
+extern "C" int spb_score_gram_large_i32(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Cs,
+                                        int64_t cs_rows, const int32_t* d_pos, const int32_t* d_hr, const int32_t* d_hm,
+                                        double* d_scores, double* d_info, double* d_ws, void* stream) {
+  SPB_REQUIRE(cs_rows >= 0 && cs_rows <= 65535 && (cs_rows == 0 || (d_Cs && d_pos && d_hr && d_hm)),
+              "spb_score_gram_large_i32: bad correction strip");
+  GramView gv{nullptr, d_Gi, ld, d_Cs, cs_rows, d_pos, d_hr, d_hm};
+  return score_gram_large(gv, k, batch, d_scores, d_info, d_ws, stream);
 }

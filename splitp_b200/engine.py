@@ -434,7 +434,10 @@ class CountScorer:
         self.table = table
         self._s0 = {}
         self._G = {}
+        self._Gi = {}
         self._ws = {}
+        self._batch_bytes = None
+        self.int32_gram = True  # large dense splits keep G as int32 + correction strip (half the eigen-stage traffic)
         self.gram_hook = None  # optional wrapper (fn, nb) around the Gram launch (bench.py times it with CUDA events)
 
     @property
@@ -471,6 +474,49 @@ class CountScorer:
             n = int(lib.spb_gram_u8_ws(rows_pad, pitch, layout, 1))
             self._ws[key] = _empty(self.NB * rows_pad * rows_pad, torch.int64) if n else None
         return self._s0[key], g, self._ws[key]
+
+    def _use_i32(self, layout, rows_pad, pitch):
+        return self.int32_gram and layout == SPB_S0_TILED and rows_pad >= 2048 and rows_pad % 256 == 0 and pitch <= 32768
+
+    def _buffers_i32(self, rows_pad, batch):
+        """int32 Gram batch + correction strip (rows sized by the number of high counts of the table)."""
+        cs_rows = max(self.n_hi, 1)
+        b = self._Gi.get(rows_pad)
+        if b is None or b["G"].shape[0] < batch or b["Cs"].shape[1] < cs_rows:
+            b = self._Gi[rows_pad] = {
+                "G": _empty((batch, rows_pad, rows_pad), torch.int32),
+                "Cs": _empty((batch, cs_rows, rows_pad), torch.float64),
+                "pos": _empty((batch, rows_pad), torch.int32),
+                "hr": _empty((batch, cs_rows), torch.int32),
+                "hm": _empty(batch, torch.int32),
+            }
+        return b
+
+    def _gram_batch_i32(self, splits, s0, buf, b0, layout, rows_pad, pitch):
+        """As _gram_batch, into the int32 Gram + strip buffers at batch offset b0."""
+        t = self.table
+        nb = len(splits)
+        arr = (_lib.SpbSplit * nb)(*splits)
+        s0_stride, g_stride = rows_pad * pitch, rows_pad * rows_pad
+        cs_rows = int(buf["Cs"].shape[1])
+        G, Cs, pos, hr, hm = buf["G"][b0:], buf["Cs"][b0:], buf["pos"][b0:], buf["hr"][b0:], buf["hm"][b0:]
+        call("spb_flatten_u8_batch", _p(t.keys), _p(t.counts), t.num, arr, nb, _p(s0), s0_stride, rows_pad, pitch, layout,
+             SPB_U8_NO_MEMSET, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num), self.hi_cap, _st())
+        run = lambda: call("spb_gram_u8_batch_i32", _p(s0), s0_stride, nb, rows_pad, pitch, _p(G), g_stride, _st())  # noqa: E731
+        run() if self.gram_hook is None else self.gram_hook(run, nb)
+        call("spb_gram_hi_strip_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
+             _p(self.hi_num), self.hi_cap, _p(Cs), cs_rows, _p(pos), _p(hr), _p(hm), _st())
+        call("spb_flatten_u8_clear_batch", _p(t.keys), t.num, arr, nb, _p(s0), s0_stride, rows_pad, pitch, layout, _st())
+
+    def _score_i32(self, buf, batch, k, want_info=False):
+        rows_pad = int(buf["G"].shape[1])
+        cs_rows = int(buf["Cs"].shape[1])
+        scores = _empty(batch, torch.float64)
+        info = _empty((batch, 8), torch.float64) if want_info else None
+        ws = _krylov_ws(k, batch)
+        call("spb_score_gram_large_i32", _p(buf["G"]), k, rows_pad, batch, _p(buf["Cs"]), cs_rows, _p(buf["pos"]), _p(buf["hr"]),
+             _p(buf["hm"]), _p(scores), _p(info), _p(ws), _st())
+        return (scores, info) if want_info else scores
 
     def _plan(self, idx_a, idx_b, reduced):
         """Orient the split so that the Gram is taken on the short side; returns the launch geometry."""
@@ -540,9 +586,12 @@ class CountScorer:
             for s, (ia, ib) in enumerate(splits_idx):
                 out[s:s + 1] = self.score(ia, ib, True)
             return out
-        if max_batch_bytes is None:  # Gram batch buffer: at most 16 GB and at most a third of what is free right now
-            held = sum(g.numel() * 8 for g in self._G.values())
-            max_batch_bytes = min(16 << 30, (torch.cuda.mem_get_info()[0] + held) // 3)
+        if max_batch_bytes is None:
+            # Gram batch buffer: at most 16 GB and at most a third of what was free when this scorer first scored.
+            # Queried ONCE: cudaMemGetInfo was measured to take 4-50 ms per call on a busy context.
+            if self._batch_bytes is None:
+                self._batch_bytes = min(16 << 30, torch.cuda.mem_get_info()[0] // 3)
+            max_batch_bytes = self._batch_bytes
         groups = {}
         for s, (ia, ib) in enumerate(splits_idx):
             groups.setdefault(min(len(ia), len(ib)), []).append(s)
@@ -550,16 +599,25 @@ class CountScorer:
         for a, members in groups.items():
             R, Cc = 4 ** a, 4 ** (n - a)
             layout, rows_pad, pitch = self.geometry(R, Cc)
-            B = int(max(1, min(len(members), max_batch, max_batch_bytes // (rows_pad * rows_pad * 8))))
-            s0, G, ws = self._buffers(layout, rows_pad, pitch, B)
+            i32 = self._use_i32(layout, rows_pad, pitch) and R > JACOBI_MAX_K
+            per_matrix = rows_pad * rows_pad * 8 if not i32 else rows_pad * rows_pad * 4 + max(self.n_hi, 1) * rows_pad * 8
+            B = int(max(1, min(len(members), max_batch, max_batch_bytes // per_matrix)))
+            if i32:
+                s0 = self._buffers(layout, rows_pad, pitch, 1)[0]
+                buf = self._buffers_i32(rows_pad, B)
+            else:
+                s0, G, ws = self._buffers(layout, rows_pad, pitch, B)
             self.gram_hook = big_hook if (big_hook is not None and R >= 4096) else None
             for c0 in range(0, len(members), B):
                 chunk = members[c0:c0 + B]
                 for b0 in range(0, len(chunk), self.NB):
                     sub = chunk[b0:b0 + self.NB]
-                    self._gram_batch([self._plan(*splits_idx[s], False)[0] for s in sub], s0, G[b0:b0 + len(sub)], ws, layout,
-                                     rows_pad, pitch)
-                sc = score_gram(G[:len(chunk)], R)
+                    plans = [self._plan(*splits_idx[s], False)[0] for s in sub]
+                    if i32:
+                        self._gram_batch_i32(plans, s0, buf, b0, layout, rows_pad, pitch)
+                    else:
+                        self._gram_batch(plans, s0, G[b0:b0 + len(sub)], ws, layout, rows_pad, pitch)
+                sc = self._score_i32(buf, len(chunk), R) if i32 else score_gram(G[:len(chunk)], R)
                 if chunk == list(range(chunk[0], chunk[0] + len(chunk))):
                     out[chunk[0]:chunk[0] + len(chunk)] = sc
                 else:

@@ -574,6 +574,43 @@ def test_config2_properties(sp, eng, oracle):
 
 
 
+def test_int32_gram_with_correction_strip(sp, eng):
+    """Large dense splits keep the Gram as int32 G0 plus the strip of the high-part correction: G0 + C equals the fp64
+    Gram bit for bit, and the batched scores equal those of the fp64 route (12 taxa, 10^6 sites, 6|6 splits)."""
+    n, N = 12, 1_000_000
+    tree, codes, tab = _count_table(sp, eng, n, N, 2)
+    scorer = eng.CountScorer(tab)
+    assert scorer.n_hi > 0
+    sixes = [s for s in sp.all_splits(tree) if len(s[0]) == 6][::23][:20]
+    idx = [eng.split_positions(s, tree.taxa) for s in sixes]
+    layout, rows_pad, pitch = scorer.geometry(4096, 4096)
+    assert scorer._use_i32(layout, rows_pad, pitch)
+    # (1) exact reconstruction for three splits of one batch
+    s0 = scorer._buffers(layout, rows_pad, pitch, 1)[0]
+    buf = scorer._buffers_i32(rows_pad, 3)
+    scorer._gram_batch_i32([scorer._plan(ia, ib, False)[0] for ia, ib in idx[:3]], s0, buf, 0, layout, rows_pad, pitch)
+    for b, (ia, ib) in enumerate(idx[:3]):
+        m = int(buf["hm"][b].item())
+        hr = buf["hr"][b, :m].to(torch.int64)
+        pos = buf["pos"][b]
+        assert m > 0 and torch.equal(torch.nonzero(pos >= 0).flatten(), hr)  # ascending distinct high rows
+        Cfull = torch.zeros((rows_pad, rows_pad), dtype=torch.float64, device=pos.device)
+        Cfull[:, hr] = buf["Cs"][b, :m].T       # columns of the high rows (symmetry)
+        Cfull[hr, :] = buf["Cs"][b, :m]         # the strip rows themselves
+        G, k = scorer.gram(ia, ib)
+        assert k == 4096
+        assert torch.equal(buf["G"][b].to(torch.float64) + Cfull, G)
+    # (2) batched scores, int32 route against the fp64 route (20 splits = one batch of 16 and one of 4)
+    got = scorer.score_many(idx).cpu().numpy()
+    scorer.int32_gram = False
+    ref = scorer.score_many(idx).cpu().numpy()
+    scorer.int32_gram = True
+    for g, r in zip(got, ref):
+        assert_score(g, r)
+    one = float(scorer.score(*idx[5])[0].item())
+    assert_score(got[5], one)
+
+
 def test_config5_random_splits_32_taxa(sp, eng, oracle):
     """BASELINE configs[4] shape: random splits of a 32-taxon tree, subflattening scores (side sizes 2..16), with an
     oracle check on a sample; plus invariance of the score under swapping the two sides."""
