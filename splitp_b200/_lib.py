@@ -8,6 +8,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 
+import numpy as np
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsplitp_b200.so")
 
@@ -36,6 +38,27 @@ def make_split(n, idx_a, idx_b):
     for i, t in enumerate(idx_b):
         s.idx_b[i] = t
     return s
+
+
+SPLIT_DTYPE = np.dtype([("n", "<i4"), ("a", "<i4"), ("b", "<i4"), ("idx_a", "u1", SPB_MAX_TAXA), ("idx_b", "u1", SPB_MAX_TAXA)])
+assert SPLIT_DTYPE.itemsize == C.sizeof(SpbSplit)
+
+
+def make_splits(n, sides_a, sides_b):
+    """Array of encoded splits built with numpy in one go (per-split ctypes filling costs microseconds each and was
+    7 % of a 2,035-split scoring step).  sides_a / sides_b: equally long sequences of position lists; all sides_a
+    must have one length and all sides_b one length.  Returns (ctypes array usable as spb_split*, numpy owner)."""
+    A = np.asarray(sides_a, dtype=np.int64).reshape(len(sides_a), -1)
+    B = np.asarray(sides_b, dtype=np.int64).reshape(len(sides_b), -1)
+    if n > SPB_MAX_TAXA or A.shape[1] > SPB_MAX_TAXA or B.shape[1] > SPB_MAX_TAXA:
+        raise ValueError(f"at most {SPB_MAX_TAXA} taxa are supported")
+    if A.shape[0] != B.shape[0] or (A.size and (A.min() < 0 or A.max() >= n)) or (B.size and (B.min() < 0 or B.max() >= n)):
+        raise ValueError("split positions out of range")
+    rec = np.zeros(A.shape[0], dtype=SPLIT_DTYPE)
+    rec["n"], rec["a"], rec["b"] = n, A.shape[1], B.shape[1]
+    rec["idx_a"][:, :A.shape[1]] = A
+    rec["idx_b"][:, :B.shape[1]] = B
+    return (SpbSplit * A.shape[0]).from_buffer(rec), rec
 
 
 if not os.path.exists(LIB_PATH):

@@ -410,15 +410,17 @@ __global__ void __launch_bounds__(256, 2) symv_block_kernel(const double* __rest
 // the bytes in flight per lane match the fp64 kernel while the bytes per element halve); the staged Q chunk is stored
 // permuted so that the two 16-byte halves of a lane's four columns come from two conflict-free arrays.  Entries of G0
 // are sums of products of bytes, 0 <= x < 2^31: (2^52 + x) - 2^52 converts exactly with one DADD (I2F.F64 is slow).
+constexpr int kSymvI32Warps = 16;
 __device__ __forceinline__ double u31_to_double(int x) { return __hiloint2double(0x43300000, x) - 4503599627370496.0; }
 
-__global__ void __launch_bounds__(256, 2) symv_block_i32_kernel(const int32_t* __restrict__ G, int64_t ld, int64_t strideG,
-                                                             const double* __restrict__ Q, int64_t strideQ,
-                                                             double* __restrict__ AQ, int k) {
+template <int NW>  // warps per CTA; a CTA covers 4 NW rows and stages every Q chunk once for all of them
+__global__ void __launch_bounds__(32 * NW, 512 / (32 * NW)) symv_block_i32_kernel(const int32_t* __restrict__ G, int64_t ld, int64_t strideG,
+                                                                              const double* __restrict__ Q, int64_t strideQ,
+                                                                              double* __restrict__ AQ, int k) {
   extern __shared__ __align__(16) double s_q[];  // [kKB][kSymvChunk], permuted inside every group of 128 columns
   const int bt = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * kSymvRows + warp * 4;
+  const int row0 = blockIdx.x * (4 * NW) + warp * 4;
   const int32_t* Gb = G + (int64_t)bt * strideG;
   const double* Qb = Q + (int64_t)bt * strideQ;
   const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(Gb) & 15) == 0);
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(256, 2) symv_block_i32_kernel(const int32_t* _
   for (int j0 = 0; j0 < k; j0 += kSymvChunk) {
     const int len = min(kSymvChunk, k - j0);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < kKB * kSymvChunk; idx += 256) {
+    for (int idx = threadIdx.x; idx < kKB * kSymvChunk; idx += 32 * NW) {
       const int c = idx / kSymvChunk, j = idx - c * kSymvChunk;
       const int w = j & 127, e = w & 3;
       const int pos = (j & ~127) + ((e >> 1) << 6) + ((w >> 2) << 1) + (e & 1);
@@ -477,37 +479,55 @@ __global__ void __launch_bounds__(256, 2) symv_block_i32_kernel(const int32_t* _
 // AQ += C Q for the strip form of the correction (GramView).  Two deterministic passes, no atomics:
 //   rows i = hr[p]:      AQ[c][i] += sum_j Cs[p][j] Q[c][j]                 (one CTA per strip row, fixed-order reduction)
 //   rows i not in hr:    AQ[c][i] += sum_p Cs[p][i] Q[c][hr[p]]             (one thread per row, p ascending)
+constexpr int kStripRowsPerCta = 4;  // Q is read once per CTA, so more rows per CTA = less L2 traffic
 __global__ void __launch_bounds__(256) strip_rows_kernel(const GramView g, const double* __restrict__ Q, int64_t strideQ,
                                                          double* __restrict__ AQ, int k) {
-  __shared__ double red[kKB][8];
+  __shared__ double red[kStripRowsPerCta][kKB][8];
   const int64_t bt = blockIdx.y;
-  const int p = blockIdx.x;
-  if (p >= g.hm[bt]) return;
-  const double* row = g.Cs + (bt * g.cs_rows + p) * g.ld;
+  const int p0 = blockIdx.x * kStripRowsPerCta;
+  const int m = g.hm[bt];
+  if (p0 >= m) return;
+  const double* rows = g.Cs + (bt * g.cs_rows + p0) * g.ld;
   const double* Qb = Q + bt * strideQ;
-  double acc[kKB];
+  double acc[kStripRowsPerCta][kKB];
 #pragma unroll
-  for (int c = 0; c < kKB; ++c) acc[c] = 0.0;
+  for (int r = 0; r < kStripRowsPerCta; ++r)
+#pragma unroll
+    for (int c = 0; c < kKB; ++c) acc[r][c] = 0.0;
   for (int j = threadIdx.x; j < k; j += 256) {
-    const double v = row[j];
-    if (v != 0.0) {
+    double v[kStripRowsPerCta];
+    bool any = false;
 #pragma unroll
-      for (int c = 0; c < kKB; ++c) acc[c] = fma(v, Qb[(int64_t)c * k + j], acc[c]);
+    for (int r = 0; r < kStripRowsPerCta; ++r) {
+      v[r] = (p0 + r < m) ? rows[(int64_t)r * g.ld + j] : 0.0;
+      any |= v[r] != 0.0;
+    }
+    if (!any) continue;
+#pragma unroll
+    for (int c = 0; c < kKB; ++c) {
+      const double q = Qb[(int64_t)c * k + j];
+#pragma unroll
+      for (int r = 0; r < kStripRowsPerCta; ++r) acc[r][c] = fma(v[r], q, acc[r][c]);
     }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int c = 0; c < kKB; ++c) {
-    double v = acc[c];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
-    if (lane == 0) red[c][warp] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < kKB) {
-    double v = 0.0;
+  for (int r = 0; r < kStripRowsPerCta; ++r)
 #pragma unroll
-    for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
-    AQ[bt * strideQ + (int64_t)threadIdx.x * k + g.hr[bt * g.cs_rows + p]] += v;
+    for (int c = 0; c < kKB; ++c) {
+      double v = acc[r][c];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+      if (lane == 0) red[r][c][warp] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < kStripRowsPerCta * kKB) {
+    const int r = threadIdx.x / kKB, c = threadIdx.x - r * kKB;
+    if (p0 + r < m) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[r][c][w];
+      AQ[bt * strideQ + (int64_t)c * k + g.hr[bt * g.cs_rows + p0 + r]] += v;
+    }
   }
 }
 
@@ -846,17 +866,20 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
   }
   const size_t symv_smem = (size_t)kKB * kSymvChunk * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(symv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
-  SPB_CUDA(cudaFuncSetAttribute(symv_block_i32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
+  SPB_CUDA(cudaFuncSetAttribute(symv_block_i32_kernel<kSymvI32Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
   for (int j = 0; j < nb; ++j) {
     double* Qj = w.Q + (int64_t)j * blk;
     double* AQj = w.AQ + (int64_t)j * blk;
     {
       dim3 grid((k + kSymvRows - 1) / kSymvRows, batch);
       if (gv.Gf) symv_block_kernel<<<grid, 256, symv_smem, st>>>(gv.Gf, ld, ld * ld, Qj, w.sQ, AQj, k);
-      else symv_block_i32_kernel<<<grid, 256, symv_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
+      else {
+        dim3 gi((k + 4 * kSymvI32Warps - 1) / (4 * kSymvI32Warps), batch);
+        symv_block_i32_kernel<kSymvI32Warps><<<gi, 32 * kSymvI32Warps, symv_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
+      }
       SPB_LAUNCH_CHECK();
       if (!gv.Gf && gv.cs_rows) {
-        dim3 rg((unsigned)gv.cs_rows, batch);
+        dim3 rg((unsigned)((gv.cs_rows + kStripRowsPerCta - 1) / kStripRowsPerCta), batch);
         strip_rows_kernel<<<rg, 256, 0, st>>>(gv, Qj, w.sQ, AQj, k);
         SPB_LAUNCH_CHECK();
         dim3 cg((k + 255) / 256, batch);

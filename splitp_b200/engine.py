@@ -496,7 +496,7 @@ class CountScorer:
         """As _gram_batch, into the int32 Gram + strip buffers at batch offset b0."""
         t = self.table
         nb = len(splits)
-        arr = (_lib.SpbSplit * nb)(*splits)
+        arr = splits if isinstance(splits, C.Array) else (_lib.SpbSplit * nb)(*splits)
         s0_stride, g_stride = rows_pad * pitch, rows_pad * rows_pad
         cs_rows = int(buf["Cs"].shape[1])
         G, Cs, pos, hr, hm = buf["G"][b0:], buf["Cs"][b0:], buf["pos"][b0:], buf["hr"][b0:], buf["hm"][b0:]
@@ -552,7 +552,7 @@ class CountScorer:
         """nb <= SPB_MAX_BATCH dense splits of equal shape, one launch per stage.  G: [nb, rows_pad, rows_pad] view."""
         t = self.table
         nb = len(splits)
-        arr = (_lib.SpbSplit * nb)(*splits)
+        arr = splits if isinstance(splits, C.Array) else (_lib.SpbSplit * nb)(*splits)
         s0_stride, g_stride = rows_pad * pitch, rows_pad * rows_pad
         call("spb_flatten_u8_batch", _p(t.keys), _p(t.counts), t.num, arr, nb, _p(s0), s0_stride, rows_pad, pitch, layout,
              SPB_U8_NO_MEMSET, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num), self.hi_cap, _st())
@@ -596,7 +596,24 @@ class CountScorer:
         for s, (ia, ib) in enumerate(splits_idx):
             groups.setdefault(min(len(ia), len(ib)), []).append(s)
         n = self.table.n
+        everyone = np.arange(n)
         for a, members in groups.items():
+            # encoded splits of the whole group in one numpy pass, short side first (= rows of the Gram side)
+            short, long_ = [], []
+            for s in members:
+                ia, ib = splits_idx[s]
+                if len(ia) > len(ib):
+                    ia, ib = ib, ia
+                short.append(ia)
+                long_.append(ib)
+            try:
+                both = np.concatenate([np.asarray(short, dtype=np.int64).reshape(len(members), -1),
+                                       np.asarray(long_, dtype=np.int64).reshape(len(members), -1)], axis=1)
+            except ValueError:
+                both = None
+            if both is None or both.shape[1] != n or not (np.sort(both, axis=1) == everyone).all():
+                raise ValueError("CountScorer: the split must cover all taxa")
+            _, rec = _lib.make_splits(n, short, long_)
             R, Cc = 4 ** a, 4 ** (n - a)
             layout, rows_pad, pitch = self.geometry(R, Cc)
             i32 = self._use_i32(layout, rows_pad, pitch) and R > JACOBI_MAX_K
@@ -611,12 +628,12 @@ class CountScorer:
             for c0 in range(0, len(members), B):
                 chunk = members[c0:c0 + B]
                 for b0 in range(0, len(chunk), self.NB):
-                    sub = chunk[b0:b0 + self.NB]
-                    plans = [self._plan(*splits_idx[s], False)[0] for s in sub]
+                    nsub = min(self.NB, len(chunk) - b0)
+                    plans = (_lib.SpbSplit * nsub).from_buffer(rec, (c0 + b0) * rec.itemsize)
                     if i32:
                         self._gram_batch_i32(plans, s0, buf, b0, layout, rows_pad, pitch)
                     else:
-                        self._gram_batch(plans, s0, G[b0:b0 + len(sub)], ws, layout, rows_pad, pitch)
+                        self._gram_batch(plans, s0, G[b0:b0 + nsub], ws, layout, rows_pad, pitch)
                 sc = self._score_i32(buf, len(chunk), R) if i32 else score_gram(G[:len(chunk)], R)
                 if chunk == list(range(chunk[0], chunk[0] + len(chunk))):
                     out[chunk[0]:chunk[0] + len(chunk)] = sc
