@@ -422,7 +422,9 @@ class CountScorer:
     every stage (the scatter / correction kernels are a few microseconds each, so batching them is what
     keeps the GPU busy)."""
 
-    NB = _lib.SPB_MAX_BATCH
+    NB = _lib.SPB_MAX_BATCH   # splits per scatter / clear launch (kernel-parameter limit)
+    GNB = 4 * NB              # matrices per Gram / correction launch: 20 tiles x 16 matrices leave the 148 persistent CTAs
+                              # with 2 or 3 tiles each (72 % efficiency at 5|7 of 12 taxa), 64 matrices level that out
 
     def __init__(self, table, hi_cap=None):
         if table.counts is None:
@@ -430,7 +432,7 @@ class CountScorer:
         self._table = None
         self.hi_cap = int(hi_cap) if hi_cap is not None else 0
         self.hi_rc = self.hi_val = None
-        self.hi_num = _zeros(self.NB, torch.int32)
+        self.hi_num = _zeros(self.GNB, torch.int32)
         self.table = table
         self._s0 = {}
         self._G = {}
@@ -452,8 +454,8 @@ class CountScorer:
         self.n_hi = int((table.counts.to(torch.int64) & 0xFFFFFFFF).ge(256).sum().item()) if table.num else 0
         if self.hi_rc is None or self.n_hi > self.hi_cap:
             self.hi_cap = max(self.hi_cap, 1024, 2 * self.n_hi)
-            self.hi_rc = _empty((self.NB, self.hi_cap, 2), torch.int32)
-            self.hi_val = _empty((self.NB, self.hi_cap), torch.int32)
+            self.hi_rc = _empty((self.GNB, self.hi_cap, 2), torch.int32)
+            self.hi_val = _empty((self.GNB, self.hi_cap), torch.int32)
 
     @staticmethod
     def geometry(rows, cols):
@@ -466,13 +468,13 @@ class CountScorer:
     def _buffers(self, layout, rows_pad, pitch, batch=1):
         key = (layout, rows_pad, pitch)
         if key not in self._s0:
-            self._s0[key] = _zeros((self.NB, rows_pad * pitch), torch.uint8)
+            self._s0[key] = _zeros((self.GNB, rows_pad * pitch), torch.uint8)
         g = self._G.get(rows_pad)
         if g is None or g.shape[0] < batch:
             g = self._G[rows_pad] = _empty((batch, rows_pad, rows_pad), torch.float64)
         if key not in self._ws:
             n = int(lib.spb_gram_u8_ws(rows_pad, pitch, layout, 1))
-            self._ws[key] = _empty(self.NB * rows_pad * rows_pad, torch.int64) if n else None
+            self._ws[key] = _empty(self.GNB * rows_pad * rows_pad, torch.int64) if n else None
         return self._s0[key], g, self._ws[key]
 
     def _use_i32(self, layout, rows_pad, pitch):
@@ -492,6 +494,19 @@ class CountScorer:
             }
         return b
 
+    def _scatter(self, arr, nb, s0, layout, rows_pad, pitch, clear=False):
+        """Scatter (or un-scatter) nb <= GNB splits into s0[0:nb], SPB_MAX_BATCH splits per launch."""
+        t = self.table
+        s0_stride, sz = rows_pad * pitch, C.sizeof(_lib.SpbSplit)
+        for j in range(0, nb, self.NB):
+            m = min(self.NB, nb - j)
+            sub = (_lib.SpbSplit * m).from_buffer(arr, j * sz)
+            if clear:
+                call("spb_flatten_u8_clear_batch", _p(t.keys), t.num, sub, m, _p(s0[j:]), s0_stride, rows_pad, pitch, layout, _st())
+            else:
+                call("spb_flatten_u8_batch", _p(t.keys), _p(t.counts), t.num, sub, m, _p(s0[j:]), s0_stride, rows_pad, pitch, layout,
+                     SPB_U8_NO_MEMSET, _p(self.hi_rc[j:]), _p(self.hi_val[j:]), _p(self.hi_num[j:]), self.hi_cap, _st())
+
     def _gram_batch_i32(self, splits, s0, buf, b0, layout, rows_pad, pitch):
         """As _gram_batch, into the int32 Gram + strip buffers at batch offset b0."""
         t = self.table
@@ -500,13 +515,12 @@ class CountScorer:
         s0_stride, g_stride = rows_pad * pitch, rows_pad * rows_pad
         cs_rows = int(buf["Cs"].shape[1])
         G, Cs, pos, hr, hm = buf["G"][b0:], buf["Cs"][b0:], buf["pos"][b0:], buf["hr"][b0:], buf["hm"][b0:]
-        call("spb_flatten_u8_batch", _p(t.keys), _p(t.counts), t.num, arr, nb, _p(s0), s0_stride, rows_pad, pitch, layout,
-             SPB_U8_NO_MEMSET, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num), self.hi_cap, _st())
+        self._scatter(arr, nb, s0, layout, rows_pad, pitch)
         run = lambda: call("spb_gram_u8_batch_i32", _p(s0), s0_stride, nb, rows_pad, pitch, _p(G), g_stride, _st())  # noqa: E731
         run() if self.gram_hook is None else self.gram_hook(run, nb)
         call("spb_gram_hi_strip_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
              _p(self.hi_num), self.hi_cap, _p(Cs), cs_rows, _p(pos), _p(hr), _p(hm), _st())
-        call("spb_flatten_u8_clear_batch", _p(t.keys), t.num, arr, nb, _p(s0), s0_stride, rows_pad, pitch, layout, _st())
+        self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
 
     def _score_i32(self, buf, batch, k, want_info=False):
         rows_pad = int(buf["G"].shape[1])
@@ -549,18 +563,17 @@ class CountScorer:
         call("spb_flatten_u8_clear", _p(t.keys), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch, layout, _st())
 
     def _gram_batch(self, splits, s0, G, ws, layout, rows_pad, pitch):
-        """nb <= SPB_MAX_BATCH dense splits of equal shape, one launch per stage.  G: [nb, rows_pad, rows_pad] view."""
-        t = self.table
+        """nb <= GNB dense splits of equal shape: scatter, ONE Gram launch, ONE correction launch, un-scatter.
+        G: [nb, rows_pad, rows_pad] view."""
         nb = len(splits)
         arr = splits if isinstance(splits, C.Array) else (_lib.SpbSplit * nb)(*splits)
         s0_stride, g_stride = rows_pad * pitch, rows_pad * rows_pad
-        call("spb_flatten_u8_batch", _p(t.keys), _p(t.counts), t.num, arr, nb, _p(s0), s0_stride, rows_pad, pitch, layout,
-             SPB_U8_NO_MEMSET, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num), self.hi_cap, _st())
+        self._scatter(arr, nb, s0, layout, rows_pad, pitch)
         run = lambda: call("spb_gram_u8_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(G), g_stride, _p(ws), _st())  # noqa: E731
         run() if self.gram_hook is None else self.gram_hook(run, nb)
         call("spb_gram_hi_correction_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
              _p(self.hi_num), self.hi_cap, _p(G), g_stride, _st())
-        call("spb_flatten_u8_clear_batch", _p(t.keys), t.num, arr, nb, _p(s0), s0_stride, rows_pad, pitch, layout, _st())
+        self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
 
     def gram(self, idx_a, idx_b, reduced=False):
         """Exact F F^T (short side) of the count flattening of one split.  Returns (G [rows_pad, rows_pad], k)."""
@@ -619,6 +632,7 @@ class CountScorer:
             i32 = self._use_i32(layout, rows_pad, pitch) and R > JACOBI_MAX_K
             per_matrix = rows_pad * rows_pad * 8 if not i32 else rows_pad * rows_pad * 4 + max(self.n_hi, 1) * rows_pad * 8
             B = int(max(1, min(len(members), max_batch, max_batch_bytes // per_matrix)))
+            B = -(-len(members) // -(-len(members) // B))  # equal chunks: no small tail batch through the eigen-solver
             if i32:
                 s0 = self._buffers(layout, rows_pad, pitch, 1)[0]
                 buf = self._buffers_i32(rows_pad, B)
@@ -627,8 +641,8 @@ class CountScorer:
             self.gram_hook = big_hook if (big_hook is not None and R >= 4096) else None
             for c0 in range(0, len(members), B):
                 chunk = members[c0:c0 + B]
-                for b0 in range(0, len(chunk), self.NB):
-                    nsub = min(self.NB, len(chunk) - b0)
+                for b0 in range(0, len(chunk), self.GNB):
+                    nsub = min(self.GNB, len(chunk) - b0)
                     plans = (_lib.SpbSplit * nsub).from_buffer(rec, (c0 + b0) * rec.itemsize)
                     if i32:
                         self._gram_batch_i32(plans, s0, buf, b0, layout, rows_pad, pitch)
