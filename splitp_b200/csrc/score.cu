@@ -411,6 +411,7 @@ __global__ void __launch_bounds__(256, 2) symv_block_kernel(const double* __rest
 // permuted so that the two 16-byte halves of a lane's four columns come from two conflict-free arrays.  Entries of G0
 // are sums of products of bytes, 0 <= x < 2^31: (2^52 + x) - 2^52 converts exactly with one DADD (I2F.F64 is slow).
 constexpr int kSymvI32Warps = 16;
+constexpr bool kSymvI32UseCols = true;  // column-owning kernel (symv_cols_i32_kernel); false = row-owning kernel
 __device__ __forceinline__ double u31_to_double(int x) { return __hiloint2double(0x43300000, x) - 4503599627370496.0; }
 
 template <int NW>  // warps per CTA; a CTA covers 4 NW rows and stages every Q chunk once for all of them
@@ -474,6 +475,87 @@ __global__ void __launch_bounds__(32 * NW, 512 / (32 * NW)) symv_block_i32_kerne
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
       if (lane == 0 && row0 + r < k) AQ[(int64_t)bt * strideQ + (int64_t)c * k + row0 + r] = v;
     }
+}
+
+// Column-owning form of the same product, using the symmetry of G0: AQ[c][j] = sum_i G0[i][j] Q[c][i].  Every lane
+// owns four adjacent columns j and keeps their 4 x 8 sums in registers for the whole kernel; a warp walks down rows
+// (one coalesced 512-byte row segment per load) and reads the 8 Q values of the row as shared-memory BROADCASTS.
+// Against the row-owning kernel above this needs no cross-lane reduction and 8 instead of 20 shared-memory / L1
+// wavefronts per 128 matrix elements (ncu on the row-owning kernel: LSU wavefronts 59 % busy, fp64 pipe 34 %, DRAM
+// 33 %: the shared-memory reads of Q were the limiter, not HBM).  The 16 warps of a CTA split the rows of every chunk;
+// their partial sums are added in warp order through shared memory (deterministic).
+constexpr int kColsWarps = 16;
+constexpr int kColsChunk = 1024;  // rows of Q staged per pass: [kColsChunk][8] doubles = 64 KB
+__global__ void __launch_bounds__(32 * kColsWarps, 1) symv_cols_i32_kernel(const int32_t* __restrict__ G, int64_t ld, int64_t strideG,
+                                                                         const double* __restrict__ Q, int64_t strideQ,
+                                                                         double* __restrict__ AQ, int k) {
+  extern __shared__ __align__(16) double s_x[];  // [kColsChunk][kKB]
+  const int bt = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.x * 128 + 4 * lane;
+  const int32_t* Gb = G + (int64_t)bt * strideG;
+  const double* Qb = Q + (int64_t)bt * strideQ;
+  const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(Gb) & 15) == 0) && col0 + 3 < k;
+  constexpr int kRowsPerWarp = kColsChunk / kColsWarps;  // 64
+  constexpr int kUnroll = 8;
+  double acc[4][kKB];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int c = 0; c < kKB; ++c) acc[e][c] = 0.0;
+  for (int i0 = 0; i0 < k; i0 += kColsChunk) {
+    const int len = min(kColsChunk, k - i0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kKB * kColsChunk; idx += 32 * kColsWarps) {
+      const int c = idx / kColsChunk, i = idx - c * kColsChunk;
+      s_x[i * kKB + c] = (i < len) ? Qb[(int64_t)c * k + i0 + i] : 0.0;
+    }
+    __syncthreads();
+    const int rbeg = warp * kRowsPerWarp;
+    for (int r = rbeg; r < rbeg + kRowsPerWarp && r < len; r += kUnroll) {
+      int4 g[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int row = i0 + r + u;
+        const int32_t* p = Gb + (int64_t)row * ld + col0;
+        if (r + u >= len || col0 >= k) g[u] = make_int4(0, 0, 0, 0);
+        else if (vec_ok) g[u] = __ldg(reinterpret_cast<const int4*>(p));
+        else g[u] = make_int4(__ldg(p), (col0 + 1 < k) ? __ldg(p + 1) : 0, (col0 + 2 < k) ? __ldg(p + 2) : 0, (col0 + 3 < k) ? __ldg(p + 3) : 0);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const double gd0 = u31_to_double(g[u].x), gd1 = u31_to_double(g[u].y), gd2 = u31_to_double(g[u].z), gd3 = u31_to_double(g[u].w);
+        const double2* xr = reinterpret_cast<const double2*>(s_x + (r + u) * kKB);  // rows beyond len hold zeros
+#pragma unroll
+        for (int h = 0; h < kKB / 2; ++h) {
+          const double2 x = xr[h];  // same address in every lane: broadcast
+          acc[0][2 * h] = fma(gd0, x.x, acc[0][2 * h]);         acc[0][2 * h + 1] = fma(gd0, x.y, acc[0][2 * h + 1]);
+          acc[1][2 * h] = fma(gd1, x.x, acc[1][2 * h]);         acc[1][2 * h + 1] = fma(gd1, x.y, acc[1][2 * h + 1]);
+          acc[2][2 * h] = fma(gd2, x.x, acc[2][2 * h]);         acc[2][2 * h + 1] = fma(gd2, x.y, acc[2][2 * h + 1]);
+          acc[3][2 * h] = fma(gd3, x.x, acc[3][2 * h]);         acc[3][2 * h + 1] = fma(gd3, x.y, acc[3][2 * h + 1]);
+        }
+      }
+    }
+  }
+  // add the 16 warps' sums in warp order: tot[c][128 columns]
+  __syncthreads();
+  double* tot = s_x;
+  for (int w = 0; w < kColsWarps; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int c = 0; c < kKB; ++c)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          double* t = tot + c * 128 + 4 * lane + e;
+          *t = (w == 0) ? acc[e][c] : *t + acc[e][c];
+        }
+    }
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < kKB * 128; idx += 32 * kColsWarps) {
+    const int c = idx / 128, j = blockIdx.x * 128 + (idx & 127);
+    if (j < k) AQ[(int64_t)bt * strideQ + (int64_t)c * k + j] = tot[idx];
+  }
 }
 
 // AQ += C Q for the strip form of the correction (GramView).  Two deterministic passes, no atomics:
@@ -867,6 +949,8 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
   const size_t symv_smem = (size_t)kKB * kSymvChunk * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(symv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
   SPB_CUDA(cudaFuncSetAttribute(symv_block_i32_kernel<kSymvI32Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
+  const size_t cols_smem = (size_t)kKB * kColsChunk * sizeof(double);
+  SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
   for (int j = 0; j < nb; ++j) {
     double* Qj = w.Q + (int64_t)j * blk;
     double* AQj = w.AQ + (int64_t)j * blk;
@@ -874,8 +958,13 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
       dim3 grid((k + kSymvRows - 1) / kSymvRows, batch);
       if (gv.Gf) symv_block_kernel<<<grid, 256, symv_smem, st>>>(gv.Gf, ld, ld * ld, Qj, w.sQ, AQj, k);
       else {
-        dim3 gi((k + 4 * kSymvI32Warps - 1) / (4 * kSymvI32Warps), batch);
-        symv_block_i32_kernel<kSymvI32Warps><<<gi, 32 * kSymvI32Warps, symv_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
+        if (kSymvI32UseCols) {
+          dim3 gi((k + 127) / 128, batch);
+          symv_cols_i32_kernel<<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
+        } else {
+          dim3 gi((k + 4 * kSymvI32Warps - 1) / (4 * kSymvI32Warps), batch);
+          symv_block_i32_kernel<kSymvI32Warps><<<gi, 32 * kSymvI32Warps, symv_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
+        }
       }
       SPB_LAUNCH_CHECK();
       if (!gv.Gf && gv.cs_rows) {
