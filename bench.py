@@ -465,10 +465,10 @@ def main():
             "fallback 1.59 PFLOP/s x2"
         roof = {"kernel": "gram_u8_umma_kernel<256> (tcgen05.mma kind::i8, 4096x4096x4096 per 6|6 split)", "bound": "tensor",
                 "achieved": flops / (ms * 1e-3) / 1e12, "peak": 2 * bf16, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / (2 * bf16),
-                "traffic": 96.7e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum = 18.2 MB + 78.5 MB per 4096^2 matrix, from the "
-                "ncu --set full capture of a single-matrix launch (profiles/r1_ncu_gram_umma_v1.txt, launches 12-14); algorithmic "
-                "16.8 MB S0 read + 134 MB G written (part of the writes is still in L2 when the kernel ends)",
-                "peak_source": which, "ms_per_matrix": ms, "launches_timed": len(prof["gram"]), "matrices_per_launch": 16,
+                "traffic": 80.8e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum = 17.1 MB + 63.7 MB per 4096^2 matrix, from the "
+                "ncu --set full capture of a 16-matrix launch (profiles/r1_ncu_c2_gram_symv_u8_final.txt, launch 24); algorithmic "
+                "16.8 MB S0 read + 67.1 MB int32 G0 written",
+                "peak_source": which, "ms_per_matrix": ms, "launches_timed": len(prof["gram"]), "matrices_per_launch": 64,
                 "executed_frac_of_algorithmic": tiles_done / tiles_all,
                 "achieved_executed": flops * tiles_done / tiles_all / (ms * 1e-3) / 1e12,
                 "frac_executed": flops * tiles_done / tiles_all / (ms * 1e-3) / 1e12 / (2 * bf16),

@@ -12,6 +12,6 @@ python scripts/ncu_step.py > gpurun_out/ncu_plain_full.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_c2.csv python scripts/ncu_step.py > gpurun_out/ncu_full.log 2>&1; echo "ncu launches rc=$?"
 python scripts/launch_summary.py gpurun_out/launches_c2.csv "ncu launch list, one c2 step (2,035 splits)" > gpurun_out/launches_c2.md; head -30 gpurun_out/launches_c2.md
 python scripts/ncu_step.py --per-size 16 > gpurun_out/ncu_plain_small.log 2>&1 && \
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"gram_u8_umma|symv_block|u8_kernel" -c 24 -o gpurun_out/prof_c2 python scripts/ncu_step.py --per-size 16 > gpurun_out/ncu_small.log 2>&1; echo "ncu full rc=$?"
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"gram_u8_umma|symv_|u8_kernel|strip_|hi_strip" -c 80 -f -o gpurun_out/prof_c2 python scripts/ncu_step.py --per-size 16 > gpurun_out/ncu_small.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out | tail -5
 timeout 300 python scripts/bench_c1.py > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err; echo "bench c1 rc=$?"; cat gpurun_out/bench_c1.json
