@@ -262,8 +262,29 @@ def cpu_reference_sample(workload, codes_np, tree, splits, budget_s=25.0):
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write there too (NCCL prints "NCCL version ..." when the
+    environment sets NCCL_DEBUG), so file descriptor 1 points at stderr for the whole run and emit() restores it."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(line, flush=True)
+
+
 def main():
     args = parse()
+    quiet_stdout()
     wl = dict(WORKLOADS[args.workload])
     if args.sites:
         wl["sites"] = args.sites
@@ -290,7 +311,7 @@ def main():
         dt = (time.perf_counter() - t0) / max(args.steps, 1)
         v = float(np.mean(vals))
         cb["value"] = v
-        print(json.dumps({"impl": "reference", "metric": "split_scores_per_sec", "value": v, "unit": "split-scores/s",
+        emit(json.dumps({"impl": "reference", "metric": "split_scores_per_sec", "value": v, "unit": "split-scores/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": wl["desc"], "sites": wl["sites"], "splits": len(splits)},
@@ -510,7 +531,7 @@ def main():
         # cheap sanity: the scores are finite and the tree's true splits rank first among their size
         sc = scores.cpu().numpy()
         out["checks"] = {"finite": bool(np.isfinite(sc).all()), "host_equals_device": bool(np.array_equal(sc, host_scores.numpy()))}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
