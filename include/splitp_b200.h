@@ -246,7 +246,9 @@ int spb_score_gram_large(const double* d_G, int64_t k, int64_t ld, int64_t batch
  * distinct rows that hold a high entry; it is returned as the strip d_Cs [nb][cs_rows][rows_pad] (fp64, exact
  * integers, zero-filled here) of those rows, with d_pos [nb][rows_pad] = strip index of a row or -1, d_hr
  * [nb][cs_rows] = the rows, d_hm [nb] = m.  cs_rows must be >= the number of high entries of the table.
- * spb_score_gram_large_i32: spb_score_gram_large on G = G0 + C (same workspace size, same d_info). */
+ * spb_score_gram_large_i32: spb_score_gram_large on G = G0 + C (same workspace size, same d_info).  d_Gi must hold
+ * the FULL symmetric matrix (both triangles, as spb_gram_u8_batch_i32 writes it) with entries in [0, 2^31): the
+ * product kernel reads it column-wise. */
 int spb_gram_u8_batch_i32(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int32_t* d_Gi,
                           int64_t g_stride, void* stream);
 int spb_gram_hi_strip_batch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int layout,

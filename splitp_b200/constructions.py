@@ -39,7 +39,6 @@ def flattening(split, pattern_probabilities, flattening_format=FlatFormat.sparse
     table = engine.table_from_mapping(pattern_probabilities)
     if table.num and max(idx_a + idx_b, default=-1) >= table.n:
         raise IndexError("string index out of range")  # pattern[taxa_indexer[s]] in the reference
-    a, b = len(idx_a), len(idx_b)
     if flattening_format is FlatFormat.reduced:
         return engine.flatten_reduced(table, idx_a, idx_b).cpu().numpy()
     if flattening_format is FlatFormat.dense:

@@ -406,83 +406,17 @@ __global__ void __launch_bounds__(256, 2) symv_block_kernel(const double* __rest
     }
 }
 
-// The same product on the 32-bit integer Gram G0.  Every lane owns FOUR adjacent columns (one 128-bit load per row, so
-// the bytes in flight per lane match the fp64 kernel while the bytes per element halve); the staged Q chunk is stored
-// permuted so that the two 16-byte halves of a lane's four columns come from two conflict-free arrays.  Entries of G0
-// are sums of products of bytes, 0 <= x < 2^31: (2^52 + x) - 2^52 converts exactly with one DADD (I2F.F64 is slow).
-constexpr int kSymvI32Warps = 16;
-constexpr bool kSymvI32UseCols = true;  // column-owning kernel (symv_cols_i32_kernel); false = row-owning kernel
+// Entries of the 32-bit integer Gram G0 are sums of products of bytes, 0 <= x < 2^31: (2^52 + x) - 2^52 converts exactly
+// with one DADD (an I2F.F64 conversion per element made the first int32 kernel conversion-bound).
 __device__ __forceinline__ double u31_to_double(int x) { return __hiloint2double(0x43300000, x) - 4503599627370496.0; }
 
-template <int NW>  // warps per CTA; a CTA covers 4 NW rows and stages every Q chunk once for all of them
-__global__ void __launch_bounds__(32 * NW, 512 / (32 * NW)) symv_block_i32_kernel(const int32_t* __restrict__ G, int64_t ld, int64_t strideG,
-                                                                              const double* __restrict__ Q, int64_t strideQ,
-                                                                              double* __restrict__ AQ, int k) {
-  extern __shared__ __align__(16) double s_q[];  // [kKB][kSymvChunk], permuted inside every group of 128 columns
-  const int bt = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * (4 * NW) + warp * 4;
-  const int32_t* Gb = G + (int64_t)bt * strideG;
-  const double* Qb = Q + (int64_t)bt * strideQ;
-  const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(Gb) & 15) == 0);
-  double acc[4][kKB];
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < kKB; ++c) acc[r][c] = 0.0;
-  for (int j0 = 0; j0 < k; j0 += kSymvChunk) {
-    const int len = min(kSymvChunk, k - j0);
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < kKB * kSymvChunk; idx += 32 * NW) {
-      const int c = idx / kSymvChunk, j = idx - c * kSymvChunk;
-      const int w = j & 127, e = w & 3;
-      const int pos = (j & ~127) + ((e >> 1) << 6) + ((w >> 2) << 1) + (e & 1);
-      s_q[c * kSymvChunk + pos] = (j < len) ? Qb[(int64_t)c * k + j0 + j] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll 2
-    for (int jb = 0; jb < len; jb += 128) {
-      const int j = jb + 4 * lane;
-      int4 g[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int32_t* p = Gb + (int64_t)(row0 + r) * ld + j0 + j;
-        if (row0 + r >= k || j >= len) g[r] = make_int4(0, 0, 0, 0);
-        else if (vec_ok && j + 3 < len) g[r] = __ldg(reinterpret_cast<const int4*>(p));
-        else g[r] = make_int4(__ldg(p), (j + 1 < len) ? __ldg(p + 1) : 0, (j + 2 < len) ? __ldg(p + 2) : 0, (j + 3 < len) ? __ldg(p + 3) : 0);
-      }
-      double gd[4][4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        gd[r][0] = u31_to_double(g[r].x); gd[r][1] = u31_to_double(g[r].y);
-        gd[r][2] = u31_to_double(g[r].z); gd[r][3] = u31_to_double(g[r].w);
-      }
-#pragma unroll
-      for (int c = 0; c < kKB; ++c) {
-        const double2 qa = *reinterpret_cast<const double2*>(s_q + c * kSymvChunk + jb + 2 * lane);
-        const double2 qb = *reinterpret_cast<const double2*>(s_q + c * kSymvChunk + jb + 64 + 2 * lane);
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-          acc[r][c] = fma(gd[r][3], qb.y, fma(gd[r][2], qb.x, fma(gd[r][1], qa.y, fma(gd[r][0], qa.x, acc[r][c]))));
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < kKB; ++c) {
-      double v = acc[r][c];
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-      if (lane == 0 && row0 + r < k) AQ[(int64_t)bt * strideQ + (int64_t)c * k + row0 + r] = v;
-    }
-}
-
-// Column-owning form of the same product, using the symmetry of G0: AQ[c][j] = sum_i G0[i][j] Q[c][i].  Every lane
+// G0 Q on the int32 Gram, column-owning form using the symmetry of G0: AQ[c][j] = sum_i G0[i][j] Q[c][i].  Every lane
 // owns four adjacent columns j and keeps their 4 x 8 sums in registers for the whole kernel; a warp walks down rows
 // (one coalesced 512-byte row segment per load) and reads the 8 Q values of the row as shared-memory BROADCASTS.
-// Against the row-owning kernel above this needs no cross-lane reduction and 8 instead of 20 shared-memory / L1
-// wavefronts per 128 matrix elements (ncu on the row-owning kernel: LSU wavefronts 59 % busy, fp64 pipe 34 %, DRAM
-// 33 %: the shared-memory reads of Q were the limiter, not HBM).  The 16 warps of a CTA split the rows of every chunk;
+// Against a row-owning int32 kernel (the layout of symv_block_kernel with 128-bit loads; measured, then removed) this
+// needs no cross-lane reduction and 8 instead of 20 shared-memory / L1 wavefronts per 128 matrix elements (ncu on the
+// row-owning kernel: LSU wavefronts 59 % busy, fp64 pipe 34 %, DRAM 33 %: the shared-memory reads of Q were the limiter,
+// not HBM; 25 us against 20.7 us per 4096^2 product).  The 16 warps of a CTA split the rows of every chunk;
 // their partial sums are added in warp order through shared memory (deterministic).
 constexpr int kColsWarps = 16;
 constexpr int kColsChunk = 1024;  // rows of Q staged per pass: [kColsChunk][8] doubles = 64 KB
@@ -948,7 +882,6 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
   }
   const size_t symv_smem = (size_t)kKB * kSymvChunk * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(symv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
-  SPB_CUDA(cudaFuncSetAttribute(symv_block_i32_kernel<kSymvI32Warps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
   const size_t cols_smem = (size_t)kKB * kColsChunk * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
   for (int j = 0; j < nb; ++j) {
@@ -958,13 +891,8 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
       dim3 grid((k + kSymvRows - 1) / kSymvRows, batch);
       if (gv.Gf) symv_block_kernel<<<grid, 256, symv_smem, st>>>(gv.Gf, ld, ld * ld, Qj, w.sQ, AQj, k);
       else {
-        if (kSymvI32UseCols) {
-          dim3 gi((k + 127) / 128, batch);
-          symv_cols_i32_kernel<<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
-        } else {
-          dim3 gi((k + 4 * kSymvI32Warps - 1) / (4 * kSymvI32Warps), batch);
-          symv_block_i32_kernel<kSymvI32Warps><<<gi, 32 * kSymvI32Warps, symv_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
-        }
+        dim3 gi((k + 127) / 128, batch);
+        symv_cols_i32_kernel<<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
       }
       SPB_LAUNCH_CHECK();
       if (!gv.Gf && gv.cs_rows) {

@@ -509,7 +509,6 @@ class CountScorer:
 
     def _gram_batch_i32(self, splits, s0, buf, b0, layout, rows_pad, pitch):
         """As _gram_batch, into the int32 Gram + strip buffers at batch offset b0."""
-        t = self.table
         nb = len(splits)
         arr = splits if isinstance(splits, C.Array) else (_lib.SpbSplit * nb)(*splits)
         s0_stride, g_stride = rows_pad * pitch, rows_pad * rows_pad

@@ -611,6 +611,21 @@ def test_int32_gram_with_correction_strip(sp, eng):
     assert_score(got[5], one)
 
 
+def test_int32_gram_without_high_counts(sp, eng):
+    """A short alignment (12 taxa, 600 sites): every count stays below 256, so the correction strip is empty (m = 0)
+    and the int32 route is G0 alone.  Both routes must agree."""
+    tree, codes, tab = _count_table(sp, eng, 12, 600, 77)
+    scorer = eng.CountScorer(tab)
+    assert scorer.n_hi == 0
+    idx = [(list(range(6)), list(range(6, 12))), ([0, 2, 4, 6, 8, 10], [1, 3, 5, 7, 9, 11])]
+    got = scorer.score_many(idx).cpu().numpy()
+    assert int(scorer._Gi[4096]["hm"][:2].sum().item()) == 0
+    scorer.int32_gram = False
+    ref = scorer.score_many(idx).cpu().numpy()
+    for g, r in zip(got, ref):
+        assert_score(g, r)
+
+
 def test_config5_random_splits_32_taxa(sp, eng, oracle):
     """BASELINE configs[4] shape: random splits of a 32-taxon tree, subflattening scores (side sizes 2..16), with an
     oracle check on a sample; plus invariance of the score under swapping the two sides."""

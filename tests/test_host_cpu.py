@@ -177,3 +177,20 @@ def test_bench_reference_arm_runs():
     import json
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_make_splits_matches_make_split():
+    """The vectorised split encoder (one numpy pass per batch) produces the same bytes as the per-split ctypes one."""
+    from splitp_b200 import _lib
+    sides_a = [[0, 1, 2], [3, 5, 7], [11, 0, 4]]
+    sides_b = [[3, 4, 5, 6, 7, 8, 9, 10, 11], [0, 1, 2, 4, 6, 8, 9, 10, 11], [1, 2, 3, 5, 6, 7, 8, 9, 10]]
+    arr, rec = _lib.make_splits(12, sides_a, sides_b)
+    assert len(arr) == 3 and rec.itemsize == 140
+    for i, (a, b) in enumerate(zip(sides_a, sides_b)):
+        assert bytes(arr[i]) == bytes(_lib.make_split(12, a, b))
+    sub = (_lib.SpbSplit * 2).from_buffer(rec, rec.itemsize)  # a batch slice shares the numpy buffer
+    assert bytes(sub[1]) == bytes(_lib.make_split(12, sides_a[2], sides_b[2]))
+    with pytest.raises(ValueError):
+        _lib.make_splits(12, [[0, 12]], [[1, 2]])
+    with pytest.raises(ValueError):
+        _lib.make_splits(65, [[0]], [[1]])
