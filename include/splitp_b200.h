@@ -116,6 +116,13 @@ int spb_compact_hash_wide(const uint64_t* d_hkeys, const uint32_t* d_hcounts, co
  * {h_idx_a} | {all other taxa}, computed from the hashed table by one lookup per (pattern, row). */
 int spb_thin_gram_wide(const uint64_t* d_hkeys, const uint32_t* d_hcounts, int64_t cap, const uint64_t* d_special, int n_taxa,
                        const uint8_t* h_idx_a, int a, double* d_G, void* stream);
+/* The same Gram with a column filter (two bitmaps of filter_words uint32 each in d_filter, zeroed here;
+ * spb_thin_filter_words(cap) = 2 x cap bits per bitmap): patterns whose column holds no second pattern skip their
+ * 4^a - 1 table lookups.  Bit-identical result; d_filter == NULL is spb_thin_gram_wide. */
+int64_t spb_thin_filter_words(int64_t cap);
+int spb_thin_gram_wide_filtered(const uint64_t* d_hkeys, const uint32_t* d_hcounts, int64_t cap, const uint64_t* d_special,
+                                int n_taxa, const uint8_t* h_idx_a, int a, uint32_t* d_filter, int64_t filter_words,
+                                double* d_G, void* stream);
 
 /* ---- a7-a10: flattening (constructions.py:7-102) ---- */
 /* value kinds for the pattern table handed to the flattening kernels */

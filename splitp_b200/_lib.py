@@ -91,6 +91,8 @@ PROTOTYPES = {
     "spb_hash_merge_wide": (_i, [_p, _p, _p, _l, _p, _p, _p, _l, _p, _p, _p]),
     "spb_compact_hash_wide": (_i, [_p, _p, _p, _l, _p, _p, _p, _l, _p, _p]),
     "spb_thin_gram_wide": (_i, [_p, _p, _l, _p, _i, C.c_char_p, _i, _p, _p]),
+    "spb_thin_filter_words": (_l, [_l]),
+    "spb_thin_gram_wide_filtered": (_i, [_p, _p, _l, _p, _i, C.c_char_p, _i, _p, _l, _p, _p]),
     "spb_flatten_coo": (_i, [_p, _l, _sp, _p, _p, _p]),
     "spb_flatten_dense": (_i, [_p, _p, _i, _d, _l, _sp, _p, _p]),
     "spb_flatten_dense_w": (_i, [_p, _p, _i, _d, _l, _sp, _p, _p, _p]),

@@ -198,8 +198,39 @@ __device__ __forceinline__ Key128 set_digit(Key128 k, int shift, uint32_t d) {
   return k;
 }
 
+__device__ __forceinline__ uint64_t column_bit(Key128 p, const ThinSplit& sp, uint64_t bit_mask) {
+  for (int t = 0; t < sp.a; ++t) p = set_digit(p, sp.shift[t], 0u);
+  return hash128(p) & bit_mask;
+}
+
+// Column filter of a thin split.  The column of a pattern is its key with the thin side's digits zeroed; a pattern
+// only has partners (same column, other row) if another pattern hashes to its column bit.  thin_mark_kernel sets
+// seen[h(column)] for every pattern and multi[h] when the bit was already set; thin_gram_wide_kernel then skips the
+// 4^a - 1 table lookups of every pattern whose multi bit is clear.  At 64 taxa nearly every site is its own pattern
+// and almost no column holds two, so the lookups (random 32-byte DRAM reads, the whole cost of the kernel) drop from
+// (4^a - 1) / 2 per pattern to the false-positive rate of the filter (about one pattern in six at 2 x cap bits).
+__global__ void __launch_bounds__(256) thin_mark_kernel(const unsigned long long* __restrict__ hkeys, int64_t cap,
+                                                        const unsigned long long* __restrict__ special, ThinSplit sp,
+                                                        uint32_t* __restrict__ seen, uint32_t* __restrict__ multi, uint64_t bit_mask) {
+  const unsigned long long spc = *special;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= cap; i += (int64_t)gridDim.x * blockDim.x) {
+    Key128 p{kAll, kAll};
+    if (i < cap) {
+      p = load_key(hkeys, (uint64_t)i);
+      if (is_empty(p)) continue;
+    } else if (spc == 0ull) {
+      continue;
+    }
+    const uint64_t h = column_bit(p, sp, bit_mask);
+    const uint32_t bit = 1u << (h & 31);
+    const uint32_t old = atomicOr(seen + (h >> 5), bit);
+    if (old & bit) atomicOr(multi + (h >> 5), bit);
+  }
+}
+
 __global__ void __launch_bounds__(256) thin_gram_wide_kernel(const unsigned long long* __restrict__ hkeys, const uint32_t* __restrict__ hcounts,
                                                              int64_t cap, const unsigned long long* __restrict__ special, ThinSplit sp,
+                                                             const uint32_t* __restrict__ multi, uint64_t bit_mask,
                                                              double* __restrict__ G) {
   // per-CTA partial Gram in 64-bit integers: shared-memory integer atomics are native (a double atomicAdd in shared
   // memory is a CAS loop, which collapses on the few row patterns that carry most sites); sum count^2 <= N^2 < 2^64
@@ -224,6 +255,10 @@ __global__ void __launch_bounds__(256) thin_gram_wide_kernel(const unsigned long
     for (int t = 0; t < sp.a; ++t) r1 = (r1 << 2) | get_digit(p, sp.shift[t]);
     // every unordered pair of patterns that differ only in their row part is found once, from its smaller row
     atomicAdd(&sG[r1 * 16 + r1], (unsigned long long)cp * (unsigned long long)cp);
+    if (multi) {
+      const uint64_t h = column_bit(p, sp, bit_mask);
+      if (!((multi[h >> 5] >> (h & 31)) & 1u)) continue;  // no other pattern shares this column
+    }
     for (int r2 = (int)r1 + 1; r2 < R; ++r2) {
       Key128 q = p;
       for (int t = 0; t < sp.a; ++t) q = set_digit(q, sp.shift[t], ((uint32_t)r2 >> (2 * (sp.a - 1 - t))) & 3u);
@@ -314,8 +349,9 @@ extern "C" int spb_compact_hash_wide(const uint64_t* d_hkeys, const uint32_t* d_
   return SPB_OK;
 }
 
-extern "C" int spb_thin_gram_wide(const uint64_t* d_hkeys, const uint32_t* d_hcounts, int64_t cap, const uint64_t* d_special, int n_taxa,
-                                  const uint8_t* h_idx_a, int a, double* d_G, void* stream) {
+extern "C" int spb_thin_gram_wide_filtered(const uint64_t* d_hkeys, const uint32_t* d_hcounts, int64_t cap, const uint64_t* d_special,
+                                           int n_taxa, const uint8_t* h_idx_a, int a, uint32_t* d_filter, int64_t filter_words,
+                                           double* d_G, void* stream) {
   int rc = check_table(d_hkeys, d_hcounts, cap, "spb_thin_gram_wide");
   if (rc) return rc;
   SPB_REQUIRE(d_special && d_G && h_idx_a, "spb_thin_gram_wide: NULL buffer");
@@ -332,8 +368,30 @@ extern "C" int spb_thin_gram_wide(const uint64_t* d_hkeys, const uint32_t* d_hco
   SPB_CUDA(cudaMemsetAsync(d_G, 0, (size_t)R * R * sizeof(double), st));
   int64_t grid = (int64_t)sm_count() * 8;
   if (grid > (cap + 256) / 256) grid = (cap + 256) / 256;
+  const uint32_t* multi = nullptr;
+  uint64_t bit_mask = 0;
+  if (d_filter) {
+    SPB_REQUIRE(filter_words >= 1 && (filter_words & (filter_words - 1)) == 0, "spb_thin_gram_wide: filter_words must be a power of two");
+    SPB_CUDA(cudaMemsetAsync(d_filter, 0, (size_t)2 * filter_words * sizeof(uint32_t), st));
+    bit_mask = (uint64_t)filter_words * 32 - 1;
+    thin_mark_kernel<<<(unsigned)grid, 256, 0, st>>>((const unsigned long long*)d_hkeys, cap, (const unsigned long long*)d_special, sp,
+                                                     d_filter, d_filter + filter_words, bit_mask);
+    SPB_LAUNCH_CHECK();
+    multi = d_filter + filter_words;
+  }
   thin_gram_wide_kernel<<<(unsigned)grid, 256, 0, st>>>((const unsigned long long*)d_hkeys, d_hcounts, cap, (const unsigned long long*)d_special,
-                                                        sp, d_G);
+                                                        sp, multi, bit_mask, d_G);
   SPB_LAUNCH_CHECK();
   return SPB_OK;
+}
+
+extern "C" int64_t spb_thin_filter_words(int64_t cap) {
+  int64_t w = 1;
+  while (w * 16 < cap) w *= 2;  // 2 x cap bits per bitmap
+  return w;
+}
+
+extern "C" int spb_thin_gram_wide(const uint64_t* d_hkeys, const uint32_t* d_hcounts, int64_t cap, const uint64_t* d_special, int n_taxa,
+                                  const uint8_t* h_idx_a, int a, double* d_G, void* stream) {
+  return spb_thin_gram_wide_filtered(d_hkeys, d_hcounts, cap, d_special, n_taxa, h_idx_a, a, nullptr, 0, d_G, stream);
 }

@@ -968,19 +968,22 @@ def merge_wide_tables(n, keys, counts, usable, taxa=None):
     return WideTable(n, hk, hc, cap, special, usable, taxa)
 
 
-def thin_split_scores(table, thin_sides):
+def thin_split_scores(table, thin_sides, filtered=True):
     """Scores of the splits {side} | {all other taxa} for sides of 1 or 2 taxon positions: exact Gram of the REDUCED
     flattening (4^a rows, one column per distinct pattern of the other taxa) from hash lookups, then the Jacobi
-    scorer.  Sides of one taxon give a 4-row matrix, hence score 0 like the reference."""
+    scorer.  Sides of one taxon give a 4-row matrix, hence score 0 like the reference.  filtered: a per-split column
+    bitmap lets patterns without a partner in their column skip the lookups (same result)."""
     out = _empty(len(thin_sides), torch.float64)
     G = _empty((len(thin_sides), 16, 16), torch.float64)
+    words = int(lib.spb_thin_filter_words(table.cap)) if filtered else 0
+    filt = _empty(2 * words, torch.int32) if filtered else None
     by_a = {1: [], 2: []}
     for s, side in enumerate(thin_sides):
         side = list(side)
         if len(side) not in (1, 2):
             raise NotImplementedError("thin_split_scores: the thin side must have 1 or 2 taxa")
-        call("spb_thin_gram_wide", _p(table.hkeys), _p(table.hcounts), table.cap, _p(table.special), table.n, bytes(side), len(side),
-             _p(G[s]), _st())
+        call("spb_thin_gram_wide_filtered", _p(table.hkeys), _p(table.hcounts), table.cap, _p(table.special), table.n, bytes(side),
+             len(side), _p(filt), words, _p(G[s]), _st())
         by_a[len(side)].append(s)
     for a, members in by_a.items():
         if not members:

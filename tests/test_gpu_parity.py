@@ -522,12 +522,20 @@ def test_thin_split_scores(sp, eng, oracle, n, N, seed):
     ref, usable = oracle.get_pattern_counts_wide(codes.cpu().numpy())
     sides = [[0, 1], [2, 5], [n - 2, n - 1], [1, n // 2], [3]]
     got = eng.thin_split_scores(tab, sides).cpu().numpy()
+    assert np.array_equal(got, eng.thin_split_scores(tab, sides, filtered=False).cpu().numpy())  # the filter changes nothing
+    words = int(eng.lib.spb_thin_filter_words(tab.cap))
+    filt = torch.empty(2 * words, dtype=torch.int32, device="cuda")
     for s, ia in enumerate(sides):
         ib = [t for t in range(n) if t not in ia]
         F = oracle.flattening_reduced_from_dict(ref, ia, ib)
         G = torch.empty((16, 16), dtype=torch.float64, device="cuda")
         eng.call("spb_thin_gram_wide", eng._p(tab.hkeys), eng._p(tab.hcounts), tab.cap, eng._p(tab.special), n, bytes(ia), len(ia),
                  eng._p(G), eng._st())
+        G2 = torch.empty((16, 16), dtype=torch.float64, device="cuda")
+        eng.call("spb_thin_gram_wide_filtered", eng._p(tab.hkeys), eng._p(tab.hcounts), tab.cap, eng._p(tab.special), n, bytes(ia),
+                 len(ia), eng._p(filt), words, eng._p(G2), eng._st())
+        R0 = 4 ** len(ia)
+        assert torch.equal(G.reshape(-1)[:R0 * R0], G2.reshape(-1)[:R0 * R0])
         R = 4 ** len(ia)
         Gd = G.cpu().numpy().reshape(-1)[:R * R].reshape(R, R)
         # rows of the reduced matrix = the USED row patterns, in ascending order: compare on those
