@@ -465,16 +465,20 @@ class CountScorer:
         rp = 128 if rows <= 128 else (rows + 255) // 256 * 256
         return SPB_S0_TILED, rp, (cols + 127) // 128 * 128
 
+    def _gnb(self, rows_pad, pitch):
+        """Matrices per Gram launch: GNB, fewer when one u8 matrix is large (the S0 batch stays within 4 GB)."""
+        return int(max(self.NB, min(self.GNB, (4 << 30) // (rows_pad * pitch))))
+
     def _buffers(self, layout, rows_pad, pitch, batch=1):
         key = (layout, rows_pad, pitch)
         if key not in self._s0:
-            self._s0[key] = _zeros((self.GNB, rows_pad * pitch), torch.uint8)
+            self._s0[key] = _zeros((self._gnb(rows_pad, pitch), rows_pad * pitch), torch.uint8)
         g = self._G.get(rows_pad)
         if g is None or g.shape[0] < batch:
             g = self._G[rows_pad] = _empty((batch, rows_pad, rows_pad), torch.float64)
         if key not in self._ws:
             n = int(lib.spb_gram_u8_ws(rows_pad, pitch, layout, 1))
-            self._ws[key] = _empty(self.GNB * rows_pad * rows_pad, torch.int64) if n else None
+            self._ws[key] = _empty(self._gnb(rows_pad, pitch) * rows_pad * rows_pad, torch.int64) if n else None
         return self._s0[key], g, self._ws[key]
 
     def _use_i32(self, layout, rows_pad, pitch):
@@ -640,8 +644,9 @@ class CountScorer:
             self.gram_hook = big_hook if (big_hook is not None and R >= 4096) else None
             for c0 in range(0, len(members), B):
                 chunk = members[c0:c0 + B]
-                for b0 in range(0, len(chunk), self.GNB):
-                    nsub = min(self.GNB, len(chunk) - b0)
+                gnb = self._gnb(rows_pad, pitch)
+                for b0 in range(0, len(chunk), gnb):
+                    nsub = min(gnb, len(chunk) - b0)
                     plans = (_lib.SpbSplit * nsub).from_buffer(rec, (c0 + b0) * rec.itemsize)
                     if i32:
                         self._gram_batch_i32(plans, s0, buf, b0, layout, rows_pad, pitch)
