@@ -175,8 +175,18 @@ def test_bench_reference_arm_runs():
                         "--sites", "20000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     import json
-    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert len(r.stdout.strip().splitlines()) == 1  # stdout carries exactly one JSON line
+    line = json.loads(r.stdout.strip())
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_bench_reference_arm_under_torchrun_env_prints_on_rank0_only():
+    """Under torchrun the reference arm runs on rank 0 alone; the other ranks exit 0 without output."""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--sites", "20000"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
 
 
 def test_make_splits_matches_make_split():
