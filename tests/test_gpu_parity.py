@@ -801,3 +801,36 @@ def test_rank1_divergence_routes_agree(sp, eng, oracle):
     part = float(eng.rank1_divergence(table, [0, 1, 2], list(range(4, 12))).item())  # taxa 3, 12..16 left out
     F = eng.flatten_reduced(table, [0, 1, 2], list(range(4, 12))).cpu().numpy()
     assert part == pytest.approx(oracle.rank_1_divergence(F), rel=1e-12)
+
+
+def test_config4_full_size_properties(sp, eng):
+    """BASELINE configs[3] at its full size (64 taxa, 10^8 sites, 128-bit keys): every usable site is counted once; the
+    Gram of a thin split has trace = sum of squared counts (every pattern is one cell of the flattening) whatever the
+    split; the column filter changes nothing; a true cherry scores below a false pair."""
+    n, N = 64, 100_000_000
+    tree = sp.trees.balanced_tree(n, 0.05)
+    codes = sp.simulation.simulate_codes(tree, sp.simulation.GTR.JukesCantor(0.5), N, seed=4)
+    wide, valid, n_, N_ = eng.pack_wide(codes)
+    del codes
+    tab = eng.count_patterns_wide(wide, valid, n_, N_)
+    del wide
+    _, counts = tab.compact(sort=False)
+    c64 = counts.to(torch.int64)
+    assert int(c64.sum().item()) == N == int(tab.divisor)
+    sq = int((c64 * c64).sum().item())
+    del counts, c64
+    words = int(eng.lib.spb_thin_filter_words(tab.cap))
+    filt = torch.empty(2 * words, dtype=torch.int32, device="cuda")
+    for side in ([0, 1], [31, 32], [5]):
+        R = 4 ** len(side)
+        G1 = torch.empty((16, 16), dtype=torch.float64, device="cuda")
+        G2 = torch.empty((16, 16), dtype=torch.float64, device="cuda")
+        eng.call("spb_thin_gram_wide", eng._p(tab.hkeys), eng._p(tab.hcounts), tab.cap, eng._p(tab.special), n, bytes(side), len(side),
+                 eng._p(G1), eng._st())
+        eng.call("spb_thin_gram_wide_filtered", eng._p(tab.hkeys), eng._p(tab.hcounts), tab.cap, eng._p(tab.special), n, bytes(side),
+                 len(side), eng._p(filt), words, eng._p(G2), eng._st())
+        g1 = G1.reshape(-1)[:R * R].reshape(R, R)
+        assert torch.equal(g1, G2.reshape(-1)[:R * R].reshape(R, R)) and torch.equal(g1, g1.T)
+        assert int(torch.diagonal(g1).sum().item()) == sq
+    cherry, false_pair = eng.thin_split_scores(tab, [[0, 1], [0, 2]]).cpu().numpy()  # positions 0, 1 = taxa t0, t1: a cherry
+    assert 0.0 <= cherry < 0.5 * false_pair
