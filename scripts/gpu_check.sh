@@ -1,3 +1,4 @@
+# Full check on one B200: all GPU tests, smoke(), the default bench line.   gpurun --timeout 2400 -- "bash scripts/gpu_check.sh"
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=600 -x > gpurun_out/t_gpu.log 2>&1; echo "pytest rc=$?"

@@ -1,3 +1,4 @@
+# ncu launch list (gpu__time_duration.sum per launch) of one c2 step -> gpurun_out/launches_c2.md
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 python scripts/ncu_step.py > gpurun_out/ncu_plain_full.log 2>&1 && \

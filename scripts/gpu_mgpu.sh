@@ -1,3 +1,4 @@
+# torchrun on N GPUs of one box: sharded-path parity (mgpu_check.py), then bench lines c2 / c3 / c5 [/ c4].   gpurun --gpus 8 -- "bash scripts/gpu_mgpu.sh 8 noc4"
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 N=${1:-2}

@@ -1,3 +1,4 @@
+# ncu --set full of the int32 product kernel (32 matrices per launch) -> gpurun_out/prof_symv*
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 python scripts/ncu_step.py --per-size 32 > gpurun_out/ncu_plain_small.log 2>&1 && \

@@ -1,3 +1,5 @@
+# Quick loop on one B200: a subset of the GPU tests (pytest -k "$1") and one bench line (workload "$2", default c2).
+#   gpurun --timeout 900 -- 'bash scripts/gpu_tb.sh "int32_gram or config2" c2'
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=300 -k "${1:-int32_gram}" > gpurun_out/t_quick.log 2>&1; echo "pytest rc=$?"
