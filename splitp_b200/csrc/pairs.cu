@@ -5,6 +5,7 @@
 // constructions.py:143-161.  So the alignment is read ONCE (pair_kernel: bit-plane AND + POPC), the
 // Hadamard-type basis change is n^2 batched 4x4x4 products (finalize / transform kernels) and each
 // split is a gather + a small Gram + Jacobi in shared memory (subflatten_score_kernel).
+#include <stdlib.h>
 #include "common.cuh"
 #include "jacobi.cuh"
 
@@ -272,6 +273,161 @@ __global__ void __launch_bounds__(kSThreads) subflatten_score_kernel(const doubl
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// One WARP per split (n <= 21 taxa: k <= 31 rows, staging matrix <= 1085 doubles).  No CTA barriers at all:
+//   gather M (k x L) -> Gram G = M M^T (lane r owns row r) -> Householder tridiagonalisation of G in the warp's
+//   shared-memory tile (lane i owns row i; v and q are exchanged through two 32-entry arrays) -> the 4 largest
+//   eigenvalues by 9-section with Sturm counts (8 lanes per eigenvalue, 18 rounds) -> score = sqrt((trace - top4) / trace).
+// About 10x fewer warp instructions than the block-wide Jacobi of subflatten_score_kernel; numerics checked on the CPU
+// in scripts/prototype_tridiag_top4.py (worst error 0.04 x the parity tolerance on 317 splits of a 20-taxon alignment).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kWarpMaxTaxa = 21;
+constexpr int kWarpLdg = 33;
+constexpr int kWarpMElems = 1120;
+constexpr int kWarpsPerCta = 4;
+struct WarpScratch {
+  double M[kWarpMElems];
+  double G[32 * kWarpLdg];
+  double v[32], q[32], d[32], e[32];
+  uint8_t la[SPB_MAX_TAXA], lb[SPB_MAX_TAXA];
+};
+
+__device__ __forceinline__ double warp_sum_all(double x) {  // butterfly: every lane ends with the same bits
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+  return x;
+}
+__device__ __forceinline__ double warp_min_all(double x) {
+  for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_xor_sync(0xFFFFFFFFu, x, o));
+  return x;
+}
+__device__ __forceinline__ double warp_max_all(double x) {
+  for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xFFFFFFFFu, x, o));
+  return x;
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta) subflatten_score_warp_kernel(const double* __restrict__ T, const double* __restrict__ total,
+                                                                                   int n, const uint64_t* __restrict__ masks_a,
+                                                                                   const uint64_t* __restrict__ masks_b, int64_t num,
+                                                                                   double* scores) {
+  extern __shared__ __align__(16) unsigned char s_warp_raw[];
+  WarpScratch& ws = reinterpret_cast<WarpScratch*>(s_warp_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const uint64_t full = (n == 64) ? ~0ull : ((1ull << n) - 1ull);
+  const double tot = *total;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t s = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); s < num; s += nwarps) {
+    __syncwarp();
+    const uint64_t ma = masks_a[s] & full;
+    const uint64_t mb = masks_b ? (masks_b[s] & full & ~ma) : (full & ~ma);
+    const int a = __popcll(ma), b = __popcll(mb);
+    for (int t = lane; t < 64; t += 32) {  // position lists in ascending taxon order, as the block-wide kernel builds them
+      const uint64_t below = (1ull << t) - 1ull;
+      if ((ma >> t) & 1ull) ws.la[__popcll(ma & below)] = (uint8_t)t;
+      if ((mb >> t) & 1ull) ws.lb[__popcll(mb & below)] = (uint8_t)t;
+    }
+    __syncwarp();
+    const int rows = 3 * a + 1, cols = 3 * b + 1;
+    const bool tr = rows > cols;
+    const int k = tr ? cols : rows, L = tr ? rows : cols;
+    if (k <= 4) {  // at most 4 singular values: the score vanishes (phylogenetics.py:293-300)
+      if (lane == 0) scores[s] = 0.0;
+      continue;
+    }
+    const int ldm = L | 1;
+    for (int idx = lane; idx < k * L; idx += 32) {
+      const int r = idx / L, c = idx - r * L;
+      ws.M[r * ldm + c] = tr ? subflat_entry(T, tot, n, ws.la, a, ws.lb, b, c, r) : subflat_entry(T, tot, n, ws.la, a, ws.lb, b, r, c);
+    }
+    __syncwarp();
+    if (lane < k) {
+      const double* x = ws.M + lane * ldm;
+      for (int c = 0; c < k; ++c) {
+        const double* y = ws.M + c * ldm;
+        double acc = 0.0;
+        for (int l = 0; l < L; ++l) acc = fma(x[l], y[l], acc);
+        ws.G[lane * kWarpLdg + c] = acc;  // G[r][c] and G[c][r] are the same fma chain: bitwise symmetric
+      }
+    }
+    __syncwarp();
+    const double trace = warp_sum_all(lane < k ? ws.G[lane * kWarpLdg + lane] : 0.0);
+    // ---- Householder tridiagonalisation: after step j, column j of the trailing block is (alpha_j, 0, ..., 0) ----
+    for (int j = 0; j + 2 < k; ++j) {
+      const bool below = lane > j && lane < k;
+      const double x = below ? ws.G[lane * kWarpLdg + j] : 0.0;
+      const double s2 = warp_sum_all(x * x);
+      const double aj = __shfl_sync(0xFFFFFFFFu, x, j + 1);
+      double alpha = 0.0;
+      if (s2 > 0.0) {  // uniform: every lane holds the same s2
+        alpha = aj > 0.0 ? -sqrt(s2) : sqrt(s2);
+        const double v = (lane == j + 1) ? aj - alpha : ((lane > j + 1 && lane < k) ? x : 0.0);
+        const double vn2 = warp_sum_all(v * v);
+        if (vn2 > 0.0) {
+          const double beta = 2.0 / vn2;
+          ws.v[lane] = v;
+          __syncwarp();
+          double p = 0.0;
+          if (below) {
+            const double* row = ws.G + lane * kWarpLdg;
+            for (int l = j + 1; l < k; ++l) p = fma(row[l], ws.v[l], p);
+            p *= beta;
+          }
+          const double K = 0.5 * beta * warp_sum_all(v * p);
+          const double qv = p - K * v;
+          ws.q[lane] = qv;
+          __syncwarp();
+          if (below) {
+            double* row = ws.G + lane * kWarpLdg;
+            for (int l = j + 1; l < k; ++l) row[l] -= v * ws.q[l] + qv * ws.v[l];
+          }
+          __syncwarp();
+        }
+      }
+      if (lane == 0) ws.e[j] = alpha;
+    }
+    __syncwarp();
+    if (lane < k) ws.d[lane] = ws.G[lane * kWarpLdg + lane];
+    if (lane == 0) ws.e[k - 2] = ws.G[(k - 1) * kWarpLdg + (k - 2)];
+    __syncwarp();
+    // ---- Gershgorin interval, then 9-section with Sturm counts: 8 lanes per wanted eigenvalue ----
+    double lo, hi;
+    {
+      const double dd = lane < k ? ws.d[lane] : 0.0;
+      const double e1 = (lane < k - 1) ? fabs(ws.e[lane]) : 0.0;
+      const double e0 = (lane > 0 && lane < k) ? fabs(ws.e[lane - 1]) : 0.0;
+      lo = warp_min_all(lane < k ? dd - e1 - e0 : 1.0e300);
+      hi = warp_max_all(lane < k ? dd + e1 + e0 : -1.0e300);
+    }
+    const int grp = lane >> 3, m = lane & 7;
+    const int want = k - 1 - grp;  // ascending index of this group's eigenvalue (k >= 5, so want >= 1)
+    double glo = lo, ghi = hi;
+    for (int round = 0; round < 18; ++round) {
+      const double w = (ghi - glo) / 9.0;
+      const double xm = glo + w * (double)(m + 1);
+      int cnt = 0;
+      double piv = ws.d[0] - xm;
+      cnt += piv < 0.0;
+      for (int i = 1; i < k; ++i) {
+        if (piv == 0.0) piv = -1.0e-300;
+        const double ee = ws.e[i - 1];
+        piv = ws.d[i] - xm - ee * ee / piv;
+        cnt += piv < 0.0;
+      }
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, cnt <= want);  // eigenvalue `want` is >= xm
+      const int t = __popc((bal >> (grp * 8)) & 0xFFu);               // sample points at or below it (prefix property)
+      const double nlo = glo + w * (double)t;
+      if (t < 8) ghi = glo + w * (double)(t + 1);
+      glo = nlo;
+    }
+    const double lam = 0.5 * (glo + ghi);
+    const double l0 = __shfl_sync(0xFFFFFFFFu, lam, 0), l1 = __shfl_sync(0xFFFFFFFFu, lam, 8);
+    const double l2 = __shfl_sync(0xFFFFFFFFu, lam, 16), l3 = __shfl_sync(0xFFFFFFFFu, lam, 24);
+    if (lane == 0) {
+      const double top = ((fmax(l0, 0.0) + fmax(l1, 0.0)) + fmax(l2, 0.0)) + fmax(l3, 0.0);
+      scores[s] = trace > 0.0 ? sqrt(fmax(trace - top, 0.0) / trace) : nan("");
+    }
+  }
+}
+
 inline size_t subflat_smem(int n, int* m_elems) {
   int h = n / 2;
   int k = 3 * h + 1, L = 3 * (n - h) + 1;
@@ -281,6 +437,13 @@ inline size_t subflat_smem(int n, int* m_elems) {
   int m2 = 4 * ((3 * (n - 1) + 2) | 1);
   *m_elems = m1 > m2 ? m1 : m2;
   return ((size_t)*m_elems + (size_t)jacobi_dim(k) * jacobi_ld(k)) * sizeof(double);
+}
+
+// The warp-per-split scorer is the default up to 21 taxa; SPB_SUBFLATTEN_WARP=0 in the environment selects the
+// block-wide Jacobi kernel instead (A/B: scripts/ab_subflatten_warp.py).
+inline bool subflatten_warp_enabled() {
+  const char* e = getenv("SPB_SUBFLATTEN_WARP");
+  return !(e && e[0] == '0');
 }
 
 }  // namespace
@@ -362,6 +525,20 @@ extern "C" int spb_subflatten_score(const double* d_T, const double* d_total, in
   SPB_REQUIRE(d_T && d_total && n_taxa >= 2 && n_taxa <= SPB_MAX_TAXA, "spb_subflatten_score: bad arguments");
   if (num <= 0) return SPB_OK;
   SPB_REQUIRE(d_masks_a && d_scores, "spb_subflatten_score: NULL buffer");
+  if (n_taxa <= kWarpMaxTaxa && subflatten_warp_enabled()) {
+    const size_t wsmem = (size_t)kWarpsPerCta * sizeof(WarpScratch);
+    SPB_CUDA(cudaFuncSetAttribute(subflatten_score_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+    int wocc = 1;
+    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, subflatten_score_warp_kernel, 32 * kWarpsPerCta, wsmem));
+    if (wocc < 1) wocc = 1;
+    int64_t wgrid = (int64_t)sm_count() * wocc;
+    const int64_t need = (num + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (wgrid > need) wgrid = need;
+    subflatten_score_warp_kernel<<<(unsigned)wgrid, 32 * kWarpsPerCta, wsmem, (cudaStream_t)stream>>>(d_T, d_total, n_taxa, d_masks_a,
+                                                                                                   d_masks_b, num, d_scores);
+    SPB_LAUNCH_CHECK();
+    return SPB_OK;
+  }
   int m_elems = 0;
   size_t smem = subflat_smem(n_taxa, &m_elems);
   SPB_CUDA(cudaFuncSetAttribute(subflatten_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
