@@ -511,8 +511,9 @@ def main():
                 "peak": hbm, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm, "traffic": None,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s", "launch_ms": ms,
                 "note": "pair_kernel is the only HBM-streaming kernel of this workload (POPC-issue bound, see DESIGN.md) and a small "
-                        "share of the step; the step is dominated by subflatten_score_kernel (gather + shared-memory Jacobi per "
-                        "split, instruction-issue bound, no HBM roofline): its throughput is `value`"}
+                        "share of the step; the step is dominated by the batched score kernel (subflatten_score_warp_kernel up to 21 taxa: "
+                        "one warp per split, tridiagonalisation + bisection; subflatten_score_kernel above: shared-memory Jacobi; "
+                        "instruction-issue bound, no HBM roofline): its throughput is `value`"}
     count_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in prof["count"]])) if prof["count"] else None
 
     if rank == 0:

@@ -203,7 +203,10 @@ int spb_pair_transform(const double* d_N, int n_taxa, double* d_T, double* d_tot
 int spb_subflatten(const double* d_T, const double* d_total, int n_taxa, const spb_split* split, double* d_out,
                    void* stream);
 /* Batched: scores of `num` splits given as bit masks over taxon positions (bit t set = taxon t on
- * side A; side B = d_masks_b[s] if non-NULL else the complement).  d_scores double [num]. */
+ * side A; side B = d_masks_b[s] if non-NULL else the complement).  d_scores double [num].
+ * Up to 21 taxa: one warp per split (Gram, Householder tridiagonalisation, the 4 largest eigenvalues by bisection,
+ * score = sqrt((trace - top4) / trace)); above: one CTA per split with a shared-memory Jacobi solver.
+ * SPB_SUBFLATTEN_WARP=0 in the environment forces the second kernel. */
 int spb_subflatten_score(const double* d_T, const double* d_total, int n_taxa, const uint64_t* d_masks_a,
                          const uint64_t* d_masks_b, int64_t num, double* d_scores, void* stream);
 
