@@ -204,3 +204,47 @@ def test_make_splits_matches_make_split():
         _lib.make_splits(12, [[0, 12]], [[1, 2]])
     with pytest.raises(ValueError):
         _lib.make_splits(65, [[0]], [[1]])
+
+
+def test_warp_scorer_model_against_lapack(oracle):
+    """The arithmetic of the warp-per-split subflattening scorer (Gram -> Householder tridiagonalisation -> 9-section
+    for the 4 largest eigenvalues -> sqrt((trace - top4) / trace)), modelled lane by lane in tests/warp_scorer_model.py,
+    stays within the parity tolerance of the reference's LAPACK route: on subflattenings of a simulated 12-taxon
+    alignment (true and random splits) and on random matrices up to k = 31, including a rank-deficient one."""
+    import torch
+    from splitp_b200 import simulation, splits as splits_mod, trees
+    from tests.warp_scorer_model import score_warp_model
+    eps = np.finfo(float).eps
+    n = 12
+    tree = trees.balanced_tree(n, 0.05)
+    codes = simulation.simulate_codes(tree, simulation.GTR((0.1, 0.2, 0.3, 0.4), (1, 2, 3, 4, 5, 6)), 100_000, seed=3,
+                                      device=torch.device("cpu")).numpy()
+    tables, total = oracle.pair_tables_from_codes(codes)
+    pos = {t: i for i, t in enumerate(tree.taxa)}
+    allsp = list(splits_mod.all_splits(tree))
+    true = [s for s in allsp if s in set(tree.splits())]
+    rng = np.random.default_rng(5)
+    sample = true[:4] + [allsp[i] for i in rng.choice(len(allsp), 8, replace=False)]
+    checked = 0
+    for s in sample:
+        M = oracle.subflattening_from_tables(tables, total, [pos[t] for t in s[0]], [pos[t] for t in s[1]])
+        if M.shape[0] > M.shape[1]:
+            M = M.T
+        if M.shape[0] <= 4:
+            continue
+        ref = oracle.split_score(M)
+        got, lams = score_warp_model(M)
+        tol = max(1e-9, 64 * eps / max(ref * ref, 1e-300))
+        assert abs(got - ref) <= tol * ref, (s, got, ref)
+        sv = np.linalg.svd(M, compute_uv=False)[:4] ** 2
+        np.testing.assert_allclose(lams, sv, rtol=0, atol=1e-13 * sv[0])
+        checked += 1
+    assert checked >= 8
+    for k, L in ((31, 31), (7, 55), (5, 9)):
+        A = rng.standard_normal((k, L))
+        A[2] = 2.0 * A[1]  # exact dependency: a zero eigenvalue
+        got, _ = score_warp_model(A)
+        sv = np.linalg.svd(A, compute_uv=False) ** 2
+        ref = float(np.sqrt(sv[4:].sum() / sv.sum()))
+        tol = max(1e-9, 64 * eps / max(ref * ref, 1e-300))  # a vanishing score (k = 5 with a zero eigenvalue) is all rounding
+        assert abs(got - ref) <= min(tol * ref, 1e-7) or abs(got - ref) <= 1e-9 * ref, (k, L, got, ref)
