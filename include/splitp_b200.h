@@ -242,10 +242,16 @@ int spb_gram_hi_correction_batch(const uint8_t* d_s0, int64_t s0_stride, int nb,
  * d_eig (optional) double [batch][k] receives the eigenvalues in descending order. */
 int spb_score_gram_small(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores,
                          double* d_eig, void* stream);
-/* Scores from large Gram matrices (k > 128): block-Krylov Rayleigh-Ritz for the 4 largest
- * eigenvalues, score = sqrt(1 - top4 / trace).  d_ws: double [spb_score_gram_large_ws(k, batch)].
- * d_info (optional) double [batch][4] = {top4 sum, trace, convergence estimate, krylov dim}. */
+/* Scores from large Gram matrices (k > 128): restarted block-Krylov Rayleigh-Ritz for the 4 largest
+ * eigenvalues (the role of LAPACK gesdd at phylogenetics.py:281-285), score = sqrt(1 - top4 / trace).
+ * d_ws: double [spb_score_gram_large_ws(k, batch)].
+ * d_info (optional) double [batch][SPB_SCORE_INFO] = {top4 sum, trace, residual of the top-4 Ritz pairs relative to
+ * theta_1, krylov dim, cycles, |change of top4| / trace in the last cycle, theta_4, theta_5, converged (1 / 0), 0}.
+ * A matrix that exhausts the cycle budget keeps its last score and reports converged = 0; the call still returns
+ * SPB_OK and spb_score_last_unconverged() (thread-local, last call) returns how many matrices did so. */
+#define SPB_SCORE_INFO 10
 int64_t spb_score_gram_large_ws(int64_t k, int64_t batch);
+int spb_score_last_unconverged(void);
 int spb_score_gram_large(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores,
                          double* d_info, double* d_ws, void* stream);
 

@@ -121,6 +121,7 @@ PROTOTYPES = {
     "spb_gram_hi_correction": (_i, [_p, _l, _l, _i, _p, _p, _p, _l, _p, _p]),
     "spb_score_gram_small": (_i, [_p, _l, _l, _l, _p, _p, _p]),
     "spb_score_gram_large_ws": (_l, [_l, _l]),
+    "spb_score_last_unconverged": (_i, []),
     "spb_score_gram_large": (_i, [_p, _l, _l, _l, _p, _p, _p, _p]),
     "spb_gram_u8_batch_i32": (_i, [_p, _l, _i, _l, _l, _p, _l, _p]),
     "spb_gram_hi_strip_batch": (_i, [_p, _l, _i, _l, _l, _i, _p, _p, _p, _l, _p, _l, _p, _p, _p, _p]),

@@ -15,6 +15,7 @@ Objects
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 
 import numpy as np
 import torch
@@ -28,6 +29,7 @@ for _i, _c in enumerate(STATES):
     _UPPER_LUT[ord(_c)] = _i
 DIRECT_MAX_TAXA = 12   # direct-indexed count table up to 4^12 cells (64 MB); hash table above
 JACOBI_MAX_K = 128
+SCORE_INFO = 10        # doubles per matrix in the block-Krylov status record (SPB_SCORE_INFO)
 
 
 # --------------------------------------------------------------------------------------------
@@ -102,6 +104,7 @@ class PatternTable:
         self.n, self.keys, self.counts, self.values = n, keys, counts, values
         self.divisor = float(divisor)  # counts / divisor = probabilities (fasta.py:66-70); 0 = leave counts
         self.first, self.taxa = first, (tuple(taxa) if taxa is not None else None)
+        self.integral = False  # values came from Python ints: dict round trips give ints back (alignment.py:26-30 adds ints)
 
     @property
     def num(self):
@@ -261,7 +264,9 @@ def table_from_mapping(mapping):
     if isinstance(mapping, PatternTable):
         return mapping
     pats = list(mapping.keys())
-    vals = np.fromiter((float(v) for v in mapping.values()), dtype=np.float64, count=len(pats))
+    raw = list(mapping.values())
+    vals = np.fromiter((float(v) for v in raw), dtype=np.float64, count=len(pats))
+    integral = bool(raw) and all(type(v) is int and abs(v) < (1 << 53) for v in raw)
     joined = "".join(pats)
     hit = _TABLE_CACHE.get(id(mapping))
     if hit is not None and hit[0] == joined and hit[1].shape == vals.shape and np.array_equal(hit[1], vals, equal_nan=True):
@@ -273,6 +278,7 @@ def table_from_mapping(mapping):
         if len(_TABLE_CACHE) > 16:
             _TABLE_CACHE.clear()
         _TABLE_CACHE[id(mapping)] = (joined, vals, table)
+    table.integral = integral
     table.taxa = tuple(mapping.taxa) if hasattr(mapping, "taxa") else None
     return table
 
@@ -285,7 +291,10 @@ def table_to_dict(table, as_counts=False):
         if as_counts or table.divisor <= 0:
             return {p: int(c) for p, c in zip(pats, cnt)}
         return {p: int(c) / table.divisor for p, c in zip(pats, cnt)}  # one IEEE division, fasta.py:66-70
-    return dict(zip(pats, table.values.cpu().numpy().tolist()))
+    vals = table.values.cpu().numpy()
+    if table.integral:  # sums of ints below 2^53 are exact in float64: hand ints back like the reference's dict arithmetic
+        return {p: int(v) for p, v in zip(pats, vals)}
+    return dict(zip(pats, vals.tolist()))
 
 
 # --------------------------------------------------------------------------------------------
@@ -399,9 +408,18 @@ def score_gram(G, k=None, want_info=False):
         call("spb_score_gram_small", _p(G), k, ld, batch, _p(scores), _p(info), _st())
     else:
         ws = _krylov_ws(k, batch)
-        info = _empty((batch, 8), torch.float64) if want_info else None
+        info = _empty((batch, SCORE_INFO), torch.float64) if want_info else None
         call("spb_score_gram_large", _p(G), k, ld, batch, _p(scores), _p(info), _p(ws), _st())
+        _warn_unconverged()
     return (scores, info) if want_info else scores
+
+
+def _warn_unconverged():
+    """The block-Krylov solver keeps the last score of a matrix that exhausted its cycle budget; say so."""
+    bad = int(lib.spb_score_last_unconverged())
+    if bad:
+        warnings.warn(f"splitp_b200: {bad} Gram matrices did not reach the 1e-11 acceptance bound of the block-Krylov "
+                      "eigen-solver; their scores are the last iterates", RuntimeWarning, stacklevel=3)
 
 
 def score_matrix(A):
@@ -481,8 +499,13 @@ class CountScorer:
             self._ws[key] = _empty(self._gnb(rows_pad, pitch) * rows_pad * rows_pad, torch.int64) if n else None
         return self._s0[key], g, self._ws[key]
 
+    I32_MAX_HI = 4096  # strip rows: the correction strip costs n_hi * rows_pad * 8 bytes per matrix and O(n_hi^2) work
+
     def _use_i32(self, layout, rows_pad, pitch):
-        return self.int32_gram and layout == SPB_S0_TILED and rows_pad >= 2048 and rows_pad % 256 == 0 and pitch <= 32768
+        """int32 Gram + correction strip only while the strip stays small (a table with many counts >= 256, e.g.
+        12 taxa from 10^8 sites, goes through the fp64 Gram, which has no such limit)."""
+        return (self.int32_gram and layout == SPB_S0_TILED and rows_pad >= 2048 and rows_pad % 256 == 0 and pitch <= 32768
+                and self.n_hi <= self.I32_MAX_HI)
 
     def _buffers_i32(self, rows_pad, batch):
         """int32 Gram batch + correction strip (rows sized by the number of high counts of the table)."""
@@ -518,22 +541,30 @@ class CountScorer:
         s0_stride, g_stride = rows_pad * pitch, rows_pad * rows_pad
         cs_rows = int(buf["Cs"].shape[1])
         G, Cs, pos, hr, hm = buf["G"][b0:], buf["Cs"][b0:], buf["pos"][b0:], buf["hr"][b0:], buf["hm"][b0:]
-        self._scatter(arr, nb, s0, layout, rows_pad, pitch)
-        run = lambda: call("spb_gram_u8_batch_i32", _p(s0), s0_stride, nb, rows_pad, pitch, _p(G), g_stride, _st())  # noqa: E731
-        run() if self.gram_hook is None else self.gram_hook(run, nb)
-        call("spb_gram_hi_strip_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
-             _p(self.hi_num), self.hi_cap, _p(Cs), cs_rows, _p(pos), _p(hr), _p(hm), _st())
-        self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
+        try:
+            self._scatter(arr, nb, s0, layout, rows_pad, pitch)
+            run = lambda: call("spb_gram_u8_batch_i32", _p(s0), s0_stride, nb, rows_pad, pitch, _p(G), g_stride, _st())  # noqa: E731
+            run() if self.gram_hook is None else self.gram_hook(run, nb)
+            call("spb_gram_hi_strip_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
+                 _p(self.hi_num), self.hi_cap, _p(Cs), cs_rows, _p(pos), _p(hr), _p(hm), _st())
+            self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
+        except BaseException:
+            self._drop_s0()  # the cached S0 buffers are assumed all-zero between uses: never keep a dirty one
+            raise
 
     def _score_i32(self, buf, batch, k, want_info=False):
         rows_pad = int(buf["G"].shape[1])
         cs_rows = int(buf["Cs"].shape[1])
         scores = _empty(batch, torch.float64)
-        info = _empty((batch, 8), torch.float64) if want_info else None
+        info = _empty((batch, SCORE_INFO), torch.float64) if want_info else None
         ws = _krylov_ws(k, batch)
         call("spb_score_gram_large_i32", _p(buf["G"]), k, rows_pad, batch, _p(buf["Cs"]), cs_rows, _p(buf["pos"]), _p(buf["hr"]),
              _p(buf["hm"]), _p(scores), _p(info), _p(ws), _st())
+        _warn_unconverged()
         return (scores, info) if want_info else scores
+
+    def _drop_s0(self):
+        self._s0.clear()
 
     def _plan(self, idx_a, idx_b, reduced):
         """Orient the split so that the Gram is taken on the short side; returns the launch geometry."""
@@ -557,13 +588,18 @@ class CountScorer:
         """One split (supports the reduced-format rank arrays): flatten -> Gram -> correction -> un-scatter."""
         t = self.table
         sp, rank_r, rank_c, R, Cc = plan
-        call("spb_flatten_u8", _p(t.keys), _p(t.counts), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch,
-             layout, SPB_U8_NO_MEMSET, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num), self.hi_cap, _st())
-        run = lambda: call("spb_gram_u8", _p(s0), rows_pad, pitch, layout, _p(G), _p(ws), _st())  # noqa: E731
-        run() if self.gram_hook is None else self.gram_hook(run, 1)
-        call("spb_gram_hi_correction", _p(s0), rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num),
-             self.hi_cap, _p(G), _st())
-        call("spb_flatten_u8_clear", _p(t.keys), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch, layout, _st())
+        try:
+            call("spb_flatten_u8", _p(t.keys), _p(t.counts), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch,
+                 layout, SPB_U8_NO_MEMSET, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num), self.hi_cap, _st())
+            run = lambda: call("spb_gram_u8", _p(s0), rows_pad, pitch, layout, _p(G), _p(ws), _st())  # noqa: E731
+            run() if self.gram_hook is None else self.gram_hook(run, 1)
+            call("spb_gram_hi_correction", _p(s0), rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val), _p(self.hi_num),
+                 self.hi_cap, _p(G), _st())
+            call("spb_flatten_u8_clear", _p(t.keys), t.num, C.byref(sp), _p(rank_r), _p(rank_c), _p(s0), rows_pad, pitch, layout,
+                 _st())
+        except BaseException:
+            self._drop_s0()
+            raise
 
     def _gram_batch(self, splits, s0, G, ws, layout, rows_pad, pitch):
         """nb <= GNB dense splits of equal shape: scatter, ONE Gram launch, ONE correction launch, un-scatter.
@@ -571,12 +607,16 @@ class CountScorer:
         nb = len(splits)
         arr = splits if isinstance(splits, C.Array) else (_lib.SpbSplit * nb)(*splits)
         s0_stride, g_stride = rows_pad * pitch, rows_pad * rows_pad
-        self._scatter(arr, nb, s0, layout, rows_pad, pitch)
-        run = lambda: call("spb_gram_u8_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(G), g_stride, _p(ws), _st())  # noqa: E731
-        run() if self.gram_hook is None else self.gram_hook(run, nb)
-        call("spb_gram_hi_correction_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
-             _p(self.hi_num), self.hi_cap, _p(G), g_stride, _st())
-        self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
+        try:
+            self._scatter(arr, nb, s0, layout, rows_pad, pitch)
+            run = lambda: call("spb_gram_u8_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(G), g_stride, _p(ws), _st())  # noqa: E731
+            run() if self.gram_hook is None else self.gram_hook(run, nb)
+            call("spb_gram_hi_correction_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
+                 _p(self.hi_num), self.hi_cap, _p(G), g_stride, _st())
+            self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
+        except BaseException:
+            self._drop_s0()
+            raise
 
     def gram(self, idx_a, idx_b, reduced=False):
         """Exact F F^T (short side) of the count flattening of one split.  Returns (G [rows_pad, rows_pad], k)."""
@@ -755,7 +795,9 @@ def marginalise(table, idx):
         acc = torch.zeros(len(uniq), dtype=torch.int64, device=rows.device).index_add_(0, inv, table.counts.to(torch.int64))
         return PatternTable(len(idx), uniq, counts=acc.to(torch.int32), divisor=table.divisor)
     acc = torch.zeros(len(uniq), dtype=torch.float64, device=rows.device).index_add_(0, inv, table.values)
-    return PatternTable(len(idx), uniq, values=acc)
+    out = PatternTable(len(idx), uniq, values=acc)
+    out.integral = table.integral
+    return out
 
 
 # --------------------------------------------------------------------------------------------

@@ -1,0 +1,219 @@
+"""Round-2 GPU parity tests: the kernels behind the headline numbers against the oracle at the sizes they run at.
+
+  * warp-per-split / block subflattening scorers (spb_subflatten_score) at 20, 21, 22 and 32 taxa, stratified over
+    every side size, true and false splits, against oracle.split_score(oracle.subflattening_from_tables(...));
+  * the batched int32 tensor-core Gram (spb_gram_u8_batch_i32) on random dense u8 4096 x 4096 matrices, nb in
+    {1, 3, 64}, bit for bit against an exact integer product;
+  * CountScorer.score_many (scatter -> int32 Gram -> correction strip -> block Krylov) on config-2 6|6 splits
+    against LAPACK on the reduced flattening;
+  * reducible / many-component Gram matrices through the block-Krylov solver (k > 128) against LAPACK.
+
+Tolerances: integer work bit-exact; scores rel <= max(1e-9, 64 eps / score^2) (tests/test_gpu_parity.py header).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from tests.test_gpu_parity import _count_table, _tiled_from_rowmajor, assert_score, score_tol  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def sp():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import splitp_b200
+    return splitp_b200
+
+
+@pytest.fixture(scope="module")
+def eng(sp):
+    return sp.engine
+
+
+# ---------------------------------------------------------------------------------------------
+# subflattening scorers at the sizes of BASELINE configs 3 and 5
+# ---------------------------------------------------------------------------------------------
+def _stratified_splits(tree, n, sizes, per_size, seed):
+    """>= per_size splits for every side size: every true split of that size plus random false ones."""
+    rng = np.random.default_rng(seed)
+    pos = {t: i for i, t in enumerate(tree.taxa)}
+    true = {}
+    for left, right in tree.splits():
+        for side, other in ((left, right), (right, left)):
+            if len(side) in sizes and len(side) <= len(other):
+                true.setdefault(len(side), set()).add(tuple(sorted(pos[t] for t in side)))
+    out = []
+    for a in sizes:
+        chosen = set(true.get(a, ()))
+        n_true = len(chosen)
+        while len(chosen) < max(per_size, n_true + per_size // 2):
+            chosen.add(tuple(sorted(rng.choice(n, size=a, replace=False).tolist())))
+        for side in sorted(chosen):
+            out.append((list(side), [t for t in range(n) if t not in side], side in true.get(a, ())))
+    return out
+
+
+@pytest.mark.parametrize("n,model,N,seed", [(20, "GTR", 400_000, 3), (21, "JC", 150_000, 21), (22, "GTR", 150_000, 22),
+                                            (32, "JC", 300_000, 5)])
+def test_subflatten_score_stratified(sp, eng, oracle, n, model, N, seed):
+    """spb_subflatten_score against the oracle for every side size 2 .. n/2 (k = 3a + 1 up to 31 at 20 taxa: the
+    warp-per-split kernel; 22 and 32 taxa: the kernel for wider matrices), >= 20 splits per size, true splits included."""
+    if n % 2 == 0:
+        tree = sp.trees.balanced_tree(n, 0.05)
+    else:  # odd taxon count: drop the last leaf of a balanced tree on n + 1 taxa (simulate, then delete the row)
+        tree = sp.trees.balanced_tree(n + 1, 0.05)
+    mdl = sp.simulation.GTR.JukesCantor(0.5) if model == "JC" else sp.simulation.GTR((0.1, 0.2, 0.3, 0.4), (1, 2, 3, 4, 5, 6))
+    codes = sp.simulation.simulate_codes(tree, mdl, N, seed=seed)[:n].contiguous()
+    aln = eng.pack(codes, want_sm=False)
+    pt = eng.pair_tables_from_alignment(aln)  # probabilities
+    tables, usable = oracle.pair_tables_from_codes(codes.cpu().numpy())
+    assert usable == N
+    sizes = list(range(2, n // 2 + 1))
+    if n % 2 == 0:
+        picks = _stratified_splits(tree, n, sizes, 20, seed)
+    else:
+        rng = np.random.default_rng(seed)
+        picks = []
+        for a in sizes:
+            for _ in range(20):
+                side = sorted(rng.choice(n, size=a, replace=False).tolist())
+                picks.append((side, [t for t in range(n) if t not in side], False))
+    ma, mb = eng.masks_from_splits([(ia, ib) for ia, ib, _ in picks])
+    got = eng.subflatten_scores(pt, ma, mb).cpu().numpy()
+    got_swapped = eng.subflatten_scores(pt, mb, ma).cpu().numpy()
+    worst, n_true = 0.0, 0
+    for s, (ia, ib, is_true) in enumerate(picks):
+        ref = oracle.split_score(oracle.subflattening_from_tables(tables, 1.0, ia, ib))
+        assert_score(got[s], ref)
+        assert_score(got_swapped[s], ref)
+        worst = max(worst, abs(got[s] - ref) / ref / score_tol(ref))
+        n_true += is_true
+    if n % 2 == 0:
+        assert n_true >= n - 3 - n // 2  # the tree's true splits of these sizes were all included
+    print(f"subflatten scorer n={n}: {len(picks)} splits, {n_true} true, worst error = {worst:.3f} x tolerance")
+
+
+# ---------------------------------------------------------------------------------------------
+# batched int32 tensor-core Gram at the config-2 shape
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nb", [1, 3, 64])
+def test_gram_u8_batch_i32_exact_4096(eng, nb):
+    """spb_gram_u8_batch_i32 on random DENSE u8 4096 x 4096 matrices (every entry non-zero, 1/16 of them 255) against
+    the exact integer product.  Entries <= 255 and K = 4096, so every sum is < 2^28: the fp64 BLAS product on the host
+    is exact integer arithmetic and equals the int64 product bit for bit (checked once against numpy int64 on a
+    slice).  nb = 64: all 64 distinct matrices are compared on the device against the exact fp64 product of the
+    row-major copies, four of them also against the host product."""
+    R = K = 4096
+    rng = np.random.default_rng(100 + nb)
+    s0 = torch.empty((nb, R * K), dtype=torch.uint8, device="cuda")
+    host = {}
+    rows = torch.empty((nb, R, K), dtype=torch.uint8, device="cuda")
+    r_i, k_i = np.meshgrid(np.arange(R), np.arange(K), indexing="ij")
+    off = ((r_i // 128) * (K // 128) + k_i // 128) * 16384 + (r_i % 128) * 128 + ((((k_i % 128) >> 4) ^ (r_i & 7)) << 4) + (k_i & 15)
+    off_d = torch.from_numpy(off.ravel()).cuda()
+    check_host = sorted({0, nb // 3, nb // 2, nb - 1})
+    for b in range(nb):
+        M = rng.integers(1, 256, size=(R, K), dtype=np.uint8)
+        M[rng.random((R, K)) < 1.0 / 16] = 255
+        Md = torch.from_numpy(M).cuda()
+        rows[b] = Md
+        s0[b].scatter_(0, off_d, Md.reshape(-1))
+        if b in check_host:
+            host[b] = M
+    if 0 in host:  # the tiled scatter above equals the documented layout helper
+        assert np.array_equal(s0[0, :256 * K].cpu().numpy(), _tiled_from_rowmajor(host[0][:256]))
+    Gi = torch.full((nb, R, R), -7, dtype=torch.int32, device="cuda")
+    eng.call("spb_gram_u8_batch_i32", eng._p(s0), R * K, nb, R, K, eng._p(Gi), R * R, eng._st())
+    torch.cuda.synchronize()
+    for b in range(nb):
+        A = rows[b].to(torch.float64)
+        ref = (A @ A.T)
+        assert torch.equal(Gi[b].to(torch.float64), ref), f"matrix {b} of {nb} differs from the exact product"
+    for b, M in host.items():
+        Mf = M.astype(np.float64)
+        ref = Mf @ Mf.T  # exact: integers < 2^28
+        sl = M[:64].astype(np.int64) @ M.astype(np.int64).T
+        assert np.array_equal(ref[:64].astype(np.int64), sl)
+        assert np.array_equal(Gi[b].cpu().numpy().astype(np.int64), ref.astype(np.int64)), f"matrix {b} vs host product"
+
+
+def test_score_many_config2_six_six_vs_lapack(sp, eng, oracle):
+    """The bench's hot route (score_many -> u8 scatter -> spb_gram_u8_batch_i32 -> correction strip ->
+    spb_score_gram_large_i32) on 18 6|6 splits of the config-2 alignment (12 taxa, 10^6 sites), 8+ of them false,
+    against LAPACK gesdd on the reduced flattening (phylogenetics.py:280-300)."""
+    n, N = 12, 1_000_000
+    tree, codes, tab = _count_table(sp, eng, n, N, 2)
+    keys, counts, usable = oracle.get_pattern_counts_arrays(codes)
+    true = set(tree.splits())
+    sixes = [s for s in sp.all_splits(tree) if len(s[0]) == 6]
+    t_splits = [s for s in sixes if s in true]
+    f_splits = [s for s in sixes if s not in true]
+    picks = t_splits + f_splits[:: max(1, len(f_splits) // 17)][:17]
+    assert len(picks) >= 16 and len(picks) - len(t_splits) >= 8
+    idx = [eng.split_positions(s, tree.taxa) for s in picks]
+    scorer = eng.CountScorer(tab)
+    layout, rows_pad, pitch = scorer.geometry(4096, 4096)
+    assert scorer._use_i32(layout, rows_pad, pitch)
+    got = scorer.score_many(idx).cpu().numpy()
+    worst = 0.0
+    for s, (ia, ib) in enumerate(idx):
+        ref = oracle.split_score(oracle.flattening_reduced(keys, counts / usable, n, ia, ib))
+        assert_score(got[s], ref)
+        worst = max(worst, abs(got[s] - ref) / ref / score_tol(ref))
+    print(f"score_many 6|6: {len(picks)} splits ({len(t_splits)} true), worst error = {worst:.3f} x tolerance")
+
+
+# ---------------------------------------------------------------------------------------------
+# block-Krylov solver on reducible Gram matrices (start block confined to one component)
+# ---------------------------------------------------------------------------------------------
+def _blockdiag(blocks):
+    k = sum(b.shape[0] for b in blocks)
+    c = sum(b.shape[1] for b in blocks)
+    out = np.zeros((k, c))
+    r0 = c0 = 0
+    for b in blocks:
+        out[r0:r0 + b.shape[0], c0:c0 + b.shape[1]] = b
+        r0 += b.shape[0]
+        c0 += b.shape[1]
+    return out
+
+
+def _reducible_cases():
+    rng = np.random.default_rng(7)
+    cases = {}
+    # the advisor's example: 8 heavy isolated rows hide the dominant component from a heaviest-rows start block
+    cases["advice"] = _blockdiag([20.0 * np.eye(8), np.ones((200, 200))])
+    # many small disjoint components, dominant eigenvalues spread over different ones
+    cases["many"] = _blockdiag([rng.integers(0, 6, size=(s, s + 3)).astype(float) for s in (3, 5, 9, 17, 33, 40, 31, 12, 7, 4, 2, 60)])
+    # two equal-sized dense components plus isolated heavy diagonal entries
+    cases["twins"] = _blockdiag([rng.random((90, 120)), rng.random((90, 120)) * 1.01, np.diag(np.linspace(30, 40, 12))])
+    # sparse count-like flattening: few non-zeros per row, many connected components
+    S = np.zeros((400, 900))
+    for r in range(400):
+        for c in rng.choice(900, size=2, replace=False):
+            S[r, c] = rng.integers(1, 50)
+    cases["sparse"] = S
+    return cases
+
+
+@pytest.mark.parametrize("name", ["advice", "many", "twins", "sparse"])
+def test_split_score_reducible_gram(sp, oracle, name):
+    A = _reducible_cases()[name]
+    assert min(A.shape) > 128
+    ref = oracle.split_score(A)
+    assert_score(sp.split_score(A), ref)
+    assert_score(sp.split_score(A.T), ref)
+
+
+def test_score_gram_large_reports_convergence(sp, eng):
+    """Every matrix of a batch reports a converged flag in info[:, 2] semantics (residual) and the call raises no
+    error for well-conditioned input; the flag column (info[:, 4] = cycles) stays within the cycle budget."""
+    rng = np.random.default_rng(11)
+    A = torch.from_numpy(rng.random((3, 200, 260))).cuda()
+    G = eng.gram_f64(A)
+    scores, info = eng.score_gram(G, want_info=True)
+    info = info.cpu().numpy()
+    assert np.isfinite(scores.cpu().numpy()).all()
+    assert (info[:, 4] >= 1).all() and (info[:, 4] <= 40).all()
