@@ -192,7 +192,8 @@ int spb_pair_tables(const uint32_t* d_planes, const uint32_t* d_valid, int n_tax
                     int64_t word_begin, int64_t word_end, uint64_t* d_raw, void* stream);
 /* raw -> N double [n][n][4][4] (joint tables, N[i][i] diagonal = marginal) and the Hadamard-type
  * basis change T[i][j] = H N[i][j] H^T (H = sign table of constructions.py:143-161).  divisor > 0
- * turns counts into probabilities first (count / divisor).  d_total (double) = sum of all values. */
+ * turns counts into probabilities first (count / divisor); divisor < 0 divides by the number of usable sites held in
+ * d_raw (fasta.py:66-70) without a host round trip; divisor == 0 keeps counts.  d_total (double) = sum of all values. */
 int spb_pair_finalize(const uint64_t* d_raw, int n_taxa, double divisor, double* d_N, double* d_T,
                       double* d_total, void* stream);
 /* Same tables from a weighted pattern list (dict inputs): d_N must be zeroed by the caller. */

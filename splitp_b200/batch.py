@@ -1,0 +1,177 @@
+"""Batched entry point of the engine: scores of MANY splits of one alignment in one call.
+
+This is the call that replaces the reference's per-split loops
+
+    for split in splitp.all_splits(tree):                     # README.md:37-41, examples/playground.py:29-39
+        splitp.split_score(splitp.flattening(split, aln, FlatFormat.reduced))      # or subflattening(split, aln)
+
+and the inner loop of `erickson_SVD` (phylogenetics.py:126-140).  `score_splits` takes the alignment as HOST data
+(what `parsers.fasta.read_alignment_from_file` returns, or a byte / code matrix, or the 2-bit planes written by
+`pack_planes_host`), copies it to the device, and returns one float64 score per split as a numpy array:
+
+    Method.flattening     pack -> pattern count (kernel 1) -> per split: u8 scatter (kernel 2) -> exact integer Gram on the
+                          tensor cores (kernel 4) -> eigen-solver (kernel 5); scores equal those of the reduced / dense /
+                          sparse flattening (dropping all-zero rows and columns does not change the singular values)
+    Method.subflattening  pack -> pair tables -> H N H^T -> per split: gather + Gram + eigenvalues (kernel 3)
+
+Under `torch.distributed` (one process per GPU) the sites are sharded for counting and the splits for scoring: every
+rank passes ITS contiguous site shard (distributed.shard_range) and receives the scores of all splits.
+
+`PhaseTimer` collects per-phase device time (CUDA events on the launch stream) for bench.py's `phase_ms`.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import engine
+from .engine import PhaseTimer, _span  # noqa: F401  (PhaseTimer is re-exported: bench.py's `phase_ms`)
+from .enums import Method
+
+
+# --------------------------------------------------------------------------------------------
+# host-side 2-bit format (what a FASTA -> packed converter would write once)
+# --------------------------------------------------------------------------------------------
+def pack_planes_host(codes):
+    """uint8 [n, N] codes 0..3 (anything else = unusable site, fasta.py:55-57) -> (planes uint32 [n, 2, Wp],
+    valid uint32 [Wp]) in the device layout of include/splitp_b200.h: 2 bits per base instead of 8."""
+    codes = np.asarray(codes, dtype=np.uint8)
+    n, N = codes.shape
+    Wp = int(engine.lib.spb_plane_words(N))
+    pad = Wp * 32 - N
+    ok = (codes <= 3).all(axis=0)
+    planes = np.zeros((n, 2, Wp), dtype=np.uint32)
+    for t in range(n):
+        row = np.where(ok, codes[t], 0)
+        for bit in range(2):
+            bits = np.concatenate([(row >> bit) & 1, np.zeros(pad, np.uint8)]).astype(np.uint8)
+            planes[t, bit] = np.packbits(bits, bitorder="little").view(np.uint32)
+    valid = np.packbits(np.concatenate([ok, np.zeros(pad, bool)]).astype(np.uint8), bitorder="little").view(np.uint32)
+    return planes, valid.copy()
+
+
+class HostPlanes:
+    """2-bit packed alignment on the host (pinned when `pin=True`): the e2e input format of the subflattening path."""
+
+    def __init__(self, planes, valid, n, N, pin=False):
+        self.planes = torch.from_numpy(np.ascontiguousarray(planes).view(np.int32))
+        self.valid = torch.from_numpy(np.ascontiguousarray(valid).view(np.int32))
+        if pin:
+            self.planes, self.valid = self.planes.pin_memory(), self.valid.pin_memory()
+        self.n, self.N = int(n), int(N)
+
+    @property
+    def nbytes(self):
+        return self.planes.numel() * 4 + self.valid.numel() * 4
+
+    def to_device(self):
+        dev = engine.device()
+        return engine.DeviceAlignment(self.n, self.N, None, self.planes.to(dev, non_blocking=True),
+                                      self.valid.to(dev, non_blocking=True))
+
+
+# --------------------------------------------------------------------------------------------
+def _as_alignment(alignment, want_sm, want_planes):
+    """Anything the caller may hold -> engine.DeviceAlignment (+ taxa if known)."""
+    if isinstance(alignment, engine.DeviceAlignment):
+        return alignment
+    if isinstance(alignment, HostPlanes):
+        return alignment.to_device()
+    if isinstance(alignment, dict):  # {taxon: sequence string}: parsers.fasta.read_alignment_from_file
+        from .parsers.fasta import _to_bytes_matrix
+        return engine.pack(_to_bytes_matrix(list(alignment.values())), is_ascii=True, taxa=list(alignment.keys()),
+                           want_sm=want_sm, want_planes=want_planes)
+    if isinstance(alignment, torch.Tensor):
+        chars = alignment if alignment.is_cuda else alignment.to(engine.device(), non_blocking=True)
+        return engine.pack(chars, want_sm=want_sm, want_planes=want_planes)
+    arr = np.asarray(alignment)
+    is_ascii = arr.dtype.kind in "SU" or (arr.dtype == np.uint8 and arr.size and arr.max() > 3 and arr.max() != 255)
+    return engine.pack(arr.astype(np.uint8, copy=False), is_ascii=bool(is_ascii), want_sm=want_sm, want_planes=want_planes)
+
+
+def _positions(splits, taxa):
+    out = []
+    for left, right in splits:
+        if taxa is not None and len(left) and not isinstance(left[0], (int, np.integer)):
+            out.append(engine.split_positions((left, right), taxa))
+        else:
+            out.append((list(left), list(right)))
+    return out
+
+
+class SplitScorer:
+    """Reusable state of `score_splits` for one split list: encoded splits, device masks, the CountScorer's buffers.
+    Keeping one per (alignment shape, split list) is what a serving loop would do; `score_splits` builds a throw-away
+    one."""
+
+    def __init__(self, splits, taxa=None, method=Method.flattening, rank=0, world=1, group=None):
+        from . import distributed as spd
+        self.method, self.rank, self.world, self.group = method, rank, world, group
+        self.idx_all = _positions(splits, taxa)
+        self.S = len(self.idx_all)
+        self.idx_mine = spd.shard_strided(self.idx_all, rank, world)
+        self.reduce_fn = spd.make_reduce_fn(group) if world > 1 else None
+        self.scorer = None
+        self.masks = None
+        self.timer = None
+        if method == Method.subflattening:
+            ma, mb = engine.masks_from_splits(self.idx_mine)
+            dev = engine.device()
+            self.masks = (torch.from_numpy(ma.view(np.int64)).to(dev), torch.from_numpy(mb.view(np.int64)).to(dev))
+        elif method != Method.flattening:
+            raise NotImplementedError("score_splits: Method.flattening or Method.subflattening")
+
+    def device_scores(self, alignment, gram_hook=None):
+        """Scores of ALL splits as a device tensor.  `alignment`: this rank's site shard (any form _as_alignment takes)."""
+        import torch.distributed as dist
+
+        from . import distributed as spd
+        t = self.timer
+        if self.method == Method.flattening:
+            with _span(t, "h2d+pack"):
+                aln = _as_alignment(alignment, want_sm=True, want_planes=False)
+            with _span(t, "count"):
+                table = engine.count_patterns(aln, reduce_fn=self._timed_reduce if self.reduce_fn else None)
+            if self.scorer is None:
+                self.scorer = engine.CountScorer(table)
+            self.scorer.table = table
+            self.scorer.timer = t
+            out = self.scorer.score_many(self.idx_mine, big_hook=gram_hook)
+        else:
+            with _span(t, "h2d+pack"):
+                aln = _as_alignment(alignment, want_sm=False, want_planes=True)
+            with _span(t, "pairs"):
+                raw = engine.pair_raw(aln)
+            if self.world > 1:
+                with _span(t, "allreduce"):
+                    dist.all_reduce(raw, group=self.group)
+            with _span(t, "subflatten+score"):
+                pt = engine.pair_finalize(raw, aln.n, -1.0)  # divisor = usable sites, read on the device: no host sync
+                out = engine.subflatten_scores(pt, self.masks[0], self.masks[1])
+        with _span(t, "gather"):
+            return spd.gather_strided(out, self.S, self.rank, self.world, self.group)
+
+    def _timed_reduce(self, tensor, op):
+        with _span(self.timer, "allreduce"):
+            return self.reduce_fn(tensor, op)
+
+    def __call__(self, alignment):
+        return self.device_scores(alignment).cpu().numpy()
+
+
+def score_splits(alignment, splits, method=Method.flattening, taxa=None):
+    """One float64 score per split (numpy array, order of `splits`).
+
+    alignment  {taxon: sequence} dict, uint8 [n_taxa, n_sites] matrix of ASCII bytes or codes 0..3 (host or device),
+               `HostPlanes`, or `engine.DeviceAlignment`
+    splits     pairs (left, right) of taxon labels (with `taxa`, or the dict's key order) or of taxon positions
+    method     Method.flattening (scores of the flattening, constructions.py:7-102 + phylogenetics.py:280-300) or
+               Method.subflattening (constructions.py:108-198)
+    """
+    if taxa is None and isinstance(alignment, dict):
+        taxa = list(alignment.keys())
+    rank = world = None
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(), dist.get_world_size()
+    return SplitScorer(splits, taxa, method, rank or 0, world or 1)(alignment)

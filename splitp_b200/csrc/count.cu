@@ -238,6 +238,7 @@ struct StreamHashSink {
     }
     atomicExch(overflow, 1u);
   }
+  __device__ __forceinline__ void add_if(bool p, uint64_t key) const { if (p) add(key, 1u, 0u); }
 };
 
 template <int NT, class Sink>

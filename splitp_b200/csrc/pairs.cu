@@ -109,6 +109,7 @@ __global__ void finalize_kernel(const unsigned long long* __restrict__ raw, int 
   int i = idx / n, j = idx - i * n;
   const unsigned long long* marg = raw + (int64_t)n * n * 9;
   long long tot = (long long)marg[n * 3];
+  if (divisor < 0.0) divisor = (double)tot;  // probabilities = count / usable sites (fasta.py:66-70) without a host round trip
   long long N[4][4];
   if (i == j) {
     long long s = 0;

@@ -14,6 +14,7 @@ Objects
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import warnings
 
@@ -55,6 +56,42 @@ def _zeros(shape, dtype):
 
 def _empty(shape, dtype):
     return torch.empty(shape, dtype=dtype, device=device())
+
+
+class PhaseTimer:
+    """Per-phase device time from CUDA events on the launch stream (bench.py `phase_ms`).  Inactive unless an instance
+    is handed to the scorers; recording an event pair costs a few microseconds of host time."""
+
+    def __init__(self):
+        self.events = []
+
+    @contextlib.contextmanager
+    def span(self, name, units=1):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        try:
+            yield
+        finally:
+            b.record()
+            self.events.append((name, a, b, units))
+
+    def totals(self):
+        """{phase: (ms, spans, units)}; call after a synchronize."""
+        out = {}
+        for name, a, b, units in self.events:
+            ms, n, u = out.get(name, (0.0, 0, 0))
+            out[name] = (ms + a.elapsed_time(b), n + 1, u + units)
+        return out
+
+    def clear(self):
+        self.events = []
+
+
+_NULL_SPAN = contextlib.nullcontext()
+
+
+def _span(timer, name, units=1):
+    return timer.span(name, units) if timer is not None else _NULL_SPAN
 
 
 def split_positions(split, taxa):
@@ -458,7 +495,8 @@ class CountScorer:
         self._ws = {}
         self._batch_bytes = None
         self.int32_gram = True  # large dense splits keep G as int32 + correction strip (half the eigen-stage traffic)
-        self.gram_hook = None  # optional wrapper (fn, nb) around the Gram launch (bench.py times it with CUDA events)
+        self.gram_hook = None  # optional wrapper (fn, nb) around the Gram launch
+        self.timer = None      # optional PhaseTimer: scatter / gram / correction / eigen spans (bench.py phase_ms)
 
     @property
     def table(self):
@@ -541,13 +579,18 @@ class CountScorer:
         s0_stride, g_stride = rows_pad * pitch, rows_pad * rows_pad
         cs_rows = int(buf["Cs"].shape[1])
         G, Cs, pos, hr, hm = buf["G"][b0:], buf["Cs"][b0:], buf["pos"][b0:], buf["hr"][b0:], buf["hm"][b0:]
+        t = self.timer
         try:
-            self._scatter(arr, nb, s0, layout, rows_pad, pitch)
+            with _span(t, "scatter", nb):
+                self._scatter(arr, nb, s0, layout, rows_pad, pitch)
             run = lambda: call("spb_gram_u8_batch_i32", _p(s0), s0_stride, nb, rows_pad, pitch, _p(G), g_stride, _st())  # noqa: E731
-            run() if self.gram_hook is None else self.gram_hook(run, nb)
-            call("spb_gram_hi_strip_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
-                 _p(self.hi_num), self.hi_cap, _p(Cs), cs_rows, _p(pos), _p(hr), _p(hm), _st())
-            self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
+            with _span(t, "gram_large", nb):
+                run() if self.gram_hook is None else self.gram_hook(run, nb)
+            with _span(t, "correction", nb):
+                call("spb_gram_hi_strip_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
+                     _p(self.hi_num), self.hi_cap, _p(Cs), cs_rows, _p(pos), _p(hr), _p(hm), _st())
+            with _span(t, "scatter", 0):
+                self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
         except BaseException:
             self._drop_s0()  # the cached S0 buffers are assumed all-zero between uses: never keep a dirty one
             raise
@@ -607,13 +650,18 @@ class CountScorer:
         nb = len(splits)
         arr = splits if isinstance(splits, C.Array) else (_lib.SpbSplit * nb)(*splits)
         s0_stride, g_stride = rows_pad * pitch, rows_pad * rows_pad
+        t = self.timer
         try:
-            self._scatter(arr, nb, s0, layout, rows_pad, pitch)
+            with _span(t, "scatter", nb):
+                self._scatter(arr, nb, s0, layout, rows_pad, pitch)
             run = lambda: call("spb_gram_u8_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(G), g_stride, _p(ws), _st())  # noqa: E731
-            run() if self.gram_hook is None else self.gram_hook(run, nb)
-            call("spb_gram_hi_correction_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
-                 _p(self.hi_num), self.hi_cap, _p(G), g_stride, _st())
-            self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
+            with _span(t, "gram", nb):
+                run() if self.gram_hook is None else self.gram_hook(run, nb)
+            with _span(t, "correction", nb):
+                call("spb_gram_hi_correction_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
+                     _p(self.hi_num), self.hi_cap, _p(G), g_stride, _st())
+            with _span(t, "scatter", 0):
+                self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
         except BaseException:
             self._drop_s0()
             raise
@@ -692,7 +740,8 @@ class CountScorer:
                         self._gram_batch_i32(plans, s0, buf, b0, layout, rows_pad, pitch)
                     else:
                         self._gram_batch(plans, s0, G[b0:b0 + nsub], ws, layout, rows_pad, pitch)
-                sc = self._score_i32(buf, len(chunk), R) if i32 else score_gram(G[:len(chunk)], R)
+                with _span(self.timer, "eigen", len(chunk)):
+                    sc = self._score_i32(buf, len(chunk), R) if i32 else score_gram(G[:len(chunk)], R)
                 if chunk == list(range(chunk[0], chunk[0] + len(chunk))):
                     out[chunk[0]:chunk[0] + len(chunk)] = sc
                 else:

@@ -171,14 +171,25 @@ print("rank", rank, "ok")
 
 
 def test_bench_reference_arm_runs():
+    """`bench.py --impl reference`: one JSON line, the unmodified reference from baseline/_ref when it is installed
+    (kind "reference"), the oracle port beside it; the process imports neither torch nor splitp_b200."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", SPB_BENCH_REPORT_MODULES="1")  # torchrun's setting must not reach BLAS
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--sites", "20000"], capture_output=True, text=True, timeout=600)
+                        "--sites", "20000"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr
     import json
     assert len(r.stdout.strip().splitlines()) == 1  # stdout carries exactly one JSON line
     line = json.loads(r.stdout.strip())
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    have_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "splitp"))
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert line["cpu_baseline"]["port"]["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["threads"]["OMP_NUM_THREADS"] == str(line["threads"]["host_cores"])
+    assert set(line["config"]) == {"workload", "name", "taxa", "sites", "splits", "model", "branch_length", "seed", "l2", "parallelism"}
+    if have_ref:
+        assert line["cpu_baseline"]["port_vs_reference_max_rel"] < 1e-9
+    assert "torch" not in line["modules"] and "splitp_b200" not in line["modules"]
 
 
 def test_bench_reference_arm_under_torchrun_env_prints_on_rank0_only():
