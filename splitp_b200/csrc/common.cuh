@@ -77,6 +77,10 @@ inline int make_split_dev(const spb_split* s, SplitDev* d, bool need_key64 = tru
   return SPB_OK;
 }
 
+// gram.cu: G0 = S0 S0^T (int32, both triangles) of nb tiled u8 matrices on the tensor cores; one K pass (pitch <= 32768)
+int gram_u8_i32_launch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int32_t* d_Gi,
+                       int64_t g_stride, cudaStream_t st);
+
 __device__ __forceinline__ uint64_t side_index(uint64_t key, const uint8_t* sh, int len) {
   uint64_t r = 0;
   for (int i = 0; i < len; ++i) r = (r << 2) | ((key >> sh[i]) & 3ull);

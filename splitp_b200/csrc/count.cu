@@ -347,14 +347,19 @@ int launch_stream(const uint32_t* d_sm, const uint32_t* d_valid, int n, int64_t 
   return SPB_ERR_ARG;
 }
 
-// SPB_COUNT_KERNEL=cache in the environment selects the round-1 cache kernel (A/B measurements)
-static bool use_stream_kernel(const void* d_sm, const void* d_first) {
+// Which kernel counts when first-site indices are not requested.  Measured on B200 (profiles/r2_count_kernels.txt, 10^8 sites):
+// direct table, 12 taxa: cache kernel 1.47 ms, stream kernel 1.96 ms -- two thirds of the sites are ~260 single-mutation
+// patterns, and fire-and-forget REDs to so few addresses serialise in the L2 atomic units (3.4e10 RED/s in total);
+// hash table, 20 taxa: stream 3.39 ms, cache 3.59 ms; 31 taxa: 2.55 ms against 2.70 ms.  So: stream for hashed tables,
+// cache for direct tables.  SPB_COUNT_KERNEL=cache / stream in the environment forces one of them (A/B runs).
+static bool use_stream_kernel(const void* d_sm, const void* d_first, bool hashed) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("SPB_COUNT_KERNEL");
-    forced = (e && e[0] == 'c') ? 1 : 0;
+    forced = (e && e[0] == 'c') ? 1 : ((e && e[0] == 's') ? 2 : 0);
   }
-  return !forced && d_first == nullptr && (reinterpret_cast<uintptr_t>(d_sm) & 15) == 0;
+  if (d_first != nullptr || (reinterpret_cast<uintptr_t>(d_sm) & 15) != 0) return false;
+  return forced == 2 || (forced == 0 && hashed);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -523,7 +528,7 @@ extern "C" int spb_count_direct(const uint32_t* d_sm, const uint32_t* d_valid, i
   SPB_REQUIRE(n_taxa >= 1 && n_taxa <= 14, "spb_count_direct: direct table needs 1 <= n_taxa <= 14 (got %d)", n_taxa);
   SPB_REQUIRE(site_begin >= 0 && site_end >= site_begin && site_end < (1ll << 32), "spb_count_direct: bad site range");
   DirectSink sink{d_table, d_first};
-  if (use_stream_kernel(d_sm, d_first))
+  if (use_stream_kernel(d_sm, d_first, false))
     return launch_stream(d_sm, d_valid, n_taxa, site_begin, site_end, StreamDirectSink{d_table}, d_usable, (cudaStream_t)stream);
   return launch_count(d_sm, d_valid, n_taxa, site_begin, site_end, sink, d_usable, (cudaStream_t)stream);
 }
@@ -536,7 +541,7 @@ extern "C" int spb_count_hash(const uint32_t* d_sm, const uint32_t* d_valid, int
   SPB_REQUIRE(cap >= 2 && (cap & (cap - 1)) == 0, "spb_count_hash: capacity must be a power of two");
   SPB_REQUIRE(site_begin >= 0 && site_end >= site_begin && site_end < (1ll << 32), "spb_count_hash: bad site range");
   HashSink sink{(unsigned long long*)d_hkeys, d_hcounts, d_hfirst, (uint64_t)cap - 1, d_overflow};
-  if (use_stream_kernel(d_sm, d_hfirst))
+  if (use_stream_kernel(d_sm, d_hfirst, true))
     return launch_stream(d_sm, d_valid, n_taxa, site_begin, site_end,
                          StreamHashSink{(unsigned long long*)d_hkeys, d_hcounts, (uint64_t)cap - 1, d_overflow}, d_usable, (cudaStream_t)stream);
   return launch_count(d_sm, d_valid, n_taxa, site_begin, site_end, sink, d_usable, (cudaStream_t)stream);

@@ -24,6 +24,7 @@
 // Only tiles touching the upper triangle (in 256-wide blocks) are computed; the rest is mirrored.
 #include "common.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 using namespace spb;
 
@@ -285,6 +286,216 @@ gram_u8_umma_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int 
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CTA-pair kernel (tcgen05 cta_group::2): the version used whenever K needs no split.
+//
+// Why: ncu on the single-CTA kernel above (round 1, 4096^2 Gram): tensor pipe 45.8 % active while the operand feed
+// ran at l1tex__m_xbar2l1tex_read_bytes = 11.5 TB/s, the L2 -> SM ceiling of the part (B300_MICROARCH: ~6300 B/clk
+// chip-wide).  A single CTA pulls 48 KB (A tile + two B tiles) per four M128 N256 K32 MMAs = 85 MAC / byte; at the
+// kind::i8 rate of 128 clk per MMA (scripts/mma_rate.cu) all 148 SMs would need 14.2 KB/clk.  A CTA pair computes a
+// 256 x 256 output block with ONE M256 N256 K32 instruction per 32 bytes of K: every CTA loads its own 128 rows of A and
+// only ITS HALF of B (128 of the 256 columns), 32 KB per stage = 128 MAC / byte, 1.5x less L2 traffic per MMA, and the
+// 16 KB saved per stage buy a 6-stage ring instead of 4.
+//
+// Roles per CTA (320 threads, both CTAs of the pair run the same code):
+//   warp 0    : TMA producer for THIS CTA's shared memory (A tile of rows 256 bi + 128 rank .., B tile 2 bj + rank)
+//   warp 1    : rank 0 = MMA issuer for the pair (one thread; tcgen05.mma.cta_group::2, commits multicast to both CTAs);
+//               rank 1 = relay: forwards "my stage s is full" to the leader's peer_full barrier (plain bulk copies
+//               can only signal a barrier of their own CTA, and the MMA reads both CTAs' shared memory)
+//   warps 2-9 : epilogue of THIS CTA's 128 accumulator rows (TMEM is per CTA): tcgen05.ld -> int32 / fp64 stores of
+//               the block and of its mirror image; accumulator release goes to the leader's tempty barrier
+// Work item = (matrix, block row bi, block column bj >= bi) in 256-row blocks, dealt round-robin to the pairs.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kStages2 = 6;
+constexpr int kStage2Bytes = 2 * kTileBytes;  // this CTA's A tile + its half of B
+
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_i8_2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void st_global_v8(int32_t* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+struct Work2 {
+  int b, bi, bj;
+};
+// w -> (matrix, block row, block column): row-major over the upper triangle, row bi holds the blocks bj = bi .. B - 1
+__device__ __forceinline__ void get_work2(int w, int B, int nblk, Work2* out) {
+  out->b = w / nblk;
+  int t = w - out->b * nblk;
+  int bi = 0;
+  while (t >= B - bi) { t -= B - bi; ++bi; }
+  out->bi = bi;
+  out->bj = bi + t;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kUmmaThreads, 1)
+gram_u8_umma2_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int B, int KT, int nblk, int num_work, int64_t ldg,
+                     double* __restrict__ G_base, int64_t g_stride, int32_t* __restrict__ Gi_base) {
+  constexpr uint32_t kIdesc = make_idesc_i8(256, 256);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);  // same offset in both CTAs (same kernel, same layout)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)kStages2 * kStage2Bytes);
+  uint64_t* full_bar = bars;                         // [kStages2] this CTA's stage has landed
+  uint64_t* empty_bar = bars + kStages2;             // [kStages2] the pair's MMAs have read the stage (multicast commit)
+  uint64_t* peer_full_bar = bars + 2 * kStages2;     // [kStages2] leader only: the peer's stage has landed (relay)
+  uint64_t* tfull_bar = bars + 3 * kStages2;         // [2] accumulator complete (multicast commit)
+  uint64_t* tempty_bar = bars + 3 * kStages2 + 2;    // [2] leader only: both CTAs' epilogues have drained the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages2 + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(smem_u32(full_bar + s), 1);
+      mbar_init(smem_u32(empty_bar + s), 1);
+      mbar_init(smem_u32(peer_full_bar + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(tfull_bar + s), 1); mbar_init(smem_u32(tempty_bar + s), 16); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before anyone arrives remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (each CTA feeds its own shared memory) =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int w = pair; w < num_work; w += npairs) {
+        Work2 wk;
+        get_work2(w, B, nblk, &wk);
+        const uint8_t* s0t = s0_base + (size_t)wk.b * s0_stride;
+        const uint8_t* a_src = s0t + (size_t)(2 * wk.bi + (int)rank) * KT * kTileBytes;
+        const uint8_t* b_src = s0t + (size_t)(2 * wk.bj + (int)rank) * KT * kTileBytes;
+        for (int kt = 0; kt < KT; ++kt) {
+          mbar_wait_cluster(smem_u32(empty_bar + stage), phase ^ 1);
+          const uint32_t fb = smem_u32(full_bar + stage);
+          mbar_expect_tx(fb, (uint32_t)kStage2Bytes);
+          uint8_t* sa = ring + (size_t)stage * kStage2Bytes;
+          bulk_g2s(smem_u32(sa), a_src + (size_t)kt * kTileBytes, kTileBytes, fb);
+          bulk_g2s(smem_u32(sa + kTileBytes), b_src + (size_t)kt * kTileBytes, kTileBytes, fb);
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer of the pair =====
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int w = pair; w < num_work; w += npairs) {
+        mbar_wait_cluster(smem_u32(tempty_bar + acc), acc_phase ^ 1);  // both epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kt = 0; kt < KT; ++kt) {
+          mbar_wait(smem_u32(full_bar + stage), phase);
+          mbar_wait_cluster(smem_u32(peer_full_bar + stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + (size_t)stage * kStage2Bytes);
+          const uint64_t da = make_desc_sw128(sa);
+          const uint64_t db = make_desc_sw128(sa + kTileBytes);
+#pragma unroll
+          for (int k = 0; k < kTile / 32; ++k)
+            umma_i8_2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kt > 0 || k > 0) ? 1u : 0u);
+          umma_commit2(smem_u32(empty_bar + stage));  // frees the slot in both CTAs once the MMAs have read it
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit2(smem_u32(tfull_bar + acc));  // accumulator complete -> both epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else if (lane == 0) {
+      // ===== relay: "stage s of CTA 1 is full" -> leader =====
+      uint32_t stage = 0, phase = 0;
+      for (int w = pair; w < num_work; w += npairs) {
+        for (int kt = 0; kt < KT; ++kt) {
+          mbar_wait(smem_u32(full_bar + stage), phase);
+          mbar_arrive_remote(map_to_cta(smem_u32(peer_full_bar + stage), 0));
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue of this CTA's 128 rows: warp q = warp % 4 owns TMEM lanes [32q, 32q + 32), two warps per quarter
+    // split the 256 accumulator columns =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t tempty_leader = map_to_cta(smem_u32(tempty_bar), 0);
+    uint32_t acc = 0, acc_phase = 0;
+    for (int w = pair; w < num_work; w += npairs) {
+      Work2 wk;
+      get_work2(w, B, nblk, &wk);
+      mbar_wait_cluster(smem_u32(tfull_bar + acc), acc_phase);
+      tc_fence_after();
+      const int row = (2 * wk.bi + (int)rank) * kTile + q * 32 + lane;
+      const bool mirror = wk.bj > wk.bi;
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < (half + 1) * 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + c0, v);
+        const int col0 = wk.bj * 256 + c0;
+        if (Gi_base) {
+          int32_t* Gi = Gi_base + (size_t)wk.b * g_stride;
+          int32_t* dst = Gi + (size_t)row * ldg + col0;
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) st_global_v8(dst + e, v + e);  // 256-bit stores: whole 32-byte sectors
+          if (mirror) {  // lanes walk consecutive rows => coalesced 128-byte segments
+#pragma unroll
+            for (int e = 0; e < 32; ++e) Gi[(size_t)(col0 + e) * ldg + row] = (int)v[e];
+          }
+        } else {
+          double* G = G_base + (size_t)wk.b * g_stride;
+          double* dst = G + (size_t)row * ldg + col0;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) *reinterpret_cast<double2*>(dst + e) = make_double2((double)(int)v[e], (double)(int)v[e + 1]);
+          if (mirror) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) G[(size_t)(col0 + e) * ldg + row] = (double)(int)v[e];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(smem_u32(tempty_bar + acc));
+        else mbar_arrive_remote(tempty_leader + acc * 8);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no multicast commit / remote arrive may target a CTA that has exited
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -561,6 +772,44 @@ UmmaPlan plan_umma(int64_t rows_pad, int64_t pitch, int nb, bool single_pass = f
   return p;
 }
 
+// Launches the CTA-pair kernel for nb matrices (no K split: one accumulation covers all of K, KT <= 256).
+int launch_umma2(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, double* d_G, int32_t* d_Gi,
+                 int64_t g_stride, cudaStream_t st) {
+  const int B = (int)(rows_pad / 256), KT = (int)(pitch / kTile);
+  const int nblk = B * (B + 1) / 2;
+  const int num_work = nblk * nb;
+  const size_t smem = (size_t)kStages2 * kStage2Bytes + 32 * 8 + 1024;
+  static int max_pairs = 0;
+  if (max_pairs == 0) {
+    SPB_CUDA(cudaFuncSetAttribute(gram_u8_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * sm_count());
+    cfg.blockDim = dim3(kUmmaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gram_u8_umma2_kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = sm_count() / 2; }
+    max_pairs = n;
+  }
+  const int pairs = num_work < max_pairs ? num_work : max_pairs;
+  gram_u8_umma2_kernel<<<2 * pairs, kUmmaThreads, smem, st>>>(d_s0, s0_stride, B, KT, nblk, num_work, rows_pad, d_G, g_stride, d_Gi);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+// SPB_GRAM_KERNEL=1cta in the environment selects the single-CTA kernel everywhere (A/B measurements)
+bool use_pair_kernel() {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("SPB_GRAM_KERNEL");
+    forced = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !forced;
+}
+
 }  // namespace
 
 extern "C" int64_t spb_s0_bytes(int64_t rows_pad, int64_t pitch) { return rows_pad * pitch; }
@@ -614,6 +863,8 @@ extern "C" int spb_gram_u8_batch(const uint8_t* d_s0, int64_t s0_stride, int nb,
     acc = (unsigned long long*)d_ws;
     SPB_CUDA(cudaMemsetAsync(acc, 0, (size_t)nb * rows_pad * rows_pad * 8, st));
   }
+  if (p.BN == 256 && p.ksplit == 1 && p.KT <= 256 && use_pair_kernel())
+    return launch_umma2(d_s0, s0_stride, nb, rows_pad, pitch, d_G, nullptr, g_stride, st);
   int grid = p.num_work < sm_count() ? p.num_work : sm_count();
   if (p.BN == 256) {
     SPB_CUDA(cudaFuncSetAttribute(gram_u8_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
@@ -634,8 +885,9 @@ extern "C" int spb_gram_u8_batch(const uint8_t* d_s0, int64_t s0_stride, int nb,
   return SPB_OK;
 }
 
-extern "C" int spb_gram_u8_batch_i32(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch,
-                                     int32_t* d_Gi, int64_t g_stride, void* stream) {
+namespace spb {
+int gram_u8_i32_launch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int32_t* d_Gi,
+                       int64_t g_stride, cudaStream_t st) {
   SPB_REQUIRE(d_s0 && d_Gi && nb >= 1 && nb <= 65535, "spb_gram_u8_batch_i32: bad arguments");
   SPB_REQUIRE(rows_pad % 256 == 0 && rows_pad >= 256 && rows_pad <= 32768 && pitch % kTile == 0 && pitch >= kTile,
               "spb_gram_u8_batch_i32: needs the tiled layout with rows_pad %% 256 == 0 and pitch %% 128 == 0 (got %lld, %lld)",
@@ -644,14 +896,21 @@ extern "C" int spb_gram_u8_batch_i32(const uint8_t* d_s0, int64_t s0_stride, int
               (long long)pitch, 256 * kTile);
   SPB_REQUIRE(nb == 1 || (s0_stride >= rows_pad * pitch && s0_stride % 16 == 0 && g_stride >= rows_pad * rows_pad),
               "spb_gram_u8_batch_i32: bad batch strides");
+  if (use_pair_kernel()) return launch_umma2(d_s0, s0_stride, nb, rows_pad, pitch, nullptr, d_Gi, g_stride, st);
   UmmaPlan p = plan_umma(rows_pad, pitch, nb, true);
   if (p.ksplit != 1) { set_error("spb_gram_u8_batch_i32: internal: K split"); return SPB_ERR_ARG; }
   int grid = p.num_work < sm_count() ? p.num_work : sm_count();
   SPB_CUDA(cudaFuncSetAttribute(gram_u8_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  gram_u8_umma_kernel<256><<<grid, kUmmaThreads, p.smem, (cudaStream_t)stream>>>(d_s0, s0_stride, p.T, p.KT, p.tiles, 1, p.kt_per_split,
-                                                                              p.num_work, rows_pad, nullptr, g_stride, nullptr, d_Gi);
+  gram_u8_umma_kernel<256><<<grid, kUmmaThreads, p.smem, st>>>(d_s0, s0_stride, p.T, p.KT, p.tiles, 1, p.kt_per_split, p.num_work, rows_pad,
+                                                             nullptr, g_stride, nullptr, d_Gi);
   SPB_LAUNCH_CHECK();
   return SPB_OK;
+}
+}  // namespace spb
+
+extern "C" int spb_gram_u8_batch_i32(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch,
+                                     int32_t* d_Gi, int64_t g_stride, void* stream) {
+  return spb::gram_u8_i32_launch(d_s0, s0_stride, nb, rows_pad, pitch, d_Gi, g_stride, (cudaStream_t)stream);
 }
 
 extern "C" int spb_gram_hi_strip_batch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int layout,

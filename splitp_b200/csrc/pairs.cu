@@ -430,14 +430,20 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) subflatten_score_warp_kerne
 }
 
 inline size_t subflat_smem(int n, int* m_elems) {
-  int h = n / 2;
-  int k = 3 * h + 1, L = 3 * (n - h) + 1;
-  // the widest staging matrix over all splits: k x ((L+1)|1) is maximised at the balanced split, but a
-  // 1|n-1 split has k=4, L=3(n-1)+1; cover both
-  int m1 = k * ((L + 1) | 1);
-  int m2 = 4 * ((3 * (n - 1) + 2) | 1);
-  *m_elems = m1 > m2 ? m1 : m2;
-  return ((size_t)*m_elems + (size_t)jacobi_dim(k) * jacobi_ld(k)) * sizeof(double);
+  // the widest staging matrix over ALL side sizes: k x ((L + 1) | 1) with k = 3 min(a, b) + 1, L = 3 max(a, b) + 1.  It is
+  // NOT maximised at the balanced split (22 taxa: 10|12 needs 31 x 39 = 1209 doubles, 11|11 only 34 x 35 = 1190: round 1
+  // sized the buffer from the balanced split and the 10|12 matrices ran 19 doubles into G -- found by
+  // tests/test_gpu_parity_r2.py::test_subflatten_score_stratified[22]); the Jacobi tile is largest at the balanced split
+  int worst = 0;
+  for (int a = 1; a <= n / 2; ++a) {
+    const int k = 3 * a + 1, L = 3 * (n - a) + 1;
+    const int m = k * ((L + 1) | 1);
+    if (m > worst) worst = m;
+  }
+  if (worst < 4 * 7) worst = 4 * 7;
+  *m_elems = worst;
+  const int kmax = 3 * (n / 2) + 1;
+  return ((size_t)*m_elems + (size_t)jacobi_dim(kmax) * jacobi_ld(kmax)) * sizeof(double);
 }
 
 // The warp-per-split scorer is the default up to 21 taxa; SPB_SUBFLATTEN_WARP=0 in the environment selects the

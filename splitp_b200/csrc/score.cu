@@ -435,6 +435,9 @@ __device__ __forceinline__ double u31_to_double(int x) { return __hiloint2double
 // their partial sums are added in warp order through shared memory (deterministic).
 constexpr int kColsWarps = 16;
 constexpr int kColsChunk = 1024;  // rows of Q staged per pass: [kColsChunk][8] doubles = 64 KB
+// gridDim.z > 1 ("row split", used when ONE matrix must fill the machine): CTA z handles the row chunks z, z + gridDim.z, ...
+// and writes its partial sums to part[z][c][j] (part = AQ argument, plane stride kKB * k); symv_reduce_parts_kernel adds the
+// planes in z order (deterministic).
 __global__ void __launch_bounds__(32 * kColsWarps, 1) symv_cols_i32_kernel(const int32_t* __restrict__ G, int64_t ld, int64_t strideG,
                                                                          const double* __restrict__ Q, int64_t strideQ,
                                                                          double* __restrict__ AQ, int k) {
@@ -452,7 +455,7 @@ __global__ void __launch_bounds__(32 * kColsWarps, 1) symv_cols_i32_kernel(const
   for (int e = 0; e < 4; ++e)
 #pragma unroll
     for (int c = 0; c < kKB; ++c) acc[e][c] = 0.0;
-  for (int i0 = 0; i0 < k; i0 += kColsChunk) {
+  for (int i0 = blockIdx.z * kColsChunk; i0 < k; i0 += gridDim.z * kColsChunk) {
     const int len = min(kColsChunk, k - i0);
     __syncthreads();
     for (int idx = threadIdx.x; idx < kKB * kColsChunk; idx += 32 * kColsWarps) {
@@ -501,10 +504,20 @@ __global__ void __launch_bounds__(32 * kColsWarps, 1) symv_cols_i32_kernel(const
     }
     __syncthreads();
   }
+  double* out = AQ + (int64_t)bt * strideQ + (gridDim.z > 1 ? (int64_t)blockIdx.z * kKB * k : 0);
   for (int idx = threadIdx.x; idx < kKB * 128; idx += 32 * kColsWarps) {
     const int c = idx / 128, j = blockIdx.x * 128 + (idx & 127);
-    if (j < k) AQ[(int64_t)bt * strideQ + (int64_t)c * k + j] = tot[idx];
+    if (j < k) out[(int64_t)c * k + j] = tot[idx];
   }
+}
+
+// AQ[i] = sum_z part[z][i] (z ascending), i < kKB * k
+__global__ void symv_reduce_parts_kernel(const double* __restrict__ part, int nparts, int64_t elems, double* __restrict__ AQ) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= elems) return;
+  double s = 0.0;
+  for (int z = 0; z < nparts; ++z) s += part[(int64_t)z * elems + i];
+  AQ[i] = s;
 }
 
 // AQ += C Q for the strip form of the correction (GramView).  Two deterministic passes, no atomics:
@@ -866,6 +879,21 @@ extern "C" int64_t spb_score_gram_large_ws(int64_t k, int64_t batch) {
   return krylov_layout(k, batch, nullptr, &w);
 }
 
+static bool accept_matrix(const double* inf, int cycle) {
+  // Convergence of the sum of the 4 largest Ritz values.  Kato-Temple: |theta - lambda| <= res^2 / gap with
+  // gap = separation of the wanted cluster from the rest of the spectrum, estimated by (theta_4 - theta_5) /
+  // theta_1.  The error that matters is relative to the radicand 1 - top4 / trace (it becomes the score), so a
+  // matrix is accepted when res^2 <= 1e-11 * gap * radicand (100x below the 1e-9 parity tolerance), or when its
+  // residual is at rounding level, or when the Ritz values have stopped moving at a residual that rounding can
+  // explain (res <= 1e-9; the looser 1e-6 of round 1 accepted residuals far above the stated bound).
+  const double top = inf[0], tr = inf[1], res = inf[2], delta = inf[5];
+  if (!(tr > 0.0)) return true;
+  const double radicand = fmax(1.0 - top / tr, 1e-12);
+  const double t1 = fmax(top, 1e-300);
+  const double gap = fmin(fmax((inf[6] - inf[7]) / t1, 1e-6), 1.0);
+  return res <= 1e-13 || res * res <= 1e-11 * gap * radicand || (cycle > 0 && delta <= 1e-16 && res <= 1e-9);
+}
+
 // One Krylov cycle with `nb` blocks (dim = 8 nb).  first = 1 starts from the heaviest rows of G plus pseudo-random
 // vectors (krylov_start_rows_kernel), otherwise from the Ritz vectors the previous cycle left in Q_0.
 static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first, const KrylovWs& w, cudaStream_t st) {
@@ -978,21 +1006,7 @@ static int score_gram_large(const GramView& gv, int64_t k64, int64_t batch64, do
     SPB_CUDA(cudaStreamSynchronize(st));
     done = true;
     for (int b = 0; b < batch; ++b) {
-      // Convergence of the sum of the 4 largest Ritz values.  Kato-Temple: |theta - lambda| <= res^2 / gap with
-      // gap = separation of the wanted cluster from the rest of the spectrum, estimated by (theta_4 - theta_5) /
-      // theta_1.  The error that matters is relative to the radicand 1 - top4 / trace (it becomes the score), so a
-      // matrix is accepted when res^2 <= 1e-11 * gap * radicand (100x below the 1e-9 parity tolerance), or when its
-      // residual is at rounding level, or when the Ritz values have stopped moving at a residual that rounding can
-      // explain (res <= 1e-9; the looser 1e-6 of round 1 accepted residuals far above the stated bound).
-      const double* inf = h_info.data() + (size_t)b * kInfo;
-      const double top = inf[0], tr = inf[1], res = inf[2], delta = inf[5];
-      bool ok = true;
-      if (tr > 0.0) {
-        const double radicand = fmax(1.0 - top / tr, 1e-12);
-        const double t1 = fmax(top, 1e-300);
-        const double gap = fmin(fmax((inf[6] - inf[7]) / t1, 1e-6), 1.0);
-        ok = res <= 1e-13 || res * res <= 1e-11 * gap * radicand || (cycle > 0 && delta <= 1e-16 && res <= 1e-9);
-      }
+      const bool ok = accept_matrix(h_info.data() + (size_t)b * kInfo, cycle);
       h_flag[b] = ok ? 1.0 : 0.0;
       if (!ok) done = false;
     }
@@ -1009,12 +1023,182 @@ static int score_gram_large(const GramView& gv, int64_t k64, int64_t batch64, do
   return SPB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Streamed scoring of large count flattenings: Gram -> G S -> G (G S) per matrix while G0 sits in L2.
+//
+// The batched route above writes 64 int32 Gram matrices (4.3 GB) to HBM and streams each of them back twice, once per
+// block of the first Krylov cycle; the two products cost as much as the tensor-core Gram itself (ncu, round 1: 20.7 us
+// per 4096^2 product at 3.2 TB/s).  One 4096^2 int32 Gram is 67 MB and the L2 holds 126 MB, so here every matrix goes
+// through  Gram -> X1 = G S -> X2 = G X1  back to back into ONE reused G0 buffer: both products read G0 from L2, and
+// because the buffer is overwritten by the next Gram before most of it is evicted, G0 hardly reaches HBM at all.
+// To have no small kernels between the two products, the whole orthogonalisation of the 2-block Krylov cycle is
+// DEFERRED and applied afterwards, batched over all matrices, as 8 x 8 linear maps on (S, X1, X2):
+//     Q0 = U0 S,  G Q0 = U0 X1,  G^2 Q0-part = U0 X2          (SVQB twice)
+//     W  = G Q0 - C Q0,  G W = U0 X2 - C (G Q0)               (classical Gram-Schmidt twice, C = Q0 (G Q0)^T)
+//     Q1 = U1 W,  G Q1 = U1 (G W)                              (SVQB twice)
+// which spans the same subspace as the batched cycle (S = 4 heaviest rows of G + 4 pseudo-random vectors).  The price is
+// cancellation in G W when a split is (nearly) rank 4: the residual then stalls near 1e-8 and the matrix is reported as
+// unconverged; the caller re-scores those few through the batched route (measured on the config-2 alignment: only the
+// tree's true 6|6 split; its score from this route is still within 4e-12 of LAPACK).
+// ------------------------------------------------------------------------------------------
+static int stream_products(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int32_t* d_Gi,
+                           const GramView& strips, int k, const KrylovWs& w, double* h_timing, cudaStream_t st) {
+  const int64_t ld = rows_pad;
+  const int64_t blk = (int64_t)kKB * k;
+  const size_t cols_smem = (size_t)kKB * kColsChunk * sizeof(double);
+  SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
+  int zsplit = (k + kColsChunk - 1) / kColsChunk;
+  if (zsplit > 8) zsplit = 8;
+  // the split-row partial sums reuse the inner-product scratch (part): zsplit * 8 * k doubles
+  if ((int64_t)zsplit * blk > w.part_elems) zsplit = 1;
+  static thread_local std::vector<cudaEvent_t> evs;  // [3 per matrix]: gram begin, gram end, products end
+  if (h_timing) {
+    while ((int)evs.size() < 3 * nb) { cudaEvent_t e; SPB_CUDA(cudaEventCreate(&e)); evs.push_back(e); }
+  }
+  int rc;
+  for (int b = 0; b < nb; ++b) {
+    if (h_timing) SPB_CUDA(cudaEventRecord(evs[3 * b], st));
+    if ((rc = gram_u8_i32_launch(d_s0 + (size_t)b * s0_stride, s0_stride, 1, rows_pad, pitch, d_Gi, rows_pad * rows_pad, st))) return rc;
+    if (h_timing) SPB_CUDA(cudaEventRecord(evs[3 * b + 1], st));
+    GramView gv{nullptr, d_Gi, ld, strips.cs_rows ? strips.Cs + (int64_t)b * strips.cs_rows * ld : nullptr, strips.cs_rows,
+                strips.cs_rows ? strips.pos + (int64_t)b * ld : nullptr, strips.cs_rows ? strips.hr + (int64_t)b * strips.cs_rows : nullptr,
+                strips.cs_rows ? strips.hm + b : nullptr};
+    double* Qb = w.Q + (int64_t)b * w.sQ;    // block 0 = S, block 1 = W (filled later)
+    double* AQb = w.AQ + (int64_t)b * w.sQ;  // block 0 = X1 = G S, block 1 = X2 = G X1
+    double* diag = w.diag + (int64_t)b * k;
+    int* idx = reinterpret_cast<int*>(w.idx) + (int64_t)b * kKB;
+    dim3 g1((k + 255) / 256, 1);
+    gram_diag_kernel<<<g1, 256, 0, st>>>(gv, k, diag);
+    SPB_LAUNCH_CHECK();
+    krylov_top8_kernel<<<1, 256, 0, st>>>(diag, k, idx);
+    SPB_LAUNCH_CHECK();
+    krylov_start_rows_kernel<<<g1, 256, 0, st>>>(gv, idx, Qb, w.sQ, k);
+    SPB_LAUNCH_CHECK();
+    for (int prod = 0; prod < 2; ++prod) {
+      const double* src = prod == 0 ? Qb : AQb;
+      double* dst = prod == 0 ? AQb : AQb + blk;
+      dim3 gi((k + 127) / 128, 1, zsplit);
+      symv_cols_i32_kernel<<<gi, 32 * kColsWarps, cols_smem, st>>>(d_Gi, ld, ld * ld, src, w.sQ, zsplit > 1 ? w.part : dst, k);
+      SPB_LAUNCH_CHECK();
+      if (zsplit > 1) {
+        symv_reduce_parts_kernel<<<(unsigned)((blk + 255) / 256), 256, 0, st>>>(w.part, zsplit, blk, dst);
+        SPB_LAUNCH_CHECK();
+      }
+      if (gv.cs_rows) {
+        dim3 rg((unsigned)((gv.cs_rows + kStripRowsPerCta - 1) / kStripRowsPerCta), 1);
+        strip_rows_kernel<<<rg, 256, 0, st>>>(gv, src, w.sQ, dst, k);
+        SPB_LAUNCH_CHECK();
+        dim3 cg((k + 255) / 256, 1);
+        strip_cols_kernel<<<cg, 256, 0, st>>>(gv, src, w.sQ, dst, k);
+        SPB_LAUNCH_CHECK();
+      }
+    }
+    if (h_timing) SPB_CUDA(cudaEventRecord(evs[3 * b + 2], st));
+  }
+  if (h_timing) {
+    SPB_CUDA(cudaStreamSynchronize(st));
+    double gram_ms = 0.0, prod_ms = 0.0;
+    for (int b = 0; b < nb; ++b) {
+      float a = 0.f, c = 0.f;
+      SPB_CUDA(cudaEventElapsedTime(&a, evs[3 * b], evs[3 * b + 1]));
+      SPB_CUDA(cudaEventElapsedTime(&c, evs[3 * b + 1], evs[3 * b + 2]));
+      gram_ms += a; prod_ms += c;
+    }
+    h_timing[0] = gram_ms; h_timing[1] = prod_ms;
+  }
+  return SPB_OK;
+}
+
+// deferred orthogonalisation + Rayleigh-Ritz of the 2-block cycle, batched over all matrices (see the header above)
+static int stream_rayleigh_ritz(int k, int batch, const KrylovWs& w, double* d_scores, cudaStream_t st) {
+  const int64_t blk = (int64_t)kKB * k;
+  int rc;
+  dim3 gk((k + 255) / 256, batch);
+  auto svqb_pass = [&](double* W, double* F1, double* F2) -> int {  // W <- U W with U from W W^T; the followers get the same U
+    if ((rc = dot_product(W, w.sQ, W, w.sQ, kKB, kKB, k, batch, w.S, kKB, w.sS, w.part, st))) return rc;
+    krylov_svqb_factor_kernel<<<batch, 64, 0, st>>>(w.S, w.sS, w.U);
+    SPB_LAUNCH_CHECK();
+    double* targets[3] = {W, F1, F2};
+    for (double* t : targets) {
+      if (!t) continue;
+      krylov_svqb_apply_kernel<<<gk, 256, 0, st>>>(t, w.sQ, w.U, k);
+      SPB_LAUNCH_CHECK();
+    }
+    return SPB_OK;
+  };
+  double* Q0 = w.Q;          // S -> Q0
+  double* X1 = w.AQ;         // G S -> G Q0
+  double* X2 = w.AQ + blk;   // G X1 -> G W -> G Q1
+  double* W = w.Q + blk;     // Q1
+  for (int pass = 0; pass < 2; ++pass)
+    if ((rc = svqb_pass(Q0, X1, X2))) return rc;
+  {
+    dim3 grid((unsigned)((blk + 255) / 256), batch);
+    copy_block_kernel<<<grid, 256, 0, st>>>(X1, w.sQ, W, w.sQ, blk);
+    SPB_LAUNCH_CHECK();
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    if ((rc = dot_product(Q0, w.sQ, W, w.sQ, kKB, kKB, k, batch, w.C, kKB, w.sC, w.part, st))) return rc;
+    krylov_subtract_kernel<<<gk, 256, 0, st>>>(W, w.sQ, Q0, w.sQ, w.C, w.sC, kKB, k);
+    SPB_LAUNCH_CHECK();
+    krylov_subtract_kernel<<<gk, 256, 0, st>>>(X2, w.sQ, X1, w.sQ, w.C, w.sC, kKB, k);
+    SPB_LAUNCH_CHECK();
+  }
+  for (int pass = 0; pass < 2; ++pass)
+    if ((rc = svqb_pass(W, X2, nullptr))) return rc;
+  const int dim = 2 * kKB;
+  if ((rc = dot_product(w.Q, w.sQ, w.AQ, w.sQ, dim, dim, k, batch, w.T, kKDim, w.sT, w.part, st))) return rc;
+  size_t smem = (size_t)2 * dim * (dim | 1) * sizeof(double);
+  SPB_CUDA(cudaFuncSetAttribute(krylov_rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  krylov_rr_kernel<<<batch, 256, smem, st>>>(w.T, w.sT, dim, w.diag, k, w.Vtop, w.theta, w.res2, w.info);
+  SPB_LAUNCH_CHECK();
+  krylov_ritz_kernel<<<gk, 256, 0, st>>>(w.Q, w.AQ, w.sQ, w.Vtop, w.theta, w.res2, dim, k);
+  SPB_LAUNCH_CHECK();
+  krylov_finish_kernel<<<(batch + 127) / 128, 128, 0, st>>>(w.theta, w.res2, w.info, d_scores, batch);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
 extern "C" int spb_score_last_unconverged(void) { return g_last_unconverged; }
 
 extern "C" int spb_score_gram_large(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores, double* d_info,
                                     double* d_ws, void* stream) {
   GramView gv{d_G, nullptr, ld, nullptr, 0, nullptr, nullptr, nullptr};
   return score_gram_large(gv, k, batch, d_scores, d_info, d_ws, stream);
+}
+
+extern "C" int spb_score_u8_stream(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int64_t k,
+                                   int32_t* d_Gi, const double* d_Cs, int64_t cs_rows, const int32_t* d_pos, const int32_t* d_hr,
+                                   const int32_t* d_hm, double* d_scores, double* d_info, double* d_ws, double* h_timing,
+                                   void* stream) {
+  SPB_REQUIRE(d_s0 && d_Gi && d_scores && d_ws && nb >= 1 && nb <= 65535 && k > kJacobiMaxK && k <= rows_pad && k < (1 << 24),
+              "spb_score_u8_stream: bad arguments (need k > %d)", kJacobiMaxK);
+  SPB_REQUIRE(cs_rows >= 0 && cs_rows <= 65535 && (cs_rows == 0 || (d_Cs && d_pos && d_hr && d_hm)), "spb_score_u8_stream: bad correction strip");
+  cudaStream_t st = (cudaStream_t)stream;
+  KrylovWs w;
+  krylov_layout(k, nb, d_ws, &w);
+  SPB_CUDA(cudaMemsetAsync(w.info, 0, (size_t)nb * kInfo * sizeof(double), st));
+  GramView strips{nullptr, nullptr, rows_pad, d_Cs, cs_rows, d_pos, d_hr, d_hm};
+  int rc;
+  if ((rc = stream_products(d_s0, s0_stride, nb, rows_pad, pitch, d_Gi, strips, (int)k, w, h_timing, st))) return rc;
+  if ((rc = stream_rayleigh_ritz((int)k, nb, w, d_scores, st))) return rc;
+  static thread_local std::vector<double> h_info;
+  static thread_local std::vector<double> h_flag;
+  h_info.resize((size_t)nb * kInfo);
+  h_flag.assign((size_t)nb, 0.0);
+  SPB_CUDA(cudaMemcpyAsync(h_info.data(), w.info, (size_t)nb * kInfo * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SPB_CUDA(cudaStreamSynchronize(st));
+  int bad = 0;
+  for (int b = 0; b < nb; ++b) {
+    const bool ok = accept_matrix(h_info.data() + (size_t)b * kInfo, 0);
+    h_flag[b] = ok ? 1.0 : 0.0;
+    bad += ok ? 0 : 1;
+  }
+  SPB_CUDA(cudaMemcpy2DAsync(w.info + 8, kInfo * sizeof(double), h_flag.data(), sizeof(double), sizeof(double), (size_t)nb,
+                             cudaMemcpyHostToDevice, st));
+  g_last_unconverged = bad;
+  if (d_info) SPB_CUDA(cudaMemcpyAsync(d_info, w.info, (size_t)nb * kInfo * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return SPB_OK;
 }
 
 extern "C" int spb_score_gram_large_i32(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Cs,

@@ -139,6 +139,26 @@ def test_gram_u8_batch_i32_exact_4096(eng, nb):
         assert np.array_equal(Gi[b].cpu().numpy().astype(np.int64), ref.astype(np.int64)), f"matrix {b} vs host product"
 
 
+@pytest.mark.parametrize("R,K,nb", [(256, 512, 150), (512, 1024, 80), (768, 384, 40), (1024, 2048, 37)])
+def test_gram_u8_batch_pair_kernel_fp64_exact(eng, R, K, nb):
+    """spb_gram_u8_batch with enough matrices that K is not split: the CTA-pair (cta_group::2) kernel with the fp64
+    epilogue, diagonal and off-diagonal 256-blocks, mirrored halves, odd numbers of work items per pair.  Bit-exact
+    against the integer product."""
+    rng = np.random.default_rng(R + K + nb)
+    M = rng.integers(0, 256, size=(nb, R, K), dtype=np.uint8)
+    M[rng.random((nb, R, K)) < 0.5] = 0
+    M[0] = 255
+    s0 = torch.from_numpy(np.stack([_tiled_from_rowmajor(M[b]) for b in range(nb)])).cuda()
+    G = torch.full((nb, R, R), -1.0, dtype=torch.float64, device="cuda")
+    n_ws = int(eng.lib.spb_gram_u8_ws(R, K, 1, nb))
+    assert n_ws == 0, "this shape is meant to run without a K split"
+    eng.call("spb_gram_u8_batch", eng._p(s0), R * K, nb, R, K, 1, eng._p(G), R * R, None, eng._st())
+    torch.cuda.synchronize()
+    Mf = M.astype(np.float64)
+    ref = np.stack([Mf[b] @ Mf[b].T for b in range(nb)])  # exact: integers < 2^53
+    np.testing.assert_array_equal(G.cpu().numpy(), ref)
+
+
 def test_score_many_config2_six_six_vs_lapack(sp, eng, oracle):
     """The bench's hot route (score_many -> u8 scatter -> spb_gram_u8_batch_i32 -> correction strip ->
     spb_score_gram_large_i32) on 18 6|6 splits of the config-2 alignment (12 taxa, 10^6 sites), 8+ of them false,
@@ -163,6 +183,27 @@ def test_score_many_config2_six_six_vs_lapack(sp, eng, oracle):
         assert_score(got[s], ref)
         worst = max(worst, abs(got[s] - ref) / ref / score_tol(ref))
     print(f"score_many 6|6: {len(picks)} splits ({len(t_splits)} true), worst error = {worst:.3f} x tolerance")
+    # the streamed route (Gram -> products while G0 is in L2, the default) against the batched int32 route
+    assert scorer.stream_large
+    scorer.stream_large = False
+    batched = scorer.score_many(idx).cpu().numpy()
+    scorer.stream_large = True
+    for s in range(len(idx)):
+        assert_score(got[s], batched[s])
+        ref = oracle.split_score(oracle.flattening_reduced(keys, counts / usable, n, *idx[s])) if s < 2 else None
+        if ref is not None:
+            assert_score(batched[s], ref)
+    # the true split fails the single-cycle acceptance test of the streamed route and is re-scored: both answers agree
+    sbuf = scorer._buffers_stream(rows_pad, len(idx))
+    s0 = scorer._buffers(layout, rows_pad, pitch, 1)[0]
+    plans = [scorer._plan(ia, ib, False)[0] for ia, ib in idx]
+    sc1, conv = scorer._score_stream(plans, s0, sbuf, layout, rows_pad, pitch, 4096)
+    sc1 = sc1.cpu().numpy()
+    n_bad = 0 if conv is None else int((~conv).sum().item())
+    print(f"streamed route: {n_bad} of {len(idx)} matrices flagged for re-scoring")
+    assert n_bad <= len(t_splits) + 2
+    for s in range(len(idx)):
+        assert_score(sc1[s], got[s], extra=50.0)  # even the flagged ones are close (their residual bound is what fails)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -205,6 +246,16 @@ def test_split_score_reducible_gram(sp, oracle, name):
     ref = oracle.split_score(A)
     assert_score(sp.split_score(A), ref)
     assert_score(sp.split_score(A.T), ref)
+
+
+def test_sub_alignment_keeps_integer_counts(sp):
+    """Alignment.sub_alignment of an integer-count alignment returns ints, like the reference's dict arithmetic
+    (alignment.py:26-30)."""
+    aln = sp.Alignment({"ACGT": 3, "ACGA": 2, "TCGT": 5, "AAAA": 1}, ("w", "x", "y", "z"))
+    sub = aln.sub_alignment(("x", "y"))
+    assert dict(sub) == {"CG": 10, "AA": 1} and all(type(v) is int for v in sub.values())
+    fl = sp.Alignment({"ACGT": 0.25, "ACGA": 0.75}, ("w", "x", "y", "z")).sub_alignment(("w", "z"))
+    assert dict(fl) == {"AT": 0.25, "AA": 0.75}
 
 
 def test_score_gram_large_reports_convergence(sp, eng):
