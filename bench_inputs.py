@@ -70,6 +70,7 @@ def simulate_codes(num_taxa, branch_length, model, num_sites, seed):
     rng = np.random.default_rng(int(seed))
     N = int(num_sites)
     M = expm(float(branch_length) * rate_matrix(model))  # column = parent state (simulation.py:18-19)
+    M = M / M.sum(axis=0, keepdims=True)                # random.choices normalises the column (matters for GTR)
     cdf = np.cumsum(M, axis=0).T.copy()                 # [parent state, cumulative child state]
     pending = {}
     for node in range(1, len(parent)):

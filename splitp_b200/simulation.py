@@ -45,7 +45,10 @@ class GTR:
 
 
 def simulate_codes(tree, model, sequence_length, seed=0, device=None):
-    """uint8 [n_taxa, sequence_length] of codes 0..3, rows in `tree.taxa` order."""
+    """uint8 [n_taxa, sequence_length] of codes 0..3, rows in `tree.taxa` order.  `tree`: a `trees.Tree`, or the
+    reference's `Phylogeny` (anything with a `.networkx_graph` carrying `branch_length` node attributes and `.taxa`)."""
+    from .trees import as_tree
+    tree = as_tree(tree)
     device = torch.device(device) if device is not None else engine.device()
     gen = torch.Generator(device=device)
     gen.manual_seed(int(seed))
@@ -60,6 +63,9 @@ def simulate_codes(tree, model, sequence_length, seed=0, device=None):
         t = tree.branch_length[node]
         if t not in cache:
             M = np.asarray(model.transition_matrix(t), dtype=np.float64)  # column = parent state
+            # random.choices(states, weights=M[:, parent]) (simulation.py:18-19) normalises the column; it matters for
+            # non-symmetric GTR matrices, whose columns do not sum to 1
+            M = M / M.sum(axis=0, keepdims=True)
             cache[t] = torch.from_numpy(np.cumsum(M, axis=0).T.copy()).to(device)  # [parent, cumulative child]
         cdf = cache[t]
         par = tree.parent[node]
@@ -79,7 +85,8 @@ def simulate_codes(tree, model, sequence_length, seed=0, device=None):
 
 
 def generate_alignment(tree, model, sequence_length, seed=0):
-    """{pattern: count / float(sequence_length)} in lexicographic A<C<G<T order (simulation.py:42-56)."""
+    """{pattern: count / float(sequence_length)} in lexicographic A<C<G<T order (simulation.py:42-56).  `tree` may be
+    the reference's `Phylogeny`, `model` anything with `.transition_matrix(t)` (the reference's `model.GTR` included)."""
     codes = simulate_codes(tree, model, sequence_length, seed)
     if codes.shape[0] > 31:  # 128-bit pattern keys
         wide, valid, n, N = engine.pack_wide(codes)

@@ -51,6 +51,37 @@ class Tree:
                 yield f'{"".join(left)}|{"".join(right)}' if as_strings else (left, right)
 
 
+def as_tree(obj):
+    """`Tree` as is; the reference's `Phylogeny` (phylogeny.py:13-56: a networkx DiGraph in `.networkx_graph`, edges
+    parent -> child, the branch above a node in its `branch_length` attribute, leaves named by taxon, `.taxa` the sort
+    order) converted to the parent-array form the simulator walks."""
+    if hasattr(obj, "parent") and hasattr(obj, "names"):
+        return obj
+    graph = getattr(obj, "networkx_graph", None)
+    if graph is None:
+        raise TypeError("expected a splitp_b200.trees.Tree or a Phylogeny-like object with .networkx_graph")
+    roots = [v for v, d in graph.in_degree() if d == 0]
+    if len(roots) != 1:
+        raise ValueError("the tree must have exactly one root")
+    parent, names, bls, order = [-1], {}, [0.0], [roots[0]]
+    index = {roots[0]: 0}
+    for v in order:  # breadth first: parents precede their children in the numbering
+        kids = list(graph.successors(v))
+        if not kids:
+            names[index[v]] = str(v)
+        for c in kids:
+            index[c] = len(parent)
+            parent.append(index[v])
+            bl = graph.nodes[c].get("branch_length", 0.0)
+            bls.append(float(bl) if bl is not None else 0.0)
+            order.append(c)
+    tree = Tree(parent, names, bls)
+    taxa = getattr(obj, "taxa", None)
+    if taxa is not None:
+        tree.taxa = [str(t) for t in taxa]
+    return tree
+
+
 def _leaf_name(i, num_taxa):
     return str(np.base_repr(i, base=max(i + 1, 2))) if num_taxa <= 36 else f"t{i}"
 

@@ -259,3 +259,142 @@ def test_warp_scorer_model_against_lapack(oracle):
         ref = float(np.sqrt(sv[4:].sum() / sv.sum()))
         tol = max(1e-9, 64 * eps / max(ref * ref, 1e-300))  # a vanishing score (k = 5 with a zero eigenvalue) is all rounding
         assert abs(got - ref) <= min(tol * ref, 1e-7) or abs(got - ref) <= 1e-9 * ref, (k, L, got, ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# alignment simulators against the reference's pattern distribution
+# ---------------------------------------------------------------------------------------------
+def _chi2_pvalue(observed, expected):
+    import scipy.stats
+    keep = expected > 0
+    assert observed[~keep].sum() == 0
+    # pool cells with an expectation below 5 into one (the usual validity rule of the chi-square approximation)
+    small = keep & (expected < 5)
+    obs = np.concatenate([observed[keep & ~small], [observed[small].sum()]])
+    exp = np.concatenate([expected[keep & ~small], [expected[small].sum()]])
+    if exp[-1] == 0:
+        obs, exp = obs[:-1], exp[:-1]
+    stat = ((obs - exp) ** 2 / exp).sum()
+    return float(scipy.stats.chi2.sf(stat, len(exp) - 1)), float(stat), len(exp) - 1
+
+
+def _pattern_counts(codes, patterns):
+    n = codes.shape[0]
+    keys = np.zeros(codes.shape[1], dtype=np.int64)
+    for r in codes:
+        keys = keys * 4 + r
+    cnt = np.bincount(keys, minlength=4 ** n)
+    lut = {c: i for i, c in enumerate("ACGT")}
+    idx = [sum(lut[ch] * 4 ** (n - 1 - i) for i, ch in enumerate(p)) for p in patterns]
+    return cnt[idx].astype(np.float64), int(cnt.sum() - cnt[idx].sum())
+
+
+@pytest.fixture(scope="module")
+def golden_patternprobs():
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "golden_patternprobs.json")) as f:
+        return json.load(f)
+
+
+def test_simulators_match_reference_pattern_probabilities(golden_patternprobs):
+    """Chi-square goodness of fit of both generators (splitp_b200.simulation.simulate_codes on the CPU device, and
+    bench_inputs.simulate_codes) against the EXACT pattern probabilities the reference computes
+    (simulation.get_pattern_probabilities, splitp/simulation.py:71-157) for 4- and 6-taxon Jukes-Cantor trees."""
+    import bench_inputs as BI
+    from splitp_b200 import simulation, trees
+    for case in golden_patternprobs["exact"]:
+        n, bl = case["n"], case["branch_length"]
+        N = 400_000 if n == 4 else 1_500_000
+        probs = np.asarray(case["probs"])
+        tree = trees.balanced_tree(n, bl)
+        assert list(tree.taxa) == case["taxa"]
+        for name, codes in (("torch", simulation.simulate_codes(tree, simulation.GTR.JukesCantor(0.5), N, seed=11, device="cpu").numpy()),
+                            ("numpy", BI.simulate_codes(n, bl, "JC", N, seed=11))):
+            obs, missing = _pattern_counts(codes, case["patterns"])
+            assert missing == 0
+            p, stat, dof = _chi2_pvalue(obs, probs * N)
+            assert p > 1e-4, (name, n, bl, p, stat, dof)
+
+
+def test_simulators_match_reference_generate_alignment_gtr(golden_patternprobs):
+    """GTR (non-symmetric transition matrix): two-sample chi-square of both generators against a seeded sample of the
+    reference's own generate_alignment (splitp/simulation.py:9-56; 4 taxa, 40,000 sites).  The reference draws the child
+    state from the NORMALISED column of expm(t Q); without that normalisation this test fails."""
+    import bench_inputs as BI
+    import scipy.stats
+    from splitp_b200 import simulation, trees
+    case = golden_patternprobs["sampled"][0]
+    n, bl, Nref = case["n"], case["branch_length"], case["sites"]
+    ref_counts = dict(zip(case["patterns"], case["counts"]))
+    tree = trees.balanced_tree(n, bl)
+    N = 2_000_000
+    gens = (("torch", simulation.simulate_codes(tree, simulation.GTR((0.1, 0.2, 0.3, 0.4), (1, 2, 3, 4, 5, 6)), N, seed=5, device="cpu").numpy()),
+            ("numpy", BI.simulate_codes(n, bl, "GTR", N, seed=5)))
+    import itertools
+    patterns = ["".join(p) for p in itertools.product("ACGT", repeat=n)]
+    ref = np.asarray([ref_counts.get(p, 0) for p in patterns], dtype=np.float64)
+    for name, codes in gens:
+        mine, _ = _pattern_counts(codes, patterns)
+        expected = mine / N * Nref  # our large sample as the (nearly exact) model for the reference's 40,000 draws
+        p, stat, dof = _chi2_pvalue(ref, expected)
+        assert p > 1e-4, (name, p, stat, dof)
+    # and the un-normalised column (round 1's generator) is rejected by the same test: the fixture has the power to tell
+    M = simulation.GTR((0.1, 0.2, 0.3, 0.4), (1, 2, 3, 4, 5, 6)).transition_matrix(bl)
+    assert abs(M.sum(axis=0) - 1).max() > 0.02
+    del scipy
+
+
+def test_simulate_codes_accepts_reference_phylogeny_like_tree():
+    """simulate_codes / generate_alignment take the reference's Phylogeny (duck-typed: .networkx_graph with branch_length
+    node attributes, .taxa): same alignment as from the equivalent trees.Tree."""
+    import networkx as nx
+    from splitp_b200 import simulation, trees
+
+    own = trees.balanced_tree(6, 0.07)
+
+    class FakePhylogeny:  # the attributes of splitp.phylogeny.Phylogeny the simulator reads
+        def __init__(self, tree):
+            g = nx.DiGraph()
+            label = {i: (tree.names[i] if i in tree.names else f"n{i}") for i in range(len(tree.parent))}
+            for i, p in enumerate(tree.parent):
+                g.add_node(label[i], branch_length=tree.branch_length[i] if p >= 0 else None)
+            for i, p in enumerate(tree.parent):
+                if p >= 0:
+                    g.add_edge(label[p], label[i])
+            self.networkx_graph = g
+            self.taxa = sorted(tree.names.values())
+
+    conv = trees.as_tree(FakePhylogeny(own))
+    assert sorted(conv.names.values()) == sorted(own.names.values()) and conv.taxa == own.taxa
+    assert sorted(conv.branch_length) == sorted(own.branch_length)
+    a = simulation.simulate_codes(FakePhylogeny(own), simulation.GTR.JukesCantor(0.5), 200_000, seed=3, device="cpu").numpy()
+    # same topology and branch lengths => same pattern distribution (node numbering, hence the random stream, differs)
+    b = simulation.simulate_codes(own, simulation.GTR.JukesCantor(0.5), 4_000_000, seed=4, device="cpu").numpy()  # 20x: "the model"
+    import itertools
+    patterns = ["".join(p) for p in itertools.product("ACGT", repeat=6)]
+    ca, _ = _pattern_counts(a, patterns)
+    cb, _ = _pattern_counts(b, patterns)
+    p, stat, dof = _chi2_pvalue(ca, np.maximum(cb, 1e-9) / cb.sum() * ca.sum())
+    assert p > 1e-4, (p, stat, dof)
+
+
+def test_as_tree_on_the_real_reference_phylogeny():
+    """With the unmodified reference installed in baseline/_ref: splitp.trees.balanced_newick_tree -> trees.as_tree gives
+    the topology, leaf names, taxa order and branch lengths of trees.balanced_tree (same true splits)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "splitp")):
+        pytest.skip("baseline/_ref not installed")
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import warnings; warnings.simplefilter('ignore')\n"
+        "import splitp\n"
+        "from splitp_b200 import trees\n"
+        "for n in (4, 6, 10, 12, 20):\n"
+        "    ref = splitp.trees.balanced_newick_tree(n, 0.05)\n"
+        "    conv, own = trees.as_tree(ref), trees.balanced_tree(n, 0.05)\n"
+        "    assert list(conv.taxa) == list(own.taxa) == list(ref.taxa)\n"
+        "    assert set(conv.splits()) == set(own.splits()) == set(ref.splits())\n"
+        "    assert sorted(conv.branch_length) == sorted(own.branch_length)\n"
+        "print('ok')\n" % (ref_dir, ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
