@@ -102,15 +102,57 @@ def _leaves(cluster):
     return (cluster,) if isinstance(cluster, str) else tuple(cluster)
 
 
-def erickson_SVD(alignment, taxa=None, method=Method.flattening, show_work=False):
+FLATTENING_DENSE_MAX_TAXA = 12   # batched dense route of erickson_SVD(Method.flattening): 4^n cells per split (134 MB at 12 taxa)
+FLATTENING_BATCH_BYTES = 4 << 30
+
+
+def _flattening_scores_batched(table, idx_list):
+    """split_score(flattening(split, aln, FlatFormat.reduced)) for many splits that cover all taxa, without a host round
+    trip per split: the DENSE flattening of every split (rows = its shorter side; transposing changes no singular
+    value, and the all-zero rows / columns the reduced format drops add only zero singular values) goes into one batch
+    per side size, followed by ONE batched fp64 Gram and ONE batched eigen-solver call per batch.  A reduced matrix with
+    min(shape) <= 4 scores exactly 0.0 (at most 4 singular values), as split_score gives for the materialised matrix."""
+    dev = engine.device()
+    out = torch.zeros(len(idx_list), dtype=torch.float64, device=dev)
+    groups = {}
+    for s, (ia, ib) in enumerate(idx_list):
+        short, long_ = (ia, ib) if len(ia) <= len(ib) else (ib, ia)
+        groups.setdefault(len(short), []).append((s, short, long_))
+    n = table.n
+    for a, members in groups.items():
+        R, Cc = 4 ** a, 4 ** (n - a)
+        if R <= 4:
+            continue  # at most 4 rows: score 0
+        per = max(1, int(FLATTENING_BATCH_BYTES // (R * Cc * 8 + R * R * 8)))
+        for c0 in range(0, len(members), per):
+            chunk = members[c0:c0 + per]
+            F = engine._empty((len(chunk), R, Cc), torch.float64)
+            vp, kind, div = table.val_args()
+            for j, (_, short, long_) in enumerate(chunk):
+                sp = engine.make_split(n, short, long_)
+                engine.call("spb_flatten_dense_w", engine._p(table.keys), vp, kind, div, table.num, engine.C.byref(sp),
+                            engine._p(F[j]), None, engine._st())
+            G = engine.gram_f64(F)
+            sc = engine.score_gram(G, R)
+            used_rows = (torch.diagonal(G, dim1=1, dim2=2) > 0).sum(dim=1)
+            used_cols = (F != 0).any(dim=1).sum(dim=1)
+            sc = torch.where((used_rows <= 4) | (used_cols <= 4), torch.zeros_like(sc), sc)
+            out.index_copy_(0, torch.tensor([s for s, _, _ in chunk], dtype=torch.int64, device=dev), sc)
+            del F, G
+    return out
+
+
+def erickson_SVD(alignment, taxa=None, method=Method.flattening, show_work=False, trace=None):
     """Agglomerative tree inference from split scores (reference: splitp/phylogenetics.py:99-171).
 
     At every step each pair of current clusters is joined tentatively, the split (joined leaves | all other leaves)
     is scored -- reduced flattening + split score (`Method.flattening`) or subflattening + split score
     (`Method.subflattening`) -- and the best-scoring pair is merged; scores are memoised per split.  Returns the
     n - 2 chosen splits as sorted 2-tuples of leaf tuples, like the reference.  The candidate splits of a step are
-    scored as ONE batch on the device: the batched subflattening kernel for `Method.subflattening`, device-resident
-    reduced flattenings for `Method.flattening`.  `Method.mutual_information` scores a split by the rank-1 divergence of
+    scored as ONE batch on the device: the batched subflattening kernel for `Method.subflattening`; for
+    `Method.flattening` (up to 12 taxa) the dense flattenings of a whole side-size class, one batched fp64 Gram and one
+    batched eigen-solver call; for `Method.mutual_information` the divergences are queued for all candidates and read back
+    once per step.  `trace` (an optional list, not in the reference's signature) receives the candidate scores of every step.  `Method.mutual_information` scores a split by the rank-1 divergence of
     its flattening (phylogenetics.py:136-140, 364-373), computed straight from the pattern table.  `Method.distance`
     leaves every score at infinity, as the reference does.
     """
@@ -138,14 +180,19 @@ def erickson_SVD(alignment, taxa=None, method=Method.flattening, show_work=False
             ma, mb = engine.masks_from_splits(idx)
             return [np.float64(v) for v in engine.subflatten_scores(pair_tables, ma, mb).cpu().numpy()]
         if method == Method.flattening:
+            idx = [positions(s) for s in splits]
+            if table.n <= FLATTENING_DENSE_MAX_TAXA and all(engine.covers_all(table.n, ia, ib) for ia, ib in idx):
+                # one batch per side size: no per-split host synchronisation (ONE device -> host copy per step)
+                return [np.float64(v) for v in _flattening_scores_batched(table, idx).cpu().numpy()]
             out = []
-            for s in splits:
-                ia, ib = positions(s)
+            for ia, ib in idx:
                 F = engine.flatten_reduced(table, ia, ib)
                 out.append(np.float64(0.0) if min(F.shape) <= 4 else np.float64(engine.score_matrix(F)[0].item()))
             return out
         if method == Method.mutual_information:
-            return [np.float64(engine.rank1_divergence(table, *positions(s)).item()) for s in splits]
+            # every divergence stays on the device until the whole step is queued: ONE device -> host copy per step
+            vals = torch.cat([engine.rank1_divergence(table, *positions(s)).reshape(1) for s in splits])
+            return [np.float64(v) for v in vals.cpu().numpy()]
         return [np.inf] * len(splits)  # the reference leaves the score at infinity for the other methods
 
     chosen = []
@@ -164,6 +211,8 @@ def erickson_SVD(alignment, taxa=None, method=Method.flattening, show_work=False
         if show_work:
             print(f"Scores: { {pair: (pair, split, known[split]) for pair, split in candidates} }")
         best_pair, best_split = min(candidates, key=lambda c: known[c[1]])  # first minimum, like min() in the reference
+        if trace is not None:
+            trace.append({"chosen": tuple(sorted(best_split)), "scores": {split: known[split] for _, split in candidates}})
         chosen.append(tuple(sorted(best_split)))
         merged = best_split[0]
         taxa = tuple([c for c in taxa if c not in merged and not set(c).issubset(merged)] + [merged])

@@ -218,6 +218,36 @@ def erickson():
         json.dump(out, f)
 
 
+def erickson_trace():
+    """Per-step candidate scores of the reference's erickson_SVD, taken from its own `show_work` output
+    (phylogenetics.py:143-144 prints the {pair: (pair, split, score)} table of every agglomeration step): for every step
+    the chosen split, its score and the runner-up's score, so that a test can pin the ORDER of the picks wherever the
+    reference's margin is far above rounding noise."""
+    import contextlib
+    import io
+    with open(os.path.join(HERE, "golden_erickson.json")) as f:
+        cases = json.load(f)
+    out = []
+    for rec in cases:
+        aln = dict(zip(rec["patterns"], rec["values"]))
+        tr = {"n": rec["n"]}
+        for method in (splitp.Method.flattening, splitp.Method.subflattening, splitp.Method.mutual_information):
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                res = splitp.phylogenetics.erickson_SVD(aln, method=method, show_work=True)
+            steps = []
+            for line, chosen in zip([l for l in buf.getvalue().splitlines() if l.startswith("Scores: ")], res):
+                table = eval(line[len("Scores: "):], {"np": np, "nan": float("nan"), "inf": float("inf")})
+                vals = sorted(float(v[2]) for v in table.values() if not np.isnan(float(v[2])))
+                steps.append({"chosen": [list(s) for s in chosen], "best": vals[0], "second": vals[1] if len(vals) > 1 else None,
+                              "candidates": len(table), "nan": int(sum(np.isnan(float(v[2])) for v in table.values()))})
+            assert len(steps) == len(res)
+            tr[method.name] = steps
+        out.append(tr)
+    with open(os.path.join(HERE, "golden_erickson_trace.json"), "w") as f:
+        json.dump(out, f)
+
+
 def rank1():
     """Banned-pattern sparse flattenings (constructions.py:58-105), rank-1 / rank-k approximations and the rank-1
     divergence (phylogenetics.py:331-373), erickson_SVD with Method.mutual_information (phylogenetics.py:136-140)."""
@@ -277,6 +307,9 @@ def rank1():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "erickson_trace":
+        erickson_trace()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "erickson":
         erickson()
     elif len(sys.argv) > 1 and sys.argv[1] == "rank1":
