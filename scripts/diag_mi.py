@@ -10,7 +10,7 @@ g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_rank1.json")))
 for ri, rec in enumerate(g["erickson"]):
     aln = dict(zip(rec["patterns"], rec["values"]))
     n = len(rec["patterns"][0])
-    keys = O.patterns_to_keys(rec["patterns"])
+    keys, _ = O.patterns_to_keys(rec["patterns"])
     vals = np.asarray(rec["values"], dtype=np.float64)
     table = eng.table_from_mapping(aln)
     import itertools

@@ -347,19 +347,185 @@ int launch_stream(const uint32_t* d_sm, const uint32_t* d_valid, int n, int64_t 
   return SPB_ERR_ARG;
 }
 
+// ------------------------------------------------------------------------------------------
+// "Classified" counting kernel (direct tables): the stream kernel above plus on-chip aggregation of the SINGLE-MUTATION
+// patterns.  On a 12-taxon JC tree (branch length 0.05) 34 % of the sites are constant patterns, 37 % differ from a
+// constant pattern in exactly one taxon (4 x 12 x 3 = 144 patterns) and 29 % are spread over ~10^5 rarer patterns.  The
+// stream kernel sends 66 % of the sites to L2 as REDs, more than half of them to those 144 addresses, where they
+// serialise in the L2 atomic units (measured: 3.4e10 RED/s).  Here
+//   * c = majority of the three low digits; x = key ^ c * 0x5555..: x == 0 is a constant pattern (registers, as before);
+//   * x with exactly one non-zero digit (position p, value y) is single-mutation class (c, p, y): it increments a
+//     LANE-PRIVATE 8-bit counter hist[class][lane] in shared memory -- plain load / add / store, no atomic, no
+//     cross-lane conflict; every 15 chunks (<= 240 increments per counter) the lanes fold the 32 byte-counters of each
+//     class with dp4a into a warp-private 32-bit total, and at the end of the kernel every warp issues one RED per class;
+//   * only the remaining sites (29 %) issue a RED, spread over ~10^5 addresses.
+// ------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256) count_class_kernel(const uint32_t* __restrict__ sm, const uint16_t* __restrict__ valid16,
+                                                          int64_t chunk_begin, int64_t chunk_end, int64_t site_begin,
+                                                          int64_t site_end, uint32_t* __restrict__ table, unsigned long long* usable) {
+  constexpr int BITS = 2 * NT;
+  constexpr uint32_t MASK = (BITS == 32) ? ~0u : ((1u << BITS) - 1u);
+  constexpr uint32_t ONES = 0x55555555u & MASK;
+  constexpr int NCLS = 12 * NT;                 // (c, p, y): 4 x NT x 3
+  constexpr int NCLS_PAD = (NCLS + 31) / 32 * 32;
+  constexpr int kFlushEvery = 15;               // 15 chunks x 16 sites = 240 < 256 increments per byte counter
+  extern __shared__ __align__(16) unsigned char cls_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* hist = cls_raw + (size_t)warp * NCLS_PAD * 32;                                      // [NCLS_PAD][32 lanes] bytes
+  uint32_t* tot = reinterpret_cast<uint32_t*>(cls_raw + (size_t)8 * NCLS_PAD * 32) + warp * NCLS_PAD;  // [NCLS_PAD]
+  for (int i = lane; i < NCLS_PAD * 8; i += 32) reinterpret_cast<uint32_t*>(hist)[i] = 0u;
+  for (int i = lane; i < NCLS_PAD; i += 32) tot[i] = 0u;
+  __syncwarp();
+  uint32_t cst0 = 0, cst1 = 0, cst2 = 0, cst3 = 0, nus = 0;
+  int since_flush = 0;
+  auto flush = [&]() {
+    __syncwarp();
+    for (int cls = lane; cls < NCLS; cls += 32) {
+      uint32_t* row = reinterpret_cast<uint32_t*>(hist + (size_t)cls * 32);
+      uint32_t sum = 0;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) {
+        const int wi = (wq + lane) & 7;  // rotate: lanes of one instruction start on different words
+        sum = __dp4a(row[wi], 0x01010101u, sum);
+        row[wi] = 0u;
+      }
+      tot[cls] += sum;
+    }
+    __syncwarp();
+  };
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  // every warp runs the same number of iterations (the flush is warp-collective); out-of-range chunks are empty
+  const int64_t first = chunk_begin + (int64_t)blockIdx.x * 256 + warp * 32;
+  for (int64_t base = first; base < chunk_end; base += stride) {
+    const int64_t ch = base + lane;
+    if (ch < chunk_end) {
+      uint32_t w[NT + 2];
+      const uint32_t* src = sm + ch * NT;
+      if constexpr (NT % 4 == 0) {
+#pragma unroll
+        for (int v = 0; v < NT / 4; ++v) {
+          const uint4 x = __ldg(reinterpret_cast<const uint4*>(src) + v);
+          w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+        }
+      } else if constexpr (NT % 2 == 0) {
+#pragma unroll
+        for (int v = 0; v < NT / 2; ++v) {
+          const uint2 x = __ldg(reinterpret_cast<const uint2*>(src) + v);
+          w[2 * v] = x.x; w[2 * v + 1] = x.y;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < NT; ++v) w[v] = __ldg(src + v);
+      }
+      w[NT] = 0u; w[NT + 1] = 0u;
+      uint32_t vb = __ldg(valid16 + ch);
+      const int64_t s0 = ch * 16;
+      if (s0 < site_begin || s0 + 16 > site_end) {
+#pragma unroll
+        for (int s = 0; s < 16; ++s)
+          if (s0 + s < site_begin || s0 + s >= site_end) vb &= ~(1u << s);
+      }
+      nus += __popc(vb);
+      uint32_t packed = 0u;
+#pragma unroll
+      for (int s = 0; s < 16; ++s) {
+        const int o = s * BITS, wi = o >> 5, sh = o & 31;
+        uint32_t key = (sh + BITS <= 32) ? (w[wi] >> sh) : __funnelshift_r(w[wi], w[wi + 1], sh);
+        key &= MASK;
+        const bool ok = (vb >> s) & 1u;
+        const uint32_t d0 = key & 3u, d1 = (key >> 2) & 3u, d2 = (key >> 4) & 3u;
+        const uint32_t c = (NT >= 3) ? ((d0 == d1) ? d0 : d2) : d0;
+        const uint32_t x = key ^ (c * ONES);
+        const int p2 = 31 - __clz(x | 1u) ;           // highest set bit: the mutated digit if there is exactly one
+        const int p = p2 >> 1;
+        const uint32_t y = x >> (2 * p);               // < 4 and no lower bits set <=> exactly one digit differs
+        const bool single = x != 0u && (x & ~(3u << (2 * p))) == 0u;
+        if (ok && x == 0u) packed += 1u << (8 * c);
+        if (ok && single) {
+          unsigned char* cell = hist + ((size_t)((c * NT + p) * 3 + (y - 1)) << 5) + lane;
+          *cell = (unsigned char)(*cell + 1);
+        }
+        if (ok && x != 0u && !single) atomicAdd(table + key, 1u);
+      }
+      cst0 += packed & 255u; cst1 += (packed >> 8) & 255u; cst2 += (packed >> 16) & 255u; cst3 += packed >> 24;
+    }
+    if (++since_flush == kFlushEvery) { flush(); since_flush = 0; }
+  }
+  flush();
+  for (int cls = lane; cls < NCLS; cls += 32) {
+    const uint32_t v = tot[cls];
+    if (v) {
+      const int y = cls % 3 + 1, cp = cls / 3, p = cp % NT, c = cp / NT;
+      atomicAdd(table + (((uint32_t)c * ONES) ^ ((uint32_t)y << (2 * p))), v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cst0 += __shfl_xor_sync(0xFFFFFFFFu, cst0, o); cst1 += __shfl_xor_sync(0xFFFFFFFFu, cst1, o);
+    cst2 += __shfl_xor_sync(0xFFFFFFFFu, cst2, o); cst3 += __shfl_xor_sync(0xFFFFFFFFu, cst3, o);
+    nus += __shfl_xor_sync(0xFFFFFFFFu, nus, o);
+  }
+  if (lane == 0) {
+    if (cst0) atomicAdd(table, cst0);
+    if (cst1) atomicAdd(table + ONES, cst1);
+    if (cst2) atomicAdd(table + 2u * ONES, cst2);
+    if (cst3) atomicAdd(table + 3u * ONES, cst3);
+    if (usable && nus) atomicAdd(usable, (unsigned long long)nus);
+  }
+}
+
+template <int NT>
+int launch_class_nt(const uint32_t* d_sm, const uint32_t* d_valid, int64_t site_begin, int64_t site_end, uint32_t* d_table,
+                    uint64_t* d_usable, cudaStream_t st) {
+  constexpr int NCLS_PAD = (12 * NT + 31) / 32 * 32;
+  const size_t smem = (size_t)8 * NCLS_PAD * 32 + (size_t)8 * NCLS_PAD * 4;
+  SPB_CUDA(cudaFuncSetAttribute(count_class_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_class_kernel<NT>, 256, smem));
+  if (occ < 1) occ = 1;
+  const int64_t chunk_begin = site_begin / 16, chunk_end = (site_end + 15) / 16;
+  int64_t grid = (chunk_end - chunk_begin + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * occ;
+  if (grid > cap) grid = cap;
+  count_class_kernel<NT><<<(unsigned)grid, 256, smem, st>>>(d_sm, reinterpret_cast<const uint16_t*>(d_valid), chunk_begin, chunk_end,
+                                                          site_begin, site_end, d_table, (unsigned long long*)d_usable);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+int launch_class(const uint32_t* d_sm, const uint32_t* d_valid, int n, int64_t site_begin, int64_t site_end, uint32_t* d_table,
+                 uint64_t* d_usable, cudaStream_t st) {
+  if (site_end <= site_begin) return SPB_OK;
+#define SPB_NT(N_) case N_: return launch_class_nt<N_>(d_sm, d_valid, site_begin, site_end, d_table, d_usable, st);
+  switch (n) {
+    SPB_NT(1) SPB_NT(2) SPB_NT(3) SPB_NT(4) SPB_NT(5) SPB_NT(6) SPB_NT(7) SPB_NT(8) SPB_NT(9) SPB_NT(10) SPB_NT(11) SPB_NT(12)
+    SPB_NT(13) SPB_NT(14)
+    default: break;
+  }
+#undef SPB_NT
+  set_error("count: bad taxon count %d for the direct table", n);
+  return SPB_ERR_ARG;
+}
+
 // Which kernel counts when first-site indices are not requested.  Measured on B200 (profiles/r2_count_kernels.txt, 10^8 sites):
 // direct table, 12 taxa: cache kernel 1.47 ms, stream kernel 1.96 ms -- two thirds of the sites are ~260 single-mutation
 // patterns, and fire-and-forget REDs to so few addresses serialise in the L2 atomic units (3.4e10 RED/s in total);
 // hash table, 20 taxa: stream 3.39 ms, cache 3.59 ms; 31 taxa: 2.55 ms against 2.70 ms.  So: stream for hashed tables,
-// cache for direct tables.  SPB_COUNT_KERNEL=cache / stream in the environment forces one of them (A/B runs).
-static bool use_stream_kernel(const void* d_sm, const void* d_first, bool hashed) {
+// the classified kernel (stream + on-chip single-mutation classes) for direct tables.
+// SPB_COUNT_KERNEL=cache / stream / class in the environment forces one of them (A/B runs).
+enum CountKernel { kCountCache = 0, kCountStream = 1, kCountClass = 2 };
+static CountKernel pick_count_kernel(const void* d_sm, const void* d_first, bool hashed) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("SPB_COUNT_KERNEL");
-    forced = (e && e[0] == 'c') ? 1 : ((e && e[0] == 's') ? 2 : 0);
+    forced = !e ? 0 : (e[0] == 'c' && e[1] == 'a') ? 1 : (e[0] == 's') ? 2 : (e[0] == 'c' && e[1] == 'l') ? 3 : 0;
   }
-  if (d_first != nullptr || (reinterpret_cast<uintptr_t>(d_sm) & 15) != 0) return false;
-  return forced == 2 || (forced == 0 && hashed);
+  if (d_first != nullptr || (reinterpret_cast<uintptr_t>(d_sm) & 15) != 0) return kCountCache;
+  if (forced == 1) return kCountCache;
+  if (forced == 2) return kCountStream;
+  if (forced == 3) return hashed ? kCountStream : kCountClass;
+  return hashed ? kCountStream : kCountClass;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -528,7 +694,9 @@ extern "C" int spb_count_direct(const uint32_t* d_sm, const uint32_t* d_valid, i
   SPB_REQUIRE(n_taxa >= 1 && n_taxa <= 14, "spb_count_direct: direct table needs 1 <= n_taxa <= 14 (got %d)", n_taxa);
   SPB_REQUIRE(site_begin >= 0 && site_end >= site_begin && site_end < (1ll << 32), "spb_count_direct: bad site range");
   DirectSink sink{d_table, d_first};
-  if (use_stream_kernel(d_sm, d_first, false))
+  const CountKernel which = pick_count_kernel(d_sm, d_first, false);
+  if (which == kCountClass) return launch_class(d_sm, d_valid, n_taxa, site_begin, site_end, d_table, d_usable, (cudaStream_t)stream);
+  if (which == kCountStream)
     return launch_stream(d_sm, d_valid, n_taxa, site_begin, site_end, StreamDirectSink{d_table}, d_usable, (cudaStream_t)stream);
   return launch_count(d_sm, d_valid, n_taxa, site_begin, site_end, sink, d_usable, (cudaStream_t)stream);
 }
@@ -541,7 +709,7 @@ extern "C" int spb_count_hash(const uint32_t* d_sm, const uint32_t* d_valid, int
   SPB_REQUIRE(cap >= 2 && (cap & (cap - 1)) == 0, "spb_count_hash: capacity must be a power of two");
   SPB_REQUIRE(site_begin >= 0 && site_end >= site_begin && site_end < (1ll << 32), "spb_count_hash: bad site range");
   HashSink sink{(unsigned long long*)d_hkeys, d_hcounts, d_hfirst, (uint64_t)cap - 1, d_overflow};
-  if (use_stream_kernel(d_sm, d_hfirst, true))
+  if (pick_count_kernel(d_sm, d_hfirst, true) == kCountStream)
     return launch_stream(d_sm, d_valid, n_taxa, site_begin, site_end,
                          StreamHashSink{(unsigned long long*)d_hkeys, d_hcounts, (uint64_t)cap - 1, d_overflow}, d_usable, (cudaStream_t)stream);
   return launch_count(d_sm, d_valid, n_taxa, site_begin, site_end, sink, d_usable, (cudaStream_t)stream);

@@ -397,7 +397,7 @@ gram_u8_umma2_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int
         const uint8_t* a_src = s0t + (size_t)(2 * wk.bi + (int)rank) * KT * kTileBytes;
         const uint8_t* b_src = s0t + (size_t)(2 * wk.bj + (int)rank) * KT * kTileBytes;
         for (int kt = 0; kt < KT; ++kt) {
-          mbar_wait_cluster(smem_u32(empty_bar + stage), phase ^ 1);
+          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
           const uint32_t fb = smem_u32(full_bar + stage);
           mbar_expect_tx(fb, (uint32_t)kStage2Bytes);
           uint8_t* sa = ring + (size_t)stage * kStage2Bytes;
@@ -412,12 +412,12 @@ gram_u8_umma2_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int
       // ===== MMA issuer of the pair =====
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int w = pair; w < num_work; w += npairs) {
-        mbar_wait_cluster(smem_u32(tempty_bar + acc), acc_phase ^ 1);  // both epilogues have drained this accumulator
+        mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);  // both epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kt = 0; kt < KT; ++kt) {
           mbar_wait(smem_u32(full_bar + stage), phase);
-          mbar_wait_cluster(smem_u32(peer_full_bar + stage), phase);
+          mbar_wait(smem_u32(peer_full_bar + stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + (size_t)stage * kStage2Bytes);
           const uint64_t da = make_desc_sw128(sa);
@@ -452,7 +452,7 @@ gram_u8_umma2_kernel(const uint8_t* __restrict__ s0_base, int64_t s0_stride, int
     for (int w = pair; w < num_work; w += npairs) {
       Work2 wk;
       get_work2(w, B, nblk, &wk);
-      mbar_wait_cluster(smem_u32(tfull_bar + acc), acc_phase);
+      mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
       tc_fence_after();
       const int row = (2 * wk.bi + (int)rank) * kTile + q * 32 + lane;
       const bool mirror = wk.bj > wk.bi;

@@ -60,27 +60,15 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-// arrive on an mbarrier of another CTA of the cluster (address from map_to_cta), release at cluster scope
+// arrive on an mbarrier of another CTA of the cluster (address from map_to_cta).  Default semantics (release at CTA
+// scope), as CUTLASS' ClusterBarrier::arrive(cta_id): the barrier itself is the only thing the two CTAs share through
+// the generic proxy -- the tiles are written by bulk copies and read by the tensor core (async proxy), the accumulators
+// live in TMEM -- so no cluster-scope fence is needed.  The explicit .release.cluster / .acquire.cluster forms of the first
+// version compiled to MEMBAR.ALL.GPU + ERRBAR on every arrive and to CCTL.IVALL (invalidate all of L1) after every
+// successful wait; ncu (profiles/r2_ncu_gram_pair_v1.txt): 36 % of all stall samples of the kernel on that CCTL.IVALL, tensor
+// pipe 27 % active, 52 us per 4096^2 Gram against 39 us for the single-CTA kernel.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// wait with acquire at cluster scope: pairs with mbar_arrive_remote / multicast tcgen05.commit from the peer CTA
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > kSpinLimit) __trap();
-  }
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 }  // namespace spb

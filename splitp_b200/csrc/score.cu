@@ -433,26 +433,34 @@ __device__ __forceinline__ double u31_to_double(int x) { return __hiloint2double
 // row-owning kernel: LSU wavefronts 59 % busy, fp64 pipe 34 %, DRAM 33 %: the shared-memory reads of Q were the limiter,
 // not HBM; 25 us against 20.7 us per 4096^2 product).  The 16 warps of a CTA split the rows of every chunk;
 // their partial sums are added in warp order through shared memory (deterministic).
-constexpr int kColsWarps = 16;
-constexpr int kColsChunk = 1024;  // rows of Q staged per pass: [kColsChunk][8] doubles = 64 KB
+constexpr int kColsWarps = 8;
+constexpr int kColsChunk = 512;   // rows of Q staged per pass: [kColsChunk][8] doubles = 32 KB
+constexpr int kColsCtasPerSm = 3;
+constexpr int kColsPerLane = 2;   // columns owned by a lane: 2 -> at most 85 registers, three 8-warp CTAs (24 warps) per SM.
+                                  // The first version (4 columns, 128 registers, ONE 16-warp CTA per SM) ran at 20.7 us per
+                                  // 4096^2 product with the fp64 pipe 41 % and DRAM 40 % busy: too few warps to overlap the
+                                  // loads of one batch of rows with the FMAs of another (profiles/r1_ncu_symv_cols_i32.txt)
+constexpr int kColsPerCta = 32 * kColsPerLane;
 // gridDim.z > 1 ("row split", used when ONE matrix must fill the machine): CTA z handles the row chunks z, z + gridDim.z, ...
 // and writes its partial sums to part[z][c][j] (part = AQ argument, plane stride kKB * k); symv_reduce_parts_kernel adds the
 // planes in z order (deterministic).
-__global__ void __launch_bounds__(32 * kColsWarps, 1) symv_cols_i32_kernel(const int32_t* __restrict__ G, int64_t ld, int64_t strideG,
+// VEC: ld and k are even and the matrix is 8-byte aligned (always true for the Gram buffers of this library): every lane's
+// column pair is one aligned 64-bit load and there is no column boundary inside a pair.
+template <bool VEC>
+__global__ void __launch_bounds__(32 * kColsWarps, kColsCtasPerSm) symv_cols_i32_kernel(const int32_t* __restrict__ G, int64_t ld, int64_t strideG,
                                                                          const double* __restrict__ Q, int64_t strideQ,
                                                                          double* __restrict__ AQ, int k) {
   extern __shared__ __align__(16) double s_x[];  // [kColsChunk][kKB]
   const int bt = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col0 = blockIdx.x * 128 + 4 * lane;
+  const int col0 = blockIdx.x * kColsPerCta + kColsPerLane * lane;
   const int32_t* Gb = G + (int64_t)bt * strideG;
   const double* Qb = Q + (int64_t)bt * strideQ;
-  const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(Gb) & 15) == 0) && col0 + 3 < k;
   constexpr int kRowsPerWarp = kColsChunk / kColsWarps;  // 64
   constexpr int kUnroll = 8;
-  double acc[4][kKB];
+  double acc[kColsPerLane][kKB];
 #pragma unroll
-  for (int e = 0; e < 4; ++e)
+  for (int e = 0; e < kColsPerLane; ++e)
 #pragma unroll
     for (int c = 0; c < kKB; ++c) acc[e][c] = 0.0;
   for (int i0 = blockIdx.z * kColsChunk; i0 < k; i0 += gridDim.z * kColsChunk) {
@@ -465,31 +473,29 @@ __global__ void __launch_bounds__(32 * kColsWarps, 1) symv_cols_i32_kernel(const
     __syncthreads();
     const int rbeg = warp * kRowsPerWarp;
     for (int r = rbeg; r < rbeg + kRowsPerWarp && r < len; r += kUnroll) {
-      int4 g[kUnroll];
+      int2 g[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const int row = i0 + r + u;
         const int32_t* p = Gb + (int64_t)row * ld + col0;
-        if (r + u >= len || col0 >= k) g[u] = make_int4(0, 0, 0, 0);
-        else if (vec_ok) g[u] = __ldg(reinterpret_cast<const int4*>(p));
-        else g[u] = make_int4(__ldg(p), (col0 + 1 < k) ? __ldg(p + 1) : 0, (col0 + 2 < k) ? __ldg(p + 2) : 0, (col0 + 3 < k) ? __ldg(p + 3) : 0);
+        if (r + u >= len || col0 >= k) g[u] = make_int2(0, 0);
+        else if (VEC) g[u] = __ldg(reinterpret_cast<const int2*>(p));
+        else g[u] = make_int2(__ldg(p), (col0 + 1 < k) ? __ldg(p + 1) : 0);
       }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        const double gd0 = u31_to_double(g[u].x), gd1 = u31_to_double(g[u].y), gd2 = u31_to_double(g[u].z), gd3 = u31_to_double(g[u].w);
+        const double gd0 = u31_to_double(g[u].x), gd1 = u31_to_double(g[u].y);
         const double2* xr = reinterpret_cast<const double2*>(s_x + (r + u) * kKB);  // rows beyond len hold zeros
 #pragma unroll
         for (int h = 0; h < kKB / 2; ++h) {
           const double2 x = xr[h];  // same address in every lane: broadcast
           acc[0][2 * h] = fma(gd0, x.x, acc[0][2 * h]);         acc[0][2 * h + 1] = fma(gd0, x.y, acc[0][2 * h + 1]);
           acc[1][2 * h] = fma(gd1, x.x, acc[1][2 * h]);         acc[1][2 * h + 1] = fma(gd1, x.y, acc[1][2 * h + 1]);
-          acc[2][2 * h] = fma(gd2, x.x, acc[2][2 * h]);         acc[2][2 * h + 1] = fma(gd2, x.y, acc[2][2 * h + 1]);
-          acc[3][2 * h] = fma(gd3, x.x, acc[3][2 * h]);         acc[3][2 * h + 1] = fma(gd3, x.y, acc[3][2 * h + 1]);
         }
       }
     }
   }
-  // add the 16 warps' sums in warp order: tot[c][128 columns]
+  // add the 16 warps' sums in warp order: tot[c][kColsPerCta columns]
   __syncthreads();
   double* tot = s_x;
   for (int w = 0; w < kColsWarps; ++w) {
@@ -497,16 +503,16 @@ __global__ void __launch_bounds__(32 * kColsWarps, 1) symv_cols_i32_kernel(const
 #pragma unroll
       for (int c = 0; c < kKB; ++c)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          double* t = tot + c * 128 + 4 * lane + e;
+        for (int e = 0; e < kColsPerLane; ++e) {
+          double* t = tot + c * kColsPerCta + kColsPerLane * lane + e;
           *t = (w == 0) ? acc[e][c] : *t + acc[e][c];
         }
     }
     __syncthreads();
   }
   double* out = AQ + (int64_t)bt * strideQ + (gridDim.z > 1 ? (int64_t)blockIdx.z * kKB * k : 0);
-  for (int idx = threadIdx.x; idx < kKB * 128; idx += 32 * kColsWarps) {
-    const int c = idx / 128, j = blockIdx.x * 128 + (idx & 127);
+  for (int idx = threadIdx.x; idx < kKB * kColsPerCta; idx += 32 * kColsWarps) {
+    const int c = idx / kColsPerCta, j = blockIdx.x * kColsPerCta + (idx % kColsPerCta);
     if (j < k) out[(int64_t)c * k + j] = tot[idx];
   }
 }
@@ -928,7 +934,9 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
   const size_t symv_smem = (size_t)kKB * kSymvChunk * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(symv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
   const size_t cols_smem = (size_t)kKB * kColsChunk * sizeof(double);
-  SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
+  SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
+  SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
+  const bool cols_vec = gv.Gi && (ld % 2 == 0) && (k % 2 == 0) && (reinterpret_cast<uintptr_t>(gv.Gi) % 8 == 0);
   for (int j = 0; j < nb; ++j) {
     double* Qj = w.Q + (int64_t)j * blk;
     double* AQj = w.AQ + (int64_t)j * blk;
@@ -936,8 +944,9 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
       dim3 grid((k + kSymvRows - 1) / kSymvRows, batch);
       if (gv.Gf) symv_block_kernel<<<grid, 256, symv_smem, st>>>(gv.Gf, ld, ld * ld, Qj, w.sQ, AQj, k);
       else {
-        dim3 gi((k + 127) / 128, batch);
-        symv_cols_i32_kernel<<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
+        dim3 gi((k + kColsPerCta - 1) / kColsPerCta, batch);
+        if (cols_vec) symv_cols_i32_kernel<true><<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
+        else symv_cols_i32_kernel<false><<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
       }
       SPB_LAUNCH_CHECK();
       if (!gv.Gf && gv.cs_rows) {
@@ -1046,7 +1055,9 @@ static int stream_products(const uint8_t* d_s0, int64_t s0_stride, int nb, int64
   const int64_t ld = rows_pad;
   const int64_t blk = (int64_t)kKB * k;
   const size_t cols_smem = (size_t)kKB * kColsChunk * sizeof(double);
-  SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
+  SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
+  SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
+  const bool cols_vec = (ld % 2 == 0) && (k % 2 == 0) && (reinterpret_cast<uintptr_t>(d_Gi) % 8 == 0);
   int zsplit = (k + kColsChunk - 1) / kColsChunk;
   if (zsplit > 8) zsplit = 8;
   // the split-row partial sums reuse the inner-product scratch (part): zsplit * 8 * k doubles
@@ -1077,8 +1088,9 @@ static int stream_products(const uint8_t* d_s0, int64_t s0_stride, int nb, int64
     for (int prod = 0; prod < 2; ++prod) {
       const double* src = prod == 0 ? Qb : AQb;
       double* dst = prod == 0 ? AQb : AQb + blk;
-      dim3 gi((k + 127) / 128, 1, zsplit);
-      symv_cols_i32_kernel<<<gi, 32 * kColsWarps, cols_smem, st>>>(d_Gi, ld, ld * ld, src, w.sQ, zsplit > 1 ? w.part : dst, k);
+      dim3 gi((k + kColsPerCta - 1) / kColsPerCta, 1, zsplit);
+      if (cols_vec) symv_cols_i32_kernel<true><<<gi, 32 * kColsWarps, cols_smem, st>>>(d_Gi, ld, ld * ld, src, w.sQ, zsplit > 1 ? w.part : dst, k);
+      else symv_cols_i32_kernel<false><<<gi, 32 * kColsWarps, cols_smem, st>>>(d_Gi, ld, ld * ld, src, w.sQ, zsplit > 1 ? w.part : dst, k);
       SPB_LAUNCH_CHECK();
       if (zsplit > 1) {
         symv_reduce_parts_kernel<<<(unsigned)((blk + 255) / 256), 256, 0, st>>>(w.part, zsplit, blk, dst);

@@ -504,9 +504,10 @@ class CountScorer:
         self._ws = {}
         self._batch_bytes = None
         self.int32_gram = True  # large dense splits keep G as int32 + correction strip (half the eigen-stage traffic)
-        # ... and go through the streamed route (Gram -> products while G0 is in L2); SPB_STREAM_LARGE=0 selects the batched
-        # int32 route (A/B measurements)
-        self.stream_large = os.environ.get("SPB_STREAM_LARGE", "1") != "0"
+        # Optional streamed route (Gram -> products per matrix while G0 is in L2, spb_score_u8_stream): measured SLOWER than the
+        # batched route on B200 ("experiments"): the per-matrix launches expose the latency of the small strip /
+        # start-block kernels and leave the last wave of every Gram half empty.  SPB_STREAM_LARGE=1 enables it.
+        self.stream_large = os.environ.get("SPB_STREAM_LARGE", "0") == "1"
         self.gram_hook = None  # optional wrapper (fn, nb) around the Gram launch
         self.timer = None      # optional PhaseTimer: scatter / gram / correction / eigen spans (bench.py phase_ms)
 

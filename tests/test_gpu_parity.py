@@ -627,7 +627,7 @@ def test_int32_gram_without_high_counts(sp, eng):
     assert scorer.n_hi == 0
     idx = [(list(range(6)), list(range(6, 12))), ([0, 2, 4, 6, 8, 10], [1, 3, 5, 7, 9, 11])]
     got = scorer.score_many(idx).cpu().numpy()
-    assert int(scorer._Gs[4096]["hm"][:2].sum().item()) == 0  # the streamed route's strip buffers
+    assert int(scorer._Gi[4096]["hm"][:2].sum().item()) == 0
     scorer.int32_gram = False
     ref = scorer.score_many(idx).cpu().numpy()
     for g, r in zip(got, ref):

@@ -183,11 +183,12 @@ def test_score_many_config2_six_six_vs_lapack(sp, eng, oracle):
         assert_score(got[s], ref)
         worst = max(worst, abs(got[s] - ref) / ref / score_tol(ref))
     print(f"score_many 6|6: {len(picks)} splits ({len(t_splits)} true), worst error = {worst:.3f} x tolerance")
-    # the streamed route (Gram -> products while G0 is in L2, the default) against the batched int32 route
-    assert scorer.stream_large
-    scorer.stream_large = False
-    batched = scorer.score_many(idx).cpu().numpy()
+    # the optional streamed route (Gram -> products while G0 is in L2) against the batched int32 route (the default)
+    assert not scorer.stream_large
+    batched = got
     scorer.stream_large = True
+    got = scorer.score_many(idx).cpu().numpy()
+    scorer.stream_large = False
     for s in range(len(idx)):
         assert_score(got[s], batched[s])
         ref = oracle.split_score(oracle.flattening_reduced(keys, counts / usable, n, *idx[s])) if s < 2 else None
