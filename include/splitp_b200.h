@@ -211,6 +211,16 @@ int spb_subflatten(const double* d_T, const double* d_total, int n_taxa, const s
 int spb_subflatten_score(const double* d_T, const double* d_total, int n_taxa, const uint64_t* d_masks_a,
                          const uint64_t* d_masks_b, int64_t num, double* d_scores, void* stream);
 
+/* The same scores through TRIPLE tables (the round-2 kernel, up to 43 taxa: sides of at most 21 taxa, k = 3 min(a, b) + 1
+ * <= 64): one pass tabulates P[x][x'][y] = T3[x][y] T3[x'][y]^T (3 x 3 blocks) and the margin terms into d_tables (double
+ * [spb_subflatten_tables_doubles(n)]), after which the Gram matrix of a subflattening is a sum of a b gathered blocks --
+ * no staged matrix, one warp per split with two rows per lane, division-free Sturm counts.  tables_ready != 0 skips the
+ * tabulation (d_tables already holds the tables of this d_T). */
+int64_t spb_subflatten_tables_doubles(int n_taxa);
+int spb_subflatten_score_tables(const double* d_T, const double* d_total, int n_taxa, const uint64_t* d_masks_a,
+                                const uint64_t* d_masks_b, int64_t num, double* d_scores, double* d_tables, int tables_ready,
+                                void* stream);
+
 /* ---- a12-a14: split_score (phylogenetics.py:280-328), K = 4 hard-coded ---- */
 /* G = A A^T for row-major double A [batch][R][C] (lda = C): d_G double [batch][R][R].
  * d_ws: double workspace of spb_gram_f64_ws(R, C, batch) elements (may be NULL when that is 0). */

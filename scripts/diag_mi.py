@@ -26,6 +26,30 @@ for ri, rec in enumerate(g["erickson"]):
                 if err > 1e-10:
                     print("MISMATCH record", ri, "split", ia, ib, "ref", ref, "got", got)
     print("record", ri, "n", n, "worst rel err of rank1_divergence over all splits:", worst)
-    for rep in range(5):
-        got = [list(map(list, s)) for s in sp.erickson_SVD(aln, method=sp.Method.mutual_information)]
-        print("  rep", rep, "matches golden:", got == rec["mutual_information"], got if got != rec["mutual_information"] else "")
+    for rep in range(8):
+        tr = []
+        got = [list(map(list, s)) for s in sp.erickson_SVD(aln, method=sp.Method.mutual_information, trace=tr)]
+        ok = got == rec["mutual_information"]
+        print("  rep", rep, "matches golden:", ok)
+        if not ok:
+            for step, t in enumerate(tr):
+                print("    step", step, "chosen", t["chosen"])
+                for split, v in t["scores"].items():
+                    ia, ib = eng.split_positions(split, sorted(set(split[0]) | set(split[1])))
+                    ref = O.rank_1_divergence(O.flattening_dense(keys, vals, n, ia, ib))
+                    flag = "" if abs(v - ref) <= 1e-10 * abs(ref) else "   <-- WRONG"
+                    print("      ", split, float(v), ref, flag)
+
+# ---- erickson_SVD(Method.flattening / subflattening): our per-step candidate scores next to the reference's best / runner-up ----
+cases = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_erickson.json")))
+traces = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_erickson_trace.json")))
+for ci, (rec, tr) in enumerate(zip(cases, traces)):
+    aln = dict(zip(rec["patterns"], rec["values"]))
+    for method in (sp.Method.flattening, sp.Method.subflattening):
+        mine = []
+        got = sp.erickson_SVD(aln, method=method, trace=mine)
+        print("case", ci, "n", rec["n"], method.name)
+        for step, (r, m) in enumerate(zip(tr[method.name], mine)):
+            sc = sorted((float(v), k) for k, v in m["scores"].items())
+            print("  step", step, "ref chosen", r["chosen"], "best", r["best"], "second", r["second"])
+            print("         mine chosen", [list(x) for x in m["chosen"]], "lowest three:", [(round(v, 9), k) for v, k in sc[:3]])

@@ -45,6 +45,13 @@ template <int CG> __device__ __forceinline__ void umma_commit(uint32_t bar) {
   if (CG == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
   else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
+// cta_group::2 commit that arrives on the ISSUING CTA's barrier only (no multicast): used for the intermediate drains, so
+// that the peer CTA cannot fall a barrier phase behind (the first version multicast every commit; the peer then missed
+// phases and reported a failed check although every MMA had run: profiles/r2_mma_rate.jsonl, "bad_accumulators")
+template <int CG> __device__ __forceinline__ void umma_commit_local(uint32_t bar) {
+  if (CG == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 template <int CG, int KIND> __device__ __forceinline__ void umma(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   if (CG == 1 && KIND == 0) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
   if (CG == 2 && KIND == 0) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
@@ -74,13 +81,13 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int mmas_pe
   constexpr int kBBytes = (N / CG) * 128;          // this CTA's share of B rows
   uint8_t* sA = base;
   uint8_t* sB = base + kABytes;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(base + kABytes + kBBytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + kABytes + kBBytes);  // [0]: leader-local drains, [1]: final (both CTAs)
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
   const uint8_t one = KIND == 0 ? 1 : 0x38;        // u8 1, or e4m3 1.0
   for (int i = threadIdx.x; i < kABytes + kBBytes; i += blockDim.x) base[i] = one;
-  if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); mbar_init(smem_u32(bar + 1), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core (async proxy)
   if (warp == 0) tmem_alloc<CG>(smem_u32(slot), 512);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -96,7 +103,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int mmas_pe
     const uint64_t da = make_desc_sw128(smem_u32(sA)), db = make_desc_sw128(smem_u32(sB));
     // warm-up
     for (int k = 0; k < 4; ++k) umma<CG, KIND>(tmem_base, da + 2 * k, db + 2 * k, idesc, k > 0);
-    umma_commit<CG>(smem_u32(bar));
+    umma_commit_local<CG>(smem_u32(bar));
     ok &= mbar_wait(smem_u32(bar), 0);
     uint32_t phase = 1;
     t0 = clock64();
@@ -106,7 +113,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int mmas_pe
       for (int k = 0; k < 4; ++k) umma<CG, KIND>(tmem_base + (it & 1) * N, da + 2 * k, db + 2 * k, idesc, (it > 1 || k > 0) ? 1u : 0u);
       since += 4;
       if (since >= mmas_per_commit || it == iters - 1) {
-        umma_commit<CG>(smem_u32(bar));
+        umma_commit_local<CG>(smem_u32(bar));
         ok &= mbar_wait(smem_u32(bar), phase);  // drains the pipe once per `mmas_per_commit` MMAs
         if (!ok) break;                          // a commit that never arrives: give up instead of spinning 1250 times
         phase ^= 1;
@@ -114,13 +121,13 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int mmas_pe
       }
     }
     t1 = clock64();
+    umma_commit<CG>(smem_u32(bar + 1));          // everything has completed: tell both CTAs
+    ok &= mbar_wait(smem_u32(bar + 1), 0);
     clk_out[blockIdx.x / CG] = (unsigned long long)(t1 - t0);
   } else if (CG == 2 && warp == 1 && lane == 0 && rank == 1) {
-    // the peer receives the multicast commits on its own barrier: drain them so that phases stay in step
-    uint32_t phase = 0;
-    int commits = 1, since = 0;
-    for (int it = 0; it < iters; ++it) { since += 4; if (since >= mmas_per_commit || it == iters - 1) { ++commits; since = 0; } }
-    for (int c = 0; c < commits && ok; ++c) { ok &= mbar_wait(smem_u32(bar), phase); phase ^= 1; }
+    // the peer only waits for the final multicast commit (its accumulators are complete then); generous spin budget
+    for (int tries = 0; tries < 64 && !mbar_try_wait(smem_u32(bar + 1), 0); ++tries) mbar_wait(smem_u32(bar + 1), 0);
+    ok &= mbar_try_wait(smem_u32(bar + 1), 0);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -144,7 +151,7 @@ int run(const char* name, int grid, int iters, int per_commit) {
   unsigned long long* d_clk; int* d_bad;
   CK(cudaMalloc(&d_clk, 256 * 8)); CK(cudaMalloc(&d_bad, 4));
   CK(cudaMemset(d_clk, 0, 256 * 8)); CK(cudaMemset(d_bad, 0, 4));
-  size_t smem = 128 * 128 + (N / CG) * 128 + 64 + 1024;
+  size_t smem = 128 * 128 + (N / CG) * 128 + 64 + 1024;  // tiles + 2 barriers + TMEM slot + alignment slack
   CK(cudaFuncSetAttribute(mma_rate_kernel<CG, KIND, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;

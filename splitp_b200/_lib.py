@@ -108,6 +108,8 @@ PROTOTYPES = {
     "spb_pair_transform": (_i, [_p, _i, _p, _p, _p]),
     "spb_subflatten": (_i, [_p, _p, _i, _sp, _p, _p]),
     "spb_subflatten_score": (_i, [_p, _p, _i, _p, _p, _l, _p, _p]),
+    "spb_subflatten_tables_doubles": (_l, [_i]),
+    "spb_subflatten_score_tables": (_i, [_p, _p, _i, _p, _p, _l, _p, _p, _i, _p]),
     "spb_gram_f64_ws": (_l, [_l, _l, _l]),
     "spb_gram_f64": (_i, [_p, _l, _l, _l, _p, _p, _p]),
     "spb_s0_bytes": (_l, [_l, _l]),

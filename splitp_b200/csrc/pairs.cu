@@ -429,6 +429,287 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) subflatten_score_warp_kerne
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Round-2 scorer: one warp per split, Gram matrix from TRIPLE tables, k = 3 min(a, b) + 1 up to 64.
+//
+// The first warp kernel staged the k x L subflattening in shared memory (8.7 KB of its 18.5 KB per warp -> 12 warps per
+// SM) and took its Gram from it (k L / 32 dependent fma chains of length L per lane, two shared-memory loads per fma);
+// ncu: ~190 k cycles per split for ~25 k warp instructions, i.e. latency-bound.  But S S^T has block structure: with
+// row taxa A, column taxa B and T[x][y] = H N_xy H^T (4 x 4),
+//     G[(i,c), (i',c')] = sum_{y in B} P[A_i][A_i'][y][c][c'] + m[A_i][c] m[A_i'][c'],   P[x][x'][y] = T3[x][y] T3[x'][y]^T  (3 x 3)
+//     G[(i,c), last]    = sum_{y in B} R[A_i][y][c] + m[A_i][c] total,                    R[x][y][c] = sum_{d<3} T[x][y][c][d] T[y][y][3][d]
+//     G[last, last]     = sum_{y in B} D[y] + total^2,        D[y] = sum_{d<3} T[y][y][3][d]^2,   m[x][c] = T[x][x][c][3]
+// so after ONE pass that tabulates P, R, D, m (n^3 3x3 blocks: 576 KB at 20 taxa, 2.4 MB at 32, L2-resident), a split needs
+// a b gathers of 3 doubles per row instead of the staged matrix.  Without the staging tile a warp needs k (k|1) + 4 k
+// doubles (8.7 KB at k = 31), a lane owns rows i and i + 32 (k <= 64: sides up to 21 taxa, all of BASELINE config 5), and the
+// Sturm counts of the bisection use the determinant recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (one dependent
+// fma per step, rescaled by powers of two) instead of the pivot recurrence with its fp64 division per step.
+// The arithmetic is modelled lane by lane in tests/warp_scorer_model.py (score_warp2_model) and checked against LAPACK.
+// ---------------------------------------------------------------------------------------------------
+struct TripleTables {
+  const double* P;  // [n][n][n][3][3]
+  const double* R;  // [n][n][3]
+  const double* D;  // [n]
+  const double* m;  // [n][3]
+  int n;
+};
+
+__global__ void triple_tables_kernel(const double* __restrict__ T, int n, double* P, double* R, double* D, double* m) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n3 = (int64_t)n * n * n;
+  if (g >= n3) return;
+  const int y = (int)(g % n), xp = (int)((g / n) % n), x = (int)(g / ((int64_t)n * n));
+  if (x <= xp) {
+    const double* Tx = T + ((int64_t)x * n + y) * 16;
+    const double* Tp = T + ((int64_t)xp * n + y) * 16;
+    double* out = P + (((int64_t)x * n + xp) * n + y) * 9;
+    double* mir = P + (((int64_t)xp * n + x) * n + y) * 9;
+    for (int c = 0; c < 3; ++c)
+      for (int cp = 0; cp < 3; ++cp) {
+        double acc = 0.0;
+        for (int d = 0; d < 3; ++d) acc = acc + Tx[c * 4 + d] * Tp[cp * 4 + d];
+        out[c * 3 + cp] = acc;
+        mir[cp * 3 + c] = acc;  // the mirrored copy makes the Gram matrices bitwise symmetric
+      }
+  }
+  if (xp == 0) {  // (x, y) pairs: R
+    const double* Tx = T + ((int64_t)x * n + y) * 16;
+    const double* Ty = T + ((int64_t)y * n + y) * 16;
+    for (int c = 0; c < 3; ++c) {
+      double acc = 0.0;
+      for (int d = 0; d < 3; ++d) acc = acc + Tx[c * 4 + d] * Ty[12 + d];
+      R[((int64_t)x * n + y) * 3 + c] = acc;
+    }
+    if (x == 0) {
+      double acc = 0.0;
+      for (int d = 0; d < 3; ++d) acc = acc + Ty[12 + d] * Ty[12 + d];
+      D[y] = acc;
+      for (int c = 0; c < 3; ++c) m[y * 3 + c] = Ty[c * 4 + 3];
+    }
+  }
+}
+
+constexpr int kW2MaxK = 64;
+constexpr int kW2WarpsPerCta = 4;
+
+// Householder tridiagonalisation of the symmetric k x k matrix G (leading dimension ldg, warp-private shared memory;
+// lane owns rows lane + 32 t) followed by the 4 largest eigenvalues by 9-section; returns their clamped sum.
+template <int ROWS>
+__device__ __forceinline__ double warp2_top4(double* G, int ldg, int k, double* sv, double* sq, double* sd, double* se, int lane) {
+  for (int j = 0; j + 2 < k; ++j) {
+    double x[ROWS], v[ROWS];
+    double part = 0.0;
+#pragma unroll
+    for (int t = 0; t < ROWS; ++t) {
+      const int r = lane + 32 * t;
+      x[t] = (r > j && r < k) ? G[r * ldg + j] : 0.0;
+      part = fma(x[t], x[t], part);
+    }
+    const double s2 = warp_sum_all(part);
+    double aj = 0.0;
+#pragma unroll
+    for (int t = 0; t < ROWS; ++t) {
+      const double cand = __shfl_sync(0xFFFFFFFFu, x[t], (j + 1) & 31);
+      if (((j + 1) >> 5) == t) aj = cand;
+    }
+    double alpha = 0.0;
+    if (s2 > 0.0) {  // uniform: every lane holds the same s2
+      alpha = aj > 0.0 ? -sqrt(s2) : sqrt(s2);
+      part = 0.0;
+#pragma unroll
+      for (int t = 0; t < ROWS; ++t) {
+        const int r = lane + 32 * t;
+        v[t] = (r == j + 1) ? aj - alpha : ((r > j + 1 && r < k) ? x[t] : 0.0);
+        part = fma(v[t], v[t], part);
+      }
+      const double vn2 = warp_sum_all(part);
+      if (vn2 > 0.0) {
+        const double beta = 2.0 / vn2;
+#pragma unroll
+        for (int t = 0; t < ROWS; ++t) sv[lane + 32 * t] = v[t];
+        __syncwarp();
+        double pr[ROWS];
+        part = 0.0;
+#pragma unroll
+        for (int t = 0; t < ROWS; ++t) {
+          const int r = lane + 32 * t;
+          double acc = 0.0;
+          if (r > j && r < k) {
+            const double* row = G + r * ldg;
+            for (int l = j + 1; l < k; ++l) acc = fma(row[l], sv[l], acc);
+            acc *= beta;
+          }
+          pr[t] = acc;
+          part = fma(v[t], acc, part);
+        }
+        const double K = 0.5 * beta * warp_sum_all(part);
+        double qv[ROWS];
+#pragma unroll
+        for (int t = 0; t < ROWS; ++t) {
+          qv[t] = pr[t] - K * v[t];
+          sq[lane + 32 * t] = qv[t];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < ROWS; ++t) {
+          const int r = lane + 32 * t;
+          if (r > j && r < k) {
+            double* row = G + r * ldg;
+            for (int l = j + 1; l < k; ++l) row[l] -= v[t] * sq[l] + qv[t] * sv[l];
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) se[j] = alpha;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < ROWS; ++t) {
+    const int r = lane + 32 * t;
+    if (r < k) sd[r] = G[r * ldg + r];
+  }
+  if (lane == 0) se[k - 2] = G[(k - 1) * ldg + (k - 2)];
+  __syncwarp();
+  // Gershgorin interval
+  double lo = 1.0e300, hi = -1.0e300;
+#pragma unroll
+  for (int t = 0; t < ROWS; ++t) {
+    const int r = lane + 32 * t;
+    if (r < k) {
+      const double e1 = (r < k - 1) ? fabs(se[r]) : 0.0;
+      const double e0 = (r > 0) ? fabs(se[r - 1]) : 0.0;
+      lo = fmin(lo, sd[r] - e1 - e0);
+      hi = fmax(hi, sd[r] + e1 + e0);
+    }
+  }
+  lo = warp_min_all(lo);
+  hi = warp_max_all(hi);
+  __syncwarp();
+  if (lane < k - 1) se[lane] = se[lane] * se[lane];  // the recurrence only needs e^2
+  if (ROWS > 1 && lane + 32 < k - 1) se[lane + 32] = se[lane + 32] * se[lane + 32];
+  __syncwarp();
+  // 9-section with Sturm counts, 8 lanes per wanted eigenvalue.  Count = sign changes of the determinant sequence
+  // p_{-1} = 1, p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}; (p_i, p_{i-1}) is rescaled when it leaves [2^-300, 2^300]
+  const int grp = lane >> 3, mm = lane & 7;
+  const int want = k - 1 - grp;
+  double glo = lo, ghi = hi;
+  for (int round = 0; round < 18; ++round) {
+    const double w = (ghi - glo) / 9.0;
+    const double xm = glo + w * (double)(mm + 1);
+    double pm = 1.0, p = sd[0] - xm;
+    bool neg = p < 0.0;
+    int cnt = neg ? 1 : 0;
+    for (int i = 1; i < k; ++i) {
+      double pn = fma(sd[i] - xm, p, -(se[i - 1] * pm));
+      if (pn == 0.0) pn = neg ? 1.0e-300 : -1.0e-300;  // a zero counts as a sign change
+      pm = p;
+      p = pn;
+      const double ap = fabs(p);
+      if (ap > 2.037035976334486e90) { p *= 4.909093465297727e-91; pm *= 4.909093465297727e-91; }          // 2^300, 2^-300
+      else if (ap < 4.909093465297727e-91 && fabs(pm) < 4.909093465297727e-91) { p *= 2.037035976334486e90; pm *= 2.037035976334486e90; }
+      const bool nneg = p < 0.0;
+      cnt += (nneg != neg) ? 1 : 0;
+      neg = nneg;
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, cnt <= want);  // eigenvalue `want` is >= xm
+    const int t = __popc((bal >> (grp * 8)) & 0xFFu);               // sample points at or below it (prefix property)
+    const double nlo = glo + w * (double)t;
+    if (t < 8) ghi = glo + w * (double)(t + 1);
+    glo = nlo;
+  }
+  const double lam = 0.5 * (glo + ghi);
+  const double l0 = __shfl_sync(0xFFFFFFFFu, lam, 0), l1 = __shfl_sync(0xFFFFFFFFu, lam, 8);
+  const double l2 = __shfl_sync(0xFFFFFFFFu, lam, 16), l3 = __shfl_sync(0xFFFFFFFFu, lam, 24);
+  return ((fmax(l0, 0.0) + fmax(l1, 0.0)) + fmax(l2, 0.0)) + fmax(l3, 0.0);
+}
+
+__global__ void __launch_bounds__(32 * kW2WarpsPerCta) subflatten_score_warp2_kernel(const TripleTables tt, const double* __restrict__ total,
+                                                                                    const uint64_t* __restrict__ masks_a,
+                                                                                    const uint64_t* __restrict__ masks_b, int64_t num,
+                                                                                    double* scores, int kcap, int warp_doubles) {
+  extern __shared__ __align__(16) double s_w2[];
+  double* base = s_w2 + (size_t)(threadIdx.x >> 5) * warp_doubles;
+  const int ldg = kcap | 1;
+  double* G = base;                       // [kcap][ldg]
+  double* sv = G + (size_t)kcap * ldg;    // 4 x 64
+  double* sq = sv + 64;
+  double* sd = sq + 64;
+  double* se = sd + 64;
+  uint8_t* la = reinterpret_cast<uint8_t*>(se + 64);  // row-side taxa (<= 21), then column-side taxa (<= 64)
+  uint8_t* lb = la + 32;
+  const int lane = threadIdx.x & 31;
+  const int n = tt.n;
+  const uint64_t full = (n == 64) ? ~0ull : ((1ull << n) - 1ull);
+  const double tot = *total;
+  const int64_t nwarps = (int64_t)gridDim.x * kW2WarpsPerCta;
+  for (int64_t s = (int64_t)blockIdx.x * kW2WarpsPerCta + (threadIdx.x >> 5); s < num; s += nwarps) {
+    __syncwarp();
+    uint64_t ma = masks_a[s] & full;
+    uint64_t mb = masks_b ? (masks_b[s] & full & ~ma) : (full & ~ma);
+    if (__popcll(ma) > __popcll(mb)) { const uint64_t t = ma; ma = mb; mb = t; }  // rows = the smaller side (S S^T and S^T S share
+    const int a = __popcll(ma), b = __popcll(mb);                                 // their non-zero eigenvalues)
+    const int k = 3 * a + 1;
+    if (k <= 4 || b == 0) {  // at most 4 singular values: the score vanishes (phylogenetics.py:293-300)
+      if (lane == 0) scores[s] = 0.0;
+      continue;
+    }
+    if (k > kcap) {  // not reachable through spb_subflatten_score_tables (the host routes such batches elsewhere)
+      if (lane == 0) scores[s] = nan("");
+      continue;
+    }
+    for (int t = lane; t < 64; t += 32) {  // position lists in ascending taxon order
+      const uint64_t below = (1ull << t) - 1ull;
+      if ((ma >> t) & 1ull) la[__popcll(ma & below)] = (uint8_t)t;
+      if ((mb >> t) & 1ull) lb[__popcll(mb & below)] = (uint8_t)t;
+    }
+    __syncwarp();
+    // ---- Gram matrix from the triple tables: lane owns rows lane, lane + 32 ----
+    for (int r = lane; r < k; r += 32) {
+      double* row = G + r * ldg;
+      if (r < 3 * a) {
+        const int i = r / 3, c = r - 3 * i;
+        const int x = la[i];
+        const double mxc = tt.m[x * 3 + c];
+        for (int ip = 0; ip < a; ++ip) {
+          const int xp = la[ip];
+          const double* src = tt.P + (((int64_t)x * n + xp) * n) * 9 + c * 3;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+          for (int jj = 0; jj < b; ++jj) {
+            const double* q = src + (int)lb[jj] * 9;
+            a0 = a0 + __ldg(q); a1 = a1 + __ldg(q + 1); a2 = a2 + __ldg(q + 2);
+          }
+          row[3 * ip] = fma(mxc, tt.m[xp * 3], a0);
+          row[3 * ip + 1] = fma(mxc, tt.m[xp * 3 + 1], a1);
+          row[3 * ip + 2] = fma(mxc, tt.m[xp * 3 + 2], a2);
+        }
+        double acc = 0.0;
+        for (int jj = 0; jj < b; ++jj) acc = acc + __ldg(tt.R + ((int64_t)x * n + lb[jj]) * 3 + c);
+        row[3 * a] = fma(mxc, tot, acc);
+      } else {
+        for (int ip = 0; ip < a; ++ip) {
+          const int xp = la[ip];
+#pragma unroll
+          for (int cp = 0; cp < 3; ++cp) {
+            double acc = 0.0;
+            for (int jj = 0; jj < b; ++jj) acc = acc + __ldg(tt.R + ((int64_t)xp * n + lb[jj]) * 3 + cp);
+            row[3 * ip + cp] = fma(tt.m[xp * 3 + cp], tot, acc);
+          }
+        }
+        double acc = 0.0;
+        for (int jj = 0; jj < b; ++jj) acc = acc + __ldg(tt.D + lb[jj]);
+        row[3 * a] = fma(tot, tot, acc);
+      }
+    }
+    __syncwarp();
+    double part = 0.0;
+    for (int r = lane; r < k; r += 32) part += G[r * ldg + r];
+    const double trace = warp_sum_all(part);
+    const double top = (k <= 32) ? warp2_top4<1>(G, ldg, k, sv, sq, sd, se, lane) : warp2_top4<2>(G, ldg, k, sv, sq, sd, se, lane);
+    if (lane == 0) scores[s] = trace > 0.0 ? sqrt(fmax(trace - top, 0.0) / trace) : nan("");
+  }
+}
+
 inline size_t subflat_smem(int n, int* m_elems) {
   // the widest staging matrix over ALL side sizes: k x ((L + 1) | 1) with k = 3 min(a, b) + 1, L = 3 max(a, b) + 1.  It is
   // NOT maximised at the balanced split (22 taxa: 10|12 needs 31 x 39 = 1209 doubles, 11|11 only 34 x 35 = 1190: round 1
@@ -523,6 +804,49 @@ extern "C" int spb_subflatten(const double* d_T, const double* d_total, int n_ta
   int blocks = (cells + 127) / 128;
   if (blocks > 64) blocks = 64;
   subflatten_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(d_T, d_total, n_taxa, sp, d_out);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int64_t spb_subflatten_tables_doubles(int n_taxa) {
+  const int64_t n = n_taxa;
+  return n * n * n * 9 + n * n * 3 + n + n * 3 + 8;
+}
+
+// Scores through the triple-table warp kernel (header: spb_subflatten_score_tables).
+extern "C" int spb_subflatten_score_tables(const double* d_T, const double* d_total, int n_taxa, const uint64_t* d_masks_a,
+                                           const uint64_t* d_masks_b, int64_t num, double* d_scores, double* d_tables,
+                                           int tables_ready, void* stream) {
+  SPB_REQUIRE(d_T && d_total && d_tables && n_taxa >= 2 && n_taxa <= SPB_MAX_TAXA, "spb_subflatten_score_tables: bad arguments");
+  const int kcap = 3 * (n_taxa / 2) + 1;  // largest k = 3 min(a, b) + 1 over all splits of n taxa
+  SPB_REQUIRE(kcap <= kW2MaxK, "spb_subflatten_score_tables: handles sides of up to %d taxa (n <= %d); use spb_subflatten_score",
+              (kW2MaxK - 1) / 3, 2 * ((kW2MaxK - 1) / 3) + 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = n_taxa;
+  double* P = d_tables;
+  double* R = P + n * n * n * 9;
+  double* D = R + n * n * 3;
+  double* m = D + n;
+  if (!tables_ready) {
+    const int64_t n3 = n * n * n;
+    triple_tables_kernel<<<(unsigned)((n3 + 127) / 128), 128, 0, st>>>(d_T, n_taxa, P, R, D, m);
+    SPB_LAUNCH_CHECK();
+  }
+  if (num <= 0) return SPB_OK;
+  SPB_REQUIRE(d_masks_a && d_scores, "spb_subflatten_score_tables: NULL buffer");
+  const int ldg = kcap | 1;
+  const int warp_doubles = kcap * ldg + 4 * 64 + 16;  // G, v / q / d / e, 96 bytes of taxon lists (padded to 128)
+  const size_t smem = (size_t)kW2WarpsPerCta * warp_doubles * sizeof(double);
+  SPB_CUDA(cudaFuncSetAttribute(subflatten_score_warp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, subflatten_score_warp2_kernel, 32 * kW2WarpsPerCta, smem));
+  if (occ < 1) occ = 1;
+  int64_t grid = (int64_t)sm_count() * occ;
+  const int64_t need = (num + kW2WarpsPerCta - 1) / kW2WarpsPerCta;
+  if (grid > need) grid = need;
+  TripleTables tt{P, R, D, m, n_taxa};
+  subflatten_score_warp2_kernel<<<(unsigned)grid, 32 * kW2WarpsPerCta, smem, st>>>(tt, d_total, d_masks_a, d_masks_b, num, d_scores, kcap,
+                                                                               warp_doubles);
   SPB_LAUNCH_CHECK();
   return SPB_OK;
 }

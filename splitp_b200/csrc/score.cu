@@ -435,8 +435,8 @@ __device__ __forceinline__ double u31_to_double(int x) { return __hiloint2double
 // their partial sums are added in warp order through shared memory (deterministic).
 constexpr int kColsWarps = 8;
 constexpr int kColsChunk = 512;   // rows of Q staged per pass: [kColsChunk][8] doubles = 32 KB
-constexpr int kColsCtasPerSm = 3;
-constexpr int kColsPerLane = 2;   // columns owned by a lane: 2 -> at most 85 registers, three 8-warp CTAs (24 warps) per SM.
+constexpr int kColsCtasPerSm = 2;
+constexpr int kColsPerLane = 2;   // columns owned by a lane: 2 -> 32 accumulators + two batches of 8 rows in registers, two 8-warp CTAs per SM.
                                   // The first version (4 columns, 128 registers, ONE 16-warp CTA per SM) ran at 20.7 us per
                                   // 4096^2 product with the fp64 pipe 41 % and DRAM 40 % busy: too few warps to overlap the
                                   // loads of one batch of rows with the FMAs of another (profiles/r1_ncu_symv_cols_i32.txt)
@@ -471,17 +471,20 @@ __global__ void __launch_bounds__(32 * kColsWarps, kColsCtasPerSm) symv_cols_i32
       s_x[i * kKB + c] = (i < len) ? Qb[(int64_t)c * k + i0 + i] : 0.0;
     }
     __syncthreads();
+    // software pipeline: the loads of the NEXT batch of rows are in flight while this batch is multiplied (ncu on the
+    // un-pipelined form: 46 % of all stall samples were long-scoreboard waits on these loads, DRAM 28 % busy)
     const int rbeg = warp * kRowsPerWarp;
-    for (int r = rbeg; r < rbeg + kRowsPerWarp && r < len; r += kUnroll) {
-      int2 g[kUnroll];
+    const int rend = min(rbeg + kRowsPerWarp, len);
+    auto load_batch = [&](int2 (&g)[kUnroll], int r) {
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        const int row = i0 + r + u;
-        const int32_t* p = Gb + (int64_t)row * ld + col0;
+        const int32_t* p = Gb + (int64_t)(i0 + r + u) * ld + col0;
         if (r + u >= len || col0 >= k) g[u] = make_int2(0, 0);
         else if (VEC) g[u] = __ldg(reinterpret_cast<const int2*>(p));
         else g[u] = make_int2(__ldg(p), (col0 + 1 < k) ? __ldg(p + 1) : 0);
       }
+    };
+    auto mul_batch = [&](const int2 (&g)[kUnroll], int r) {
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const double gd0 = u31_to_double(g[u].x), gd1 = u31_to_double(g[u].y);
@@ -491,6 +494,18 @@ __global__ void __launch_bounds__(32 * kColsWarps, kColsCtasPerSm) symv_cols_i32
           const double2 x = xr[h];  // same address in every lane: broadcast
           acc[0][2 * h] = fma(gd0, x.x, acc[0][2 * h]);         acc[0][2 * h + 1] = fma(gd0, x.y, acc[0][2 * h + 1]);
           acc[1][2 * h] = fma(gd1, x.x, acc[1][2 * h]);         acc[1][2 * h + 1] = fma(gd1, x.y, acc[1][2 * h + 1]);
+        }
+      }
+    };
+    if (rbeg < rend) {
+      int2 ga[kUnroll], gb[kUnroll];
+      load_batch(ga, rbeg);
+      for (int r = rbeg; r < rend; r += 2 * kUnroll) {
+        if (r + kUnroll < rend) load_batch(gb, r + kUnroll);
+        mul_batch(ga, r);
+        if (r + kUnroll < rend) {
+          if (r + 2 * kUnroll < rend) load_batch(ga, r + 2 * kUnroll);
+          mul_batch(gb, r + kUnroll);
         }
       }
     }

@@ -31,6 +31,7 @@ for _i, _c in enumerate(STATES):
     _UPPER_LUT[ord(_c)] = _i
 DIRECT_MAX_TAXA = 12   # direct-indexed count table up to 4^12 cells (64 MB); hash table above
 JACOBI_MAX_K = 128
+SUBFLATTEN_TABLES_MAX_TAXA = 43  # triple-table subflattening scorer: k = 3 floor(n / 2) + 1 <= 64
 SCORE_INFO = 10        # doubles per matrix in the block-Krylov status record (SPB_SCORE_INFO)
 
 
@@ -862,6 +863,7 @@ def score_splits_counts(table, splits_idx, reduced=False):
 class PairTables:
     def __init__(self, n, N_tab, T, total):
         self.n, self.N, self.T, self.total = n, N_tab, T, total
+        self.triples = None  # triple tables of the round-2 scorer (built on first use by subflatten_scores)
 
 
 def pair_raw(aln, word_begin=0, word_end=None):
@@ -921,7 +923,14 @@ def subflatten_scores(pt, masks_a, masks_b=None):
         return torch.from_numpy(np.ascontiguousarray(m).view(np.int64)).to(device())
     ma, mb = up(masks_a), up(masks_b)
     out = _empty(int(ma.shape[0]), torch.float64)
-    call("spb_subflatten_score", _p(pt.T), _p(pt.total), pt.n, _p(ma), _p(mb), int(ma.shape[0]), _p(out), _st())
+    if pt.n <= SUBFLATTEN_TABLES_MAX_TAXA and os.environ.get("SPB_SUBFLATTEN_KERNEL", "tables") == "tables":
+        ready = pt.triples is not None
+        if not ready:
+            pt.triples = _empty(int(lib.spb_subflatten_tables_doubles(pt.n)), torch.float64)
+        call("spb_subflatten_score_tables", _p(pt.T), _p(pt.total), pt.n, _p(ma), _p(mb), int(ma.shape[0]), _p(out), _p(pt.triples),
+             int(ready), _st())
+    else:  # sides above 21 taxa (or SPB_SUBFLATTEN_KERNEL=staged for A/B runs): the kernels that stage the subflattening
+        call("spb_subflatten_score", _p(pt.T), _p(pt.total), pt.n, _p(ma), _p(mb), int(ma.shape[0]), _p(out), _st())
     return out
 
 

@@ -318,3 +318,30 @@ def test_erickson_pick_order_matches_reference_trace(sp):
         mine = []
         got = [list(map(list, s)) for s in sp.erickson_SVD(aln, method=sp.Method.mutual_information, trace=mine)]
         assert got == rec["mutual_information"]
+
+
+@pytest.mark.parametrize("n,seed", [(20, 7), (22, 8), (44, 9)])
+def test_subflatten_score_staged_kernels_still_agree(sp, eng, oracle, monkeypatch, n, seed):
+    """The kernels that stage the subflattening (round 1: warp-per-split up to 21 taxa, block-wide Jacobi above) remain the
+    route for more than 43 taxa; SPB_SUBFLATTEN_KERNEL=staged forces them below that.  Both routes against the oracle."""
+    N = 120_000
+    tree = sp.trees.balanced_tree(n, 0.05)
+    codes = sp.simulation.simulate_codes(tree, sp.simulation.GTR.JukesCantor(0.5), N, seed=seed)
+    pt = eng.pair_tables_from_alignment(eng.pack(codes, want_sm=False))
+    tables, _ = oracle.pair_tables_from_codes(codes.cpu().numpy())
+    rng = np.random.default_rng(seed)
+    picks = []
+    for a in range(2, n // 2 + 1):
+        for _ in range(6):
+            side = sorted(rng.choice(n, size=a, replace=False).tolist())
+            picks.append((side, [t for t in range(n) if t not in side]))
+    ma, mb = eng.masks_from_splits(picks)
+    monkeypatch.setenv("SPB_SUBFLATTEN_KERNEL", "staged")
+    staged = eng.subflatten_scores(pt, ma, mb).cpu().numpy()
+    monkeypatch.delenv("SPB_SUBFLATTEN_KERNEL")
+    default = eng.subflatten_scores(pt, ma, mb).cpu().numpy()
+    assert (pt.triples is not None) == (n <= eng.SUBFLATTEN_TABLES_MAX_TAXA)
+    for s, (ia, ib) in enumerate(picks):
+        ref = oracle.split_score(oracle.subflattening_from_tables(tables, 1.0, ia, ib))
+        assert_score(staged[s], ref)
+        assert_score(default[s], ref)

@@ -398,3 +398,41 @@ def test_as_tree_on_the_real_reference_phylogeny():
         "print('ok')\n" % (ref_dir, ROOT))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_warp2_scorer_model_against_lapack(oracle):
+    """The arithmetic of the round-2 subflattening scorer (Gram matrix from triple tables -> Householder with two rows per
+    lane -> division-free Sturm counts), modelled in tests/warp_scorer_model.py, against LAPACK: subflattenings of simulated
+    12- and 20-taxon alignments (k up to 31) and random / rank-deficient Gram matrices up to k = 64."""
+    import bench_inputs as BI
+    from tests.warp_scorer_model import gram_from_triples, score_warp2_model, triple_tables
+    eps = np.finfo(float).eps
+    for n, model, N in ((12, "JC", 100_000), (20, "GTR", 150_000)):
+        codes = BI.simulate_codes(n, 0.05, model, N, seed=n)
+        tables, _ = oracle.pair_tables_from_codes(codes)
+        H = oracle.H4.astype(float)
+        T = np.einsum("cx,ijxy,dy->ijcd", H, tables, H)
+        tabs = triple_tables(T, 1.0)
+        rng = np.random.default_rng(n)
+        sides = [sorted(rng.choice(n, size=a, replace=False).tolist()) for a in range(2, n // 2 + 1) for _ in range(2)]
+        sides.append(list(range(n // 2)))  # the tree's balanced true split
+        for side in sides:
+            other = [t for t in range(n) if t not in side]
+            la, lb = (side, other) if len(side) <= len(other) else (other, side)
+            S = oracle.subflattening_from_tables(tables, 1.0, la, lb)
+            G = gram_from_triples(tabs, 1.0, la, lb)
+            assert np.array_equal(G, G.T)  # bitwise symmetric by construction (mirrored table, commutative products)
+            np.testing.assert_allclose(G, S @ S.T, rtol=0, atol=4 * eps * np.abs(S @ S.T).max())
+            ref = oracle.split_score(S)
+            got, _ = score_warp2_model(G)
+            assert abs(got - ref) <= max(1e-9, 64 * eps / ref ** 2) * ref, (n, side, got, ref)
+    rng = np.random.default_rng(0)
+    for k, L in ((5, 40), (17, 17), (33, 60), (49, 49), (64, 70)):
+        M = rng.standard_normal((k, L))
+        if k == 17:
+            M[5:] = M[:12] * 0.5  # rank deficient
+        G = M @ M.T
+        lam = np.sort(np.linalg.eigvalsh(G))[::-1]
+        ref = np.sqrt(max(lam[4:].sum(), 0.0) / lam.sum())
+        got, _ = score_warp2_model(G)
+        assert abs(got - ref) <= 1e-12 * max(ref, 1.0), (k, got, ref)
