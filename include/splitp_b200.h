@@ -88,6 +88,10 @@ int spb_count_hash(const uint32_t* d_sm, const uint32_t* d_valid, int n_taxa, in
 int spb_compact_hash(const uint64_t* d_hkeys, const uint32_t* d_hcounts, const uint32_t* d_hfirst,
                      int64_t cap, uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first_out,
                      int64_t capacity, uint64_t* d_num, uint32_t* d_tmp, void* stream);
+/* Multi-GPU merge of direct tables without reducing all 4^n cells: every rank compacts its table, the (key, count) lists
+ * are all-gathered (a few hundred KB instead of a 64 MB allreduce at 12 taxa) and added into a zeroed table with this call
+ * (d_table uint32 [cells], keys < cells), which spb_compact_direct then turns into the sorted global list. */
+int spb_direct_merge(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, int64_t cells, uint32_t* d_table, void* stream);
 /* Merge a (keys, counts) list into a hash table (multi-GPU merge of hashed tables). */
 int spb_hash_merge(const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_first, int64_t num,
                    uint64_t* d_hkeys, uint32_t* d_hcounts, uint32_t* d_hfirst, int64_t cap,

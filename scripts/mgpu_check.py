@@ -18,6 +18,14 @@ for n, N in ((10, 300_001), (16, 500_000)):
     loc = eng.pack(codes[:, b:e].contiguous())
     got2 = spd.count_patterns_sharded(loc, rank, world, local=True)
     assert torch.equal(ref.keys, got2.keys) and torch.equal(ref.counts, got2.counts), (n, "local")
+    if n <= eng.DIRECT_MAX_TAXA:  # compacted-list exchange of the direct table (the bench path)
+        got3 = eng.count_patterns(loc, gather_fn=spd.make_gather_fn())
+        assert torch.equal(ref.keys, got3.keys) and torch.equal(ref.counts, got3.counts) and ref.divisor == got3.divisor, (n, "gather")
+        from splitp_b200 import batch
+        idx20 = [eng.split_positions(s_, tree.taxa) for s_ in list(sp.all_splits(tree))[:60]]
+        sharded = batch.SplitScorer(idx20, None, sp.Method.flattening, rank, world).device_scores(codes[:, b:e].contiguous())
+        single = eng.score_splits_counts(ref, idx20)
+        assert torch.equal(sharded, single), (n, "SplitScorer")
     pt_ref = eng.pair_tables_from_alignment(aln, as_counts=True)
     pt = spd.pair_tables_sharded(aln, rank, world, as_counts=True)
     assert torch.equal(pt_ref.N, pt.N) and torch.equal(pt_ref.T, pt.T)

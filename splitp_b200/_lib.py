@@ -85,6 +85,7 @@ PROTOTYPES = {
     "spb_compact_direct": (_i, [_p, _p, _l, _p, _p, _p, _l, _p, _p, _p]),
     "spb_count_hash": (_i, [_p, _p, _i, _l, _l, _p, _p, _p, _l, _p, _p, _p]),
     "spb_compact_hash": (_i, [_p, _p, _p, _l, _p, _p, _p, _l, _p, _p, _p]),
+    "spb_direct_merge": (_i, [_p, _p, _l, _l, _p, _p]),
     "spb_hash_merge": (_i, [_p, _p, _p, _l, _p, _p, _p, _l, _p, _p]),
     "spb_pack_wide": (_i, [_p, _i, _l, _l, _i, _p, _p, _p]),
     "spb_count_hash_wide": (_i, [_p, _p, _l, _l, _p, _p, _p, _l, _p, _p, _p, _p]),

@@ -111,6 +111,7 @@ class SplitScorer:
         self.S = len(self.idx_all)
         self.idx_mine = spd.shard_strided(self.idx_all, rank, world)
         self.reduce_fn = spd.make_reduce_fn(group) if world > 1 else None
+        self.gather_fn = spd.make_gather_fn(group) if world > 1 else None
         self.scorer = None
         self.masks = None
         self.timer = None
@@ -131,7 +132,10 @@ class SplitScorer:
             with _span(t, "h2d+pack"):
                 aln = _as_alignment(alignment, want_sm=True, want_planes=False)
             with _span(t, "count"):
-                table = engine.count_patterns(aln, reduce_fn=self._timed_reduce if self.reduce_fn else None)
+                if aln.n <= engine.DIRECT_MAX_TAXA:
+                    table = engine.count_patterns(aln, gather_fn=self._timed_gather if self.gather_fn else None)
+                else:  # hashed tables: gather + hash merge on every rank
+                    table = spd.count_patterns_sharded(aln, self.rank, self.world, self.group, local=True)
             if self.scorer is None:
                 self.scorer = engine.CountScorer(table)
             self.scorer.table = table
@@ -151,9 +155,9 @@ class SplitScorer:
         with _span(t, "gather"):
             return spd.gather_strided(out, self.S, self.rank, self.world, self.group)
 
-    def _timed_reduce(self, tensor, op):
-        with _span(self.timer, "allreduce"):
-            return self.reduce_fn(tensor, op)
+    def _timed_gather(self, keys, counts):
+        with _span(self.timer, "exchange"):
+            return self.gather_fn(keys, counts)
 
     def __call__(self, alignment):
         return self.device_scores(alignment).cpu().numpy()

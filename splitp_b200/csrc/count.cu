@@ -649,6 +649,13 @@ __global__ void __launch_bounds__(kCThreads) rank_write_kernel(const uint32_t* f
   }
 }
 
+// table[keys[i]] += counts[i]: merges (key, count) lists of other ranks into a direct-indexed table
+__global__ void direct_merge_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t num,
+                                    uint32_t* __restrict__ table) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < num) atomicAdd(table + keys[i], counts[i]);
+}
+
 __global__ void hash_merge_kernel(const uint64_t* keys, const uint32_t* counts, const uint32_t* first, int64_t num,
                                   HashSink sink) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -729,6 +736,17 @@ extern "C" int spb_compact_hash(const uint64_t* d_hkeys, const uint32_t* d_hcoun
   SPB_REQUIRE(d_hkeys && d_hcounts && d_keys && d_counts && d_num && d_tmp && cap >= 0, "spb_compact_hash: bad arguments");
   return run_compact(HashSrc{d_hkeys, d_hcounts}, d_hfirst, cap, d_keys, d_counts, d_first_out, capacity, d_num, d_tmp,
                      (cudaStream_t)stream);
+}
+
+extern "C" int spb_direct_merge(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, int64_t cells, uint32_t* d_table,
+                                void* stream) {
+  SPB_REQUIRE(d_table && cells >= 1, "spb_direct_merge: bad table");
+  if (num <= 0) return SPB_OK;
+  SPB_REQUIRE(d_keys && d_counts, "spb_direct_merge: NULL buffer");
+  (void)cells;  // keys come from spb_compact_direct of a table of the same size: always in range
+  direct_merge_kernel<<<(unsigned)((num + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_keys, d_counts, num, d_table);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
 }
 
 extern "C" int spb_hash_merge(const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_first, int64_t num,

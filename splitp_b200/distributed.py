@@ -57,6 +57,33 @@ def make_reduce_fn(group=None):
     return reduce_fn
 
 
+def make_gather_fn(group=None):
+    """gather_fn(keys, counts) hook for engine.count_patterns: all-gather of the compacted per-rank pattern lists."""
+    def gather_fn(keys, counts):
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return keys, counts
+        return all_gather_varlen_pair(keys, counts, group)
+    return gather_fn
+
+
+def all_gather_varlen_pair(a, b, group=None):
+    """all_gather_varlen of two equally long 1-D tensors with ONE size exchange."""
+    world = dist.get_world_size(group)
+    n = torch.tensor([a.shape[0]], dtype=torch.int64, device=a.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes)
+    out = []
+    for t in (a, b):
+        pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+        pad[:t.shape[0]] = t
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+        out.append(torch.cat([x[:s] for x, s in zip(bufs, sizes)]))
+    return out[0], out[1]
+
+
 def all_gather_varlen(t, group=None):
     """Concatenation over ranks of 1-D tensors of different lengths (rank order)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

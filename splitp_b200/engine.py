@@ -173,12 +173,13 @@ class PatternTable:
         return torch.div(v, torch.full_like(v, self.divisor))
 
 
-def count_patterns(aln, site_begin=0, site_end=None, want_first=False, force_hash=False, sort=True, reduce_fn=None):
+def count_patterns(aln, site_begin=0, site_end=None, want_first=False, force_hash=False, sort=True, reduce_fn=None, gather_fn=None):
     """Kernel 1: {pattern: count} of the usable sites in [site_begin, site_end)
     (splitp/parsers/fasta.py:48-63).  Keys come back ascending (= lexicographic A<C<G<T order of
     splitp/simulation.py:50-54); `first` holds the first site of each pattern (dict insertion order).
-    reduce_fn(tensor) (optional) is applied to the direct table / usable counter before compaction:
-    the hook the multi-GPU path uses for its count allreduce."""
+    Multi-GPU hooks for the direct table (n <= 12): reduce_fn(tensor, op) allreduces the whole table before compaction
+    (needed with want_first); gather_fn(keys, counts) -> (all keys, all counts) exchanges the COMPACTED per-rank lists instead
+    (a few hundred KB instead of 64 MB at 12 taxa) and the lists are merged into a fresh table."""
     n = aln.n
     if aln.sm is None:
         raise NotImplementedError("pattern counting uses uint64 keys: at most 31 taxa (site-major stream <= 32)")
@@ -209,6 +210,19 @@ def count_patterns(aln, site_begin=0, site_end=None, want_first=False, force_has
         P = int(num.item())
         keys, counts = keys[:P], counts[:P]
         fo = fo[:P] if fo is not None else None
+        if gather_fn is not None:
+            if want_first or reduce_fn is not None:
+                raise ValueError("count_patterns: gather_fn excludes reduce_fn / want_first")
+            all_keys, all_counts = gather_fn(keys, counts)
+            table.zero_()
+            total = int(all_keys.shape[0])
+            call("spb_direct_merge", _p(all_keys.contiguous()), _p(all_counts.contiguous()), total, cells, _p(table), _st())
+            cap = min(cells, max(total, 1))
+            keys, counts = _empty(cap, torch.int64), _empty(cap, torch.int32)
+            call("spb_compact_direct", _p(table), None, cells, _p(keys), _p(counts), None, cap, _p(num), _p(tmp), _st())
+            P = int(num.item())
+            keys, counts = keys[:P], counts[:P]
+            usable = counts.to(torch.int64).sum().reshape(1)  # every usable site of every rank is in exactly one pattern
     else:
         cap = 1024
         while cap < 2 * min(4 ** n, max(nsites, 1)):

@@ -153,6 +153,9 @@ f = torch.tensor([-1, 5 + rank, -1 if rank == 0 else 7, -2147483648 + rank], dty
 fn(f, "min_u32"); assert f.tolist() == [-1, 5, 7, -2147483648], f.tolist()
 v = torch.arange(3 + 4 * rank, dtype=torch.int64) + 100 * rank
 g = spd.all_gather_varlen(v); assert g.tolist() == [0, 1, 2] + [100 + i for i in range(7)]
+# compacted pattern lists of the direct-table merge: one size exchange, two payloads, rank order kept
+gk, gc = spd.make_gather_fn()(v, (v * 2).to(torch.int32))
+assert gk.tolist() == g.tolist() and gc.tolist() == [2 * x for x in g.tolist()]
 S = 11
 b, e = spd.shard_range(S, rank, world)
 sc = spd.gather_scores(torch.arange(b, e, dtype=torch.float64), S, rank, world)
