@@ -56,6 +56,19 @@ lw, lv, _, lN = eng.pack_wide(codes[:, b:e].contiguous())
 got2 = spd.count_patterns_wide_sharded(lw, lv, n_, lN, rank, world, local=True)
 kg2, cg2 = got2.compact()
 assert torch.equal(kr, kg2) and torch.equal(cr, cg2)
+# hash-partitioned merge: the partitions are disjoint, their union is the global table, replication restores it
+part, usable_all = spd.count_patterns_wide_partitioned(lw, lv, n_, lN, rank, world)
+assert usable_all == int(ref.divisor)
+kp, cp = part.compact()
+if world > 1:
+    owner = spd._owner_of(kp, world)
+    assert bool((owner == rank).all()), "a partition holds a key it does not own"
+    sizes = spd.all_gather_varlen(torch.tensor([kp.shape[0]], dtype=torch.int64, device=kp.device))
+    assert int(sizes.sum().item()) == kr.shape[0], (sizes.tolist(), kr.shape[0])
+    assert int(sizes.max().item()) < 0.75 * kr.shape[0] or world == 1  # memory per rank shrinks
+full = spd.replicate_wide_table(part, n_, usable_all, world)
+kf, cf = full.compact()
+assert torch.equal(kr, kf) and torch.equal(cr, cf)
 sides = [[0, 1], [5, 40], [62, 63]]
 assert torch.equal(eng.thin_split_scores(ref, sides), eng.thin_split_scores(got2, sides))
 if world > 1:

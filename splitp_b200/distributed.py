@@ -168,6 +168,69 @@ def pair_tables_sharded(aln, rank, world, group=None, as_counts=False):
     return engine.pair_finalize(raw, aln.n, 0.0 if as_counts else float(int(raw[-1].item())))
 
 
+def _owner_of(keys, world):
+    """Owner rank of every pattern key (hash partition): a multiplicative mix of the key words, reduced modulo world.
+    keys: int64 [P] (uint64 keys) or int64 [P, 2] (128-bit keys {lo, hi})."""
+    k = keys if keys.dim() == 1 else keys[:, 0] ^ (keys[:, 1] * -7046029254386353131)  # 0x9E3779B97F4A7C15 as int64
+    k = (k ^ (k >> 31)) * -4658895280553007687  # 0xBF58476D1CE4E5B9 as int64; arithmetic shift keeps the mix deterministic
+    k = k ^ (k >> 29)
+    return (k & 0x7FFFFFFF) % world
+
+
+def exchange_by_owner(keys, counts, world, group=None):
+    """Hash-partitioned exchange: every (key, count) entry travels to the rank that owns its key
+    (all_to_all with uneven splits); returns the entries this rank owns, duplicates from different ranks included.
+    On NVSwitch the all-to-all is uniform-cost, so the partition needs no topology awareness."""
+    if world == 1:
+        return keys, counts
+    owner = _owner_of(keys, world)
+    order = torch.argsort(owner, stable=True)
+    keys, counts, owner = keys[order].contiguous(), counts[order].contiguous(), owner[order]
+    send = torch.bincount(owner, minlength=world).to(torch.int64)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    send_l, recv_l = send.tolist(), recv.tolist()
+    total = int(sum(recv_l))
+    width = 1 if keys.dim() == 1 else keys.shape[1]
+    rk = torch.empty((total,) if width == 1 else (total, width), dtype=keys.dtype, device=keys.device)
+    rc = torch.empty(total, dtype=counts.dtype, device=counts.device)
+    dist.all_to_all_single(rk, keys, output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
+    dist.all_to_all_single(rc, counts, output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
+    return rk, rc
+
+
+def count_patterns_wide_partitioned(wide, valid, n, N, rank, world, group=None, local=True):
+    """128-bit-key pattern compression with a hash-PARTITIONED result: every rank compresses its site shard, the
+    (key, count) lists are exchanged by owner (exchange_by_owner) and merged locally, so that rank r ends up holding
+    the patterns it owns with their GLOBAL counts: memory and merge work per rank shrink with the number of ranks (the
+    replicate-everything form, count_patterns_wide_sharded, re-hashes every pattern of every rank on every rank).
+    Returns (partition WideTable, usable sites of the whole alignment)."""
+    from . import engine
+    b, e = (0, N) if local else shard_range(N, rank, world, 32)
+    mine = engine.count_patterns_wide(wide, valid, n, N, b, e)
+    usable = torch.tensor([int(mine.divisor)], dtype=torch.int64, device=wide.device)
+    if world == 1:
+        return mine, int(usable.item())
+    dist.all_reduce(usable, group=group)
+    keys, counts = mine.compact(sort=False)
+    rk, rc = exchange_by_owner(keys, counts, world, group)
+    part = engine.merge_wide_tables(n, rk, rc, int(usable.item()))
+    return part, int(usable.item())
+
+
+def replicate_wide_table(part, n, usable, world, group=None):
+    """Full table on every rank from the hash partitions: the merged, duplicate-free partitions are all-gathered and
+    inserted (what consumers that look patterns up across the whole table -- the thin-split Gram -- need)."""
+    from . import engine
+    if world == 1:
+        return part
+    keys, counts = part.compact(sort=False)
+    lo = all_gather_varlen(keys[:, 0].contiguous(), group)
+    hi = all_gather_varlen(keys[:, 1].contiguous(), group)
+    cnt = all_gather_varlen(counts, group)
+    return engine.merge_wide_tables(n, torch.stack([lo, hi], dim=1), cnt, usable)
+
+
 def count_patterns_wide_sharded(wide, valid, n, N, rank, world, group=None, local=False):
     """128-bit-key pattern table of the whole alignment: every rank compresses its site range (or its local shard),
     the per-rank (key, count) lists are all-gathered and merged into one table on every rank.  At 64 taxa nearly

@@ -156,6 +156,17 @@ g = spd.all_gather_varlen(v); assert g.tolist() == [0, 1, 2] + [100 + i for i in
 # compacted pattern lists of the direct-table merge: one size exchange, two payloads, rank order kept
 gk, gc = spd.make_gather_fn()(v, (v * 2).to(torch.int32))
 assert gk.tolist() == g.tolist() and gc.tolist() == [2 * x for x in g.tolist()]
+# hash-partitioned exchange: every entry ends up on its owner, nothing is lost, duplicates from both ranks are kept
+keys = torch.arange(50, dtype=torch.int64) * 7919 + rank * 3            # ranks share no key ...
+keys = torch.cat([keys, torch.tensor([123456789, 42], dtype=torch.int64)])  # ... except these two
+cnts = torch.ones_like(keys, dtype=torch.int32) * (rank + 1)
+rk, rc = spd.exchange_by_owner(keys, cnts, world)
+assert bool((spd._owner_of(rk, world) == rank).all())
+tot = torch.tensor([rk.shape[0], int(rc.sum())], dtype=torch.int64); dist.all_reduce(tot)
+assert tot.tolist() == [104, 52 * 1 + 52 * 2], tot.tolist()
+wk = torch.stack([keys, keys * 31 + 5], dim=1)                             # 128-bit keys (lo, hi)
+rk2, rc2 = spd.exchange_by_owner(wk, cnts, world)
+assert rk2.shape[1] == 2 and bool((spd._owner_of(rk2, world) == rank).all())
 S = 11
 b, e = spd.shard_range(S, rank, world)
 sc = spd.gather_scores(torch.arange(b, e, dtype=torch.float64), S, rank, world)
