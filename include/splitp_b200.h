@@ -285,20 +285,6 @@ int spb_gram_u8_batch_i32(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_
 int spb_gram_hi_strip_batch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int layout,
                             const int32_t* d_hi_rc, const uint32_t* d_hi_val, const uint32_t* d_hi_num, int64_t hi_cap,
                             double* d_Cs, int64_t cs_rows, int32_t* d_pos, int32_t* d_hr, int32_t* d_hm, void* stream);
-/* Streamed form of the three calls above for a batch of large count flattenings (k > 128): per matrix b,
- *   G0 = S0_b S0_b^T (tensor cores) -> X1 = G S -> X2 = G X1        (G = G0 + strip correction of matrix b)
- * run back to back into ONE int32 buffer d_Gi [rows_pad][rows_pad] that is reused by every matrix, so both products read
- * G0 from L2 and G0 is overwritten before it is written back to HBM.  The orthogonalisation of the 2-block Krylov cycle
- * is applied afterwards to (S, X1, X2), batched over the nb matrices, followed by the same Rayleigh-Ritz / acceptance
- * test as spb_score_gram_large.  Matrices that fail the test (converged = 0 in d_info, count in
- * spb_score_last_unconverged()) keep the score of this single cycle and should be re-scored with
- * spb_gram_u8_batch_i32 + spb_score_gram_large_i32: the deferred orthogonalisation loses accuracy on (nearly) rank-4
- * matrices.  Strip buffers as produced by spb_gram_hi_strip_batch for the same nb matrices.  d_ws: double
- * [spb_score_gram_large_ws(k, nb)].  h_timing (HOST, optional, double[2]): device milliseconds spent in the nb Gram
- * launches and in the nb x 2 products (CUDA events on `stream`; the call synchronises the stream either way). */
-int spb_score_u8_stream(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int64_t k, int32_t* d_Gi,
-                        const double* d_Cs, int64_t cs_rows, const int32_t* d_pos, const int32_t* d_hr, const int32_t* d_hm,
-                        double* d_scores, double* d_info, double* d_ws, double* h_timing, void* stream);
 int spb_score_gram_large_i32(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Cs, int64_t cs_rows,
                              const int32_t* d_pos, const int32_t* d_hr, const int32_t* d_hm, double* d_scores, double* d_info,
                              double* d_ws, void* stream);

@@ -128,7 +128,6 @@ PROTOTYPES = {
     "spb_score_gram_large": (_i, [_p, _l, _l, _l, _p, _p, _p, _p]),
     "spb_gram_u8_batch_i32": (_i, [_p, _l, _i, _l, _l, _p, _l, _p]),
     "spb_gram_hi_strip_batch": (_i, [_p, _l, _i, _l, _l, _i, _p, _p, _p, _l, _p, _l, _p, _p, _p, _p]),
-    "spb_score_u8_stream": (_i, [_p, _l, _i, _l, _l, _l, _p, _p, _l, _p, _p, _p, _p, _p, _p, C.POINTER(C.c_double), _p]),
     "spb_score_gram_large_i32": (_i, [_p, _l, _l, _l, _p, _l, _p, _p, _p, _p, _p, _p, _p]),
     "spb_mi_partials": (_l, []),
     "spb_marginals_dense": (_i, [_p, _l, _l, _l, _p, _p, _p]),

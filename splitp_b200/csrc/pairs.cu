@@ -586,31 +586,50 @@ __device__ __forceinline__ double warp2_top4(double* G, int ldg, int k, double* 
   lo = warp_min_all(lo);
   hi = warp_max_all(hi);
   __syncwarp();
-  if (lane < k - 1) se[lane] = se[lane] * se[lane];  // the recurrence only needs e^2
-  if (ROWS > 1 && lane + 32 < k - 1) se[lane + 32] = se[lane + 32] * se[lane + 32];
+  // The Sturm recurrence runs on the matrix scaled by 1 / max(|lo|, |hi|) (|d_i - x| <= 2, e_i^2 <= 1: at most a factor 3 of
+  // growth per step, so overflow is impossible for k <= 64), with e squared once.
+  const double nrm = fmax(fabs(lo), fabs(hi));
+  const double inv = nrm > 0.0 ? 1.0 / nrm : 1.0;
+#pragma unroll
+  for (int t = 0; t < ROWS; ++t) {
+    const int r = lane + 32 * t;
+    if (r < k) sd[r] *= inv;
+    if (r < k - 1) se[r] = (se[r] * inv) * (se[r] * inv);
+  }
   __syncwarp();
   // 9-section with Sturm counts, 8 lanes per wanted eigenvalue.  Count = sign changes of the determinant sequence
-  // p_{-1} = 1, p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}; (p_i, p_{i-1}) is rescaled when it leaves [2^-300, 2^300]
+  // p_{-1} = 1, p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}.  Every 4 steps the pair (p_i, p_{i-1}) is multiplied by the power
+  // of two that brings max(|p_i|, |p_{i-1}|) back to [1, 2) (exponent arithmetic, no branch): underflow -- the recurrence
+  // shrinks by |d_i - x| per step -- can then never reach the denormal range (4 steps lose at most 4 x 53 + ... bits of a
+  // value that starts in [1, 2)); signs are unaffected.  An exact zero p_i counts as positive (measure-zero event: x is
+  // then an eigenvalue of a leading block and either side of it is a correct answer for the bisection).
   const int grp = lane >> 3, mm = lane & 7;
   const int want = k - 1 - grp;
-  double glo = lo, ghi = hi;
+  double glo = lo * inv, ghi = hi * inv;
   for (int round = 0; round < 18; ++round) {
     const double w = (ghi - glo) / 9.0;
     const double xm = glo + w * (double)(mm + 1);
     double pm = 1.0, p = sd[0] - xm;
-    bool neg = p < 0.0;
-    int cnt = neg ? 1 : 0;
-    for (int i = 1; i < k; ++i) {
-      double pn = fma(sd[i] - xm, p, -(se[i - 1] * pm));
-      if (pn == 0.0) pn = neg ? 1.0e-300 : -1.0e-300;  // a zero counts as a sign change
+    int cnt = __double2hiint(p) < 0 ? 1 : 0;
+    int i = 1;
+    for (; i + 3 < k; i += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double pn = fma(sd[i + u] - xm, p, -(se[i + u - 1] * pm));
+        cnt += (int)(((unsigned)__double2hiint(pn) ^ (unsigned)__double2hiint(p)) >> 31);
+        pm = p;
+        p = pn;
+      }
+      const int ex = (__double2hiint(fmax(fabs(p), fabs(pm))) >> 20) & 0x7FF;        // biased exponent of the larger one
+      const double sc = __hiloint2double((2046 - (ex > 0 ? ex : 1023)) << 20, 0);     // 2^(1023 - ex); 1 when both are zero
+      p *= sc;
+      pm *= sc;
+    }
+    for (; i < k; ++i) {
+      const double pn = fma(sd[i] - xm, p, -(se[i - 1] * pm));
+      cnt += (int)(((unsigned)__double2hiint(pn) ^ (unsigned)__double2hiint(p)) >> 31);
       pm = p;
       p = pn;
-      const double ap = fabs(p);
-      if (ap > 2.037035976334486e90) { p *= 4.909093465297727e-91; pm *= 4.909093465297727e-91; }          // 2^300, 2^-300
-      else if (ap < 4.909093465297727e-91 && fabs(pm) < 4.909093465297727e-91) { p *= 2.037035976334486e90; pm *= 2.037035976334486e90; }
-      const bool nneg = p < 0.0;
-      cnt += (nneg != neg) ? 1 : 0;
-      neg = nneg;
     }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, cnt <= want);  // eigenvalue `want` is >= xm
     const int t = __popc((bal >> (grp * 8)) & 0xFFu);               // sample points at or below it (prefix property)
@@ -618,6 +637,8 @@ __device__ __forceinline__ double warp2_top4(double* G, int ldg, int k, double* 
     if (t < 8) ghi = glo + w * (double)(t + 1);
     glo = nlo;
   }
+  glo *= nrm;
+  ghi *= nrm;
   const double lam = 0.5 * (glo + ghi);
   const double l0 = __shfl_sync(0xFFFFFFFFu, lam, 0), l1 = __shfl_sync(0xFFFFFFFFu, lam, 8);
   const double l2 = __shfl_sync(0xFFFFFFFFu, lam, 16), l3 = __shfl_sync(0xFFFFFFFFu, lam, 24);
@@ -664,41 +685,49 @@ __global__ void __launch_bounds__(32 * kW2WarpsPerCta) subflatten_score_warp2_ke
       if ((mb >> t) & 1ull) lb[__popcll(mb & below)] = (uint8_t)t;
     }
     __syncwarp();
-    // ---- Gram matrix from the triple tables: lane owns rows lane, lane + 32 ----
-    for (int r = lane; r < k; r += 32) {
-      double* row = G + r * ldg;
-      if (r < 3 * a) {
+    // ---- Gram matrix from the triple tables.  Work items (i, i' >= i, c) = 3 entries G[3i + c][3i' .. 3i' + 2], dealt round-robin
+    // to the lanes and written to both triangles (bitwise symmetric by construction); then the last row / column. ----
+    {
+      const int npairs = a * (a + 1) / 2;
+      for (int t = lane; t < 3 * npairs; t += 32) {
+        const int q = t / 3, c = t - 3 * q;
+        int i = 0, rem = q;
+        while (rem >= a - i) { rem -= a - i; ++i; }  // row-major over the upper triangle: row i holds i' = i .. a - 1
+        const int ip = i + rem;
+        const int x = la[i], xp = la[ip];
+        const double* src = tt.P + (((int64_t)x * n + xp) * n) * 9 + c * 3;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        int jj = 0;
+        for (; jj + 1 < b; jj += 2) {  // two column taxa per iteration: six independent loads in flight
+          const double* q0 = src + (int)lb[jj] * 9;
+          const double* q1 = src + (int)lb[jj + 1] * 9;
+          const double u0 = __ldg(q0), u1 = __ldg(q0 + 1), u2 = __ldg(q0 + 2);
+          const double v0 = __ldg(q1), v1 = __ldg(q1 + 1), v2 = __ldg(q1 + 2);
+          a0 = (a0 + u0) + v0; a1 = (a1 + u1) + v1; a2 = (a2 + u2) + v2;
+        }
+        if (jj < b) {
+          const double* q0 = src + (int)lb[jj] * 9;
+          a0 = a0 + __ldg(q0); a1 = a1 + __ldg(q0 + 1); a2 = a2 + __ldg(q0 + 2);
+        }
+        const double mxc = tt.m[x * 3 + c];
+        const double g0 = fma(mxc, tt.m[xp * 3], a0), g1 = fma(mxc, tt.m[xp * 3 + 1], a1), g2 = fma(mxc, tt.m[xp * 3 + 2], a2);
+        const int r = 3 * i + c, cc = 3 * ip;
+        G[r * ldg + cc] = g0; G[r * ldg + cc + 1] = g1; G[r * ldg + cc + 2] = g2;
+        G[cc * ldg + r] = g0; G[(cc + 1) * ldg + r] = g1; G[(cc + 2) * ldg + r] = g2;
+      }
+      for (int r = lane; r < 3 * a; r += 32) {  // last column / row
         const int i = r / 3, c = r - 3 * i;
         const int x = la[i];
-        const double mxc = tt.m[x * 3 + c];
-        for (int ip = 0; ip < a; ++ip) {
-          const int xp = la[ip];
-          const double* src = tt.P + (((int64_t)x * n + xp) * n) * 9 + c * 3;
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-          for (int jj = 0; jj < b; ++jj) {
-            const double* q = src + (int)lb[jj] * 9;
-            a0 = a0 + __ldg(q); a1 = a1 + __ldg(q + 1); a2 = a2 + __ldg(q + 2);
-          }
-          row[3 * ip] = fma(mxc, tt.m[xp * 3], a0);
-          row[3 * ip + 1] = fma(mxc, tt.m[xp * 3 + 1], a1);
-          row[3 * ip + 2] = fma(mxc, tt.m[xp * 3 + 2], a2);
-        }
         double acc = 0.0;
         for (int jj = 0; jj < b; ++jj) acc = acc + __ldg(tt.R + ((int64_t)x * n + lb[jj]) * 3 + c);
-        row[3 * a] = fma(mxc, tot, acc);
-      } else {
-        for (int ip = 0; ip < a; ++ip) {
-          const int xp = la[ip];
-#pragma unroll
-          for (int cp = 0; cp < 3; ++cp) {
-            double acc = 0.0;
-            for (int jj = 0; jj < b; ++jj) acc = acc + __ldg(tt.R + ((int64_t)xp * n + lb[jj]) * 3 + cp);
-            row[3 * ip + cp] = fma(tt.m[xp * 3 + cp], tot, acc);
-          }
-        }
+        const double g = fma(tt.m[x * 3 + c], tot, acc);
+        G[r * ldg + 3 * a] = g;
+        G[3 * a * ldg + r] = g;
+      }
+      if (lane == 0) {
         double acc = 0.0;
         for (int jj = 0; jj < b; ++jj) acc = acc + __ldg(tt.D + lb[jj]);
-        row[3 * a] = fma(tot, tot, acc);
+        G[3 * a * ldg + 3 * a] = fma(tot, tot, acc);
       }
     }
     __syncwarp();

@@ -434,83 +434,116 @@ __device__ __forceinline__ double u31_to_double(int x) { return __hiloint2double
 // not HBM; 25 us against 20.7 us per 4096^2 product).  The 16 warps of a CTA split the rows of every chunk;
 // their partial sums are added in warp order through shared memory (deterministic).
 constexpr int kColsWarps = 8;
-constexpr int kColsChunk = 512;   // rows of Q staged per pass: [kColsChunk][8] doubles = 32 KB
 constexpr int kColsCtasPerSm = 2;
-constexpr int kColsPerLane = 2;   // columns owned by a lane: 2 -> 32 accumulators + two batches of 8 rows in registers, two 8-warp CTAs per SM.
-                                  // The first version (4 columns, 128 registers, ONE 16-warp CTA per SM) ran at 20.7 us per
-                                  // 4096^2 product with the fp64 pipe 41 % and DRAM 40 % busy: too few warps to overlap the
-                                  // loads of one batch of rows with the FMAs of another (profiles/r1_ncu_symv_cols_i32.txt)
+constexpr int kColsPerLane = 2;
 constexpr int kColsPerCta = 32 * kColsPerLane;
-// gridDim.z > 1 ("row split", used when ONE matrix must fill the machine): CTA z handles the row chunks z, z + gridDim.z, ...
-// and writes its partial sums to part[z][c][j] (part = AQ argument, plane stride kKB * k); symv_reduce_parts_kernel adds the
-// planes in z order (deterministic).
+constexpr int kColsQRows = 64;   // rows of Q^T per warp-private staging buffer: 64 x 8 doubles = 4 KB, double-buffered
+// Tuning history of this kernel (67 MB int32 per 4096^2 product; floors: 10.3 us from HBM, 8.1 us from the fp64 pipe):
+//   v1 (round 1): 4 columns per lane, ONE 16-warp CTA per SM at 128 registers, Q staged per 1024-row chunk behind two CTA
+//       barriers: 20.7 us (ncu: DRAM 40 %, fp64 41 %, 46 % of the stall samples are long-scoreboard waits on the G loads);
+//   v2: 2 columns per lane, 24 warps per SM: 29.9 us cold / no change in the step (more warps, but each restarts its load
+//       pipeline after every barrier with only 64 rows between barriers);
+//   v2b: + software-pipelined loads (next batch of 8 rows in flight while this one is multiplied): 25.4 us cold, step
+//       unchanged: 22 % of the samples still sit on the first use after each chunk barrier, 13 % on the Q staging stores;
+//   v3 (this one): no CTA barrier in the main loop at all.  A warp owns a CONTIGUOUS run of rows for the whole kernel and
+//       streams them with the two-batch load pipeline; the Q values of its rows come from a transposed copy Q^T [row][8]
+//       (krylov_transpose_kernel), fetched 64 rows (one contiguous 4 KB piece) at a time into a warp-private,
+//       double-buffered shared-memory tile with cp.async, read back as broadcasts.
 // VEC: ld and k are even and the matrix is 8-byte aligned (always true for the Gram buffers of this library): every lane's
 // column pair is one aligned 64-bit load and there is no column boundary inside a pair.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Qt[bt][row][c] = Q[bt][c][row] for row < k, zero for k <= row < k_pad
+__global__ void krylov_transpose_kernel(const double* __restrict__ Q, int64_t strideQ, double* __restrict__ Qt, int64_t strideQt, int k,
+                                        int k_pad) {
+  const int64_t bt = blockIdx.y;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= k_pad) return;
+  double v[kKB];
+#pragma unroll
+  for (int c = 0; c < kKB; ++c) v[c] = row < k ? Q[bt * strideQ + (int64_t)c * k + row] : 0.0;
+  double2* dst = reinterpret_cast<double2*>(Qt + bt * strideQt + (int64_t)row * kKB);
+#pragma unroll
+  for (int h = 0; h < kKB / 2; ++h) dst[h] = make_double2(v[2 * h], v[2 * h + 1]);
+}
+
+inline int symv_rows_per_warp(int k) { return ((k + kColsWarps - 1) / kColsWarps + kColsQRows - 1) / kColsQRows * kColsQRows; }
+inline int symv_k_pad(int k) { return symv_rows_per_warp(k) * kColsWarps; }
+
 template <bool VEC>
 __global__ void __launch_bounds__(32 * kColsWarps, kColsCtasPerSm) symv_cols_i32_kernel(const int32_t* __restrict__ G, int64_t ld, int64_t strideG,
-                                                                         const double* __restrict__ Q, int64_t strideQ,
-                                                                         double* __restrict__ AQ, int k) {
-  extern __shared__ __align__(16) double s_x[];  // [kColsChunk][kKB]
+                                                                                     const double* __restrict__ Qt, int64_t strideQt,
+                                                                                     double* __restrict__ AQ, int64_t strideQ, int k,
+                                                                                     int rows_per_warp) {
+  extern __shared__ __align__(16) double s_x[];  // [kColsWarps][2][kColsQRows][kKB]
   const int bt = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.x * kColsPerCta + kColsPerLane * lane;
   const int32_t* Gb = G + (int64_t)bt * strideG;
-  const double* Qb = Q + (int64_t)bt * strideQ;
-  constexpr int kRowsPerWarp = kColsChunk / kColsWarps;  // 64
+  const double* Qtb = Qt + (int64_t)bt * strideQt;
+  double* xs = s_x + (size_t)warp * 2 * kColsQRows * kKB;
   constexpr int kUnroll = 8;
   double acc[kColsPerLane][kKB];
 #pragma unroll
   for (int e = 0; e < kColsPerLane; ++e)
 #pragma unroll
     for (int c = 0; c < kKB; ++c) acc[e][c] = 0.0;
-  for (int i0 = blockIdx.z * kColsChunk; i0 < k; i0 += gridDim.z * kColsChunk) {
-    const int len = min(kColsChunk, k - i0);
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < kKB * kColsChunk; idx += 32 * kColsWarps) {
-      const int c = idx / kColsChunk, i = idx - c * kColsChunk;
-      s_x[i * kKB + c] = (i < len) ? Qb[(int64_t)c * k + i0 + i] : 0.0;
+  const int row_begin = warp * rows_per_warp;
+  const int row_end = min(k, row_begin + rows_per_warp);
+  auto fetch_q = [&](int chunk, int buf) {  // rows [row_begin + 64 chunk, + 64) of Q^T: 4 KB contiguous (Q^T is zero-padded to k_pad)
+    const double* src = Qtb + (int64_t)(row_begin + chunk * kColsQRows) * kKB;
+    double* dst = xs + buf * kColsQRows * kKB;
+#pragma unroll
+    for (int i = 0; i < kColsQRows * kKB / 64; ++i) cp_async16(dst + (i * 32 + lane) * 2, src + (i * 32 + lane) * 2);
+    cp_async_commit();
+  };
+  auto load_batch = [&](int2 (&g)[kUnroll], int r) {
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int32_t* p = Gb + (int64_t)(r + u) * ld + col0;
+      if (r + u >= row_end || col0 >= k) g[u] = make_int2(0, 0);
+      else if (VEC) g[u] = __ldg(reinterpret_cast<const int2*>(p));
+      else g[u] = make_int2(__ldg(p), (col0 + 1 < k) ? __ldg(p + 1) : 0);
     }
-    __syncthreads();
-    // software pipeline: the loads of the NEXT batch of rows are in flight while this batch is multiplied (ncu on the
-    // un-pipelined form: 46 % of all stall samples were long-scoreboard waits on these loads, DRAM 28 % busy)
-    const int rbeg = warp * kRowsPerWarp;
-    const int rend = min(rbeg + kRowsPerWarp, len);
-    auto load_batch = [&](int2 (&g)[kUnroll], int r) {
+  };
+  auto mul_batch = [&](const int2 (&g)[kUnroll], const double* xrows) {
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int32_t* p = Gb + (int64_t)(i0 + r + u) * ld + col0;
-        if (r + u >= len || col0 >= k) g[u] = make_int2(0, 0);
-        else if (VEC) g[u] = __ldg(reinterpret_cast<const int2*>(p));
-        else g[u] = make_int2(__ldg(p), (col0 + 1 < k) ? __ldg(p + 1) : 0);
-      }
-    };
-    auto mul_batch = [&](const int2 (&g)[kUnroll], int r) {
+    for (int u = 0; u < kUnroll; ++u) {
+      const double gd0 = u31_to_double(g[u].x), gd1 = u31_to_double(g[u].y);
+      const double2* xr = reinterpret_cast<const double2*>(xrows + u * kKB);
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const double gd0 = u31_to_double(g[u].x), gd1 = u31_to_double(g[u].y);
-        const double2* xr = reinterpret_cast<const double2*>(s_x + (r + u) * kKB);  // rows beyond len hold zeros
-#pragma unroll
-        for (int h = 0; h < kKB / 2; ++h) {
-          const double2 x = xr[h];  // same address in every lane: broadcast
-          acc[0][2 * h] = fma(gd0, x.x, acc[0][2 * h]);         acc[0][2 * h + 1] = fma(gd0, x.y, acc[0][2 * h + 1]);
-          acc[1][2 * h] = fma(gd1, x.x, acc[1][2 * h]);         acc[1][2 * h + 1] = fma(gd1, x.y, acc[1][2 * h + 1]);
-        }
+      for (int h = 0; h < kKB / 2; ++h) {
+        const double2 x = xr[h];  // same address in every lane: broadcast
+        acc[0][2 * h] = fma(gd0, x.x, acc[0][2 * h]);         acc[0][2 * h + 1] = fma(gd0, x.y, acc[0][2 * h + 1]);
+        acc[1][2 * h] = fma(gd1, x.x, acc[1][2 * h]);         acc[1][2 * h + 1] = fma(gd1, x.y, acc[1][2 * h + 1]);
       }
-    };
-    if (rbeg < rend) {
-      int2 ga[kUnroll], gb[kUnroll];
-      load_batch(ga, rbeg);
-      for (int r = rbeg; r < rend; r += 2 * kUnroll) {
-        if (r + kUnroll < rend) load_batch(gb, r + kUnroll);
-        mul_batch(ga, r);
-        if (r + kUnroll < rend) {
-          if (r + 2 * kUnroll < rend) load_batch(ga, r + 2 * kUnroll);
-          mul_batch(gb, r + kUnroll);
-        }
+    }
+  };
+  if (row_begin < row_end) {
+    const int nchunks = (row_end - row_begin + kColsQRows - 1) / kColsQRows;
+    int2 ga[kUnroll], gb[kUnroll];
+    fetch_q(0, 0);
+    load_batch(ga, row_begin);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      if (ch + 1 < nchunks) { fetch_q(ch + 1, (ch + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+      __syncwarp();
+      const double* xc = xs + (ch & 1) * kColsQRows * kKB;
+      const int r0 = row_begin + ch * kColsQRows;
+#pragma unroll 1
+      for (int b = 0; b < kColsQRows / kUnroll; b += 2) {  // batches of 8 rows, two per iteration (register double buffer)
+        load_batch(gb, r0 + (b + 1) * kUnroll);
+        mul_batch(ga, xc + b * kUnroll * kKB);
+        load_batch(ga, r0 + (b + 2) * kUnroll);            // first batch of the next chunk when b + 2 == 8: rows >= row_end load zeros
+        mul_batch(gb, xc + (b + 1) * kUnroll * kKB);
       }
+      __syncwarp();  // every lane is done with this buffer before the fetch of chunk ch + 2 overwrites it
     }
   }
-  // add the 16 warps' sums in warp order: tot[c][kColsPerCta columns]
+  // add the warps' sums in warp order: tot[c][kColsPerCta columns]
   __syncthreads();
   double* tot = s_x;
   for (int w = 0; w < kColsWarps; ++w) {
@@ -525,20 +558,11 @@ __global__ void __launch_bounds__(32 * kColsWarps, kColsCtasPerSm) symv_cols_i32
     }
     __syncthreads();
   }
-  double* out = AQ + (int64_t)bt * strideQ + (gridDim.z > 1 ? (int64_t)blockIdx.z * kKB * k : 0);
+  double* out = AQ + (int64_t)bt * strideQ;
   for (int idx = threadIdx.x; idx < kKB * kColsPerCta; idx += 32 * kColsWarps) {
     const int c = idx / kColsPerCta, j = blockIdx.x * kColsPerCta + (idx % kColsPerCta);
     if (j < k) out[(int64_t)c * k + j] = tot[idx];
   }
-}
-
-// AQ[i] = sum_z part[z][i] (z ascending), i < kKB * k
-__global__ void symv_reduce_parts_kernel(const double* __restrict__ part, int nparts, int64_t elems, double* __restrict__ AQ) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= elems) return;
-  double s = 0.0;
-  for (int z = 0; z < nparts; ++z) s += part[(int64_t)z * elems + i];
-  AQ[i] = s;
 }
 
 // AQ += C Q for the strip form of the correction (GramView).  Two deterministic passes, no atomics:
@@ -833,7 +857,7 @@ __global__ void krylov_finish_kernel(const double* __restrict__ theta, const dou
 thread_local int g_last_unconverged = 0;  // spb_score_last_unconverged()
 
 struct KrylovWs {
-  double *Q, *AQ, *C, *S, *U, *T, *Vtop, *theta, *res2, *info, *part, *idx, *diag;
+  double *Q, *AQ, *C, *S, *U, *T, *Vtop, *theta, *res2, *info, *part, *idx, *diag, *Qt;
   int64_t sQ, sC, sS, sT, part_elems;
 };
 
@@ -856,6 +880,7 @@ static int64_t krylov_layout(int64_t k, int64_t batch, double* base, KrylovWs* w
   w->info = take(batch * kInfo);
   w->idx = take(batch * kKB);  // int[8] per matrix (start rows), stored in double-sized slots
   w->diag = take(batch * k);   // diagonal of G (start-row choice, trace)
+  w->Qt = take(batch * (int64_t)symv_k_pad((int)k) * kKB);  // transposed, zero-padded copy of the block being multiplied (int32 route)
   // partial sums of the inner-product kernel: ceil(k / 128) chunks of the largest (96 x 96) product
   w->part_elems = batch * ((k + kDotChunk - 1) / kDotChunk) * (int64_t)kKDim * kKDim;
   w->part = take(w->part_elems);
@@ -948,10 +973,11 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
   }
   const size_t symv_smem = (size_t)kKB * kSymvChunk * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(symv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)symv_smem));
-  const size_t cols_smem = (size_t)kKB * kColsChunk * sizeof(double);
+  const size_t cols_smem = (size_t)kColsWarps * 2 * kColsQRows * kKB * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
   SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
   const bool cols_vec = gv.Gi && (ld % 2 == 0) && (k % 2 == 0) && (reinterpret_cast<uintptr_t>(gv.Gi) % 8 == 0);
+  const int rpw = symv_rows_per_warp(k), k_pad = symv_k_pad(k);
   for (int j = 0; j < nb; ++j) {
     double* Qj = w.Q + (int64_t)j * blk;
     double* AQj = w.AQ + (int64_t)j * blk;
@@ -959,9 +985,12 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
       dim3 grid((k + kSymvRows - 1) / kSymvRows, batch);
       if (gv.Gf) symv_block_kernel<<<grid, 256, symv_smem, st>>>(gv.Gf, ld, ld * ld, Qj, w.sQ, AQj, k);
       else {
+        dim3 tg((k_pad + 255) / 256, batch);
+        krylov_transpose_kernel<<<tg, 256, 0, st>>>(Qj, w.sQ, w.Qt, (int64_t)k_pad * kKB, k, k_pad);
+        SPB_LAUNCH_CHECK();
         dim3 gi((k + kColsPerCta - 1) / kColsPerCta, batch);
-        if (cols_vec) symv_cols_i32_kernel<true><<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
-        else symv_cols_i32_kernel<false><<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, Qj, w.sQ, AQj, k);
+        if (cols_vec) symv_cols_i32_kernel<true><<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, w.Qt, (int64_t)k_pad * kKB, AQj, w.sQ, k, rpw);
+        else symv_cols_i32_kernel<false><<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, w.Qt, (int64_t)k_pad * kKB, AQj, w.sQ, k, rpw);
       }
       SPB_LAUNCH_CHECK();
       if (!gv.Gf && gv.cs_rows) {
@@ -1047,185 +1076,12 @@ static int score_gram_large(const GramView& gv, int64_t k64, int64_t batch64, do
   return SPB_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// Streamed scoring of large count flattenings: Gram -> G S -> G (G S) per matrix while G0 sits in L2.
-//
-// The batched route above writes 64 int32 Gram matrices (4.3 GB) to HBM and streams each of them back twice, once per
-// block of the first Krylov cycle; the two products cost as much as the tensor-core Gram itself (ncu, round 1: 20.7 us
-// per 4096^2 product at 3.2 TB/s).  One 4096^2 int32 Gram is 67 MB and the L2 holds 126 MB, so here every matrix goes
-// through  Gram -> X1 = G S -> X2 = G X1  back to back into ONE reused G0 buffer: both products read G0 from L2, and
-// because the buffer is overwritten by the next Gram before most of it is evicted, G0 hardly reaches HBM at all.
-// To have no small kernels between the two products, the whole orthogonalisation of the 2-block Krylov cycle is
-// DEFERRED and applied afterwards, batched over all matrices, as 8 x 8 linear maps on (S, X1, X2):
-//     Q0 = U0 S,  G Q0 = U0 X1,  G^2 Q0-part = U0 X2          (SVQB twice)
-//     W  = G Q0 - C Q0,  G W = U0 X2 - C (G Q0)               (classical Gram-Schmidt twice, C = Q0 (G Q0)^T)
-//     Q1 = U1 W,  G Q1 = U1 (G W)                              (SVQB twice)
-// which spans the same subspace as the batched cycle (S = 4 heaviest rows of G + 4 pseudo-random vectors).  The price is
-// cancellation in G W when a split is (nearly) rank 4: the residual then stalls near 1e-8 and the matrix is reported as
-// unconverged; the caller re-scores those few through the batched route (measured on the config-2 alignment: only the
-// tree's true 6|6 split; its score from this route is still within 4e-12 of LAPACK).
-// ------------------------------------------------------------------------------------------
-static int stream_products(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int32_t* d_Gi,
-                           const GramView& strips, int k, const KrylovWs& w, double* h_timing, cudaStream_t st) {
-  const int64_t ld = rows_pad;
-  const int64_t blk = (int64_t)kKB * k;
-  const size_t cols_smem = (size_t)kKB * kColsChunk * sizeof(double);
-  SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
-  SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
-  const bool cols_vec = (ld % 2 == 0) && (k % 2 == 0) && (reinterpret_cast<uintptr_t>(d_Gi) % 8 == 0);
-  int zsplit = (k + kColsChunk - 1) / kColsChunk;
-  if (zsplit > 8) zsplit = 8;
-  // the split-row partial sums reuse the inner-product scratch (part): zsplit * 8 * k doubles
-  if ((int64_t)zsplit * blk > w.part_elems) zsplit = 1;
-  static thread_local std::vector<cudaEvent_t> evs;  // [3 per matrix]: gram begin, gram end, products end
-  if (h_timing) {
-    while ((int)evs.size() < 3 * nb) { cudaEvent_t e; SPB_CUDA(cudaEventCreate(&e)); evs.push_back(e); }
-  }
-  int rc;
-  for (int b = 0; b < nb; ++b) {
-    if (h_timing) SPB_CUDA(cudaEventRecord(evs[3 * b], st));
-    if ((rc = gram_u8_i32_launch(d_s0 + (size_t)b * s0_stride, s0_stride, 1, rows_pad, pitch, d_Gi, rows_pad * rows_pad, st))) return rc;
-    if (h_timing) SPB_CUDA(cudaEventRecord(evs[3 * b + 1], st));
-    GramView gv{nullptr, d_Gi, ld, strips.cs_rows ? strips.Cs + (int64_t)b * strips.cs_rows * ld : nullptr, strips.cs_rows,
-                strips.cs_rows ? strips.pos + (int64_t)b * ld : nullptr, strips.cs_rows ? strips.hr + (int64_t)b * strips.cs_rows : nullptr,
-                strips.cs_rows ? strips.hm + b : nullptr};
-    double* Qb = w.Q + (int64_t)b * w.sQ;    // block 0 = S, block 1 = W (filled later)
-    double* AQb = w.AQ + (int64_t)b * w.sQ;  // block 0 = X1 = G S, block 1 = X2 = G X1
-    double* diag = w.diag + (int64_t)b * k;
-    int* idx = reinterpret_cast<int*>(w.idx) + (int64_t)b * kKB;
-    dim3 g1((k + 255) / 256, 1);
-    gram_diag_kernel<<<g1, 256, 0, st>>>(gv, k, diag);
-    SPB_LAUNCH_CHECK();
-    krylov_top8_kernel<<<1, 256, 0, st>>>(diag, k, idx);
-    SPB_LAUNCH_CHECK();
-    krylov_start_rows_kernel<<<g1, 256, 0, st>>>(gv, idx, Qb, w.sQ, k);
-    SPB_LAUNCH_CHECK();
-    for (int prod = 0; prod < 2; ++prod) {
-      const double* src = prod == 0 ? Qb : AQb;
-      double* dst = prod == 0 ? AQb : AQb + blk;
-      dim3 gi((k + kColsPerCta - 1) / kColsPerCta, 1, zsplit);
-      if (cols_vec) symv_cols_i32_kernel<true><<<gi, 32 * kColsWarps, cols_smem, st>>>(d_Gi, ld, ld * ld, src, w.sQ, zsplit > 1 ? w.part : dst, k);
-      else symv_cols_i32_kernel<false><<<gi, 32 * kColsWarps, cols_smem, st>>>(d_Gi, ld, ld * ld, src, w.sQ, zsplit > 1 ? w.part : dst, k);
-      SPB_LAUNCH_CHECK();
-      if (zsplit > 1) {
-        symv_reduce_parts_kernel<<<(unsigned)((blk + 255) / 256), 256, 0, st>>>(w.part, zsplit, blk, dst);
-        SPB_LAUNCH_CHECK();
-      }
-      if (gv.cs_rows) {
-        dim3 rg((unsigned)((gv.cs_rows + kStripRowsPerCta - 1) / kStripRowsPerCta), 1);
-        strip_rows_kernel<<<rg, 256, 0, st>>>(gv, src, w.sQ, dst, k);
-        SPB_LAUNCH_CHECK();
-        dim3 cg((k + 255) / 256, 1);
-        strip_cols_kernel<<<cg, 256, 0, st>>>(gv, src, w.sQ, dst, k);
-        SPB_LAUNCH_CHECK();
-      }
-    }
-    if (h_timing) SPB_CUDA(cudaEventRecord(evs[3 * b + 2], st));
-  }
-  if (h_timing) {
-    SPB_CUDA(cudaStreamSynchronize(st));
-    double gram_ms = 0.0, prod_ms = 0.0;
-    for (int b = 0; b < nb; ++b) {
-      float a = 0.f, c = 0.f;
-      SPB_CUDA(cudaEventElapsedTime(&a, evs[3 * b], evs[3 * b + 1]));
-      SPB_CUDA(cudaEventElapsedTime(&c, evs[3 * b + 1], evs[3 * b + 2]));
-      gram_ms += a; prod_ms += c;
-    }
-    h_timing[0] = gram_ms; h_timing[1] = prod_ms;
-  }
-  return SPB_OK;
-}
-
-// deferred orthogonalisation + Rayleigh-Ritz of the 2-block cycle, batched over all matrices (see the header above)
-static int stream_rayleigh_ritz(int k, int batch, const KrylovWs& w, double* d_scores, cudaStream_t st) {
-  const int64_t blk = (int64_t)kKB * k;
-  int rc;
-  dim3 gk((k + 255) / 256, batch);
-  auto svqb_pass = [&](double* W, double* F1, double* F2) -> int {  // W <- U W with U from W W^T; the followers get the same U
-    if ((rc = dot_product(W, w.sQ, W, w.sQ, kKB, kKB, k, batch, w.S, kKB, w.sS, w.part, st))) return rc;
-    krylov_svqb_factor_kernel<<<batch, 64, 0, st>>>(w.S, w.sS, w.U);
-    SPB_LAUNCH_CHECK();
-    double* targets[3] = {W, F1, F2};
-    for (double* t : targets) {
-      if (!t) continue;
-      krylov_svqb_apply_kernel<<<gk, 256, 0, st>>>(t, w.sQ, w.U, k);
-      SPB_LAUNCH_CHECK();
-    }
-    return SPB_OK;
-  };
-  double* Q0 = w.Q;          // S -> Q0
-  double* X1 = w.AQ;         // G S -> G Q0
-  double* X2 = w.AQ + blk;   // G X1 -> G W -> G Q1
-  double* W = w.Q + blk;     // Q1
-  for (int pass = 0; pass < 2; ++pass)
-    if ((rc = svqb_pass(Q0, X1, X2))) return rc;
-  {
-    dim3 grid((unsigned)((blk + 255) / 256), batch);
-    copy_block_kernel<<<grid, 256, 0, st>>>(X1, w.sQ, W, w.sQ, blk);
-    SPB_LAUNCH_CHECK();
-  }
-  for (int pass = 0; pass < 2; ++pass) {
-    if ((rc = dot_product(Q0, w.sQ, W, w.sQ, kKB, kKB, k, batch, w.C, kKB, w.sC, w.part, st))) return rc;
-    krylov_subtract_kernel<<<gk, 256, 0, st>>>(W, w.sQ, Q0, w.sQ, w.C, w.sC, kKB, k);
-    SPB_LAUNCH_CHECK();
-    krylov_subtract_kernel<<<gk, 256, 0, st>>>(X2, w.sQ, X1, w.sQ, w.C, w.sC, kKB, k);
-    SPB_LAUNCH_CHECK();
-  }
-  for (int pass = 0; pass < 2; ++pass)
-    if ((rc = svqb_pass(W, X2, nullptr))) return rc;
-  const int dim = 2 * kKB;
-  if ((rc = dot_product(w.Q, w.sQ, w.AQ, w.sQ, dim, dim, k, batch, w.T, kKDim, w.sT, w.part, st))) return rc;
-  size_t smem = (size_t)2 * dim * (dim | 1) * sizeof(double);
-  SPB_CUDA(cudaFuncSetAttribute(krylov_rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  krylov_rr_kernel<<<batch, 256, smem, st>>>(w.T, w.sT, dim, w.diag, k, w.Vtop, w.theta, w.res2, w.info);
-  SPB_LAUNCH_CHECK();
-  krylov_ritz_kernel<<<gk, 256, 0, st>>>(w.Q, w.AQ, w.sQ, w.Vtop, w.theta, w.res2, dim, k);
-  SPB_LAUNCH_CHECK();
-  krylov_finish_kernel<<<(batch + 127) / 128, 128, 0, st>>>(w.theta, w.res2, w.info, d_scores, batch);
-  SPB_LAUNCH_CHECK();
-  return SPB_OK;
-}
-
 extern "C" int spb_score_last_unconverged(void) { return g_last_unconverged; }
 
 extern "C" int spb_score_gram_large(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores, double* d_info,
                                     double* d_ws, void* stream) {
   GramView gv{d_G, nullptr, ld, nullptr, 0, nullptr, nullptr, nullptr};
   return score_gram_large(gv, k, batch, d_scores, d_info, d_ws, stream);
-}
-
-extern "C" int spb_score_u8_stream(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int64_t k,
-                                   int32_t* d_Gi, const double* d_Cs, int64_t cs_rows, const int32_t* d_pos, const int32_t* d_hr,
-                                   const int32_t* d_hm, double* d_scores, double* d_info, double* d_ws, double* h_timing,
-                                   void* stream) {
-  SPB_REQUIRE(d_s0 && d_Gi && d_scores && d_ws && nb >= 1 && nb <= 65535 && k > kJacobiMaxK && k <= rows_pad && k < (1 << 24),
-              "spb_score_u8_stream: bad arguments (need k > %d)", kJacobiMaxK);
-  SPB_REQUIRE(cs_rows >= 0 && cs_rows <= 65535 && (cs_rows == 0 || (d_Cs && d_pos && d_hr && d_hm)), "spb_score_u8_stream: bad correction strip");
-  cudaStream_t st = (cudaStream_t)stream;
-  KrylovWs w;
-  krylov_layout(k, nb, d_ws, &w);
-  SPB_CUDA(cudaMemsetAsync(w.info, 0, (size_t)nb * kInfo * sizeof(double), st));
-  GramView strips{nullptr, nullptr, rows_pad, d_Cs, cs_rows, d_pos, d_hr, d_hm};
-  int rc;
-  if ((rc = stream_products(d_s0, s0_stride, nb, rows_pad, pitch, d_Gi, strips, (int)k, w, h_timing, st))) return rc;
-  if ((rc = stream_rayleigh_ritz((int)k, nb, w, d_scores, st))) return rc;
-  static thread_local std::vector<double> h_info;
-  static thread_local std::vector<double> h_flag;
-  h_info.resize((size_t)nb * kInfo);
-  h_flag.assign((size_t)nb, 0.0);
-  SPB_CUDA(cudaMemcpyAsync(h_info.data(), w.info, (size_t)nb * kInfo * sizeof(double), cudaMemcpyDeviceToHost, st));
-  SPB_CUDA(cudaStreamSynchronize(st));
-  int bad = 0;
-  for (int b = 0; b < nb; ++b) {
-    const bool ok = accept_matrix(h_info.data() + (size_t)b * kInfo, 0);
-    h_flag[b] = ok ? 1.0 : 0.0;
-    bad += ok ? 0 : 1;
-  }
-  SPB_CUDA(cudaMemcpy2DAsync(w.info + 8, kInfo * sizeof(double), h_flag.data(), sizeof(double), sizeof(double), (size_t)nb,
-                             cudaMemcpyHostToDevice, st));
-  g_last_unconverged = bad;
-  if (d_info) SPB_CUDA(cudaMemcpyAsync(d_info, w.info, (size_t)nb * kInfo * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  return SPB_OK;
 }
 
 extern "C" int spb_score_gram_large_i32(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Cs,

@@ -515,14 +515,9 @@ class CountScorer:
         self._s0 = {}
         self._G = {}
         self._Gi = {}
-        self._Gs = {}
         self._ws = {}
         self._batch_bytes = None
         self.int32_gram = True  # large dense splits keep G as int32 + correction strip (half the eigen-stage traffic)
-        # Optional streamed route (Gram -> products per matrix while G0 is in L2, spb_score_u8_stream): measured SLOWER than the
-        # batched route on B200 ("experiments"): the per-matrix launches expose the latency of the small strip /
-        # start-block kernels and leave the last wave of every Gram half empty.  SPB_STREAM_LARGE=1 enables it.
-        self.stream_large = os.environ.get("SPB_STREAM_LARGE", "0") == "1"
         self.gram_hook = None  # optional wrapper (fn, nb) around the Gram launch
         self.timer = None      # optional PhaseTimer: scatter / gram / correction / eigen spans (bench.py phase_ms)
 
@@ -586,51 +581,6 @@ class CountScorer:
                 "hm": _empty(batch, torch.int32),
             }
         return b
-
-    def _buffers_stream(self, rows_pad, batch):
-        """ONE reused int32 Gram + the correction strips of `batch` matrices (the streamed route, spb_score_u8_stream)."""
-        cs_rows = max(self.n_hi, 1)
-        b = self._Gs.get(rows_pad)
-        if b is None or b["Cs"].shape[0] < batch or b["Cs"].shape[1] < cs_rows:
-            b = self._Gs[rows_pad] = {
-                "G": _empty((rows_pad, rows_pad), torch.int32),
-                "Cs": _empty((batch, cs_rows, rows_pad), torch.float64),
-                "pos": _empty((batch, rows_pad), torch.int32),
-                "hr": _empty((batch, cs_rows), torch.int32),
-                "hm": _empty(batch, torch.int32),
-            }
-        return b
-
-    def _score_stream(self, splits, s0, buf, layout, rows_pad, pitch, k):
-        """nb <= GNB large dense splits through the streamed route.  Returns (scores [nb], converged bool [nb] or None)."""
-        nb = len(splits)
-        arr = splits if isinstance(splits, C.Array) else (_lib.SpbSplit * nb)(*splits)
-        s0_stride = rows_pad * pitch
-        cs_rows = int(buf["Cs"].shape[1])
-        scores = _empty(nb, torch.float64)
-        info = _empty((nb, SCORE_INFO), torch.float64)
-        ws = _krylov_ws(k, nb)
-        t = self.timer
-        timing = (C.c_double * 2)() if t is not None else None
-        try:
-            with _span(t, "scatter", nb):
-                self._scatter(arr, nb, s0, layout, rows_pad, pitch)
-            with _span(t, "correction", nb):
-                call("spb_gram_hi_strip_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
-                     _p(self.hi_num), self.hi_cap, _p(buf["Cs"]), cs_rows, _p(buf["pos"]), _p(buf["hr"]), _p(buf["hm"]), _st())
-            with _span(t, "gram+eigen_stream", nb):
-                call("spb_score_u8_stream", _p(s0), s0_stride, nb, rows_pad, pitch, k, _p(buf["G"]), _p(buf["Cs"]), cs_rows,
-                     _p(buf["pos"]), _p(buf["hr"]), _p(buf["hm"]), _p(scores), _p(info), _p(ws), timing, _st())
-            if timing is not None:
-                t.add("gram_large", timing[0], nb)
-                t.add("products_stream", timing[1], nb)
-            with _span(t, "scatter", 0):
-                self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
-        except BaseException:
-            self._drop_s0()
-            raise
-        bad = int(lib.spb_score_last_unconverged())
-        return scores, (info[:, 8] > 0.5) if bad else None
 
     def _scatter(self, arr, nb, s0, layout, rows_pad, pitch, clear=False):
         """Scatter (or un-scatter) nb <= GNB splits into s0[0:nb], SPB_MAX_BATCH splits per launch."""
@@ -797,11 +747,6 @@ class CountScorer:
             per_matrix = rows_pad * rows_pad * 8 if not i32 else rows_pad * rows_pad * 4 + max(self.n_hi, 1) * rows_pad * 8
             B = int(max(1, min(len(members), max_batch, max_batch_bytes // per_matrix)))
             B = -(-len(members) // -(-len(members) // B))  # equal chunks: no small tail batch through the eigen-solver
-            stream = i32 and self.stream_large
-            if stream:
-                s0 = self._buffers(layout, rows_pad, pitch, 1)[0]
-                self._score_many_stream(members, rec, s0, layout, rows_pad, pitch, R, out)
-                continue
             if i32:
                 s0 = self._buffers(layout, rows_pad, pitch, 1)[0]
                 buf = self._buffers_i32(rows_pad, B)
@@ -826,36 +771,6 @@ class CountScorer:
                     out.index_copy_(0, torch.tensor(chunk, dtype=torch.int64, device=out.device), sc)
             self.gram_hook = None
         return out
-
-    def _score_many_stream(self, members, rec, s0, layout, rows_pad, pitch, R, out):
-        """The 4^a >= 2048 classes: streamed route, GNB matrices per call; matrices that fail its single-cycle acceptance test
-        (nearly rank-4 flattenings: the true splits) are collected and re-scored through the batched int32 route."""
-        gnb = self._gnb(rows_pad, pitch)
-        sbuf = self._buffers_stream(rows_pad, min(gnb, len(members)))
-        redo = []
-        dev = out.device
-        for c0 in range(0, len(members), gnb):
-            chunk = members[c0:c0 + gnb]
-            plans = (_lib.SpbSplit * len(chunk)).from_buffer(rec, c0 * rec.itemsize)
-            sc, conv = self._score_stream(plans, s0, sbuf, layout, rows_pad, pitch, R)
-            if chunk == list(range(chunk[0], chunk[0] + len(chunk))):
-                out[chunk[0]:chunk[0] + len(chunk)] = sc
-            else:
-                out.index_copy_(0, torch.tensor(chunk, dtype=torch.int64, device=dev), sc)
-            if conv is not None:
-                redo += [(c0 + j) for j in torch.nonzero(~conv).flatten().tolist()]
-        if not redo:
-            return
-        buf = self._buffers_i32(rows_pad, min(len(redo), gnb))
-        for r0 in range(0, len(redo), gnb):
-            part = redo[r0:r0 + gnb]
-            plans = (_lib.SpbSplit * len(part))()
-            for j, m in enumerate(part):
-                C.memmove(C.byref(plans, j * C.sizeof(_lib.SpbSplit)), rec[m:m + 1].ctypes.data, C.sizeof(_lib.SpbSplit))
-            self._gram_batch_i32(plans, s0, buf, 0, layout, rows_pad, pitch)
-            with _span(self.timer, "eigen", len(part)):
-                sc = self._score_i32(buf, len(part), R)
-            out.index_copy_(0, torch.tensor([members[m] for m in part], dtype=torch.int64, device=dev), sc)
 
     def check_hi(self):
         """Kept for API stability: the capacity is guaranteed by construction (see the `table` setter)."""

@@ -195,6 +195,22 @@ def erickson_SVD(alignment, taxa=None, method=Method.flattening, show_work=False
             return [np.float64(v) for v in vals.cpu().numpy()]
         return [np.inf] * len(splits)  # the reference leaves the score at infinity for the other methods
 
+    def score_canonical(splits):
+        """Both orientations of one bipartition ((A, B) and (B, A)) get the SAME float: the score is orientation-free
+        mathematically (transposed matrix), but computed twice it differs in the last bits (order of the atomic sums), and
+        erickson's `min` over candidates that contain both orientations would then be decided by that noise -- the
+        reference's own LAPACK results for F and F^T coincide exactly on its golden runs (best == runner-up in its
+        show_work trace), where `min` keeps the first candidate.  Scoring each bipartition once reproduces that."""
+        canon = [s if s[0] <= s[1] else (s[1], s[0]) for s in splits]
+        todo = []
+        for c in canon:
+            if c not in canonical_scores and c not in todo:
+                todo.append(c)
+        if todo:
+            canonical_scores.update(zip(todo, score_new(todo)))
+        return [canonical_scores[c] for c in canon]
+
+    canonical_scores = {}
     chosen = []
     while len(chosen) < num_taxa - 2:
         candidates = []
@@ -207,7 +223,7 @@ def erickson_SVD(alignment, taxa=None, method=Method.flattening, show_work=False
             if split not in known and split not in fresh:
                 fresh.append(split)
         if fresh:
-            known.update(zip(fresh, score_new(fresh)))
+            known.update(zip(fresh, score_canonical(fresh)))
         if show_work:
             print(f"Scores: { {pair: (pair, split, known[split]) for pair, split in candidates} }")
         best_pair, best_split = min(candidates, key=lambda c: known[c[1]])  # first minimum, like min() in the reference

@@ -144,24 +144,29 @@ def gram_from_triples(tabs, total, la, lb):
 
 def sturm_count_division_free(d, e2, k, x):
     """Number of eigenvalues of the symmetric tridiagonal (d, e) below x from the determinant recurrence
-    p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}: one sign change per eigenvalue below x.  No division; the pair
-    (p_i, p_{i-1}) is rescaled by a power of two when it leaves [2^-300, 2^300]."""
-    big, small = 2.0 ** 300, 2.0 ** -300
+    p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}: one sign change per eigenvalue below x.  No division.  (d, e2) are
+    scaled so that |d_i - x| <= 2 and e2 <= 1 (no overflow for k <= 64); every 4 steps the pair (p_i, p_{i-1}) is
+    multiplied by the power of two that brings the larger one back to [1, 2), as the kernel does with exponent
+    arithmetic.  An exact zero counts as positive."""
+    import math
     pm, p = 1.0, d[0] - x
-    cnt = int(p < 0.0)
-    neg = p < 0.0
-    for i in range(1, k):
+    cnt = int(math.copysign(1.0, p) < 0)
+    i = 1
+    while i + 3 < k:
+        for u in range(4):
+            pn = (d[i + u] - x) * p - e2[i + u - 1] * pm
+            cnt += int((math.copysign(1.0, pn) < 0) != (math.copysign(1.0, p) < 0))
+            pm, p = p, pn
+        big = max(abs(p), abs(pm))
+        if big > 0.0 and big >= 2.2250738585072014e-308:
+            sc = 2.0 ** (-math.frexp(big)[1] + 1)
+            p, pm = p * sc, pm * sc
+        i += 4
+    while i < k:
         pn = (d[i] - x) * p - e2[i - 1] * pm
-        if pn == 0.0:
-            pn = -1.0e-300 if not neg else 1.0e-300  # a zero counts as a sign change, like the pivot form's -1e-300
+        cnt += int((math.copysign(1.0, pn) < 0) != (math.copysign(1.0, p) < 0))
         pm, p = p, pn
-        if abs(p) > big:
-            p, pm = p * small, pm * small
-        elif abs(p) < small and abs(pm) < small:
-            p, pm = p * big, pm * big
-        nneg = p < 0.0
-        cnt += int(nneg != neg)
-        neg = nneg
+        i += 1
     return cnt
 
 
@@ -196,23 +201,26 @@ def score_warp2_model(G):
     for i in range(k):
         d[i] = G[i, i]
     e[k - 2] = G[k - 1, k - 2]
-    e2 = e * e
     off = lambda i: abs(e[i]) if 0 <= i < k - 1 else 0.0  # noqa: E731
     lo = min(d[i] - off(i) - off(i - 1) for i in range(k))
     hi = max(d[i] + off(i) + off(i - 1) for i in range(k))
+    nrm = max(abs(lo), abs(hi))
+    inv = 1.0 / nrm if nrm > 0.0 else 1.0
+    ds = d * inv
+    e2 = (e * inv) * (e * inv)
     lams = []
     for grp in range(4):
         want = k - 1 - grp
-        glo, ghi = lo, hi
+        glo, ghi = lo * inv, hi * inv
         for _ in range(18):
             w = (ghi - glo) / 9.0
             t = 0
             for mm in range(8):
-                t += int(sturm_count_division_free(d, e2, k, glo + w * (mm + 1)) <= want)
+                t += int(sturm_count_division_free(ds, e2, k, glo + w * (mm + 1)) <= want)
             nlo = glo + w * t
             if t < 8:
                 ghi = glo + w * (t + 1)
             glo = nlo
-        lams.append(0.5 * (glo + ghi))
+        lams.append(0.5 * (glo * nrm + ghi * nrm))
     top = ((max(lams[0], 0.0) + max(lams[1], 0.0)) + max(lams[2], 0.0)) + max(lams[3], 0.0)
     return (float(np.sqrt(max(trace - top, 0.0) / trace)) if trace > 0 else float("nan")), lams
