@@ -560,13 +560,14 @@ class CountScorer:
             self._ws[key] = _empty(self._gnb(rows_pad, pitch) * rows_pad * rows_pad, torch.int64) if n else None
         return self._s0[key], g, self._ws[key]
 
+    I32_MIN_ROWS = int(os.environ.get("SPB_I32_MIN_ROWS", "1024"))  # 1024: the 5|7 class of 12 taxa as well (round 1: 2048)
     I32_MAX_HI = 4096  # strip rows: the correction strip costs n_hi * rows_pad * 8 bytes per matrix and O(n_hi^2) work
 
     def _use_i32(self, layout, rows_pad, pitch):
         """int32 Gram + correction strip only while the strip stays small (a table with many counts >= 256, e.g.
         12 taxa from 10^8 sites, goes through the fp64 Gram, which has no such limit)."""
-        return (self.int32_gram and layout == SPB_S0_TILED and rows_pad >= 2048 and rows_pad % 256 == 0 and pitch <= 32768
-                and self.n_hi <= self.I32_MAX_HI)
+        return (self.int32_gram and layout == SPB_S0_TILED and rows_pad >= self.I32_MIN_ROWS and rows_pad % 256 == 0
+                and pitch <= 32768 and self.n_hi <= self.I32_MAX_HI)
 
     def _buffers_i32(self, rows_pad, batch):
         """int32 Gram batch + correction strip (rows sized by the number of high counts of the table)."""
