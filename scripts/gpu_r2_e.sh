@@ -11,3 +11,5 @@ python scripts/ncu_step.py --per-size 8 > gpurun_out/r2e_ncu_plain_small.log 2>&
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"gram_u8_umma2|symv_cols" -c 6 -f -o gpurun_out/r2e_prof_c2 python scripts/ncu_step.py --per-size 8 > gpurun_out/r2e_ncu_full.log 2>&1; echo "ncu c2 rc=$?"
 python scripts/ncu_step.py --workload c3 --sites 1000000 > gpurun_out/r2e_ncu_plain_c3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"subflatten_score" -c 1 -f -o gpurun_out/r2e_prof_c3 python scripts/ncu_step.py --workload c3 --sites 1000000 > gpurun_out/r2e_ncu_c3.log 2>&1; echo "ncu c3 rc=$?"
+for kern in class cache; do SPB_COUNT_KERNEL=$kern python scripts/ncu_count.py > gpurun_out/r2e_count_plain_$kern.log 2>&1 && \
+SPB_COUNT_KERNEL=$kern ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"count_" -c 1 -f -o gpurun_out/r2e_prof_count_$kern python scripts/ncu_count.py > gpurun_out/r2e_ncu_count_$kern.log 2>&1; echo "ncu count($kern) rc=$?"; cat gpurun_out/r2e_count_plain_$kern.log; done
