@@ -17,6 +17,7 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import os
+import threading
 import warnings
 
 import numpy as np
@@ -443,10 +444,12 @@ _KRYLOV_WS = {}
 
 
 def _krylov_ws(k, batch):
+    """Workspace of the block-Krylov solver, one per CUDA stream (size classes scored concurrently must not share it)."""
     need = int(lib.spb_score_gram_large_ws(k, batch))
-    ws = _KRYLOV_WS.get("ws")
+    key = int(torch.cuda.current_stream().cuda_stream)
+    ws = _KRYLOV_WS.get(key)
     if ws is None or ws.numel() < need or ws.device != device():
-        ws = _KRYLOV_WS["ws"] = _empty(need, torch.float64)
+        ws = _KRYLOV_WS[key] = _empty(need, torch.float64)
     return ws
 
 
@@ -509,8 +512,13 @@ class CountScorer:
             raise ValueError("CountScorer needs a PatternTable with integer counts")
         self._table = None
         self.hi_cap = int(hi_cap) if hi_cap is not None else 0
-        self.hi_rc = self.hi_val = None
-        self.hi_num = _zeros(self.GNB, torch.int32)
+        # Size classes are scored on up to NSTREAMS CUDA streams at once (one host thread per stream): while one class sits in
+        # the latency-bound small kernels of its eigen-solver, the Gram / G Q kernels of another fill the SMs.  Buffers that a
+        # class writes per launch (the high-part triplets) exist once per stream slot.
+        self.nstreams = max(1, int(os.environ.get("SPB_SCORE_STREAMS", "2")))
+        self._tl = threading.local()
+        self._hi = {}
+        self._side = None
         self.table = table
         self._s0 = {}
         self._G = {}
@@ -531,10 +539,26 @@ class CountScorer:
         high-part buffers are sized once per table: no per-split overflow tracking is needed."""
         self._table = table
         self.n_hi = int((table.counts.to(torch.int64) & 0xFFFFFFFF).ge(256).sum().item()) if table.num else 0
-        if self.hi_rc is None or self.n_hi > self.hi_cap:
+        if not self._hi or self.n_hi > self.hi_cap:
             self.hi_cap = max(self.hi_cap, 1024, 2 * self.n_hi)
-            self.hi_rc = _empty((self.GNB, self.hi_cap, 2), torch.int32)
-            self.hi_val = _empty((self.GNB, self.hi_cap), torch.int32)
+            self._hi = {slot: (_empty((self.GNB, self.hi_cap, 2), torch.int32), _empty((self.GNB, self.hi_cap), torch.int32),
+                               _zeros(self.GNB, torch.int32)) for slot in range(self.nstreams)}
+
+    @property
+    def _slot(self):
+        return getattr(self._tl, "slot", 0)
+
+    @property
+    def hi_rc(self):
+        return self._hi[self._slot][0]
+
+    @property
+    def hi_val(self):
+        return self._hi[self._slot][1]
+
+    @property
+    def hi_num(self):
+        return self._hi[self._slot][2]
 
     @staticmethod
     def geometry(rows, cols):
@@ -724,54 +748,93 @@ class CountScorer:
         for s, (ia, ib) in enumerate(splits_idx):
             groups.setdefault(min(len(ia), len(ib)), []).append(s)
         n = self.table.n
-        everyone = np.arange(n)
-        for a, members in groups.items():
-            # encoded splits of the whole group in one numpy pass, short side first (= rows of the Gram side)
-            short, long_ = [], []
-            for s in members:
-                ia, ib = splits_idx[s]
-                if len(ia) > len(ib):
-                    ia, ib = ib, ia
-                short.append(ia)
-                long_.append(ib)
+        tasks = sorted(groups.items(), key=lambda g: -(4.0 ** (2 * g[0])) * 4.0 ** (n - g[0]) * len(g[1]))  # Gram work, descending
+        if self.nstreams == 1 or len(tasks) == 1:
+            for a, members in tasks:
+                self._score_group(splits_idx, a, members, out, max_batch, max_batch_bytes)
+            return out
+        # two host threads, two streams: greedy split of the classes by Gram work (largest class alone on the caller's stream)
+        load, mine, theirs = [0.0, 0.0], [], []
+        for a, members in tasks:
+            cost = (4.0 ** (2 * a)) * 4.0 ** (n - a) * len(members)
+            slot = 0 if load[0] <= load[1] else 1
+            load[slot] += cost
+            (mine if slot == 0 else theirs).append((a, members))
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=out.device)
+        side, dev_index, failure = self._side, out.device.index, []
+        side.wait_stream(main)  # the table and `out` were produced on the caller's stream
+
+        def worker():
             try:
-                both = np.concatenate([np.asarray(short, dtype=np.int64).reshape(len(members), -1),
-                                       np.asarray(long_, dtype=np.int64).reshape(len(members), -1)], axis=1)
-            except ValueError:
-                both = None
-            if both is None or both.shape[1] != n or not (np.sort(both, axis=1) == everyone).all():
-                raise ValueError("CountScorer: the split must cover all taxa")
-            _, rec = _lib.make_splits(n, short, long_)
-            R, Cc = 4 ** a, 4 ** (n - a)
-            layout, rows_pad, pitch = self.geometry(R, Cc)
-            i32 = self._use_i32(layout, rows_pad, pitch) and R > JACOBI_MAX_K
-            per_matrix = rows_pad * rows_pad * 8 if not i32 else rows_pad * rows_pad * 4 + max(self.n_hi, 1) * rows_pad * 8
-            B = int(max(1, min(len(members), max_batch, max_batch_bytes // per_matrix)))
-            B = -(-len(members) // -(-len(members) // B))  # equal chunks: no small tail batch through the eigen-solver
-            if i32:
-                s0 = self._buffers(layout, rows_pad, pitch, 1)[0]
-                buf = self._buffers_i32(rows_pad, B)
-            else:
-                s0, G, ws = self._buffers(layout, rows_pad, pitch, B)
-            self.gram_hook = big_hook if (big_hook is not None and R >= 4096) else None
-            for c0 in range(0, len(members), B):
-                chunk = members[c0:c0 + B]
-                gnb = self._gnb(rows_pad, pitch)
-                for b0 in range(0, len(chunk), gnb):
-                    nsub = min(gnb, len(chunk) - b0)
-                    plans = (_lib.SpbSplit * nsub).from_buffer(rec, (c0 + b0) * rec.itemsize)
-                    if i32:
-                        self._gram_batch_i32(plans, s0, buf, b0, layout, rows_pad, pitch)
-                    else:
-                        self._gram_batch(plans, s0, G[b0:b0 + nsub], ws, layout, rows_pad, pitch)
-                with _span(self.timer, "eigen", len(chunk)):
-                    sc = self._score_i32(buf, len(chunk), R) if i32 else score_gram(G[:len(chunk)], R)
-                if chunk == list(range(chunk[0], chunk[0] + len(chunk))):
-                    out[chunk[0]:chunk[0] + len(chunk)] = sc
-                else:
-                    out.index_copy_(0, torch.tensor(chunk, dtype=torch.int64, device=out.device), sc)
-            self.gram_hook = None
+                torch.cuda.set_device(dev_index)
+                self._tl.slot = 1
+                with torch.cuda.stream(side):
+                    for a, members in theirs:
+                        self._score_group(splits_idx, a, members, out, max_batch, max_batch_bytes)
+            except BaseException as exc:  # noqa: BLE001  (re-raised on the calling thread)
+                failure.append(exc)
+
+        th = threading.Thread(target=worker, name="splitp_b200-score-stream-1")
+        th.start()
+        try:
+            for a, members in mine:
+                self._score_group(splits_idx, a, members, out, max_batch, max_batch_bytes)
+        finally:
+            th.join()
+            main.wait_stream(side)
+        if failure:
+            raise failure[0]
         return out
+
+    def _score_group(self, splits_idx, a, members, out, max_batch, max_batch_bytes):
+        """All splits whose shorter side has `a` taxa (equal shapes): batched scatter / Gram / correction / eigen-solver."""
+        n = self.table.n
+        everyone = np.arange(n)
+        # encoded splits of the whole group in one numpy pass, short side first (= rows of the Gram side)
+        short, long_ = [], []
+        for s in members:
+            ia, ib = splits_idx[s]
+            if len(ia) > len(ib):
+                ia, ib = ib, ia
+            short.append(ia)
+            long_.append(ib)
+        try:
+            both = np.concatenate([np.asarray(short, dtype=np.int64).reshape(len(members), -1),
+                                   np.asarray(long_, dtype=np.int64).reshape(len(members), -1)], axis=1)
+        except ValueError:
+            both = None
+        if both is None or both.shape[1] != n or not (np.sort(both, axis=1) == everyone).all():
+            raise ValueError("CountScorer: the split must cover all taxa")
+        _, rec = _lib.make_splits(n, short, long_)
+        R, Cc = 4 ** a, 4 ** (n - a)
+        layout, rows_pad, pitch = self.geometry(R, Cc)
+        i32 = self._use_i32(layout, rows_pad, pitch) and R > JACOBI_MAX_K
+        per_matrix = rows_pad * rows_pad * 8 if not i32 else rows_pad * rows_pad * 4 + max(self.n_hi, 1) * rows_pad * 8
+        B = int(max(1, min(len(members), max_batch, max_batch_bytes // per_matrix)))
+        B = -(-len(members) // -(-len(members) // B))  # equal chunks: no small tail batch through the eigen-solver
+        if i32:
+            s0 = self._buffers(layout, rows_pad, pitch, 1)[0]
+            buf = self._buffers_i32(rows_pad, B)
+        else:
+            s0, G, ws = self._buffers(layout, rows_pad, pitch, B)
+        for c0 in range(0, len(members), B):
+            chunk = members[c0:c0 + B]
+            gnb = self._gnb(rows_pad, pitch)
+            for b0 in range(0, len(chunk), gnb):
+                nsub = min(gnb, len(chunk) - b0)
+                plans = (_lib.SpbSplit * nsub).from_buffer(rec, (c0 + b0) * rec.itemsize)
+                if i32:
+                    self._gram_batch_i32(plans, s0, buf, b0, layout, rows_pad, pitch)
+                else:
+                    self._gram_batch(plans, s0, G[b0:b0 + nsub], ws, layout, rows_pad, pitch)
+            with _span(self.timer, "eigen", len(chunk)):
+                sc = self._score_i32(buf, len(chunk), R) if i32 else score_gram(G[:len(chunk)], R)
+            if chunk == list(range(chunk[0], chunk[0] + len(chunk))):
+                out[chunk[0]:chunk[0] + len(chunk)] = sc
+            else:
+                out.index_copy_(0, torch.tensor(chunk, dtype=torch.int64, device=out.device), sc)
 
     def check_hi(self):
         """Kept for API stability: the capacity is guaranteed by construction (see the `table` setter)."""
