@@ -599,10 +599,11 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
     hbm = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"
     roof = None
-    if method == "flattening" and "gram_large" in phases:
-        ms_tot, launches_timed, mats = phases["gram_large"]
+    R = 4 ** (n // 2)
+    gram_key = f"gram_i32_r{R}"  # span of the int32 tensor-core Gram launches of the balanced splits (engine.CountScorer)
+    if method == "flattening" and gram_key in phases:
+        ms_tot, launches_timed, mats = phases[gram_key]
         ms = ms_tot / max(mats, 1)
-        R = 4 ** (n // 2)
         ops_alg = 2.0 * R ** 3                       # 2 R^2 C per balanced split (GEMM convention)
         blocks = R // 256
         exec_frac = (blocks * (blocks + 1) / 2) / (blocks * blocks)  # 256 x 256 blocks touching the upper triangle
@@ -628,6 +629,7 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
                 "ms_per_matrix": ms, "launches_timed": launches_timed, "matrices_timed": mats,
                 "matrices_per_launch": mats / max(launches_timed, 1),
                 "share_of_step": ms_tot / max(sum(step_ms), 1e-9),
+                "concurrent_streams": int(os.environ.get("SPB_SCORE_STREAMS", "2")),
                 "traffic": traffic, "traffic_note": traffic_note or "dram bytes per matrix from the ncu --set full capture: see profiles/"}
     elif method == "thin" and "count" in phases:
         ms = phases["count"][0] / max(phases["count"][1], 1)

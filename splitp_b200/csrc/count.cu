@@ -355,9 +355,8 @@ int launch_stream(const uint32_t* d_sm, const uint32_t* d_valid, int n, int64_t 
 // serialise in the L2 atomic units (measured: 3.4e10 RED/s).  Here
 //   * c = majority of the three low digits; x = key ^ c * 0x5555..: x == 0 is a constant pattern (registers, as before);
 //   * x with exactly one non-zero digit (position p, value y) is single-mutation class (c, p, y): it increments a
-//     LANE-PRIVATE 8-bit counter hist[class][lane] in shared memory -- plain load / add / store, no atomic, no
-//     cross-lane conflict; every 15 chunks (<= 240 increments per counter) the lanes fold the 32 byte-counters of each
-//     class with dp4a into a warp-private 32-bit total, and at the end of the kernel every warp issues one RED per class;
+//     WARP-PRIVATE 32-bit counter in shared memory (fire-and-forget atomic); at the end of the kernel every warp issues one
+//     RED per class;
 //   * only the remaining sites (29 %) issue a RED, spread over ~10^5 addresses.
 // ------------------------------------------------------------------------------------------
 template <int NT>
@@ -369,38 +368,18 @@ __global__ void __launch_bounds__(256) count_class_kernel(const uint32_t* __rest
   constexpr uint32_t ONES = 0x55555555u & MASK;
   constexpr int NCLS = 12 * NT;                 // (c, p, y): 4 x NT x 3
   constexpr int NCLS_PAD = (NCLS + 31) / 32 * 32;
-  constexpr int kFlushEvery = 15;               // 15 chunks x 16 sites = 240 < 256 increments per byte counter
-  extern __shared__ __align__(16) unsigned char cls_raw[];
+  // warp-private 32-bit class counters, updated with fire-and-forget shared-memory atomics.  (v1 kept lane-private byte
+  // counters updated by load / add / store: no atomics, but the 16 updates of a chunk formed one dependent chain through
+  // shared memory -- ncu: 56 % of the stall samples on the short scoreboard at 50 % occupancy, 1.12 ms per 10^8 sites.)
+  __shared__ uint32_t hist_all[8 * NCLS_PAD];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* hist = cls_raw + (size_t)warp * NCLS_PAD * 32;                                      // [NCLS_PAD][32 lanes] bytes
-  uint32_t* tot = reinterpret_cast<uint32_t*>(cls_raw + (size_t)8 * NCLS_PAD * 32) + warp * NCLS_PAD;  // [NCLS_PAD]
-  for (int i = lane; i < NCLS_PAD * 8; i += 32) reinterpret_cast<uint32_t*>(hist)[i] = 0u;
-  for (int i = lane; i < NCLS_PAD; i += 32) tot[i] = 0u;
+  uint32_t* hist = hist_all + warp * NCLS_PAD;
+  for (int i = lane; i < NCLS_PAD; i += 32) hist[i] = 0u;
   __syncwarp();
   uint32_t cst0 = 0, cst1 = 0, cst2 = 0, cst3 = 0, nus = 0;
-  int since_flush = 0;
-  auto flush = [&]() {
-    __syncwarp();
-    for (int cls = lane; cls < NCLS; cls += 32) {
-      uint32_t* row = reinterpret_cast<uint32_t*>(hist + (size_t)cls * 32);
-      uint32_t sum = 0;
-#pragma unroll
-      for (int wq = 0; wq < 8; ++wq) {
-        const int wi = (wq + lane) & 7;  // rotate: lanes of one instruction start on different words
-        sum = __dp4a(row[wi], 0x01010101u, sum);
-        row[wi] = 0u;
-      }
-      tot[cls] += sum;
-    }
-    __syncwarp();
-  };
   const int64_t stride = (int64_t)gridDim.x * 256;
-  // every warp runs the same number of iterations (the flush is warp-collective); out-of-range chunks are empty
-  const int64_t first = chunk_begin + (int64_t)blockIdx.x * 256 + warp * 32;
-  for (int64_t base = first; base < chunk_end; base += stride) {
-    const int64_t ch = base + lane;
+  auto load_chunk = [&](uint32_t (&w)[NT + 2], uint32_t& vb, int64_t ch) {
     if (ch < chunk_end) {
-      uint32_t w[NT + 2];
       const uint32_t* src = sm + ch * NT;
       if constexpr (NT % 4 == 0) {
 #pragma unroll
@@ -418,43 +397,53 @@ __global__ void __launch_bounds__(256) count_class_kernel(const uint32_t* __rest
 #pragma unroll
         for (int v = 0; v < NT; ++v) w[v] = __ldg(src + v);
       }
-      w[NT] = 0u; w[NT + 1] = 0u;
-      uint32_t vb = __ldg(valid16 + ch);
-      const int64_t s0 = ch * 16;
-      if (s0 < site_begin || s0 + 16 > site_end) {
+      vb = __ldg(valid16 + ch);
+    } else {
 #pragma unroll
-        for (int s = 0; s < 16; ++s)
-          if (s0 + s < site_begin || s0 + s >= site_end) vb &= ~(1u << s);
-      }
-      nus += __popc(vb);
-      uint32_t packed = 0u;
-#pragma unroll
-      for (int s = 0; s < 16; ++s) {
-        const int o = s * BITS, wi = o >> 5, sh = o & 31;
-        uint32_t key = (sh + BITS <= 32) ? (w[wi] >> sh) : __funnelshift_r(w[wi], w[wi + 1], sh);
-        key &= MASK;
-        const bool ok = (vb >> s) & 1u;
-        const uint32_t d0 = key & 3u, d1 = (key >> 2) & 3u, d2 = (key >> 4) & 3u;
-        const uint32_t c = (NT >= 3) ? ((d0 == d1) ? d0 : d2) : d0;
-        const uint32_t x = key ^ (c * ONES);
-        const int p2 = 31 - __clz(x | 1u) ;           // highest set bit: the mutated digit if there is exactly one
-        const int p = p2 >> 1;
-        const uint32_t y = x >> (2 * p);               // < 4 and no lower bits set <=> exactly one digit differs
-        const bool single = x != 0u && (x & ~(3u << (2 * p))) == 0u;
-        if (ok && x == 0u) packed += 1u << (8 * c);
-        if (ok && single) {
-          unsigned char* cell = hist + ((size_t)((c * NT + p) * 3 + (y - 1)) << 5) + lane;
-          *cell = (unsigned char)(*cell + 1);
-        }
-        if (ok && x != 0u && !single) atomicAdd(table + key, 1u);
-      }
-      cst0 += packed & 255u; cst1 += (packed >> 8) & 255u; cst2 += (packed >> 16) & 255u; cst3 += packed >> 24;
+      for (int v = 0; v < NT; ++v) w[v] = 0u;
+      vb = 0u;
     }
-    if (++since_flush == kFlushEvery) { flush(); since_flush = 0; }
+    w[NT] = 0u; w[NT + 1] = 0u;
+  };
+  uint32_t wa[NT + 2], wb[NT + 2];
+  uint32_t va, vbn;
+  int64_t ch = chunk_begin + (int64_t)blockIdx.x * 256 + threadIdx.x;
+  load_chunk(wa, va, ch);
+  for (; ch < chunk_end; ch += stride) {
+    load_chunk(wb, vbn, ch + stride);  // the next chunk is in flight while this one is classified
+    uint32_t vb = va;
+    const int64_t s0 = ch * 16;
+    if (s0 < site_begin || s0 + 16 > site_end) {
+#pragma unroll
+      for (int s = 0; s < 16; ++s)
+        if (s0 + s < site_begin || s0 + s >= site_end) vb &= ~(1u << s);
+    }
+    nus += __popc(vb);
+    uint32_t packed = 0u;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      const int o = s * BITS, wi = o >> 5, sh = o & 31;
+      uint32_t key = (sh + BITS <= 32) ? (wa[wi] >> sh) : __funnelshift_r(wa[wi], wa[wi + 1], sh);
+      key &= MASK;
+      const bool ok = (vb >> s) & 1u;
+      const uint32_t d0 = key & 3u, d1 = (key >> 2) & 3u, d2 = (key >> 4) & 3u;
+      const uint32_t c = (NT >= 3) ? ((d0 == d1) ? d0 : d2) : d0;
+      const uint32_t x = key ^ (c * ONES);
+      const int p = (31 - __clz(x | 1u)) >> 1;         // digit of the highest set bit: the mutated digit if there is exactly one
+      const uint32_t y = x >> (2 * p);
+      const bool single = x != 0u && (x & ~(3u << (2 * p))) == 0u;
+      if (ok && x == 0u) packed += 1u << (8 * c);
+      if (ok && single) atomicAdd(hist + (c * NT + p) * 3 + (y - 1), 1u);
+      if (ok && x != 0u && !single) atomicAdd(table + key, 1u);
+    }
+    cst0 += packed & 255u; cst1 += (packed >> 8) & 255u; cst2 += (packed >> 16) & 255u; cst3 += packed >> 24;
+#pragma unroll
+    for (int v = 0; v < NT + 2; ++v) wa[v] = wb[v];
+    va = vbn;
   }
-  flush();
+  __syncwarp();
   for (int cls = lane; cls < NCLS; cls += 32) {
-    const uint32_t v = tot[cls];
+    const uint32_t v = hist[cls];
     if (v) {
       const int y = cls % 3 + 1, cp = cls / 3, p = cp % NT, c = cp / NT;
       atomicAdd(table + (((uint32_t)c * ONES) ^ ((uint32_t)y << (2 * p))), v);
@@ -478,9 +467,7 @@ __global__ void __launch_bounds__(256) count_class_kernel(const uint32_t* __rest
 template <int NT>
 int launch_class_nt(const uint32_t* d_sm, const uint32_t* d_valid, int64_t site_begin, int64_t site_end, uint32_t* d_table,
                     uint64_t* d_usable, cudaStream_t st) {
-  constexpr int NCLS_PAD = (12 * NT + 31) / 32 * 32;
-  const size_t smem = (size_t)8 * NCLS_PAD * 32 + (size_t)8 * NCLS_PAD * 4;
-  SPB_CUDA(cudaFuncSetAttribute(count_class_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = 0;
   int occ = 1;
   SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_class_kernel<NT>, 256, smem));
   if (occ < 1) occ = 1;

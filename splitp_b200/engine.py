@@ -632,7 +632,7 @@ class CountScorer:
             with _span(t, "scatter", nb):
                 self._scatter(arr, nb, s0, layout, rows_pad, pitch)
             run = lambda: call("spb_gram_u8_batch_i32", _p(s0), s0_stride, nb, rows_pad, pitch, _p(G), g_stride, _st())  # noqa: E731
-            with _span(t, "gram_large", nb):
+            with _span(t, f"gram_i32_r{rows_pad}", nb):  # int32 tensor-core Gram, one span name per row count (bench.py roofline)
                 run() if self.gram_hook is None else self.gram_hook(run, nb)
             with _span(t, "correction", nb):
                 call("spb_gram_hi_strip_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
