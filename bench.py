@@ -629,7 +629,7 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
                 "ms_per_matrix": ms, "launches_timed": launches_timed, "matrices_timed": mats,
                 "matrices_per_launch": mats / max(launches_timed, 1),
                 "share_of_step": ms_tot / max(sum(step_ms), 1e-9),
-                "concurrent_streams": int(os.environ.get("SPB_SCORE_STREAMS", "2")),
+                "concurrent_streams": int(os.environ.get("SPB_SCORE_STREAMS", "1")),
                 "traffic": traffic, "traffic_note": traffic_note or "dram bytes per matrix from the ncu --set full capture: see profiles/"}
     elif method == "thin" and "count" in phases:
         ms = phases["count"][0] / max(phases["count"][1], 1)

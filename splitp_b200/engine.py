@@ -512,10 +512,10 @@ class CountScorer:
             raise ValueError("CountScorer needs a PatternTable with integer counts")
         self._table = None
         self.hi_cap = int(hi_cap) if hi_cap is not None else 0
-        # Size classes are scored on up to NSTREAMS CUDA streams at once (one host thread per stream): while one class sits in
-        # the latency-bound small kernels of its eigen-solver, the Gram / G Q kernels of another fill the SMs.  Buffers that a
-        # class writes per launch (the high-part triplets) exist once per stream slot.
-        self.nstreams = max(1, int(os.environ.get("SPB_SCORE_STREAMS", "2")))
+        # Size classes can be scored on up to NSTREAMS CUDA streams at once (one host thread per stream; buffers that a class
+        # writes per launch exist once per stream slot).  Measured on B200 (12 taxa, 10^6 sites): 67.0 ms with two streams
+        # against 66.5 ms with one, at N = 1 and N = 2 alike -- the big kernels already fill the SMs -- so the default is 1.
+        self.nstreams = max(1, int(os.environ.get("SPB_SCORE_STREAMS", "1")))
         self._tl = threading.local()
         self._hi = {}
         self._side = None
