@@ -14,8 +14,10 @@ steps): c3 (configs[2], the north-star target: 20-taxon GTR tree, 10M sites, sub
 c5 (configs[4]: 10^5 random splits of a 32-taxon tree) and c4 (configs[3] scaled to 10M sites: 64 taxa, 128-bit pattern
 compression + thin reduced-flattening scores).
 
-N > 1 (torchrun): sites are sharded for counting (integer allreduce of the count table / pair statistics) and splits
-are sharded for scoring; total work is fixed => "scaling": "strong".  N > 1 lines carry `phase_ms`.
+N > 1 (torchrun): splits are sharded for scoring; sites are sharded for counting (exchange of the compacted pattern lists /
+integer allreduce of the pair statistics) unless counting the whole alignment on every rank is cheaper than that exchange
+(c2: 0.16 ms against 1.5 ms on 8 ranks; `config.parallelism` says which); total work is fixed => "scaling": "strong".
+All lines carry `phase_ms`.
 
 `--impl reference` times the UNMODIFIED reference (pip-installed into the git-ignored baseline/_ref) on
 the host cores: get_pattern_counts over all sites + flattening(reduced) + split_score for a stratified sample of
@@ -97,11 +99,18 @@ def split_list(wl, max_splits=None):
     return out[:max_splits] if max_splits else out
 
 
+def sites_replicated(wl, world):
+    """Mirror of splitp_b200.batch.replicate_sites (kept here so that the reference arm does not import the package)."""
+    return wl["method"] == "flattening" and world > 1 and float(wl["n"]) * float(wl["sites"]) <= 2.0e8
+
+
 def config_of(name, wl, n_splits, world):
     """The `config` object: identical keys and values in both arms."""
+    par = f"splits sharded x{world}, sites replicated (counting them all is cheaper than the exchange)" \
+        if sites_replicated(wl, world) else f"sites+splits sharded x{world}"
     return {"workload": wl["desc"], "name": name, "taxa": wl["n"], "sites": wl["sites"], "splits": n_splits,
             "model": wl["model"], "branch_length": wl["bl"], "seed": wl["seed"],
-            "l2": "flushed between timed steps (256 MB fill)", "parallelism": f"sites+splits sharded x{world}"}
+            "l2": "flushed between timed steps (256 MB fill)", "parallelism": par}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -493,7 +502,9 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
         model = sp.simulation.GTR.JukesCantor(0.5) if wl["model"] == "JC" else sp.simulation.GTR((0.1, 0.2, 0.3, 0.4), (1, 2, 3, 4, 5, 6))
         codes_full = sp.simulation.simulate_codes(tree, model, N, wl["seed"])
         codes_np = None
-    sb, se = spd.shard_range(N, rank, world, 32)
+    replicated = sites_replicated(wl, world)
+    assert replicated == (method == "flattening" and batch.replicate_sites(n, N, world))
+    sb, se = (0, N) if replicated else spd.shard_range(N, rank, world, 32)
     codes_dev = codes_full[:, sb:se].contiguous()
     if method == "subflattening":  # e2e input: the 2-bit host format (4 bases per byte instead of 1)
         planes, valid = batch.pack_planes_host(codes_dev.cpu().numpy())
@@ -522,7 +533,7 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
         call_name = "engine.pack_wide + distributed.count_patterns_wide_sharded + engine.thin_split_scores"
     else:
         scorer = batch.SplitScorer(idx_all, None, sp.Method.flattening if method == "flattening" else sp.Method.subflattening,
-                                   rank, world)
+                                   rank, world, sites="replicated" if replicated else "shard")
 
         def run(inp, t=None):
             scorer.timer = t
@@ -650,7 +661,7 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
     if method == "flattening" and "count" in phases:
         ms = phases["count"][0] / max(phases["count"][1], 1)
         nbytes = (se - sb) * n / 4.0 + (se - sb) / 8.0
-        count_roof = {"kernel": "count stage: count_stream_kernel + compaction" + (" + allreduce" if world > 1 else ""),
+        count_roof = {"kernel": "count stage: count_class_kernel + compaction" + (" + list exchange" if world > 1 and not replicated else ""),
                       "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                       "frac": nbytes / (ms * 1e-3) / 1e9 / hbm, "stage_ms": ms,
                       "note": "stage time includes the 64 MB table memset + compaction; kernel-only figures: profiles/r2_count_*"}

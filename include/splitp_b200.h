@@ -37,7 +37,7 @@ typedef enum {
 } spb_status;
 
 #define SPB_MAX_TAXA 64
-#define SPB_MAX_BATCH 16 /* splits per batched flatten launch */
+#define SPB_MAX_BATCH 64 /* splits per batched flatten launch (their descriptors travel as ONE 9 KB kernel parameter) */
 #define SPB_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 
 typedef struct {
@@ -288,6 +288,13 @@ int spb_gram_hi_strip_batch(const uint8_t* d_s0, int64_t s0_stride, int nb, int6
 int spb_score_gram_large_i32(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Cs, int64_t cs_rows,
                              const int32_t* d_pos, const int32_t* d_hr, const int32_t* d_hm, double* d_scores, double* d_info,
                              double* d_ws, void* stream);
+/* Diagnostic: d_AQ = G0 d_Q for `batch` int32 Gram matrices through ONE of the product kernels of the eigen-solver
+ * (variant 0: column-owning FMA kernel; 1..6: fp64 tensor-core (DMMA) kernels), launched exactly as the solver launches
+ * them.  d_Q, d_AQ: [batch][8][k] doubles; d_Qt: spb_symv_i32_ws(k, batch) doubles of scratch.  For tests and
+ * scripts/symv_bench.py; the product path reaches these kernels through spb_score_gram_large_i32. */
+int64_t spb_symv_i32_ws(int64_t k, int64_t batch);
+int spb_symv_i32(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Q, double* d_AQ, double* d_Qt, int variant,
+                 void* stream);
 
 /* ---- marginals, rank-1 approximation and rank-1 divergence of a flattening ----
  * reference: phylogenetics.py:331-341 (r = column sums, c = row sums, approximation = r^T c),

@@ -26,6 +26,8 @@ for n, N in ((10, 300_001), (16, 500_000)):
         sharded = batch.SplitScorer(idx20, None, sp.Method.flattening, rank, world).device_scores(codes[:, b:e].contiguous())
         single = eng.score_splits_counts(ref, idx20)
         assert torch.equal(sharded, single), (n, "SplitScorer")
+        repl = batch.SplitScorer(idx20, None, sp.Method.flattening, rank, world, sites="replicated").device_scores(codes)
+        assert torch.equal(repl, single), (n, "SplitScorer, replicated sites")
     pt_ref = eng.pair_tables_from_alignment(aln, as_counts=True)
     pt = spd.pair_tables_sharded(aln, rank, world, as_counts=True)
     assert torch.equal(pt_ref.N, pt.N) and torch.equal(pt_ref.T, pt.T)

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsplitp_b200.so")
 
 SPB_MAX_TAXA = 64
-SPB_MAX_BATCH = 16
+SPB_MAX_BATCH = 64
 SPB_VAL_U32, SPB_VAL_F64 = 0, 1
 SPB_S0_ROWMAJOR, SPB_S0_TILED, SPB_S0_K4MAJOR = 0, 1, 2
 SPB_U8_NO_MEMSET = 1
@@ -129,6 +129,8 @@ PROTOTYPES = {
     "spb_gram_u8_batch_i32": (_i, [_p, _l, _i, _l, _l, _p, _l, _p]),
     "spb_gram_hi_strip_batch": (_i, [_p, _l, _i, _l, _l, _i, _p, _p, _p, _l, _p, _l, _p, _p, _p, _p]),
     "spb_score_gram_large_i32": (_i, [_p, _l, _l, _l, _p, _l, _p, _p, _p, _p, _p, _p, _p]),
+    "spb_symv_i32_ws": (_l, [_l, _l]),
+    "spb_symv_i32": (_i, [_p, _l, _l, _l, _p, _p, _p, _i, _p]),
     "spb_mi_partials": (_l, []),
     "spb_marginals_dense": (_i, [_p, _l, _l, _l, _p, _p, _p]),
     "spb_mi_dense": (_i, [_p, _l, _l, _l, _p, _p, _p, _p, _p]),

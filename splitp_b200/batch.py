@@ -14,8 +14,12 @@ and the inner loop of `erickson_SVD` (phylogenetics.py:126-140).  `score_splits`
                           sparse flattening (dropping all-zero rows and columns does not change the singular values)
     Method.subflattening  pack -> pair tables -> H N H^T -> per split: gather + Gram + eigenvalues (kernel 3)
 
-Under `torch.distributed` (one process per GPU) the sites are sharded for counting and the splits for scoring: every
-rank passes ITS contiguous site shard (distributed.shard_range) and receives the scores of all splits.
+Under `torch.distributed` (one process per GPU) the splits are dealt to the ranks for scoring and every rank receives
+the scores of all splits.  The counting stage has two forms: `sites="shard"` -- every rank passes ITS contiguous site
+shard (distributed.shard_range) and the pattern tables are merged -- or `sites="replicated"` -- every rank passes the
+WHOLE alignment and counts it itself, with no exchange at all.  The second form wins while counting the whole alignment
+is cheaper than the exchange (`replicate_sites`: 12 taxa x 10^6 sites count in 0.16 ms, the list exchange between 8
+ranks takes 1.5 ms).
 
 `PhaseTimer` collects per-phase device time (CUDA events on the launch stream) for bench.py's `phase_ms`.
 """
@@ -99,19 +103,32 @@ def _positions(splits, taxa):
     return out
 
 
+# Counting n taxa x N sites costs about 1.1 ms per 1.2e9 site-taxa (count_class_kernel, B200); merging the ranks' pattern
+# lists costs 0.4 ms (2 ranks) .. 1.5 ms (8 ranks) whatever the size.  Below this many site-taxa every rank counts everything.
+REPLICATE_MAX_SITE_TAXA = 2.0e8
+
+
+def replicate_sites(n_taxa, n_sites, world):
+    """True when `SplitScorer(..., sites="replicated")` is the faster form of the counting stage (flattening scores)."""
+    return world > 1 and float(n_taxa) * float(n_sites) <= REPLICATE_MAX_SITE_TAXA
+
+
 class SplitScorer:
     """Reusable state of `score_splits` for one split list: encoded splits, device masks, the CountScorer's buffers.
     Keeping one per (alignment shape, split list) is what a serving loop would do; `score_splits` builds a throw-away
     one."""
 
-    def __init__(self, splits, taxa=None, method=Method.flattening, rank=0, world=1, group=None):
+    def __init__(self, splits, taxa=None, method=Method.flattening, rank=0, world=1, group=None, sites="shard"):
         from . import distributed as spd
+        if sites not in ("shard", "replicated"):
+            raise ValueError('sites must be "shard" or "replicated"')
         self.method, self.rank, self.world, self.group = method, rank, world, group
+        self.count_world = 1 if sites == "replicated" else world  # ranks that share the counting stage
         self.idx_all = _positions(splits, taxa)
         self.S = len(self.idx_all)
         self.idx_mine = spd.shard_strided(self.idx_all, rank, world)
-        self.reduce_fn = spd.make_reduce_fn(group) if world > 1 else None
-        self.gather_fn = spd.make_gather_fn(group) if world > 1 else None
+        self.reduce_fn = spd.make_reduce_fn(group) if self.count_world > 1 else None
+        self.gather_fn = spd.make_gather_fn(group) if self.count_world > 1 else None
         self.scorer = None
         self.masks = None
         self.timer = None
@@ -123,7 +140,8 @@ class SplitScorer:
             raise NotImplementedError("score_splits: Method.flattening or Method.subflattening")
 
     def device_scores(self, alignment, gram_hook=None):
-        """Scores of ALL splits as a device tensor.  `alignment`: this rank's site shard (any form _as_alignment takes)."""
+        """Scores of ALL splits as a device tensor.  `alignment`: this rank's site shard, or the whole alignment when the
+        scorer was built with sites="replicated" (any form _as_alignment takes)."""
         import torch.distributed as dist
 
         from . import distributed as spd
@@ -134,8 +152,10 @@ class SplitScorer:
             with _span(t, "count"):
                 if aln.n <= engine.DIRECT_MAX_TAXA:
                     table = engine.count_patterns(aln, gather_fn=self._timed_gather if self.gather_fn else None)
-                else:  # hashed tables: gather + hash merge on every rank
+                elif self.count_world > 1:  # hashed tables: gather + hash merge on every rank
                     table = spd.count_patterns_sharded(aln, self.rank, self.world, self.group, local=True)
+                else:
+                    table = engine.count_patterns(aln)
             if self.scorer is None:
                 self.scorer = engine.CountScorer(table)
             self.scorer.table = table
@@ -146,7 +166,7 @@ class SplitScorer:
                 aln = _as_alignment(alignment, want_sm=False, want_planes=True)
             with _span(t, "pairs"):
                 raw = engine.pair_raw(aln)
-            if self.world > 1:
+            if self.count_world > 1:
                 with _span(t, "allreduce"):
                     dist.all_reduce(raw, group=self.group)
             with _span(t, "subflatten+score"):

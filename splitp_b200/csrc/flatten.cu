@@ -71,7 +71,7 @@ __device__ __forceinline__ int64_t s0_cell(int layout, int64_t rows_pad, int64_t
   return (int64_t)((rt * KT + kt) * 16384ull + rr * 128u + ((((kk >> 4) ^ (rr & 7u))) << 4) + (kk & 15u));
 }
 
-struct SplitBatch {  // passed by value as a kernel parameter (16 x 140 bytes)
+struct SplitBatch {  // passed by value as a kernel parameter (64 x 140 bytes; CUDA >= 12.1 takes up to 32,764 bytes)
   SplitDev s[SPB_MAX_BATCH];
 };
 

@@ -565,6 +565,192 @@ __global__ void __launch_bounds__(32 * kColsWarps, kColsCtasPerSm) symv_cols_i32
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// G0 Q on the fp64 tensor cores (DMMA m8n8k4): the 8 vectors of the block are exactly the N = 8 of the instruction.
+//   D[v][n] += sum_{kq<4} A[v][kq] B[kq][n],  A[v][kq] = Q^T[r + kq][v],  B[kq][n] = G0[r + kq][column(n)]
+// Fragment layout (PTX m8n8k4 .f64): lane l holds A[l / 4][l % 4], B[l % 4][l / 4] and D[l / 4][2 (l % 4) + {0, 1}].
+// Lane l loads ONE 128-bit piece G0[r + l % 4][c0 + 4 (l / 4) .. + 3]: a warp-wide load covers 4 rows x 128 bytes (four
+// full lines), and element j of the piece is the B operand of MMA j, whose column index n stands for column c0 + 4 n + j.
+// So lane l ends up with vector v = l / 4 of the 8 adjacent columns c0 + 8 (l % 4) + {j, 4 + j}.  Against the column-owning
+// kernel above: 1 + 1 loads, 4 conversions and 4 MMAs per 128 matrix elements instead of 54 instructions, no shared memory in
+// the main loop, and half the registers -- twice the warps and four times the bytes in flight per SM.
+// CW = 32-column groups per warp (the A fragment is shared by them), U = row quads in flight per lane.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ int4 ldg_stream_v4(const int32_t* p) {
+  int4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+constexpr int kDmmaWarps = 8;
+template <int CW, int U>
+__global__ void __launch_bounds__(32 * kDmmaWarps) symv_dmma_i32_kernel(const int32_t* __restrict__ G, int64_t ld, int64_t strideG,
+                                                                       const double* __restrict__ Qt, int64_t strideQt,
+                                                                       double* __restrict__ AQ, int64_t strideQ, int k, int rows_per_warp) {
+  __shared__ double red[kDmmaWarps][kKB][32 * CW];
+  const int bt = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kq = lane & 3, grp = lane >> 2;
+  const int col0 = blockIdx.x * 32 * CW;
+  const int32_t* Gl = G + (int64_t)bt * strideG + col0 + 4 * grp;
+  const double* Ql = Qt + (int64_t)bt * strideQt + grp;
+  double acc[CW][4][2];
+#pragma unroll
+  for (int w = 0; w < CW; ++w)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[w][j][0] = acc[w][j][1] = 0.0;
+  const int row_begin = warp * rows_per_warp;
+  const int row_end = min(k, row_begin + rows_per_warp);   // k and rows_per_warp are multiples of 4 U (checked by the launcher)
+#pragma unroll 1
+  for (int r = row_begin + kq; r < row_end; r += 4 * U) {
+    int4 g[U][CW];
+    double a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int32_t* p = Gl + (int64_t)(r + 4 * u) * ld;
+#pragma unroll
+      for (int w = 0; w < CW; ++w) g[u][w] = ldg_stream_v4(p + 32 * w);
+      a[u] = __ldg(Ql + (int64_t)(r + 4 * u) * kKB);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int w = 0; w < CW; ++w) {
+        dmma884(acc[w][0][0], acc[w][0][1], a[u], u31_to_double(g[u][w].x));
+        dmma884(acc[w][1][0], acc[w][1][1], a[u], u31_to_double(g[u][w].y));
+        dmma884(acc[w][2][0], acc[w][2][1], a[u], u31_to_double(g[u][w].z));
+        dmma884(acc[w][3][0], acc[w][3][1], a[u], u31_to_double(g[u][w].w));
+      }
+  }
+#pragma unroll
+  for (int w = 0; w < CW; ++w)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[warp][grp][32 * w + 8 * kq + j] = acc[w][j][0];
+      red[warp][grp][32 * w + 8 * kq + 4 + j] = acc[w][j][1];
+    }
+  __syncthreads();
+  double* out = AQ + (int64_t)bt * strideQ;
+  for (int idx = threadIdx.x; idx < kKB * 32 * CW; idx += 32 * kDmmaWarps) {  // warps added in warp order: deterministic
+    const int c = idx / (32 * CW), jj = idx - c * (32 * CW);
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kDmmaWarps; ++w) v += red[w][c][jj];
+    out[(int64_t)c * k + col0 + jj] = v;
+  }
+}
+
+// The same kernel with an explicit register double buffer: the loads of the NEXT batch of U row quads are issued before the
+// MMAs of this one (ptxas schedules the plain form above for minimum registers: two loads in flight per lane, 48 registers).
+template <int CW, int U>
+__global__ void __launch_bounds__(32 * kDmmaWarps) symv_dmma_pipe_i32_kernel(const int32_t* __restrict__ G, int64_t ld, int64_t strideG,
+                                                                            const double* __restrict__ Qt, int64_t strideQt,
+                                                                            double* __restrict__ AQ, int64_t strideQ, int k,
+                                                                            int rows_per_warp) {
+  __shared__ double red[kDmmaWarps][kKB][32 * CW];
+  const int bt = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kq = lane & 3, grp = lane >> 2;
+  const int col0 = blockIdx.x * 32 * CW;
+  const int32_t* Gl = G + (int64_t)bt * strideG + col0 + 4 * grp;
+  const double* Ql = Qt + (int64_t)bt * strideQt + grp;
+  double acc[CW][4][2];
+#pragma unroll
+  for (int w = 0; w < CW; ++w)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[w][j][0] = acc[w][j][1] = 0.0;
+  const int row_begin = warp * rows_per_warp;
+  const int row_end = min(k, row_begin + rows_per_warp);   // the row count is a multiple of 8 U (checked by the launcher)
+  auto load = [&](int4 (&g)[U][CW], double (&a)[U], int r) {
+    const bool on = r < row_end;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int32_t* p = Gl + (int64_t)(r + 4 * u) * ld;
+#pragma unroll
+      for (int w = 0; w < CW; ++w) g[u][w] = on ? ldg_stream_v4(p + 32 * w) : make_int4(0, 0, 0, 0);
+      a[u] = on ? __ldg(Ql + (int64_t)(r + 4 * u) * kKB) : 0.0;
+    }
+  };
+  auto mul = [&](const int4 (&g)[U][CW], const double (&a)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int w = 0; w < CW; ++w) {
+        dmma884(acc[w][0][0], acc[w][0][1], a[u], u31_to_double(g[u][w].x));
+        dmma884(acc[w][1][0], acc[w][1][1], a[u], u31_to_double(g[u][w].y));
+        dmma884(acc[w][2][0], acc[w][2][1], a[u], u31_to_double(g[u][w].z));
+        dmma884(acc[w][3][0], acc[w][3][1], a[u], u31_to_double(g[u][w].w));
+      }
+  };
+  int4 ga[U][CW], gb[U][CW];
+  double aa[U], ab[U];
+  load(ga, aa, row_begin + kq);
+#pragma unroll 1
+  for (int r = row_begin + kq; r < row_end; r += 8 * U) {
+    load(gb, ab, r + 4 * U);
+    mul(ga, aa);
+    load(ga, aa, r + 8 * U);
+    mul(gb, ab);
+  }
+#pragma unroll
+  for (int w = 0; w < CW; ++w)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[warp][grp][32 * w + 8 * kq + j] = acc[w][j][0];
+      red[warp][grp][32 * w + 8 * kq + 4 + j] = acc[w][j][1];
+    }
+  __syncthreads();
+  double* out = AQ + (int64_t)bt * strideQ;
+  for (int idx = threadIdx.x; idx < kKB * 32 * CW; idx += 32 * kDmmaWarps) {
+    const int c = idx / (32 * CW), jj = idx - c * (32 * CW);
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kDmmaWarps; ++w) v += red[w][c][jj];
+    out[(int64_t)c * k + col0 + jj] = v;
+  }
+}
+
+// which G0 Q kernel: 0 = column-owning FMA kernel, 1..3 = DMMA kernel <CW, U> = <1, 8>, <2, 4>, <1, 4>,
+// 4..6 = pipelined DMMA kernel <1, 4>, <2, 2>, <2, 4>
+static int symv_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SPB_SYMV_KERNEL");
+    v = e ? atoi(e) : 4;  // measured per 4096^2 product inside a 48-matrix launch (scripts/symv_bench.py, B200): variant 0: 17.3 us,
+                          // 1: 15.6, 2: 14.0, 3: 12.3, 4: 11.4 (5.9 TB/s = 0.90 of the HBM peak), 5: 12.4, 6: 11.7
+    if (v < 0 || v > 6) v = 4;
+  }
+  return v;
+}
+inline bool symv_dmma_ok(int k, int64_t ld, const void* G) {
+  return k % (kDmmaWarps * 32) == 0 && ld % 4 == 0 && reinterpret_cast<uintptr_t>(G) % 16 == 0;
+}
+static void launch_symv_dmma(int variant, const int32_t* G, int64_t ld, int64_t strideG, const double* Qt, int64_t strideQt, double* AQ,
+                             int64_t strideQ, int k, int batch, cudaStream_t st) {
+  const int rpw = k / kDmmaWarps;  // a multiple of 32 = 4 U for every U <= 8
+  if (variant == 4) {
+    dim3 grid(k / 32, batch);
+    symv_dmma_pipe_i32_kernel<1, 4><<<grid, 32 * kDmmaWarps, 0, st>>>(G, ld, strideG, Qt, strideQt, AQ, strideQ, k, rpw);
+  } else if (variant == 5) {
+    dim3 grid(k / 64, batch);
+    symv_dmma_pipe_i32_kernel<2, 2><<<grid, 32 * kDmmaWarps, 0, st>>>(G, ld, strideG, Qt, strideQt, AQ, strideQ, k, rpw);
+  } else if (variant == 6) {
+    dim3 grid(k / 64, batch);
+    symv_dmma_pipe_i32_kernel<2, 4><<<grid, 32 * kDmmaWarps, 0, st>>>(G, ld, strideG, Qt, strideQt, AQ, strideQ, k, rpw);
+  } else if (variant == 2) {
+    dim3 grid(k / 64, batch);
+    symv_dmma_i32_kernel<2, 4><<<grid, 32 * kDmmaWarps, 0, st>>>(G, ld, strideG, Qt, strideQt, AQ, strideQ, k, rpw);
+  } else if (variant == 3) {
+    dim3 grid(k / 32, batch);
+    symv_dmma_i32_kernel<1, 4><<<grid, 32 * kDmmaWarps, 0, st>>>(G, ld, strideG, Qt, strideQt, AQ, strideQ, k, rpw);
+  } else {
+    dim3 grid(k / 32, batch);
+    symv_dmma_i32_kernel<1, 8><<<grid, 32 * kDmmaWarps, 0, st>>>(G, ld, strideG, Qt, strideQt, AQ, strideQ, k, rpw);
+  }
+}
+
 // AQ += C Q for the strip form of the correction (GramView).  Two deterministic passes, no atomics:
 //   rows i = hr[p]:      AQ[c][i] += sum_j Cs[p][j] Q[c][j]                 (one CTA per strip row, fixed-order reduction)
 //   rows i not in hr:    AQ[c][i] += sum_p Cs[p][i] Q[c][hr[p]]             (one thread per row, p ascending)
@@ -989,7 +1175,9 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
         krylov_transpose_kernel<<<tg, 256, 0, st>>>(Qj, w.sQ, w.Qt, (int64_t)k_pad * kKB, k, k_pad);
         SPB_LAUNCH_CHECK();
         dim3 gi((k + kColsPerCta - 1) / kColsPerCta, batch);
-        if (cols_vec) symv_cols_i32_kernel<true><<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, w.Qt, (int64_t)k_pad * kKB, AQj, w.sQ, k, rpw);
+        if (symv_variant() > 0 && symv_dmma_ok(k, ld, gv.Gi))
+          launch_symv_dmma(symv_variant(), gv.Gi, ld, ld * ld, w.Qt, (int64_t)k_pad * kKB, AQj, w.sQ, k, batch, st);
+        else if (cols_vec) symv_cols_i32_kernel<true><<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, w.Qt, (int64_t)k_pad * kKB, AQj, w.sQ, k, rpw);
         else symv_cols_i32_kernel<false><<<gi, 32 * kColsWarps, cols_smem, st>>>(gv.Gi, ld, ld * ld, w.Qt, (int64_t)k_pad * kKB, AQj, w.sQ, k, rpw);
       }
       SPB_LAUNCH_CHECK();
@@ -1091,4 +1279,36 @@ extern "C" int spb_score_gram_large_i32(const int32_t* d_Gi, int64_t k, int64_t 
               "spb_score_gram_large_i32: bad correction strip");
   GramView gv{nullptr, d_Gi, ld, d_Cs, cs_rows, d_pos, d_hr, d_hm};
   return score_gram_large(gv, k, batch, d_scores, d_info, d_ws, stream);
+}
+
+// Diagnostic entry: AQ = G0 Q for a batch of int32 Gram matrices through one chosen kernel (0 = column-owning FMA kernel,
+// 1..3 = DMMA kernels), exactly as krylov_cycle launches them.  d_Q, d_AQ: [batch][8][k]; d_Qt: spb_symv_i32_ws(k, batch)
+// doubles of scratch.  Used by tests/test_gpu_parity_r2.py and scripts/symv_bench.py, not by the product path.
+extern "C" int64_t spb_symv_i32_ws(int64_t k, int64_t batch) { return (int64_t)symv_k_pad((int)k) * kKB * batch; }
+
+extern "C" int spb_symv_i32(const int32_t* d_Gi, int64_t k64, int64_t ld, int64_t batch64, const double* d_Q, double* d_AQ, double* d_Qt,
+                            int variant, void* stream) {
+  SPB_REQUIRE(d_Gi && d_Q && d_AQ && d_Qt && k64 > 0 && k64 <= (1 << 20) && ld >= k64 && batch64 > 0 && batch64 <= 65535,
+              "spb_symv_i32: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int k = (int)k64, batch = (int)batch64;
+  const int rpw = symv_rows_per_warp(k), k_pad = symv_k_pad(k);
+  const int64_t sQ = (int64_t)kKB * k;
+  dim3 tg((k_pad + 255) / 256, batch);
+  krylov_transpose_kernel<<<tg, 256, 0, st>>>(d_Q, sQ, d_Qt, (int64_t)k_pad * kKB, k, k_pad);
+  SPB_LAUNCH_CHECK();
+  if (variant > 0) {
+    SPB_REQUIRE(variant <= 6 && symv_dmma_ok(k, ld, d_Gi), "spb_symv_i32: the DMMA kernels need k % 256 == 0, ld % 4 == 0");
+    launch_symv_dmma(variant, d_Gi, ld, ld * ld, d_Qt, (int64_t)k_pad * kKB, d_AQ, sQ, k, batch, st);
+  } else {
+    const size_t cols_smem = (size_t)kColsWarps * 2 * kColsQRows * kKB * sizeof(double);
+    SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
+    SPB_CUDA(cudaFuncSetAttribute(symv_cols_i32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
+    const bool vec = (ld % 2 == 0) && (k % 2 == 0) && (reinterpret_cast<uintptr_t>(d_Gi) % 8 == 0);
+    dim3 gi((k + kColsPerCta - 1) / kColsPerCta, batch);
+    if (vec) symv_cols_i32_kernel<true><<<gi, 32 * kColsWarps, cols_smem, st>>>(d_Gi, ld, ld * ld, d_Qt, (int64_t)k_pad * kKB, d_AQ, sQ, k, rpw);
+    else symv_cols_i32_kernel<false><<<gi, 32 * kColsWarps, cols_smem, st>>>(d_Gi, ld, ld * ld, d_Qt, (int64_t)k_pad * kKB, d_AQ, sQ, k, rpw);
+  }
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
 }

@@ -503,8 +503,8 @@ class CountScorer:
     every stage (the scatter / correction kernels are a few microseconds each, so batching them is what
     keeps the GPU busy)."""
 
-    NB = _lib.SPB_MAX_BATCH   # splits per scatter / clear launch (kernel-parameter limit)
-    GNB = 4 * NB              # matrices per Gram / correction launch: 20 tiles x 16 matrices leave the 148 persistent CTAs
+    NB = _lib.SPB_MAX_BATCH   # splits per scatter / clear launch (kernel-parameter limit); 16 in round 1: 266 launches per c2 step
+    GNB = 64                  # matrices per Gram / correction launch: 20 tiles x 16 matrices leave the 148 persistent CTAs
                               # with 2 or 3 tiles each (72 % efficiency at 5|7 of 12 taxa), 64 matrices level that out
 
     def __init__(self, table, hi_cap=None):
@@ -570,7 +570,7 @@ class CountScorer:
 
     def _gnb(self, rows_pad, pitch):
         """Matrices per Gram launch: GNB, fewer when one u8 matrix is large (the S0 batch stays within 4 GB)."""
-        return int(max(self.NB, min(self.GNB, (4 << 30) // (rows_pad * pitch))))
+        return int(max(16, min(self.GNB, (4 << 30) // (rows_pad * pitch))))
 
     def _buffers(self, layout, rows_pad, pitch, batch=1):
         key = (layout, rows_pad, pitch)

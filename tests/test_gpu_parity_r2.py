@@ -323,3 +323,35 @@ def test_subflatten_score_staged_kernels_still_agree(sp, eng, oracle, monkeypatc
         ref = oracle.split_score(oracle.subflattening_from_tables(tables, 1.0, ia, ib))
         assert_score(staged[s], ref)
         assert_score(default[s], ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# G0 Q product kernels of the eigen-solver (column-owning FMA kernel and the fp64 tensor-core kernels)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,nb", [(256, 3), (1024, 5), (4096, 2)])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
+def test_symv_i32_kernels_against_fp64_matmul(eng, k, nb, variant):
+    """AQ[c][j] = sum_i G0[i][j] Q[c][i] with G0 entries up to 2^31 - 1: every variant within 64 eps of the fp64 product
+    (the kernels differ only in summation order); integer-valued Q gives a bit-exact answer."""
+    import ctypes as C
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(100 + k + variant)
+    G = torch.randint(0, (1 << 31) - 1, (nb, k, k), dtype=torch.int32, device=dev, generator=g)
+    G[0, 5, 7] = (1 << 31) - 1
+    lib = eng.lib
+    Qt = torch.empty(int(lib.spb_symv_i32_ws(k, nb)), dtype=torch.float64, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for integral in (True, False):
+        if integral:
+            Q = torch.randint(-3, 4, (nb, 8, k), device=dev, generator=g).to(torch.float64)
+        else:
+            Q = torch.randn((nb, 8, k), dtype=torch.float64, device=dev, generator=g)
+        AQ = torch.full_like(Q, float("nan"))
+        rc = lib.spb_symv_i32(G.data_ptr(), k, k, nb, Q.data_ptr(), AQ.data_ptr(), Qt.data_ptr(), variant, st)
+        assert rc == 0, lib.spb_last_error()
+        ref = torch.stack([Q[b] @ G[b].double() for b in range(nb)])
+        if integral:  # |sum| < 4096 * 3 * 2^31 < 2^53: exact in any order
+            assert torch.equal(AQ, ref)
+        else:
+            bound = 64 * np.finfo(np.float64).eps * (Q.abs() @ G.double().abs()).max().item()
+            assert (AQ - ref).abs().max().item() <= bound
