@@ -285,6 +285,16 @@ int spb_gram_u8_batch_i32(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_
 int spb_gram_hi_strip_batch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int layout,
                             const int32_t* d_hi_rc, const uint32_t* d_hi_val, const uint32_t* d_hi_num, int64_t hi_cap,
                             double* d_Cs, int64_t cs_rows, int32_t* d_pos, int32_t* d_hr, int32_t* d_hm, void* stream);
+/* spb_gram_hi_strip_batch with the cross terms S0 H^T + H S0^T taken from the PATTERN TABLE (a join of the pattern list with
+ * the high list on the column index) instead of from column scans of S0: same d_Cs / d_pos / d_hr / d_hm, bit for bit.
+ * h_splits: the nb <= SPB_MAX_BATCH splits the S0 buffers were scattered with (every split covers all taxa);
+ * d_ws: spb_gram_hi_strip_table_ws(nb, pitch, hi_cap) int32 of scratch.  Only the first d_hm[b] rows of a strip are written
+ * (and read by spb_score_gram_large_i32). */
+int64_t spb_gram_hi_strip_table_ws(int nb, int64_t pitch, int64_t hi_cap);
+int spb_gram_hi_strip_batch_table(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* h_splits, int nb,
+                                  int64_t rows_pad, int64_t pitch, const int32_t* d_hi_rc, const uint32_t* d_hi_val,
+                                  const uint32_t* d_hi_num, int64_t hi_cap, double* d_Cs, int64_t cs_rows, int32_t* d_pos, int32_t* d_hr,
+                                  int32_t* d_hm, int32_t* d_ws, void* stream);
 int spb_score_gram_large_i32(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Cs, int64_t cs_rows,
                              const int32_t* d_pos, const int32_t* d_hr, const int32_t* d_hm, double* d_scores, double* d_info,
                              double* d_ws, void* stream);

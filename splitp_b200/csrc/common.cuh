@@ -81,6 +81,9 @@ inline int make_split_dev(const spb_split* s, SplitDev* d, bool need_key64 = tru
 int gram_u8_i32_launch(const uint8_t* d_s0, int64_t s0_stride, int nb, int64_t rows_pad, int64_t pitch, int32_t* d_Gi,
                        int64_t g_stride, cudaStream_t st);
 
+// pairs.cu: scores of `batch` symmetric k x k matrices (4 < k <= 64, leading dimension ld, stride ld * ld), one warp per matrix
+int score_gram_warp_launch(const double* d_G, int k, int64_t ld, int64_t batch, double* d_scores, cudaStream_t st);
+
 __device__ __forceinline__ uint64_t side_index(uint64_t key, const uint8_t* sh, int len) {
   uint64_t r = 0;
   for (int i = 0; i < len; ++i) r = (r << 2) | ((key >> sh[i]) & 3ull);

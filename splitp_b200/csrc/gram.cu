@@ -743,6 +743,70 @@ __global__ void __launch_bounds__(256) hi_strip_self_kernel(const int32_t* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The cross terms of the strip from the PATTERN TABLE instead of from S0 (round 2).  hi_strip_cross_kernel reads, for every
+// high entry (r, c, v), the whole column c of S0: rows_pad bytes, each in its own 128-byte line of the tiled layout (1 M sector
+// reads per 4096^2 matrix with 256 high entries).  But S0 holds one cell per pattern of the table, so the same sum is a join of
+// the pattern list with the high list on the column index: chain the high entries of every column (colmap / next), then one
+// pass over the patterns -- (r', c', s = count & 255) -- walks the chain of column c'.  60 k patterns instead of 1 M cells.
+// Values are integers below 2^53: the atomics are exact and order-independent.
+// ---------------------------------------------------------------------------------------------------
+struct SplitBatchG {  // as SplitBatch of flatten.cu: the splits of one launch, passed by value
+  SplitDev s[SPB_MAX_BATCH];
+};
+
+__global__ void hi_chain_kernel(const int32_t* __restrict__ hi_rc_base, const uint32_t* __restrict__ hi_num_base, int64_t hi_cap,
+                                int32_t* __restrict__ colmap_base, int64_t pitch, int32_t* __restrict__ next_base) {
+  const int b = blockIdx.y;
+  int64_t n = hi_num_base[b];
+  if (n > hi_cap) n = hi_cap;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int32_t c = hi_rc_base[((size_t)b * hi_cap + e) * 2 + 1];
+  next_base[(size_t)b * hi_cap + e] = atomicExch(colmap_base + (size_t)b * pitch + c, (int32_t)e + 1);  // 0 = end of chain
+}
+
+__global__ void __launch_bounds__(256) hi_join_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t num,
+                                                      const __grid_constant__ SplitBatchG sb, int64_t R, int64_t pitch,
+                                                      const int32_t* __restrict__ hi_rc_base, const uint32_t* __restrict__ hi_val_base,
+                                                      int64_t hi_cap, const int32_t* __restrict__ colmap_base,
+                                                      const int32_t* __restrict__ next_base, const int32_t* __restrict__ pos_base,
+                                                      double* __restrict__ Cs_base, int64_t cs_rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num) return;
+  const uint32_t s = counts[i] & 255u;
+  if (s == 0) return;
+  const int b = blockIdx.y;
+  const SplitDev& sp = sb.s[b];
+  const uint64_t k = keys[i];
+  const int64_t ri = (int64_t)side_index(k, sp.sh_a, sp.a), ci = (int64_t)side_index(k, sp.sh_b, sp.b);
+  int32_t e = colmap_base[(size_t)b * pitch + ci];
+  if (e == 0) return;
+  const int32_t* hi_rc = hi_rc_base + (size_t)b * 2 * hi_cap;
+  const uint32_t* hi_val = hi_val_base + (size_t)b * hi_cap;
+  const int32_t* next = next_base + (size_t)b * hi_cap;
+  const int32_t* pos = pos_base + (size_t)b * R;
+  double* Cs = Cs_base + (size_t)b * cs_rows * R;
+  const int pi = pos[ri];
+  while (e) {
+    const int32_t e0 = e - 1;
+    const int64_t r = hi_rc[2 * e0];
+    const double t = (double)hi_val[e0] * (double)s;
+    const int pr = pos[r];
+    if (pr >= 0) atomicAdd(Cs + (int64_t)pr * R + ri, t);   // (H S0^T)[r][i]
+    if (pi >= 0) atomicAdd(Cs + (int64_t)pi * R + r, t);    // (S0 H^T)[i][r], kept only for strip rows
+    e = next[e0];
+  }
+}
+
+// zero the strip rows that are in use (rows >= hm[b] are never read)
+__global__ void strip_zero_kernel(double* __restrict__ Cs_base, int64_t cs_rows, int64_t R, const int32_t* __restrict__ hm) {
+  const int b = blockIdx.z, p = blockIdx.y;
+  if (p >= hm[b]) return;
+  double2* row = reinterpret_cast<double2*>(Cs_base + ((size_t)b * cs_rows + p) * R);
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < R / 2; j += (int64_t)gridDim.x * blockDim.x) row[j] = make_double2(0.0, 0.0);
+}
+
 struct UmmaPlan {
   int BN, T, KT, tiles, ksplit, kt_per_split, num_work;
   size_t smem;
@@ -929,6 +993,55 @@ extern "C" int spb_gram_hi_strip_batch(const uint8_t* d_s0, int64_t s0_stride, i
   hi_strip_cross_kernel<<<grid, 256, 0, st>>>(d_s0, s0_stride, layout, rows_pad, pitch, d_hi_rc, d_hi_val, d_hi_num, hi_cap, d_pos, d_Cs,
                                               cs_rows);
   SPB_LAUNCH_CHECK();
+  int64_t gx = (4 * (int64_t)sm_count() + nb - 1) / nb;
+  dim3 sg((unsigned)gx, (unsigned)nb);
+  hi_strip_self_kernel<<<sg, 256, 0, st>>>(d_hi_rc, d_hi_val, d_hi_num, hi_cap, rows_pad, d_pos, d_Cs, cs_rows);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+
+extern "C" int64_t spb_gram_hi_strip_table_ws(int nb, int64_t pitch, int64_t hi_cap) { return (int64_t)nb * (pitch + hi_cap); }
+
+extern "C" int spb_gram_hi_strip_batch_table(const uint64_t* d_keys, const uint32_t* d_counts, int64_t num, const spb_split* h_splits,
+                                             int nb, int64_t rows_pad, int64_t pitch, const int32_t* d_hi_rc, const uint32_t* d_hi_val,
+                                             const uint32_t* d_hi_num, int64_t hi_cap, double* d_Cs, int64_t cs_rows, int32_t* d_pos,
+                                             int32_t* d_hr, int32_t* d_hm, int32_t* d_ws, void* stream) {
+  SPB_REQUIRE(h_splits && d_hi_rc && d_hi_val && d_hi_num && d_pos && d_hm && d_ws && hi_cap >= 0 && nb >= 1 && nb <= SPB_MAX_BATCH &&
+                  cs_rows >= 0 && cs_rows <= 65535 && rows_pad % 2 == 0,
+              "spb_gram_hi_strip_table: bad arguments");
+  SPB_REQUIRE(cs_rows == 0 || (d_Cs && d_hr), "spb_gram_hi_strip_table: NULL strip");
+  SPB_REQUIRE(num <= 0 || (d_keys && d_counts), "spb_gram_hi_strip_table: NULL pattern table");
+  SplitBatchG sb;
+  for (int b = 0; b < nb; ++b) {
+    int rc = make_split_dev(h_splits + b, &sb.s[b]);
+    if (rc) return rc;
+    SPB_REQUIRE(sb.s[b].a + sb.s[b].b == sb.s[b].n && sb.s[b].a <= 15 && sb.s[b].b <= 15 && rows_pad >= (1ll << (2 * sb.s[b].a)) &&
+                    pitch >= (1ll << (2 * sb.s[b].b)),
+                "spb_gram_hi_strip_table: every split must cover all taxa and fit rows_pad x pitch");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  hi_rows_kernel<<<nb, 1024, 0, st>>>(d_hi_rc, d_hi_num, hi_cap, rows_pad, d_pos, d_hr, cs_rows, d_hm);
+  SPB_LAUNCH_CHECK();
+  if (hi_cap == 0 || cs_rows == 0) return SPB_OK;
+  {
+    dim3 zg((unsigned)((rows_pad / 2 + 255) / 256 > 8 ? 8 : (rows_pad / 2 + 255) / 256), (unsigned)cs_rows, (unsigned)nb);
+    strip_zero_kernel<<<zg, 256, 0, st>>>(d_Cs, cs_rows, rows_pad, d_hm);
+    SPB_LAUNCH_CHECK();
+  }
+  int32_t* colmap = d_ws;
+  int32_t* next = d_ws + (size_t)nb * pitch;
+  SPB_CUDA(cudaMemsetAsync(colmap, 0, (size_t)nb * pitch * sizeof(int32_t), st));
+  {
+    dim3 cg((unsigned)((hi_cap + 255) / 256), (unsigned)nb);
+    hi_chain_kernel<<<cg, 256, 0, st>>>(d_hi_rc, d_hi_num, hi_cap, colmap, pitch, next);
+    SPB_LAUNCH_CHECK();
+  }
+  if (num > 0) {
+    dim3 jg((unsigned)((num + 255) / 256), (unsigned)nb);
+    hi_join_kernel<<<jg, 256, 0, st>>>(d_keys, d_counts, num, sb, rows_pad, pitch, d_hi_rc, d_hi_val, hi_cap, colmap, next, d_pos, d_Cs,
+                                       cs_rows);
+    SPB_LAUNCH_CHECK();
+  }
   int64_t gx = (4 * (int64_t)sm_count() + nb - 1) / nb;
   dim3 sg((unsigned)gx, (unsigned)nb);
   hi_strip_self_kernel<<<sg, 256, 0, st>>>(d_hi_rc, d_hi_val, d_hi_num, hi_cap, rows_pad, d_pos, d_Cs, cs_rows);

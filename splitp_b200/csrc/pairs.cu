@@ -739,6 +739,38 @@ __global__ void __launch_bounds__(32 * kW2WarpsPerCta) subflatten_score_warp2_ke
   }
 }
 
+// The same eigen stage for symmetric k x k matrices that already exist in global memory (k <= 64): the Gram matrices of the
+// thin size classes of a count flattening (2|10, 3|9 of 12 taxa: k = 16, 64).  One warp per matrix: copy to the warp-private tile,
+// trace, Householder + 9-section.  Replaces the cyclic Jacobi kernel (score.cu: 0.58 ms per launch whatever the batch, two
+// barriers per rotation round) where only the score is wanted.
+__global__ void __launch_bounds__(32 * kW2WarpsPerCta) gram_score_warp_kernel(const double* __restrict__ Gin, int k, int64_t ld, int64_t batch,
+                                                                             double* __restrict__ scores, int warp_doubles) {
+  extern __shared__ __align__(16) double s_w2[];
+  double* base = s_w2 + (size_t)(threadIdx.x >> 5) * warp_doubles;
+  const int ldg = k | 1;
+  double* G = base;                    // [k][ldg]
+  double* sv = G + (size_t)k * ldg;    // 4 x 64
+  double* sq = sv + 64;
+  double* sd = sq + 64;
+  double* se = sd + 64;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * kW2WarpsPerCta;
+  for (int64_t s = (int64_t)blockIdx.x * kW2WarpsPerCta + (threadIdx.x >> 5); s < batch; s += nwarps) {
+    __syncwarp();
+    const double* src = Gin + s * ld * ld;
+    for (int t = lane; t < k * k; t += 32) {
+      const int r = t / k, c = t - r * k;
+      G[r * ldg + c] = (c >= r) ? src[(int64_t)r * ld + c] : src[(int64_t)c * ld + r];  // upper triangle, mirrored: bitwise symmetric
+    }
+    __syncwarp();
+    double part = 0.0;
+    for (int r = lane; r < k; r += 32) part += G[r * ldg + r];
+    const double trace = warp_sum_all(part);
+    const double top = (k <= 32) ? warp2_top4<1>(G, ldg, k, sv, sq, sd, se, lane) : warp2_top4<2>(G, ldg, k, sv, sq, sd, se, lane);
+    if (lane == 0) scores[s] = trace > 0.0 ? sqrt(fmax(trace - top, 0.0) / trace) : nan("");
+  }
+}
+
 inline size_t subflat_smem(int n, int* m_elems) {
   // the widest staging matrix over ALL side sizes: k x ((L + 1) | 1) with k = 3 min(a, b) + 1, L = 3 max(a, b) + 1.  It is
   // NOT maximised at the balanced split (22 taxa: 10|12 needs 31 x 39 = 1209 doubles, 11|11 only 34 x 35 = 1190: round 1
@@ -879,6 +911,23 @@ extern "C" int spb_subflatten_score_tables(const double* d_T, const double* d_to
   SPB_LAUNCH_CHECK();
   return SPB_OK;
 }
+
+namespace spb {
+int score_gram_warp_launch(const double* d_G, int k, int64_t ld, int64_t batch, double* d_scores, cudaStream_t st) {
+  const int warp_doubles = k * (k | 1) + 4 * 64;
+  const size_t smem = (size_t)kW2WarpsPerCta * warp_doubles * sizeof(double);
+  SPB_CUDA(cudaFuncSetAttribute(gram_score_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gram_score_warp_kernel, 32 * kW2WarpsPerCta, smem));
+  if (occ < 1) occ = 1;
+  int64_t grid = (int64_t)sm_count() * occ;
+  const int64_t need = (batch + kW2WarpsPerCta - 1) / kW2WarpsPerCta;
+  if (grid > need) grid = need;
+  gram_score_warp_kernel<<<(unsigned)grid, 32 * kW2WarpsPerCta, smem, st>>>(d_G, k, ld, batch, d_scores, warp_doubles);
+  SPB_LAUNCH_CHECK();
+  return SPB_OK;
+}
+}  // namespace spb
 
 extern "C" int spb_subflatten_score(const double* d_T, const double* d_total, int n_taxa, const uint64_t* d_masks_a,
                                     const uint64_t* d_masks_b, int64_t num, double* d_scores, void* stream) {

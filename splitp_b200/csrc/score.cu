@@ -9,6 +9,8 @@
 // total is trace(G) = ||F||_F^2.
 #include "common.cuh"
 #include "jacobi.cuh"
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 using namespace spb;
@@ -156,6 +158,72 @@ __global__ void __launch_bounds__(256) dot_kernel(const double* __restrict__ A, 
     }
 }
 
+// D (8 x 8, fp64) += A (8 x 4) B (4 x 8) on the fp64 tensor cores.  Fragments (PTX m8n8k4 .f64): lane l holds A[l / 4][l % 4],
+// B[l % 4][l / 4] and D[l / 4][2 (l % 4) + {0, 1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// The same inner products for M, N in {8, 16} (every product of the two-block Krylov cycle) on the fp64 tensor cores: ONE CTA per
+// matrix, its 8 warps split the k positions, a lane loads 4 consecutive doubles of row l / 4 of every 8-row tile of A and of B
+// per 16 positions (element t = k-slot l % 4 of MMA t), the warps' 8 x 8 tiles are added in warp order.  No partial buffer and
+// no reduce launch: 63 + 63 launches of the c2 step (35 + 5 us each at 64 matrices) become 63.
+template <int MT, int NT>
+__global__ void __launch_bounds__(256) dot_dmma_kernel(const double* __restrict__ A, int64_t strideA, const double* __restrict__ B,
+                                                       int64_t strideB, int k, double* __restrict__ Cout, int64_t ldc, int64_t strideC) {
+  __shared__ double red[8][8 * MT][8 * NT];
+  const int bt = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kq = lane & 3, grp = lane >> 2;
+  const double* Ab = A + (int64_t)bt * strideA + (int64_t)grp * k + 4 * kq;
+  const double* Bb = B + (int64_t)bt * strideB + (int64_t)grp * k + 4 * kq;
+  double acc[MT][NT][2];
+#pragma unroll
+  for (int a = 0; a < MT; ++a)
+#pragma unroll
+    for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const int per_warp = k / 8;  // a multiple of 16 (launcher)
+  const int p_end = (warp + 1) * per_warp;
+#pragma unroll 2
+  for (int p = warp * per_warp; p < p_end; p += 16) {
+    double2 a01[MT], a23[MT], b01[NT], b23[NT];
+#pragma unroll
+    for (int a = 0; a < MT; ++a) {
+      a01[a] = *reinterpret_cast<const double2*>(Ab + (int64_t)(8 * a) * k + p);
+      a23[a] = *reinterpret_cast<const double2*>(Ab + (int64_t)(8 * a) * k + p + 2);
+    }
+#pragma unroll
+    for (int b = 0; b < NT; ++b) {
+      b01[b] = *reinterpret_cast<const double2*>(Bb + (int64_t)(8 * b) * k + p);
+      b23[b] = *reinterpret_cast<const double2*>(Bb + (int64_t)(8 * b) * k + p + 2);
+    }
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+      for (int b = 0; b < NT; ++b) {
+        dmma884(acc[a][b][0], acc[a][b][1], a01[a].x, b01[b].x);
+        dmma884(acc[a][b][0], acc[a][b][1], a01[a].y, b01[b].y);
+        dmma884(acc[a][b][0], acc[a][b][1], a23[a].x, b23[b].x);
+        dmma884(acc[a][b][0], acc[a][b][1], a23[a].y, b23[b].y);
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < MT; ++a)
+#pragma unroll
+    for (int b = 0; b < NT; ++b) {
+      red[warp][8 * a + grp][8 * b + 2 * kq] = acc[a][b][0];
+      red[warp][8 * a + grp][8 * b + 2 * kq + 1] = acc[a][b][1];
+    }
+  __syncthreads();
+  if (threadIdx.x < 64 * MT * NT) {
+    const int i = threadIdx.x / (8 * NT), j = threadIdx.x - i * (8 * NT);
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][i][j];
+    Cout[(int64_t)bt * strideC + (int64_t)i * ldc + j] = v;
+  }
+}
+
 struct GemmArgs {
   const double* A; int64_t lda, strideA;
   const double* B; int64_t ldb, strideB;
@@ -203,6 +271,16 @@ static int choose_ksplit(int M, int N, int K, int batch) {
 // C (ldc, strideC) = A B^T for the tall-skinny Krylov operands; part must hold batch * ceil(k/128) * M * N doubles
 static int dot_product(const double* A, int64_t strideA, const double* B, int64_t strideB, int M, int N, int k, int batch,
                        double* C, int64_t ldc, int64_t strideC, double* part, cudaStream_t st) {
+  static const bool dmma_dots = [] { const char* e = getenv("SPB_DOT_KERNEL"); return !(e && !strcmp(e, "simt")); }();
+  if (dmma_dots && (M == 8 || M == 16) && (N == 8 || N == 16) && k % 128 == 0 && strideA % 2 == 0 && strideB % 2 == 0 &&
+      reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0) {
+    if (M == 8 && N == 8) dot_dmma_kernel<1, 1><<<batch, 256, 0, st>>>(A, strideA, B, strideB, k, C, ldc, strideC);
+    else if (M == 16 && N == 8) dot_dmma_kernel<2, 1><<<batch, 256, 0, st>>>(A, strideA, B, strideB, k, C, ldc, strideC);
+    else if (M == 8 && N == 16) dot_dmma_kernel<1, 2><<<batch, 256, 0, st>>>(A, strideA, B, strideB, k, C, ldc, strideC);
+    else dot_dmma_kernel<2, 2><<<batch, 256, 0, st>>>(A, strideA, B, strideB, k, C, ldc, strideC);
+    SPB_LAUNCH_CHECK();
+    return SPB_OK;
+  }
   const int nchunks = (k + kDotChunk - 1) / kDotChunk;
   const size_t smem = (size_t)(M + N) * (kDotChunk + 1) * sizeof(double);
   dim3 grid(nchunks, batch);
@@ -576,9 +654,6 @@ __global__ void __launch_bounds__(32 * kColsWarps, kColsCtasPerSm) symv_cols_i32
 // the main loop, and half the registers -- twice the warps and four times the bytes in flight per SM.
 // CW = 32-column groups per warp (the A fragment is shared by them), U = row quads in flight per lane.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 __device__ __forceinline__ int4 ldg_stream_v4(const int32_t* p) {
   int4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -802,6 +877,67 @@ __global__ void __launch_bounds__(256) strip_rows_kernel(const GramView g, const
 #pragma unroll
       for (int w = 0; w < 8; ++w) v += red[r][c][w];
       AQ[bt * strideQ + (int64_t)c * k + g.hr[bt * g.cs_rows + p0 + r]] += v;
+    }
+  }
+}
+
+// The row pass on the fp64 tensor cores: Y[v][p] = sum_j Q[v][j] Cs[p][j] is an (8 x k) x (k x m) product, M = 8 vectors, N = 8
+// strip rows per MMA, K = columns.  A CTA owns 64 strip rows (8 groups of 8), its 8 warps split the columns; per 16 columns a
+// lane loads 4 consecutive doubles of Q[l / 4][.] (shared by all 8 groups) and of Cs[p0 + 8 g + l / 4][.] per group, element t of
+// both being the k-slot l % 4 of MMA t (any pairing of k-slots with columns works as long as A and B use the same one).
+// Q is read once per 64 strip rows instead of once per 4 (strip_rows_kernel: 8.6 MB of Q for a 4.3 MB strip).
+constexpr int kStripDmmaRows = 64;
+__global__ void __launch_bounds__(256) strip_rows_dmma_kernel(const GramView g, const double* __restrict__ Q, int64_t strideQ,
+                                                              double* __restrict__ AQ, int k) {
+  __shared__ double red[8][kStripDmmaRows][kKB];
+  const int64_t bt = blockIdx.y;
+  const int p0 = blockIdx.x * kStripDmmaRows;
+  const int m = g.hm[bt];
+  if (p0 >= m) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kq = lane & 3, grp = lane >> 2;
+  const double* Qb = Q + bt * strideQ + (int64_t)grp * k + 4 * kq;
+  const double* Cb = g.Cs + (bt * g.cs_rows + p0 + grp) * g.ld + 4 * kq;
+  const int ngroups = min(kStripDmmaRows / 8, (m - p0 + 7) / 8);
+  double acc[kStripDmmaRows / 8][2];
+#pragma unroll
+  for (int gi = 0; gi < kStripDmmaRows / 8; ++gi) acc[gi][0] = acc[gi][1] = 0.0;
+  const int cols_per_warp = k / 8;  // a multiple of 16 (launcher)
+  const int j_end = (warp + 1) * cols_per_warp;
+#pragma unroll 1
+  for (int j = warp * cols_per_warp; j < j_end; j += 16) {
+    const double2 a01 = __ldg(reinterpret_cast<const double2*>(Qb + j)), a23 = __ldg(reinterpret_cast<const double2*>(Qb + j + 2));
+    double2 b01[kStripDmmaRows / 8], b23[kStripDmmaRows / 8];
+#pragma unroll
+    for (int gi = 0; gi < kStripDmmaRows / 8; ++gi) {
+      const bool on = gi < ngroups && p0 + 8 * gi + grp < m;  // rows >= m of a strip are never initialised
+      const double* src = Cb + (int64_t)(8 * gi) * g.ld + j;
+      b01[gi] = on ? __ldg(reinterpret_cast<const double2*>(src)) : make_double2(0.0, 0.0);
+      b23[gi] = on ? __ldg(reinterpret_cast<const double2*>(src + 2)) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int gi = 0; gi < kStripDmmaRows / 8; ++gi) {
+      if (gi < ngroups) {  // warp-uniform
+        dmma884(acc[gi][0], acc[gi][1], a01.x, b01[gi].x);
+        dmma884(acc[gi][0], acc[gi][1], a01.y, b01[gi].y);
+        dmma884(acc[gi][0], acc[gi][1], a23.x, b23[gi].x);
+        dmma884(acc[gi][0], acc[gi][1], a23.y, b23[gi].y);
+      }
+    }
+  }
+#pragma unroll
+  for (int gi = 0; gi < kStripDmmaRows / 8; ++gi) {  // lane: vector grp, strip rows 8 gi + 2 kq + {0, 1}
+    red[warp][8 * gi + 2 * kq][grp] = acc[gi][0];
+    red[warp][8 * gi + 2 * kq + 1][grp] = acc[gi][1];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kStripDmmaRows * kKB; idx += 256) {
+    const int pr = idx / kKB, c = idx - pr * kKB;
+    if (p0 + pr < m) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][pr][c];
+      AQ[bt * strideQ + (int64_t)c * k + g.hr[bt * g.cs_rows + p0 + pr]] += v;
     }
   }
 }
@@ -1093,6 +1229,9 @@ extern "C" int spb_score_gram_small(const double* d_G, int64_t k, int64_t ld, in
   SPB_REQUIRE(d_G && d_scores && k >= 1 && k <= kJacobiMaxK && ld >= k && batch >= 0,
               "spb_score_gram_small: need 1 <= k <= %d (got %lld)", kJacobiMaxK, (long long)k);
   if (batch == 0) return SPB_OK;
+  // Score only (no eigenvalue list), 4 < k <= 64: warp-per-matrix Householder + 9-section (pairs.cu) instead of the Jacobi sweep
+  static const bool jacobi_only = [] { const char* e = getenv("SPB_SMALL_EIG"); return e && !strcmp(e, "jacobi"); }();
+  if (!d_eig && k > 4 && k <= 64 && !jacobi_only) return score_gram_warp_launch(d_G, (int)k, ld, batch, d_scores, (cudaStream_t)stream);
   size_t smem = (size_t)jacobi_dim((int)k) * jacobi_ld((int)k) * sizeof(double);
   SPB_CUDA(cudaFuncSetAttribute(score_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int threads = k <= 32 ? 128 : 256;
@@ -1182,8 +1321,14 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
       }
       SPB_LAUNCH_CHECK();
       if (!gv.Gf && gv.cs_rows) {
-        dim3 rg((unsigned)((gv.cs_rows + kStripRowsPerCta - 1) / kStripRowsPerCta), batch);
-        strip_rows_kernel<<<rg, 256, 0, st>>>(gv, Qj, w.sQ, AQj, k);
+        if (symv_variant() > 0 && k % 128 == 0 && ld % 2 == 0 && reinterpret_cast<uintptr_t>(gv.Cs) % 16 == 0 &&
+            reinterpret_cast<uintptr_t>(Qj) % 16 == 0 && w.sQ % 2 == 0) {
+          dim3 rg((unsigned)((gv.cs_rows + kStripDmmaRows - 1) / kStripDmmaRows), batch);
+          strip_rows_dmma_kernel<<<rg, 256, 0, st>>>(gv, Qj, w.sQ, AQj, k);
+        } else {
+          dim3 rg((unsigned)((gv.cs_rows + kStripRowsPerCta - 1) / kStripRowsPerCta), batch);
+          strip_rows_kernel<<<rg, 256, 0, st>>>(gv, Qj, w.sQ, AQj, k);
+        }
         SPB_LAUNCH_CHECK();
         dim3 cg((k + 255) / 256, batch);
         strip_cols_kernel<<<cg, 256, 0, st>>>(gv, Qj, w.sQ, AQj, k);

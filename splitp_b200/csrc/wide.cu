@@ -239,22 +239,40 @@ __global__ void __launch_bounds__(256) thin_gram_wide_kernel(const unsigned long
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sG[i] = 0ull;
   __syncthreads();
   const unsigned long long spc = *special;
-  // slot index cap stands for the all-ones pattern, which lives outside the table
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= cap; i += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  // slot index cap stands for the all-ones pattern, which lives outside the table.  Warp-uniform trip count: the diagonal term is
+  // aggregated over the warp with full-mask intrinsics before the lanes diverge into the look-ups.
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base <= cap; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = base + lane;
     Key128 p{kAll, kAll};
     uint32_t cp = 0;
+    bool valid = false;
     if (i < cap) {
       p = load_key(hkeys, (uint64_t)i);
-      if (is_empty(p)) continue;
-      cp = hcounts[i];
-    } else {
-      if (spc == 0ull) continue;
+      valid = !is_empty(p);
+      if (valid) cp = hcounts[i];
+    } else if (i == cap && spc != 0ull) {
+      valid = true;
       cp = (uint32_t)spc;
     }
     uint32_t r1 = 0;
     for (int t = 0; t < sp.a; ++t) r1 = (r1 << 2) | get_digit(p, sp.shift[t]);
+    // Diagonal term count^2.  Nearly all sites sit in a handful of rows, so one shared-memory atomic per pattern serialises the CTA
+    // on a few addresses (and 16 register accumulators cost half the resident warps of this latency-bound kernel: measured 3.2 ms
+    // against 2.4 ms per split).  Patterns seen once -- almost all at 64 taxa -- are counted per (warp, row) with one atomic.
+    {
+      const uint32_t tag = valid ? ((r1 << 1) | (cp == 1u ? 1u : 0u)) : 0xFFFFFFFFu;
+      const unsigned peers = __match_any_sync(0xFFFFFFFFu, tag);
+      if (valid) {
+        if (cp == 1u) {
+          if (lane == __ffs(peers) - 1) atomicAdd(&sG[r1 * 16 + r1], (unsigned long long)__popc(peers));
+        } else {
+          atomicAdd(&sG[r1 * 16 + r1], (unsigned long long)cp * (unsigned long long)cp);
+        }
+      }
+    }
+    if (!valid) continue;
     // every unordered pair of patterns that differ only in their row part is found once, from its smaller row
-    atomicAdd(&sG[r1 * 16 + r1], (unsigned long long)cp * (unsigned long long)cp);
     if (multi) {
       const uint64_t h = column_bit(p, sp, bit_mask);
       if (!((multi[h >> 5] >> (h & 31)) & 1u)) continue;  // no other pattern shares this column
@@ -387,7 +405,15 @@ extern "C" int spb_thin_gram_wide_filtered(const uint64_t* d_hkeys, const uint32
 
 extern "C" int64_t spb_thin_filter_words(int64_t cap) {
   int64_t w = 1;
-  while (w * 16 < cap) w *= 2;  // 2 x cap bits per bitmap
+  // bits per bitmap: 8 x cap by default (false-positive rate of the column filter ~ patterns / bits: 1 in 16 at a half-full
+  // table; 2 x cap bits, the round-1 size, let one pattern in six through to its 4^a - 1 random table reads)
+  static int per_cap = 0;
+  if (!per_cap) {
+    const char* e = getenv("SPB_THIN_FILTER_BITS_PER_SLOT");
+    per_cap = e ? atoi(e) : 8;
+    if (per_cap < 1 || per_cap > 64) per_cap = 8;
+  }
+  while (w * 32 < cap * per_cap) w *= 2;
   return w;
 }
 

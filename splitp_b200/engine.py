@@ -525,6 +525,8 @@ class CountScorer:
         self._Gi = {}
         self._ws = {}
         self._batch_bytes = None
+        self._hi_ws = {}
+        self.strip_from_table = os.environ.get("SPB_STRIP_KERNEL", "table") != "scan"  # A/B switch: column scans of S0 (round 1)
         self.int32_gram = True  # large dense splits keep G as int32 + correction strip (half the eigen-stage traffic)
         self.gram_hook = None  # optional wrapper (fn, nb) around the Gram launch
         self.timer = None      # optional PhaseTimer: scatter / gram / correction / eigen spans (bench.py phase_ms)
@@ -607,6 +609,15 @@ class CountScorer:
             }
         return b
 
+    def _strip_ws(self, pitch):
+        """int32 scratch of spb_gram_hi_strip_batch_table for this thread's stream slot."""
+        key = (getattr(self._tl, "slot", 0), int(pitch))
+        ws = self._hi_ws.get(key)
+        need = int(_lib.lib.spb_gram_hi_strip_table_ws(self.GNB, int(pitch), self.hi_cap))
+        if ws is None or ws.numel() < need:
+            ws = self._hi_ws[key] = _empty(need, torch.int32)
+        return ws
+
     def _scatter(self, arr, nb, s0, layout, rows_pad, pitch, clear=False):
         """Scatter (or un-scatter) nb <= GNB splits into s0[0:nb], SPB_MAX_BATCH splits per launch."""
         t = self.table
@@ -635,8 +646,14 @@ class CountScorer:
             with _span(t, f"gram_i32_r{rows_pad}", nb):  # int32 tensor-core Gram, one span name per row count (bench.py roofline)
                 run() if self.gram_hook is None else self.gram_hook(run, nb)
             with _span(t, "correction", nb):
-                call("spb_gram_hi_strip_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
-                     _p(self.hi_num), self.hi_cap, _p(Cs), cs_rows, _p(pos), _p(hr), _p(hm), _st())
+                if self.strip_from_table and nb <= self.NB:
+                    tb = self.table  # cross terms by a join of the pattern list with the high list (no column scans of S0)
+                    call("spb_gram_hi_strip_batch_table", _p(tb.keys), _p(tb.counts), tb.num, arr, nb, rows_pad, pitch, _p(self.hi_rc),
+                         _p(self.hi_val), _p(self.hi_num), self.hi_cap, _p(Cs), cs_rows, _p(pos), _p(hr), _p(hm),
+                         _p(self._strip_ws(pitch)), _st())
+                else:
+                    call("spb_gram_hi_strip_batch", _p(s0), s0_stride, nb, rows_pad, pitch, layout, _p(self.hi_rc), _p(self.hi_val),
+                         _p(self.hi_num), self.hi_cap, _p(Cs), cs_rows, _p(pos), _p(hr), _p(hm), _st())
             with _span(t, "scatter", 0):
                 self._scatter(arr, nb, s0, layout, rows_pad, pitch, clear=True)
         except BaseException:
@@ -934,7 +951,21 @@ def marginalise(table, idx):
     """Pattern table over the taxa positions `idx` (ascending): values of collapsing patterns are added."""
     idx = sorted(idx)
     rows, _ = flatten_coo(table, idx, [])
-    uniq, inv = torch.unique(rows, return_inverse=True)
+    if table.counts is not None and len(idx) <= DIRECT_MAX_TAXA:
+        # integer counts, at most 12 taxa: add into the direct-indexed table and compact it (the library's own kernels; the
+        # compaction returns the keys in ascending order, as torch.unique did)
+        m, cells, total = len(idx), 4 ** len(idx), int(rows.shape[0])
+        if int(table.counts.to(torch.int64).sum().item()) >= 2 ** 31:
+            raise OverflowError("marginalise: pattern counts above 2^31 - 1 do not fit the 32-bit count table")
+        direct = _zeros(cells, torch.int32)
+        call("spb_direct_merge", _p(rows.contiguous()), _p(table.counts.contiguous()), total, cells, _p(direct), _st())
+        cap = min(cells, max(total, 1))
+        keys, counts, num = _empty(cap, torch.int64), _empty(cap, torch.int32), _zeros(1, torch.int64)
+        tmp = _empty(int(lib.spb_compact_tmp_words(cells)), torch.int32)
+        call("spb_compact_direct", _p(direct), None, cells, _p(keys), _p(counts), None, cap, _p(num), _p(tmp), _st())
+        P = int(num.item())
+        return PatternTable(m, keys[:P], counts=counts[:P], divisor=table.divisor)
+    uniq, inv = torch.unique(rows, return_inverse=True)  # larger sub-alignments / probability tables: library sort (DESIGN.md section 7)
     if table.counts is not None:
         acc = torch.zeros(len(uniq), dtype=torch.int64, device=rows.device).index_add_(0, inv, table.counts.to(torch.int64))
         return PatternTable(len(idx), uniq, counts=acc.to(torch.int32), divisor=table.divisor)

@@ -355,3 +355,62 @@ def test_symv_i32_kernels_against_fp64_matmul(eng, k, nb, variant):
         else:
             bound = 64 * np.finfo(np.float64).eps * (Q.abs() @ G.double().abs()).max().item()
             assert (AQ - ref).abs().max().item() <= bound
+
+
+# ---------------------------------------------------------------------------------------------
+# correction strip: join of the pattern table with the high list against the column scans of S0
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("a", [5, 6])
+def test_correction_strip_from_table_equals_column_scan(sp, eng, a):
+    """spb_gram_hi_strip_batch_table against spb_gram_hi_strip_batch on the same scattered splits (12 taxa, 10^6 sites):
+    pos, hr, hm and the strip rows in use agree bit for bit (integer-valued fp64 sums)."""
+    n, N = 12, 1_000_000
+    tree, codes, tab = _count_table(sp, eng, n, N, 2)
+    splits = [s for s in sp.all_splits(tree) if len(s[0]) == a][::37][:9]
+    idx = [eng.split_positions(s, tree.taxa) for s in splits]
+    got = {}
+    for mode in (True, False):
+        scorer = eng.CountScorer(tab)
+        scorer.strip_from_table = mode
+        R, Ccols = 4 ** a, 4 ** (n - a)
+        layout, rows_pad, pitch = scorer.geometry(R, Ccols)
+        assert scorer._use_i32(layout, rows_pad, pitch)
+        s0 = scorer._buffers(layout, rows_pad, pitch, len(idx))[0]
+        buf = scorer._buffers_i32(rows_pad, len(idx))
+        buf["Cs"].fill_(float("nan"))  # rows >= hm are never written by the table form and never read
+        scorer._gram_batch_i32([scorer._plan(ia, ib, False)[0] for ia, ib in idx], s0, buf, 0, layout, rows_pad, pitch)
+        torch.cuda.synchronize()
+        got[mode] = {k: v[: len(idx)].clone() for k, v in buf.items()}
+    for key in ("pos", "hm", "G"):
+        assert torch.equal(got[True][key], got[False][key]), key
+    for b in range(len(idx)):
+        m = int(got[True]["hm"][b].item())
+        assert m > 0
+        assert torch.equal(got[True]["hr"][b, :m], got[False]["hr"][b, :m])
+        assert torch.equal(got[True]["Cs"][b, :m], got[False]["Cs"][b, :m])
+
+
+# ---------------------------------------------------------------------------------------------
+# small Gram matrices: warp-per-matrix Householder + 9-section against the Jacobi kernel and LAPACK
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [5, 16, 31, 33, 64])
+def test_score_gram_small_warp_path_against_lapack(eng, k):
+    """engine.score_gram without the eigenvalue list takes the warp-per-matrix kernel (k <= 64); with it, the Jacobi kernel.
+    Both against LAPACK singular values of integer count flattenings with planted rank-4 structure (small scores)."""
+    rng = np.random.default_rng(40 + k)
+    mats, want = [], []
+    for t in range(24):
+        cols = 4 * k + 7
+        base = rng.integers(1, 2000, size=(k, 4)).astype(np.float64) @ rng.integers(1, 50, size=(4, cols)).astype(np.float64)
+        noise = rng.poisson(0.5 if t % 2 else 30.0, size=(k, cols)).astype(np.float64)
+        F = base + noise
+        G = F @ F.T  # exact: integers far below 2^53
+        sv = np.linalg.svd(F, compute_uv=False)  # the reference's route (phylogenetics.py:282-300)
+        want.append(np.sqrt((sv[4:] ** 2).sum() / (sv ** 2).sum()))
+        mats.append(G)
+    G = torch.from_numpy(np.stack(mats)).cuda()
+    fast = eng.score_gram(G, k).cpu().numpy()
+    slow, eig = eng.score_gram(G, k, want_info=True)
+    for f, s, w in zip(fast, slow.cpu().numpy(), want):
+        assert_score(f, w)
+        assert_score(s, w)
