@@ -106,8 +106,9 @@ def sites_replicated(wl, world):
 
 def config_of(name, wl, n_splits, world):
     """The `config` object: identical keys and values in both arms."""
-    par = f"splits sharded x{world}, sites replicated (counting them all is cheaper than the exchange)" \
-        if sites_replicated(wl, world) else f"sites+splits sharded x{world}"
+    par = f"splits sharded x{world} (contiguous runs of the size-class-ordered list, cut at equal modelled cost), sites " \
+          f"replicated (counting them all is cheaper than the exchange)" if sites_replicated(wl, world) \
+        else f"sites+splits sharded x{world}"
     return {"workload": wl["desc"], "name": name, "taxa": wl["n"], "sites": wl["sites"], "splits": n_splits,
             "model": wl["model"], "branch_length": wl["bl"], "seed": wl["seed"],
             "l2": "flushed between timed steps (256 MB fill)", "parallelism": par}

@@ -14,7 +14,8 @@ and the inner loop of `erickson_SVD` (phylogenetics.py:126-140).  `score_splits`
                           sparse flattening (dropping all-zero rows and columns does not change the singular values)
     Method.subflattening  pack -> pair tables -> H N H^T -> per split: gather + Gram + eigenvalues (kernel 3)
 
-Under `torch.distributed` (one process per GPU) the splits are dealt to the ranks for scoring and every rank receives
+Under `torch.distributed` (one process per GPU) the splits are dealt to the ranks for scoring (flattening scores: contiguous
+runs of the size-class-ordered list cut at equal modelled cost; subflattening scores: round-robin) and every rank receives
 the scores of all splits.  The counting stage has two forms: `sites="shard"` -- every rank passes ITS contiguous site
 shard (distributed.shard_range) and the pattern tables are merged -- or `sites="replicated"` -- every rank passes the
 WHOLE alignment and counts it itself, with no exchange at all.  The second form wins while counting the whole alignment
@@ -126,7 +127,21 @@ class SplitScorer:
         self.count_world = 1 if sites == "replicated" else world  # ranks that share the counting stage
         self.idx_all = _positions(splits, taxa)
         self.S = len(self.idx_all)
-        self.idx_mine = spd.shard_strided(self.idx_all, rank, world)
+        self.positions = None
+        if method == Method.flattening and world > 1 and self.S:
+            # contiguous runs of the class-ordered list, cut at equal modelled cost (distributed.partition_by_cost): most ranks
+            # then score ONE size class in one batch instead of an eighth of every class
+            n = len(self.idx_all[0][0]) + len(self.idx_all[0][1])
+            cls = [min(len(ia), len(ib)) for ia, ib in self.idx_all]
+            per = {a: spd.flattening_cost_us(n, a) for a in set(cls)}
+            order = sorted(range(self.S), key=lambda i: (-per[cls[i]], i))
+            ranges = spd.partition_by_cost([cls[i] for i in order], [per[cls[i]] for i in order],
+                                           {a: spd.flattening_fixed_us(a) for a in per}, world)
+            mine = order[ranges[rank][0]:ranges[rank][1]]
+            self.idx_mine = [self.idx_all[i] for i in mine]
+            self.positions = mine
+        else:
+            self.idx_mine = spd.shard_strided(self.idx_all, rank, world)
         self.reduce_fn = spd.make_reduce_fn(group) if self.count_world > 1 else None
         self.gather_fn = spd.make_gather_fn(group) if self.count_world > 1 else None
         self.scorer = None
@@ -173,6 +188,10 @@ class SplitScorer:
                 pt = engine.pair_finalize(raw, aln.n, -1.0)  # divisor = usable sites, read on the device: no host sync
                 out = engine.subflatten_scores(pt, self.masks[0], self.masks[1])
         with _span(t, "gather"):
+            if self.positions is not None:
+                if not isinstance(self.positions, torch.Tensor):
+                    self.positions = torch.tensor(self.positions, dtype=torch.int64, device=out.device)
+                return spd.gather_by_position(out, self.positions, self.S, self.group)
             return spd.gather_strided(out, self.S, self.rank, self.world, self.group)
 
     def _timed_gather(self, keys, counts):

@@ -132,6 +132,85 @@ def gather_strided(local_scores, total, rank, world, group=None):
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# cost-balanced split partition for the count-flattening scores
+# ------------------------------------------------------------------------------------------------
+# A strided deal gives every rank an eighth of EVERY size class: five small batches per rank, each with its own chain of
+# latency-bound solver kernels (8 GPUs, 12 taxa: 3.9 ms of eigen stage per rank against 2.5 ms = an eighth of the one-GPU stage).
+# Dealing contiguous runs of the class-ordered split list instead leaves most ranks with ONE class; the runs are cut at equal
+# modelled cost.  The model (B200 rates measured by bench.py / profiles/r2_launches_c2.md; only RATIOS between classes matter):
+#   scatter + clear  2 P byte stores at 1e11 /s
+#   Gram             max(tensor ops of the executed upper-triangle blocks at 2990 TOP/s, S0 bytes at 5 TB/s); dp4a rows <= 32: 1.5 TB/s
+#   eigen            rows >= 1024: two G0 Q products at 5.9 TB/s + strip passes + correction; below: ~1.5 us
+#   fixed            one solver chain per (rank, class): 500 us for Krylov classes (rows > 128), 100 us otherwise
+def flattening_cost_us(n_taxa, a, patterns=65536):
+    """Modelled device time of ONE count-flattening score with a short side of `a` taxa, microseconds."""
+    R, Cc = 4.0 ** a, 4.0 ** (n_taxa - a)
+    scatter = 2.0 * patterns / 1e11 * 1e6
+    rows_pad = max(R, 128.0) if R > 32 else R
+    pitch = max(Cc, 128.0)
+    if R >= 256:
+        T = rows_pad / 256.0
+        gram = T * (T + 1) / 2.0 * (256.0 * 256.0 * pitch * 2.0) / 2990e12 * 1e6
+    else:
+        gram = 0.0
+    gram = max(gram, rows_pad * pitch / (5e12 if R > 32 else 1.5e12) * 1e6)
+    if R >= 1024:
+        eigen = 2.0 * R * R * 4.0 / 5.9e12 * 1e6 + 4.0 * 130.0 * R * 8.0 / 3e12 * 1e6 + 3.0
+    else:
+        eigen = 1.5
+    return scatter + gram + eigen
+
+
+def flattening_fixed_us(a):
+    return 500.0 if 4 ** a > 128 else 100.0
+
+
+def partition_by_cost(classes, costs, fixed, world):
+    """classes[i], costs[i]: size class and modelled cost of item i of a CLASS-ORDERED list; fixed[c]: per-rank cost of touching
+    class c.  Returns `world` half-open ranges [b, e) covering the list that minimise the largest modelled rank time (its items +
+    the fixed cost of every class it touches): bisection on that bottleneck, each trial a greedy left-to-right fill."""
+    n = len(costs)
+
+    def fill(limit):
+        cuts, b = [], 0
+        for _ in range(world):
+            acc, e, cur = 0.0, b, None
+            while e < n:
+                add = costs[e] + (fixed[classes[e]] if classes[e] != cur else 0.0)
+                if acc + add > limit and e > b:
+                    break
+                acc += add
+                cur = classes[e]
+                e += 1
+            cuts.append((b, e))
+            b = e
+        return cuts if b == n else None
+
+    hi = float(sum(costs)) + sum(fixed[c] for c in set(classes)) + 1.0
+    lo = 0.0
+    best = fill(hi) or [(0, n)] + [(n, n)] * (world - 1)
+    for _ in range(50):
+        mid = 0.5 * (lo + hi)
+        cuts = fill(mid)
+        if cuts is None:
+            lo = mid
+        else:
+            hi, best = mid, cuts
+    return best
+
+
+def gather_by_position(local_scores, positions, total, group=None):
+    """Inverse of an arbitrary partition: every rank writes its scores at `positions` (int64 device tensor) of a zero vector of
+    length `total`; the SUM all-reduce then holds every score on every rank (x + 0.0 is exact)."""
+    full = torch.zeros(total, dtype=local_scores.dtype, device=local_scores.device)
+    if positions.numel():
+        full.index_copy_(0, positions, local_scores)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return full
+
+
 def count_patterns_sharded(aln, rank, world, group=None, want_first=False, local=False):
     """Pattern table of the WHOLE alignment.  local=False: every rank holds the full alignment and counts the
     site range shard_range(N, r, world, 32) of it.  local=True: `aln` IS this rank's site shard (then `first`

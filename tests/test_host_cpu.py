@@ -174,6 +174,10 @@ assert sc.tolist() == [float(i) for i in range(S)]
 mine = spd.shard_strided(list(range(S)), rank, world)
 sc = spd.gather_strided(torch.tensor(mine, dtype=torch.float64), S, rank, world)
 assert sc.tolist() == [float(i) for i in range(S)]
+# cost-balanced partition: arbitrary positions per rank, gathered by a SUM all-reduce of disjoint supports
+pos = torch.tensor([10, 0, 3, 7] if rank == 0 else [1, 2, 4, 5, 6, 8, 9], dtype=torch.int64)
+sc = spd.gather_by_position(pos.to(torch.float64) * 1.5, pos, S)
+assert sc.tolist() == [1.5 * i for i in range(S)]
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 ''')
@@ -450,3 +454,31 @@ def test_warp2_scorer_model_against_lapack(oracle):
         ref = np.sqrt(max(lam[4:].sum(), 0.0) / lam.sum())
         got, _ = score_warp2_model(G)
         assert abs(got - ref) <= 1e-12 * max(ref, 1.0), (k, got, ref)
+
+
+def test_partition_by_cost_balances_the_class_ordered_split_list():
+    """distributed.partition_by_cost on the 2,035 splits of 12 taxa: the ranges cover the list once, every rank's modelled time
+    (items + one fixed cost per class it touches) is within 3 % of the mean, and most ranks hold a single size class."""
+    import bench_inputs as BI
+    from splitp_b200 import distributed as spd
+    idx = BI.all_splits_idx(12)
+    cls = [min(len(a), len(b)) for a, b in idx]
+    per = {a: spd.flattening_cost_us(12, a, 60000) for a in set(cls)}
+    fixed = {a: spd.flattening_fixed_us(a) for a in per}
+    assert per[6] > per[5] > per[4] and per[6] > 3 * per[5]
+    order = sorted(range(len(idx)), key=lambda i: (-per[cls[i]], i))
+    for world in (1, 2, 3, 8, 16):
+        ranges = spd.partition_by_cost([cls[i] for i in order], [per[cls[i]] for i in order], fixed, world)
+        assert len(ranges) == world and ranges[0][0] == 0 and ranges[-1][1] == len(idx)
+        assert all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+        times, single = [], 0
+        for b, e in ranges:
+            cs = [cls[order[i]] for i in range(b, e)]
+            times.append(sum(per[c] for c in cs) + sum(fixed[c] for c in set(cs)))
+            single += len(set(cs)) == 1
+        assert max(times) <= 1.03 * (sum(times) / world), (world, times)
+        if world == 8:
+            assert single >= 5
+    # degenerate inputs: fewer items than ranks, one class
+    ranges = spd.partition_by_cost([3, 3], [1.0, 1.0], {3: 0.5}, 4)
+    assert [e - b for b, e in ranges] == [1, 1, 0, 0]
