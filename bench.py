@@ -578,6 +578,12 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
     phases = {k: v for k, v in timer.totals().items()}
     phase_ms = {k: round(v[0] / steps, 4) for k, v in phases.items()}
     phase_ms["step_total"] = round(sum(step_ms) / steps, 4)
+    rank_busy_ms = None
+    if world > 1:  # per-rank time before the score gather (= before waiting for the slowest rank): the balance of the split partition
+        busy = torch.tensor([(sum(step_ms) - phases.get("gather", (0.0, 0))[0]) / steps], dtype=torch.float64, device=dev)
+        allb = [torch.zeros_like(busy) for _ in range(world)]
+        dist.all_gather(allb, busy)
+        rank_busy_ms = [round(float(x.item()), 3) for x in allb]
 
     # ---- e2e: host buffers through the public batched call, H2D + D2H inside the timed region ----
     for _ in range(2):
@@ -669,6 +675,8 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
 
     if rank != 0:
         return None
+    if rank_busy_ms is not None:
+        phase_ms["rank_busy_ms"] = rank_busy_ms
     out = {"metric": "split_scores_per_sec", "value": value, "unit": "split-scores/s", "n_gpus": world, "steps": steps,
            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": {"flattening": "u8", "thin": "u128"}.get(method, "f64"), "data": "synthetic",

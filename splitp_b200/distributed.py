@@ -139,14 +139,15 @@ def gather_strided(local_scores, total, rank, world, group=None):
 # latency-bound solver kernels (8 GPUs, 12 taxa: 3.9 ms of eigen stage per rank against 2.5 ms = an eighth of the one-GPU stage).
 # Dealing contiguous runs of the class-ordered split list instead leaves most ranks with ONE class; the runs are cut at equal
 # modelled cost.  The model (B200 rates measured by bench.py / profiles/r2_launches_c2.md; only RATIOS between classes matter):
-#   scatter + clear  2 P byte stores at 1e11 /s
+#   scatter + clear  P / 3e10 s (2 P byte stores at 1e11 /s plus launch gaps) + 1.5 us of per-split launch / host overhead
+#                    (calibrated on the two-GPU run: rank 0 with 393 6|6 splits 24.3 ms, rank 1 with the rest 26.5 ms)
 #   Gram             max(tensor ops of the executed upper-triangle blocks at 2990 TOP/s, S0 bytes at 5 TB/s); dp4a rows <= 32: 1.5 TB/s
 #   eigen            rows >= 1024: two G0 Q products at 5.9 TB/s + strip passes + correction; below: ~1.5 us
 #   fixed            one solver chain per (rank, class): 500 us for Krylov classes (rows > 128), 100 us otherwise
 def flattening_cost_us(n_taxa, a, patterns=65536):
     """Modelled device time of ONE count-flattening score with a short side of `a` taxa, microseconds."""
     R, Cc = 4.0 ** a, 4.0 ** (n_taxa - a)
-    scatter = 2.0 * patterns / 1e11 * 1e6
+    scatter = patterns / 3e10 * 1e6 + 1.5  # scatter + clear phase as measured (2.0 us at 60 k patterns) + 1.5 us of launch / host overhead
     rows_pad = max(R, 128.0) if R > 32 else R
     pitch = max(Cc, 128.0)
     if R >= 256:

@@ -747,7 +747,7 @@ class CountScorer:
             return torch.full((1,), float("nan"), dtype=torch.float64, device=G.device)
         return score_gram(G, k)
 
-    def score_many(self, splits_idx, reduced=False, max_batch=256, max_batch_bytes=None, big_hook=None):
+    def score_many(self, splits_idx, reduced=False, max_batch=512, max_batch_bytes=None, big_hook=None):
         """Scores of many splits.  Dense count flattenings of equal shape are batched: their Gram matrices are
         built SPB_MAX_BATCH at a time into G[b] and ONE batched eigen-solver call scores up to `max_batch` of them
         (the Jacobi / Krylov kernels are latency-bound per matrix, so batching is what keeps all SMs busy)."""
@@ -757,10 +757,12 @@ class CountScorer:
                 out[s:s + 1] = self.score(ia, ib, True)
             return out
         if max_batch_bytes is None:
-            # Gram batch buffer: at most 16 GB and at most a third of what was free when this scorer first scored.
+            # Gram batch buffer: at most 48 GB and at most a third of what was free when this scorer first scored (16 GB / 256
+            # matrices until round 2: the 462 6|6 matrices of 12 taxa then went through the eigen-solver in 3 chunks, each with its
+            # own ~0.5 ms chain of latency-bound kernels and a host synchronisation; one chunk of 462 needs 31 GB of int32 Gram).
             # Queried ONCE: cudaMemGetInfo was measured to take 4-50 ms per call on a busy context.
             if self._batch_bytes is None:
-                self._batch_bytes = min(16 << 30, torch.cuda.mem_get_info()[0] // 3)
+                self._batch_bytes = min(48 << 30, torch.cuda.mem_get_info()[0] // 3)
             max_batch_bytes = self._batch_bytes
         n = self.table.n
         gkey = (id(splits_idx), n, "groups")
