@@ -677,6 +677,13 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
         return None
     if rank_busy_ms is not None:
         phase_ms["rank_busy_ms"] = rank_busy_ms
+    partition = None
+    if method == "flattening" and world > 1 and getattr(scorer, "_cls", None) is not None:
+        partition = {"kind": "contiguous runs of the size-class-ordered split list, cut at equal modelled cost; costs re-fitted once "
+                             "from the per-rank device times of warm-up step 2 (distributed.refit_costs)",
+                     "class_cost_us": {str(a): round(v, 2) for a, v in sorted(scorer._per.items())},
+                     "splits_per_rank": [{str(a): c for a, c in sorted(h.items())} for h in scorer._held],
+                     "refit_rank_times_us": [round(x, 1) for x in scorer.rank_times_us] if scorer.rank_times_us else None}
     out = {"metric": "split_scores_per_sec", "value": value, "unit": "split-scores/s", "n_gpus": world, "steps": steps,
            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": {"flattening": "u8", "thin": "u128"}.get(method, "f64"), "data": "synthetic",
@@ -688,6 +695,8 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
         out["roofline_count"] = count_roof
     sc = scores.cpu().numpy()
     checks = {"finite": bool(np.isfinite(sc).all()), "host_equals_device": bool(np.array_equal(sc, host_scores.numpy()))}
+    if partition is not None:
+        out["partition"] = partition
     if cpu_baseline and world == 1 and not args.no_cpu_baseline:
         if method == "flattening":
             cb, ref_scores = cpu_flattening_sample(name, wl, codes_np, idx_all, budget_s=25.0)

@@ -12,3 +12,5 @@ print("roofline", {k: r.get(k) for k in ("achieved", "peak", "frac", "ms_per_mat
 print("checks", d.get("checks"))
 for k, w in (d.get("workloads") or {}).items():
     print(" ", k, {x: w.get(x) for x in ("value", "ms_per_step", "error")}, "e2e", (w.get("e2e") or {}).get("value"))
+if d.get("partition"):
+    print("partition", d["partition"].get("class_cost_us"), d["partition"].get("splits_per_rank"), d["partition"].get("refit_rank_times_us"))

@@ -26,6 +26,8 @@ ranks takes 1.5 ms).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -128,18 +130,16 @@ class SplitScorer:
         self.idx_all = _positions(splits, taxa)
         self.S = len(self.idx_all)
         self.positions = None
+        self._steps = 0
+        self._cls = None
         if method == Method.flattening and world > 1 and self.S:
             # contiguous runs of the class-ordered list, cut at equal modelled cost (distributed.partition_by_cost): most ranks
             # then score ONE size class in one batch instead of an eighth of every class
-            n = len(self.idx_all[0][0]) + len(self.idx_all[0][1])
-            cls = [min(len(ia), len(ib)) for ia, ib in self.idx_all]
-            per = {a: spd.flattening_cost_us(n, a) for a in set(cls)}
-            order = sorted(range(self.S), key=lambda i: (-per[cls[i]], i))
-            ranges = spd.partition_by_cost([cls[i] for i in order], [per[cls[i]] for i in order],
-                                           {a: spd.flattening_fixed_us(a) for a in per}, world)
-            mine = order[ranges[rank][0]:ranges[rank][1]]
-            self.idx_mine = [self.idx_all[i] for i in mine]
-            self.positions = mine
+            self._n = len(self.idx_all[0][0]) + len(self.idx_all[0][1])
+            self._cls = [min(len(ia), len(ib)) for ia, ib in self.idx_all]
+            self._per = {a: spd.flattening_cost_us(self._n, a) for a in set(self._cls)}
+            self._fixed = {a: spd.flattening_fixed_us(a) for a in self._per}
+            self._cut()
         else:
             self.idx_mine = spd.shard_strided(self.idx_all, rank, world)
         self.reduce_fn = spd.make_reduce_fn(group) if self.count_world > 1 else None
@@ -147,12 +147,45 @@ class SplitScorer:
         self.scorer = None
         self.masks = None
         self.timer = None
+        self.refit_enabled = os.environ.get("SPB_PARTITION_REFIT", "1") != "0"
+        self.rank_times_us = None
         if method == Method.subflattening:
             ma, mb = engine.masks_from_splits(self.idx_mine)
             dev = engine.device()
             self.masks = (torch.from_numpy(ma.view(np.int64)).to(dev), torch.from_numpy(mb.view(np.int64)).to(dev))
         elif method != Method.flattening:
             raise NotImplementedError("score_splits: Method.flattening or Method.subflattening")
+
+    REFIT_AFTER_STEP = 2  # the partition is re-cut ONCE, from the rank times of this call (the first call pays the allocations)
+
+    def _cut(self):
+        """(Re)partitions the class-ordered split list from the current per-class costs."""
+        from . import distributed as spd
+        per, cls = self._per, self._cls
+        order = sorted(range(self.S), key=lambda i: (-per[cls[i]], i))
+        ranges = spd.partition_by_cost([cls[i] for i in order], [per[cls[i]] for i in order], self._fixed, self.world)
+        self._held = []
+        for b, e in ranges:
+            held = {}
+            for i in order[b:e]:
+                held[cls[i]] = held.get(cls[i], 0) + 1
+            self._held.append(held)
+        mine = order[ranges[self.rank][0]:ranges[self.rank][1]]
+        self.idx_mine = [self.idx_all[i] for i in mine]
+        self.positions = mine
+
+    def _refit(self, my_us):
+        """All ranks exchange the device time of their share, re-fit the per-class costs (distributed.refit_costs) and re-cut."""
+        import torch.distributed as dist
+
+        from . import distributed as spd
+        mine = torch.tensor([my_us], dtype=torch.float64, device=engine.device())
+        every = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(every, mine, group=self.group)
+        times = [float(x.item()) for x in every]
+        self.rank_times_us = times
+        self._per = spd.refit_costs(self._per, self._fixed, self._held, times)
+        self._cut()
 
     def device_scores(self, alignment, gram_hook=None):
         """Scores of ALL splits as a device tensor.  `alignment`: this rank's site shard, or the whole alignment when the
@@ -161,6 +194,11 @@ class SplitScorer:
 
         from . import distributed as spd
         t = self.timer
+        self._steps += 1
+        refit = self._cls is not None and self._steps == self.REFIT_AFTER_STEP and self.refit_enabled
+        if refit:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         if self.method == Method.flattening:
             with _span(t, "h2d+pack"):
                 aln = _as_alignment(alignment, want_sm=True, want_planes=False)
@@ -187,12 +225,19 @@ class SplitScorer:
             with _span(t, "subflatten+score"):
                 pt = engine.pair_finalize(raw, aln.n, -1.0)  # divisor = usable sites, read on the device: no host sync
                 out = engine.subflatten_scores(pt, self.masks[0], self.masks[1])
+        if refit:
+            ev1.record()
         with _span(t, "gather"):
             if self.positions is not None:
                 if not isinstance(self.positions, torch.Tensor):
                     self.positions = torch.tensor(self.positions, dtype=torch.int64, device=out.device)
-                return spd.gather_by_position(out, self.positions, self.S, self.group)
-            return spd.gather_strided(out, self.S, self.rank, self.world, self.group)
+                res = spd.gather_by_position(out, self.positions, self.S, self.group)
+            else:
+                res = spd.gather_strided(out, self.S, self.rank, self.world, self.group)
+        if refit:
+            ev1.synchronize()
+            self._refit(ev0.elapsed_time(ev1) * 1e3)
+        return res
 
     def _timed_gather(self, keys, counts):
         with _span(self.timer, "exchange"):

@@ -201,6 +201,30 @@ def partition_by_cost(classes, costs, fixed, world):
     return best
 
 
+RANK_BASE_US = 400.0  # per-rank time outside the per-split work: pack, count, compaction, gather
+
+
+def refit_costs(per, fixed, rank_classes, rank_times_us, ridge=0.05):
+    """Per-class costs re-fitted to MEASURED rank times.  per[a]: modelled cost per split; rank_classes[r] = {a: number of splits of
+    class a on rank r}; rank_times_us[r]: measured time of rank r.  Model: t_r = RANK_BASE_US + sum_a n_ra per[a] s_a + sum_{a on r}
+    fixed[a]; the scale factors s_a solve the ridge problem min |A s - t'|^2 + (ridge mean(t'))^2 |s - 1|^2 (few ranks leave s
+    under-determined: it then stays at the model) and are clipped to [0.5, 2]."""
+    import numpy as np
+    classes = sorted(per)
+    A = np.zeros((len(rank_classes), len(classes)))
+    t = np.zeros(len(rank_classes))
+    for r, held in enumerate(rank_classes):
+        t[r] = rank_times_us[r] - RANK_BASE_US - sum(fixed[a] for a in held)
+        for a, cnt in held.items():
+            A[r, classes.index(a)] = cnt * per[a]
+    lam = ridge * max(float(np.mean(np.abs(t))), 1.0)
+    M = np.vstack([A, lam * np.eye(len(classes))])
+    rhs = np.concatenate([t, lam * np.ones(len(classes))])
+    sol = np.linalg.lstsq(M, rhs, rcond=None)[0]
+    sol = np.clip(sol, 0.5, 2.0)
+    return {a: per[a] * float(sol[i]) for i, a in enumerate(classes)}
+
+
 def gather_by_position(local_scores, positions, total, group=None):
     """Inverse of an arbitrary partition: every rank writes its scores at `positions` (int64 device tensor) of a zero vector of
     length `total`; the SUM all-reduce then holds every score on every rank (x + 0.0 is exact)."""

@@ -482,3 +482,40 @@ def test_partition_by_cost_balances_the_class_ordered_split_list():
     # degenerate inputs: fewer items than ranks, one class
     ranges = spd.partition_by_cost([3, 3], [1.0, 1.0], {3: 0.5}, 4)
     assert [e - b for b, e in ranges] == [1, 1, 0, 0]
+
+
+def test_refit_costs_recovers_class_costs_from_rank_times():
+    """distributed.refit_costs: rank times generated from 'true' per-class costs that differ from the model by up to 30 % are
+    fitted well enough that the re-cut partition is balanced under the TRUE costs (8 ranks); with 2 ranks the fit stays near
+    the model where the data say nothing and still improves the balance."""
+    import bench_inputs as BI
+    from splitp_b200 import distributed as spd
+    idx = BI.all_splits_idx(12)
+    cls = [min(len(a), len(b)) for a, b in idx]
+    model = {a: spd.flattening_cost_us(12, a, 60000) for a in set(cls)}
+    fixed = {a: spd.flattening_fixed_us(a) for a in model}
+    truth = {2: model[2] * 1.3, 3: model[3] * 0.8, 4: model[4] * 1.2, 5: model[5] * 0.9, 6: model[6] * 1.05}
+
+    def cut(per, world):
+        order = sorted(range(len(idx)), key=lambda i: (-per[cls[i]], i))
+        ranges = spd.partition_by_cost([cls[i] for i in order], [per[cls[i]] for i in order], fixed, world)
+        held = []
+        for b, e in ranges:
+            h = {}
+            for i in order[b:e]:
+                h[cls[i]] = h.get(cls[i], 0) + 1
+            held.append(h)
+        return held
+
+    def true_times(held):
+        return [spd.RANK_BASE_US + sum(n * truth[a] for a, n in h.items()) + sum(fixed[a] for a in h) for h in held]
+
+    for world in (2, 8):
+        held = cut(model, world)
+        before = true_times(held)
+        fitted = spd.refit_costs(model, fixed, held, before)
+        after = true_times(cut(fitted, world))
+        assert max(after) < max(before)
+        if world == 8:
+            assert max(after) <= 1.03 * (sum(after) / world), after
+            assert abs(fitted[6] / truth[6] - 1) < 0.03 and abs(fitted[5] / truth[5] - 1) < 0.05
