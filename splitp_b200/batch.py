@@ -121,7 +121,7 @@ class SplitScorer:
     Keeping one per (alignment shape, split list) is what a serving loop would do; `score_splits` builds a throw-away
     one."""
 
-    def __init__(self, splits, taxa=None, method=Method.flattening, rank=0, world=1, group=None, sites="shard"):
+    def __init__(self, splits, taxa=None, method=Method.flattening, rank=0, world=1, group=None, sites="shard", refit_steps=(2,)):
         from . import distributed as spd
         if sites not in ("shard", "replicated"):
             raise ValueError('sites must be "shard" or "replicated"')
@@ -132,6 +132,9 @@ class SplitScorer:
         self.positions = None
         self._steps = 0
         self._cls = None
+        # calls after which the multi-GPU split partition is re-cut from the measured rank times (the first call pays the allocations;
+        # every re-cut needs one more call to warm the new shares up, so a benchmark lists only warm-up steps here)
+        self.refit_steps = tuple(refit_steps)
         if method == Method.flattening and world > 1 and self.S:
             # contiguous runs of the class-ordered list, cut at equal modelled cost (distributed.partition_by_cost): most ranks
             # then score ONE size class in one batch instead of an eighth of every class
@@ -155,8 +158,6 @@ class SplitScorer:
             self.masks = (torch.from_numpy(ma.view(np.int64)).to(dev), torch.from_numpy(mb.view(np.int64)).to(dev))
         elif method != Method.flattening:
             raise NotImplementedError("score_splits: Method.flattening or Method.subflattening")
-
-    REFIT_AFTER_STEP = 2  # the partition is re-cut ONCE, from the rank times of this call (the first call pays the allocations)
 
     def _cut(self):
         """(Re)partitions the class-ordered split list from the current per-class costs."""
@@ -184,7 +185,7 @@ class SplitScorer:
         dist.all_gather(every, mine, group=self.group)
         times = [float(x.item()) for x in every]
         self.rank_times_us = times
-        self._per = spd.refit_costs(self._per, self._fixed, self._held, times)
+        self._per, self._fixed = spd.refit_costs(self._per, self._fixed, self._held, times)
         self._cut()
 
     def device_scores(self, alignment, gram_hook=None):
@@ -195,7 +196,7 @@ class SplitScorer:
         from . import distributed as spd
         t = self.timer
         self._steps += 1
-        refit = self._cls is not None and self._steps == self.REFIT_AFTER_STEP and self.refit_enabled
+        refit = self._cls is not None and self._steps in self.refit_steps and self.refit_enabled
         if refit:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()

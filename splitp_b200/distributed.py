@@ -141,9 +141,11 @@ def gather_strided(local_scores, total, rank, world, group=None):
 # modelled cost.  The model (B200 rates measured by bench.py / profiles/r2_launches_c2.md; only RATIOS between classes matter):
 #   scatter + clear  P / 3e10 s (2 P byte stores at 1e11 /s plus launch gaps) + 1.5 us of per-split launch / host overhead
 #                    (calibrated on the two-GPU run: rank 0 with 393 6|6 splits 24.3 ms, rank 1 with the rest 26.5 ms)
-#   Gram             max(tensor ops of the executed upper-triangle blocks at 2990 TOP/s, S0 bytes at 5 TB/s); dp4a rows <= 32: 1.5 TB/s
-#   eigen            rows >= 1024: two G0 Q products at 5.9 TB/s + strip passes + correction; below: ~1.5 us
-#   fixed            one solver chain per (rank, class): 500 us for Krylov classes (rows > 128), 100 us otherwise
+#   Gram             max(tensor ops of the executed upper-triangle blocks at 2990 TOP/s, S0 bytes at 6 TB/s); dp4a rows <= 32: 1.5 TB/s
+#   eigen            rows >= 1024: two G0 Q products at 5.9 TB/s + strip passes + correction; below: ~0.8 us
+#   fixed            one solver chain per (rank, class): 700 us for Krylov classes (rows > 128), 140 us otherwise
+# (constants re-fitted to the per-rank times of the 8-GPU runs, profiles/r2_bench_n8.json `partition`; SplitScorer re-fits them
+# again at run time, refit_costs below)
 def flattening_cost_us(n_taxa, a, patterns=65536):
     """Modelled device time of ONE count-flattening score with a short side of `a` taxa, microseconds."""
     R, Cc = 4.0 ** a, 4.0 ** (n_taxa - a)
@@ -155,16 +157,16 @@ def flattening_cost_us(n_taxa, a, patterns=65536):
         gram = T * (T + 1) / 2.0 * (256.0 * 256.0 * pitch * 2.0) / 2990e12 * 1e6
     else:
         gram = 0.0
-    gram = max(gram, rows_pad * pitch / (5e12 if R > 32 else 1.5e12) * 1e6)
+    gram = max(gram, rows_pad * pitch / (6e12 if R > 32 else 1.5e12) * 1e6)
     if R >= 1024:
-        eigen = 2.0 * R * R * 4.0 / 5.9e12 * 1e6 + 4.0 * 130.0 * R * 8.0 / 3e12 * 1e6 + 3.0
+        eigen = 2.0 * R * R * 4.0 / 5.9e12 * 1e6 + 4.0 * 130.0 * R * 8.0 / 3e12 * 1e6 + 1.0
     else:
-        eigen = 1.5
+        eigen = 0.8
     return scatter + gram + eigen
 
 
 def flattening_fixed_us(a):
-    return 500.0 if 4 ** a > 128 else 100.0
+    return 700.0 if 4 ** a > 128 else 140.0
 
 
 def partition_by_cost(classes, costs, fixed, world):
@@ -206,23 +208,25 @@ RANK_BASE_US = 400.0  # per-rank time outside the per-split work: pack, count, c
 
 def refit_costs(per, fixed, rank_classes, rank_times_us, ridge=0.05):
     """Per-class costs re-fitted to MEASURED rank times.  per[a]: modelled cost per split; rank_classes[r] = {a: number of splits of
-    class a on rank r}; rank_times_us[r]: measured time of rank r.  Model: t_r = RANK_BASE_US + sum_a n_ra per[a] s_a + sum_{a on r}
-    fixed[a]; the scale factors s_a solve the ridge problem min |A s - t'|^2 + (ridge mean(t'))^2 |s - 1|^2 (few ranks leave s
-    under-determined: it then stays at the model) and are clipped to [0.5, 2]."""
+    class a on rank r}; rank_times_us[r]: measured time of rank r.  Model: t_r = RANK_BASE_US + sum_a n_ra per[a] s_a + s_f
+    sum_{a on r} fixed[a]; the scale factors (one per class, one for the fixed chain costs) solve the ridge problem
+    min |A s - t'|^2 + (ridge mean(t'))^2 |s - 1|^2 (few ranks leave s under-determined: it then stays at the model) and are
+    clipped to [0.5, 2].  Returns (per, fixed) rescaled."""
     import numpy as np
     classes = sorted(per)
-    A = np.zeros((len(rank_classes), len(classes)))
+    nc = len(classes)
+    A = np.zeros((len(rank_classes), nc + 1))
     t = np.zeros(len(rank_classes))
     for r, held in enumerate(rank_classes):
-        t[r] = rank_times_us[r] - RANK_BASE_US - sum(fixed[a] for a in held)
+        t[r] = rank_times_us[r] - RANK_BASE_US
+        A[r, nc] = sum(fixed[a] for a in held)
         for a, cnt in held.items():
             A[r, classes.index(a)] = cnt * per[a]
     lam = ridge * max(float(np.mean(np.abs(t))), 1.0)
-    M = np.vstack([A, lam * np.eye(len(classes))])
-    rhs = np.concatenate([t, lam * np.ones(len(classes))])
-    sol = np.linalg.lstsq(M, rhs, rcond=None)[0]
-    sol = np.clip(sol, 0.5, 2.0)
-    return {a: per[a] * float(sol[i]) for i, a in enumerate(classes)}
+    M = np.vstack([A, lam * np.eye(nc + 1)])
+    rhs = np.concatenate([t, lam * np.ones(nc + 1)])
+    sol = np.clip(np.linalg.lstsq(M, rhs, rcond=None)[0], 0.5, 2.0)
+    return ({a: per[a] * float(sol[i]) for i, a in enumerate(classes)}, {a: fixed[a] * float(sol[nc]) for a in fixed})
 
 
 def gather_by_position(local_scores, positions, total, group=None):

@@ -513,7 +513,8 @@ def test_refit_costs_recovers_class_costs_from_rank_times():
     for world in (2, 8):
         held = cut(model, world)
         before = true_times(held)
-        fitted = spd.refit_costs(model, fixed, held, before)
+        fitted, fixed_fit = spd.refit_costs(model, fixed, held, before)
+        assert all(abs(fixed_fit[a] / fixed[a] - 1) < 0.25 for a in fixed)
         after = true_times(cut(fitted, world))
         assert max(after) < max(before)
         if world == 8:
