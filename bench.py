@@ -534,8 +534,7 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
         call_name = "engine.pack_wide + distributed.count_patterns_wide_sharded + engine.thin_split_scores"
     else:
         scorer = batch.SplitScorer(idx_all, None, sp.Method.flattening if method == "flattening" else sp.Method.subflattening,
-                                   rank, world, sites="replicated" if replicated else "shard",
-                                   refit_steps=tuple(range(2, max(warmup, 3))))  # re-cut after every warm-up step but the first and last
+                                   rank, world, sites="replicated" if replicated else "shard")  # one partition re-cut, after warm-up step 2
 
         def run(inp, t=None):
             scorer.timer = t
@@ -680,8 +679,8 @@ def gpu_workload(name, wl, args, ctx, steps, warmup, max_splits=None, cpu_baseli
         phase_ms["rank_busy_ms"] = rank_busy_ms
     partition = None
     if method == "flattening" and world > 1 and getattr(scorer, "_cls", None) is not None:
-        partition = {"kind": "contiguous runs of the size-class-ordered split list, cut at equal modelled cost; costs re-fitted "
-                             "from the per-rank device times of the warm-up steps 2 .. W-1 (distributed.refit_costs)",
+        partition = {"kind": "contiguous runs of the size-class-ordered split list, cut at equal modelled cost; costs re-fitted once "
+                             "from the per-rank device times of warm-up step 2 (distributed.refit_costs)",
                      "class_cost_us": {str(a): round(v, 2) for a, v in sorted(scorer._per.items())},
                      "splits_per_rank": [{str(a): c for a, c in sorted(h.items())} for h in scorer._held],
                      "refit_rank_times_us": [round(x, 1) for x in scorer.rank_times_us] if scorer.rank_times_us else None}

@@ -133,7 +133,7 @@ class SplitScorer:
         self._steps = 0
         self._cls = None
         # calls after which the multi-GPU split partition is re-cut from the measured rank times (the first call pays the allocations;
-        # every re-cut needs one more call to warm the new shares up, so a benchmark lists only warm-up steps here)
+        # the call after a re-cut reallocates batch buffers, so two listed steps must be at least two calls apart)
         self.refit_steps = tuple(refit_steps)
         if method == Method.flattening and world > 1 and self.S:
             # contiguous runs of the class-ordered list, cut at equal modelled cost (distributed.partition_by_cost): most ranks
@@ -185,6 +185,12 @@ class SplitScorer:
         dist.all_gather(every, mine, group=self.group)
         times = [float(x.item()) for x in every]
         self.rank_times_us = times
+        # a call that paid a one-off cost (the call after a re-cut reallocates its batch buffers: measured 42 ms instead of 21 ms)
+        # says nothing about the steady state: keep the partition when any rank is more than 30 % off its modelled time
+        for held, t_us in zip(self._held, times):
+            model = spd.RANK_BASE_US + sum(c * self._per[a] + self._fixed[a] for a, c in held.items())
+            if not 0.7 * model <= t_us <= 1.3 * model:
+                return
         self._per, self._fixed = spd.refit_costs(self._per, self._fixed, self._held, times)
         self._cut()
 
