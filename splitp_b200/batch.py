@@ -186,11 +186,12 @@ class SplitScorer:
         times = [float(x.item()) for x in every]
         self.rank_times_us = times
         # a call that paid a one-off cost (the call after a re-cut reallocates its batch buffers: measured 42 ms instead of 21 ms)
-        # says nothing about the steady state: keep the partition when any rank is more than 30 % off its modelled time
-        for held, t_us in zip(self._held, times):
-            model = spd.RANK_BASE_US + sum(c * self._per[a] + self._fixed[a] for a, c in held.items())
-            if not 0.7 * model <= t_us <= 1.3 * model:
-                return
+        # says nothing about the steady state: keep the partition when a rank's measured / modelled ratio is more than 30 % off the median ratio
+        ratios = [t_us / (spd.RANK_BASE_US + sum(c * self._per[a] + self._fixed[a] for a, c in held.items()))
+                  for held, t_us in zip(self._held, times)]
+        middle = sorted(ratios)[len(ratios) // 2]
+        if any(not 0.7 * middle <= r <= 1.3 * middle for r in ratios):
+            return
         self._per, self._fixed = spd.refit_costs(self._per, self._fixed, self._held, times)
         self._cut()
 
