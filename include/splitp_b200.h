@@ -116,12 +116,12 @@ int spb_hash_merge_wide(const uint64_t* d_keys, const uint32_t* d_counts, const 
 int spb_compact_hash_wide(const uint64_t* d_hkeys, const uint32_t* d_hcounts, const uint32_t* d_hfirst, int64_t cap,
                           uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_first, int64_t capacity, uint64_t* d_num,
                           void* stream);
-/* Exact Gram F F^T (double [4^a][4^a], a = 1 or 2) of the reduced flattening (constructions.py:31-55) of the split
+/* Exact Gram F F^T (double [4^a][4^a], a = 1, 2 or 3) of the reduced flattening (constructions.py:31-55) of the split
  * {h_idx_a} | {all other taxa}, computed from the hashed table by one lookup per (pattern, row). */
 int spb_thin_gram_wide(const uint64_t* d_hkeys, const uint32_t* d_hcounts, int64_t cap, const uint64_t* d_special, int n_taxa,
                        const uint8_t* h_idx_a, int a, double* d_G, void* stream);
 /* The same Gram with a column filter (two bitmaps of filter_words uint32 each in d_filter, zeroed here;
- * spb_thin_filter_words(cap) = 2 x cap bits per bitmap): patterns whose column holds no second pattern skip their
+ * spb_thin_filter_words(cap) = 8 x cap bits per bitmap): patterns whose column holds no second pattern skip their
  * 4^a - 1 table lookups.  Bit-identical result; d_filter == NULL is spb_thin_gram_wide. */
 int64_t spb_thin_filter_words(int64_t cap);
 int spb_thin_gram_wide_filtered(const uint64_t* d_hkeys, const uint32_t* d_hcounts, int64_t cap, const uint64_t* d_special,

@@ -185,8 +185,8 @@ __global__ void compact_wide_kernel(const unsigned long long* __restrict__ hkeys
 }
 
 struct ThinSplit {
-  int a;          // taxa on the thin side (1 or 2)
-  int shift[2];   // bit position of their digits inside the 128-bit key
+  int a;          // taxa on the thin side (1, 2 or 3)
+  int shift[3];   // bit position of their digits inside the 128-bit key
 };
 
 __device__ __forceinline__ uint32_t get_digit(Key128 k, int shift) {
@@ -234,9 +234,9 @@ __global__ void __launch_bounds__(256) thin_gram_wide_kernel(const unsigned long
                                                              double* __restrict__ G) {
   // per-CTA partial Gram in 64-bit integers: shared-memory integer atomics are native (a double atomicAdd in shared
   // memory is a CAS loop, which collapses on the few row patterns that carry most sites); sum count^2 <= N^2 < 2^64
-  __shared__ unsigned long long sG[16 * 16];
+  __shared__ unsigned long long sG[64 * 64];  // R x R, row stride R (R = 4, 16 or 64)
   const int R = 1 << (2 * sp.a);
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) sG[i] = 0ull;
+  for (int i = threadIdx.x; i < R * R; i += blockDim.x) sG[i] = 0ull;
   __syncthreads();
   const unsigned long long spc = *special;
   const int lane = threadIdx.x & 31;
@@ -265,9 +265,9 @@ __global__ void __launch_bounds__(256) thin_gram_wide_kernel(const unsigned long
       const unsigned peers = __match_any_sync(0xFFFFFFFFu, tag);
       if (valid) {
         if (cp == 1u) {
-          if (lane == __ffs(peers) - 1) atomicAdd(&sG[r1 * 16 + r1], (unsigned long long)__popc(peers));
+          if (lane == __ffs(peers) - 1) atomicAdd(&sG[r1 * R + r1], (unsigned long long)__popc(peers));
         } else {
-          atomicAdd(&sG[r1 * 16 + r1], (unsigned long long)cp * (unsigned long long)cp);
+          atomicAdd(&sG[r1 * R + r1], (unsigned long long)cp * (unsigned long long)cp);
         }
       }
     }
@@ -283,15 +283,14 @@ __global__ void __launch_bounds__(256) thin_gram_wide_kernel(const unsigned long
       const uint32_t cq = table_find(hkeys, hcounts, (uint64_t)cap - 1, spc, q);
       if (cq) {
         const unsigned long long v = (unsigned long long)cp * (unsigned long long)cq;
-        atomicAdd(&sG[r1 * 16 + r2], v);
-        atomicAdd(&sG[r2 * 16 + r1], v);
+        atomicAdd(&sG[r1 * R + r2], v);
+        atomicAdd(&sG[r2 * R + r1], v);
       }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < R * R; i += blockDim.x) {
-    const int r1 = i / R, r2 = i - r1 * R;
-    const unsigned long long v = sG[r1 * 16 + r2];
+    const unsigned long long v = sG[i];
     if (v) atomicAdd(G + i, (double)v);  // integer-valued partial sums: exact and order independent below 2^53
   }
 }
@@ -373,14 +372,15 @@ extern "C" int spb_thin_gram_wide_filtered(const uint64_t* d_hkeys, const uint32
   int rc = check_table(d_hkeys, d_hcounts, cap, "spb_thin_gram_wide");
   if (rc) return rc;
   SPB_REQUIRE(d_special && d_G && h_idx_a, "spb_thin_gram_wide: NULL buffer");
-  SPB_REQUIRE(n_taxa >= 2 && n_taxa <= SPB_MAX_TAXA && a >= 1 && a <= 2, "spb_thin_gram_wide: the thin side must have 1 or 2 of <= 64 taxa");
+  SPB_REQUIRE(n_taxa >= 2 && n_taxa <= SPB_MAX_TAXA && a >= 1 && a <= 3, "spb_thin_gram_wide: the thin side must have 1, 2 or 3 of <= 64 taxa");
   ThinSplit sp;
   sp.a = a;
   for (int t = 0; t < a; ++t) {
-    SPB_REQUIRE(h_idx_a[t] < n_taxa && (t == 0 || h_idx_a[t] != h_idx_a[0]), "spb_thin_gram_wide: bad taxon positions");
+    SPB_REQUIRE(h_idx_a[t] < n_taxa && (t == 0 || h_idx_a[t] != h_idx_a[0]) && (t < 2 || h_idx_a[2] != h_idx_a[1]),
+                "spb_thin_gram_wide: bad taxon positions");
     sp.shift[t] = 2 * (n_taxa - 1 - h_idx_a[t]);
   }
-  if (a == 1) sp.shift[1] = 0;
+  for (int t = a; t < 3; ++t) sp.shift[t] = 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int R = 1 << (2 * a);
   SPB_CUDA(cudaMemsetAsync(d_G, 0, (size_t)R * R * sizeof(double), st));

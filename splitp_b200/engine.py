@@ -1218,19 +1218,20 @@ def merge_wide_tables(n, keys, counts, usable, taxa=None):
 
 
 def thin_split_scores(table, thin_sides, filtered=True):
-    """Scores of the splits {side} | {all other taxa} for sides of 1 or 2 taxon positions: exact Gram of the REDUCED
-    flattening (4^a rows, one column per distinct pattern of the other taxa) from hash lookups, then the Jacobi
+    """Scores of the splits {side} | {all other taxa} for sides of 1, 2 or 3 taxon positions: exact Gram of the REDUCED
+    flattening (4^a rows, one column per distinct pattern of the other taxa) from hash lookups, then the small-matrix
     scorer.  Sides of one taxon give a 4-row matrix, hence score 0 like the reference.  filtered: a per-split column
     bitmap lets patterns without a partner in their column skip the lookups (same result)."""
     out = _empty(len(thin_sides), torch.float64)
-    G = _empty((len(thin_sides), 16, 16), torch.float64)
+    cells = 4 ** (2 * max([len(list(s)) for s in thin_sides] + [2]))
+    G = _empty((len(thin_sides), cells), torch.float64)
     words = int(lib.spb_thin_filter_words(table.cap)) if filtered else 0
     filt = _empty(2 * words, torch.int32) if filtered else None
-    by_a = {1: [], 2: []}
+    by_a = {1: [], 2: [], 3: []}
     for s, side in enumerate(thin_sides):
         side = list(side)
-        if len(side) not in (1, 2):
-            raise NotImplementedError("thin_split_scores: the thin side must have 1 or 2 taxa")
+        if len(side) not in (1, 2, 3):
+            raise NotImplementedError("thin_split_scores: the thin side must have 1, 2 or 3 taxa")
         call("spb_thin_gram_wide_filtered", _p(table.hkeys), _p(table.hcounts), table.cap, _p(table.special), table.n, bytes(side),
              len(side), _p(filt), words, _p(G[s]), _st())
         by_a[len(side)].append(s)
@@ -1240,6 +1241,6 @@ def thin_split_scores(table, thin_sides, filtered=True):
         idx = torch.tensor(members, dtype=torch.int64, device=out.device)
         R = 4 ** a
         # the Gram of entry s occupies the leading R*R doubles of G[s] with row stride R: repack to [R, R] matrices
-        Gs = G[idx].reshape(len(members), 256)[:, :R * R].reshape(len(members), R, R).contiguous()
+        Gs = G[idx][:, :R * R].reshape(len(members), R, R).contiguous()
         out.index_copy_(0, idx, score_gram(Gs, R))
     return out
