@@ -326,7 +326,10 @@ def table_from_mapping(mapping):
         return mapping
     pats = list(mapping.keys())
     raw = list(mapping.values())
-    vals = np.fromiter((float(v) for v in raw), dtype=np.float64, count=len(pats))
+    try:  # ints / floats / numpy scalars convert at C speed (this validation runs on EVERY drop-in call: README loop, config 1)
+        vals = np.fromiter(raw, dtype=np.float64, count=len(pats))
+    except (TypeError, ValueError):
+        vals = np.fromiter((float(v) for v in raw), dtype=np.float64, count=len(pats))
     integral = bool(raw) and all(type(v) is int and abs(v) < (1 << 53) for v in raw)
     joined = "".join(pats)
     hit = _TABLE_CACHE.get(id(mapping))
