@@ -6,7 +6,11 @@
     {1, 3, 64}, bit for bit against an exact integer product;
   * CountScorer.score_many (scatter -> int32 Gram -> correction strip -> block Krylov) on config-2 6|6 splits
     against LAPACK on the reduced flattening;
-  * reducible / many-component Gram matrices through the block-Krylov solver (k > 128) against LAPACK.
+  * reducible / many-component Gram matrices through the block-Krylov solver (k > 128) against LAPACK;
+  * the seven G0 Q product kernels (column-owning FMA kernel, fp64 tensor-core kernels) against a torch fp64 product, bit-exact on
+    integer-valued vectors;
+  * the correction strip built by a join of the pattern table with the high list against the column scans of S0, bit for bit;
+  * the warp-per-matrix scorer of small Gram matrices (k <= 64) and the Jacobi kernel against LAPACK singular values.
 
 Tolerances: integer work bit-exact; scores rel <= max(1e-9, 64 eps / score^2) (tests/test_gpu_parity.py header).
 """
