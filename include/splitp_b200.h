@@ -269,6 +269,12 @@ int64_t spb_score_gram_large_ws(int64_t k, int64_t batch);
 int spb_score_last_unconverged(void);
 int spb_score_gram_large(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores,
                          double* d_info, double* d_ws, void* stream);
+/* The same with a cycle budget max_cycles in 1..40 (40 = spb_score_gram_large).  Every matrix of a batch stays in the
+ * cycle until the last one is accepted and the cycles grow (2, 2, 4, 4, 12, ... Krylov blocks), so a caller with a large
+ * batch runs the first cycles with a small budget and calls again with the few matrices whose d_info reports
+ * converged = 0. */
+int spb_score_gram_large_n(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores, double* d_info,
+                           double* d_ws, int max_cycles, void* stream);
 
 /* ---- 32-bit integer form of the exact Gram (halves the HBM traffic of the eigen stage for large matrices) ----
  * spb_gram_u8_batch_i32: G0 = S0 S0^T as int32 [nb][rows_pad][rows_pad] straight from the tensor-core accumulators
@@ -298,6 +304,9 @@ int spb_gram_hi_strip_batch_table(const uint64_t* d_keys, const uint32_t* d_coun
 int spb_score_gram_large_i32(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Cs, int64_t cs_rows,
                              const int32_t* d_pos, const int32_t* d_hr, const int32_t* d_hm, double* d_scores, double* d_info,
                              double* d_ws, void* stream);
+int spb_score_gram_large_i32_n(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Cs, int64_t cs_rows,
+                               const int32_t* d_pos, const int32_t* d_hr, const int32_t* d_hm, double* d_scores, double* d_info,
+                               double* d_ws, int max_cycles, void* stream);
 /* Diagnostic: d_AQ = G0 d_Q for `batch` int32 Gram matrices through ONE of the product kernels of the eigen-solver
  * (variant 0: column-owning FMA kernel; 1..6: fp64 tensor-core (DMMA) kernels), launched exactly as the solver launches
  * them.  d_Q, d_AQ: [batch][8][k] doubles; d_Qt: spb_symv_i32_ws(k, batch) doubles of scratch.  For tests and

@@ -126,11 +126,13 @@ PROTOTYPES = {
     "spb_score_gram_large_ws": (_l, [_l, _l]),
     "spb_score_last_unconverged": (_i, []),
     "spb_score_gram_large": (_i, [_p, _l, _l, _l, _p, _p, _p, _p]),
+    "spb_score_gram_large_n": (_i, [_p, _l, _l, _l, _p, _p, _p, _i, _p]),
     "spb_gram_u8_batch_i32": (_i, [_p, _l, _i, _l, _l, _p, _l, _p]),
     "spb_gram_hi_strip_batch": (_i, [_p, _l, _i, _l, _l, _i, _p, _p, _p, _l, _p, _l, _p, _p, _p, _p]),
     "spb_gram_hi_strip_table_ws": (_l, [_i, _l, _l]),
     "spb_gram_hi_strip_batch_table": (_i, [_p, _p, _l, _sp, _i, _l, _l, _p, _p, _p, _l, _p, _l, _p, _p, _p, _p, _p]),
     "spb_score_gram_large_i32": (_i, [_p, _l, _l, _l, _p, _l, _p, _p, _p, _p, _p, _p, _p]),
+    "spb_score_gram_large_i32_n": (_i, [_p, _l, _l, _l, _p, _l, _p, _p, _p, _p, _p, _p, _i, _p]),
     "spb_symv_i32_ws": (_l, [_l, _l]),
     "spb_symv_i32": (_i, [_p, _l, _l, _l, _p, _p, _p, _i, _p]),
     "spb_mi_partials": (_l, []),

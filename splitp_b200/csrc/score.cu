@@ -1367,7 +1367,7 @@ static int krylov_cycle(const GramView& gv, int k, int batch, int nb, bool first
 }
 
 static int score_gram_large(const GramView& gv, int64_t k64, int64_t batch64, double* d_scores, double* d_info, double* d_ws,
-                            void* stream) {
+                            void* stream, int max_cycles = 40) {
   SPB_REQUIRE((gv.Gf || gv.Gi) && d_scores && d_ws && k64 > kJacobiMaxK && gv.ld >= k64 && batch64 >= 1 && k64 < (1 << 24) &&
                   batch64 <= 65535,
               "spb_score_gram_large: need k > %d and a workspace", kJacobiMaxK);
@@ -1380,7 +1380,8 @@ static int score_gram_large(const GramView& gv, int64_t k64, int64_t batch64, do
   static thread_local std::vector<double> h_flag;
   h_info.resize((size_t)batch * kInfo);
   h_flag.assign((size_t)batch, 0.0);
-  const int kMaxCycles = 40;
+  SPB_REQUIRE(max_cycles >= 1 && max_cycles <= 40, "spb_score_gram_large: the cycle budget must be 1..40 (got %d)", max_cycles);
+  const int kMaxCycles = max_cycles;
   int rc;
   bool done = false;
   for (int cycle = 0; cycle < kMaxCycles && !done; ++cycle) {
@@ -1404,7 +1405,7 @@ static int score_gram_large(const GramView& gv, int64_t k64, int64_t batch64, do
   SPB_CUDA(cudaMemcpy2DAsync(w.info + 8, kInfo * sizeof(double), h_flag.data(), sizeof(double), sizeof(double), (size_t)batch,
                              cudaMemcpyHostToDevice, st));
   g_last_unconverged = bad;
-  if (bad) set_error("spb_score_gram_large: %d of %d matrices did not converge within %d cycles", bad, batch, kMaxCycles);
+  if (bad && kMaxCycles == 40) set_error("spb_score_gram_large: %d of %d matrices did not converge within %d cycles", bad, batch, kMaxCycles);
   if (d_info) SPB_CUDA(cudaMemcpyAsync(d_info, w.info, (size_t)batch * kInfo * sizeof(double), cudaMemcpyDeviceToDevice, st));
   return SPB_OK;
 }
@@ -1415,6 +1416,24 @@ extern "C" int spb_score_gram_large(const double* d_G, int64_t k, int64_t ld, in
                                     double* d_ws, void* stream) {
   GramView gv{d_G, nullptr, ld, nullptr, 0, nullptr, nullptr, nullptr};
   return score_gram_large(gv, k, batch, d_scores, d_info, d_ws, stream);
+}
+
+// The same solvers with a cycle budget: the whole batch stays in the cycle until its last matrix is accepted, and the cycles grow
+// (2, 2, 4, 4, 12, ... blocks), so a caller with a large batch runs the first cycles with a small budget, then calls again with the
+// few matrices that report converged = 0 (engine.score_gram / CountScorer._score_i32).
+extern "C" int spb_score_gram_large_n(const double* d_G, int64_t k, int64_t ld, int64_t batch, double* d_scores, double* d_info,
+                                      double* d_ws, int max_cycles, void* stream) {
+  GramView gv{d_G, nullptr, ld, nullptr, 0, nullptr, nullptr, nullptr};
+  return score_gram_large(gv, k, batch, d_scores, d_info, d_ws, stream, max_cycles);
+}
+
+extern "C" int spb_score_gram_large_i32_n(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Cs, int64_t cs_rows,
+                                          const int32_t* d_pos, const int32_t* d_hr, const int32_t* d_hm, double* d_scores,
+                                          double* d_info, double* d_ws, int max_cycles, void* stream) {
+  SPB_REQUIRE(cs_rows >= 0 && cs_rows <= 65535 && (cs_rows == 0 || (d_Cs && d_pos && d_hr && d_hm)),
+              "spb_score_gram_large_i32: bad correction strip");
+  GramView gv{nullptr, d_Gi, ld, d_Cs, cs_rows, d_pos, d_hr, d_hm};
+  return score_gram_large(gv, k, batch, d_scores, d_info, d_ws, stream, max_cycles);
 }
 
 extern "C" int spb_score_gram_large_i32(const int32_t* d_Gi, int64_t k, int64_t ld, int64_t batch, const double* d_Cs,

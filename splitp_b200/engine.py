@@ -473,11 +473,37 @@ def score_gram(G, k=None, want_info=False):
         info = _empty((batch, k), torch.float64) if want_info else None
         call("spb_score_gram_small", _p(G), k, ld, batch, _p(scores), _p(info), _st())
     else:
-        ws = _krylov_ws(k, batch)
-        info = _empty((batch, SCORE_INFO), torch.float64) if want_info else None
-        call("spb_score_gram_large", _p(G), k, ld, batch, _p(scores), _p(info), _p(ws), _st())
+        info = _solve_large(batch, scores,
+                            lambda sel, sc, inf, ws, budget: call("spb_score_gram_large_n", _p(G if sel is None else G.index_select(0, sel)),
+                                                                  k, ld, int(sc.shape[0]), _p(sc), _p(inf), _p(ws), budget, _st()), k)
         _warn_unconverged()
     return (scores, info) if want_info else scores
+
+
+FIRST_CYCLES = 2   # cycles the WHOLE batch runs through (two blocks each); matrices still open after them are solved as their own batch
+MIN_COMPACT = 16   # batches below this are not worth a second call
+
+
+def _solve_large(batch, scores, run, k):
+    """Block-Krylov scores of a batch with straggler compaction.  The solver keeps every matrix of a batch in the cycle until the
+    last one is accepted, and its cycles grow (2, 2, 4, 4, 12, ... blocks of 8 vectors = that many G Q products per matrix): with
+    up to 512 matrices per batch one slow matrix would cost hundreds of products.  So the whole batch gets FIRST_CYCLES cycles;
+    whatever reports converged = 0 after them is gathered into a batch of its own and solved with the full budget.
+    run(sel, scores, info, ws, budget): one solver call on the matrices `sel` (None = all).  Returns the info array [batch, 10]."""
+    info = _empty((batch, SCORE_INFO), torch.float64)
+    if batch < MIN_COMPACT:
+        run(None, scores, info, _krylov_ws(k, batch), 40)
+        return info
+    run(None, scores, info, _krylov_ws(k, batch), FIRST_CYCLES)
+    if int(lib.spb_score_last_unconverged()) == 0:
+        return info
+    sel = torch.nonzero(info[:, 8] == 0.0).flatten()
+    m = int(sel.shape[0])
+    sc2, inf2 = _empty(m, torch.float64), _empty((m, SCORE_INFO), torch.float64)
+    run(sel, sc2, inf2, _krylov_ws(k, m), 40)
+    scores.index_copy_(0, sel, sc2)
+    info.index_copy_(0, sel, inf2)
+    return info
 
 
 def _warn_unconverged():
@@ -668,10 +694,16 @@ class CountScorer:
         rows_pad = int(buf["G"].shape[1])
         cs_rows = int(buf["Cs"].shape[1])
         scores = _empty(batch, torch.float64)
-        info = _empty((batch, SCORE_INFO), torch.float64) if want_info else None
-        ws = _krylov_ws(k, batch)
-        call("spb_score_gram_large_i32", _p(buf["G"]), k, rows_pad, batch, _p(buf["Cs"]), cs_rows, _p(buf["pos"]), _p(buf["hr"]),
-             _p(buf["hm"]), _p(scores), _p(info), _p(ws), _st())
+
+        def run(sel, sc, inf, ws, budget):
+            if sel is None:
+                G, Cs, pos, hr, hm = (buf[key] for key in ("G", "Cs", "pos", "hr", "hm"))
+            else:  # the stragglers as a batch of their own (copies of their 32-bit Gram and strip: a few matrices)
+                G, Cs, pos, hr, hm = (buf[key][:batch].index_select(0, sel) for key in ("G", "Cs", "pos", "hr", "hm"))
+            call("spb_score_gram_large_i32_n", _p(G), k, rows_pad, int(sc.shape[0]), _p(Cs), cs_rows, _p(pos), _p(hr), _p(hm), _p(sc),
+                 _p(inf), _p(ws), budget, _st())
+
+        info = _solve_large(batch, scores, run, k)
         _warn_unconverged()
         return (scores, info) if want_info else scores
 

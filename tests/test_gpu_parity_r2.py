@@ -418,3 +418,41 @@ def test_score_gram_small_warp_path_against_lapack(eng, k):
     for f, s, w in zip(fast, slow.cpu().numpy(), want):
         assert_score(f, w)
         assert_score(s, w)
+
+
+# ---------------------------------------------------------------------------------------------
+# straggler compaction of the block-Krylov solver
+# ---------------------------------------------------------------------------------------------
+def test_solver_compacts_stragglers_in_a_large_batch(sp, eng, oracle):
+    """A batch of 24 Gram matrices (k = 256) in which a few need more than two Krylov cycles (flat spectra, a reducible
+    matrix) while the rest are accepted in the first: engine.score_gram gives every matrix the first two cycles and re-solves
+    only the open ones as a batch of their own.  Every score against LAPACK; the easy matrices report <= 2 cycles."""
+    rng = np.random.default_rng(21)
+    k, cols = 256, 300
+    mats, hard = [], []
+    for t in range(24):
+        if t in (3, 11, 17):      # nearly flat spectrum: slow convergence of the top-4 subspace
+            F = rng.random((k, cols)) * 0.02 + np.eye(k, cols) * (1.0 + 0.001 * rng.random(k))[:, None]
+            hard.append(t)
+        elif t == 20:             # reducible: isolated heavy rows next to a dense component
+            F = np.zeros((k, cols))
+            F[:8, :8] = 20.0 * np.eye(8)
+            F[8:, 8:] = 1.0 + 0.01 * rng.random((k - 8, cols - 8))
+            hard.append(t)
+        else:                     # rank-4 structure plus noise: accepted after one cycle
+            F = rng.integers(1, 200, size=(k, 4)).astype(np.float64) @ rng.integers(1, 9, size=(4, cols)).astype(np.float64)
+            F = F + rng.poisson(2.0, size=(k, cols))
+        mats.append(F)
+    A = torch.from_numpy(np.stack(mats)).cuda()
+    G = eng.gram_f64(A)
+    scores, info = eng.score_gram(G, want_info=True)
+    scores, info = scores.cpu().numpy(), info.cpu().numpy()
+    assert (info[:, 8] == 1.0).all()                       # everything converged in the end
+    easy = [t for t in range(24) if t not in hard]
+    assert (info[easy, 4] <= eng.FIRST_CYCLES).all()
+    for t in range(24):
+        assert_score(scores[t], oracle.split_score(mats[t]))
+    # the same matrices one by one (small batches take the solver's full budget directly): identical scores
+    for t in (0, 3, 20):
+        one = float(eng.score_gram(G[t:t + 1])[0].item())
+        assert_score(one, scores[t])
