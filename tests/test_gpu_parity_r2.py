@@ -450,6 +450,7 @@ def test_solver_compacts_stragglers_in_a_large_batch(sp, eng, oracle):
     assert (info[:, 8] == 1.0).all()                       # everything converged in the end
     easy = [t for t in range(24) if t not in hard]
     assert (info[easy, 4] <= eng.FIRST_CYCLES).all()
+    assert (info[hard, 4] > eng.FIRST_CYCLES).any()      # the second, compacted call really happened
     for t in range(24):
         assert_score(scores[t], oracle.split_score(mats[t]))
     # the same matrices one by one (small batches take the solver's full budget directly): identical scores
