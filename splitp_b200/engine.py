@@ -65,11 +65,18 @@ class PhaseTimer:
     """Per-phase device time from CUDA events on the launch stream (bench.py `phase_ms`).  Inactive unless an instance
     is handed to the scorers; recording an event pair costs a few microseconds of host time."""
 
-    def __init__(self):
+    def __init__(self, only=None):
+        """only: names of the spans to record (None = all).  A step of the 12-taxon workload has ~130 spans; recording all of
+        them costs 0.8 ms of a 47 ms step, so a benchmark times its steps with the ONE span it needs and takes the full
+        breakdown from separate passes."""
         self.events, self.extra = [], []
+        self.only = None if only is None else frozenset(only)
 
     @contextlib.contextmanager
     def span(self, name, units=1):
+        if self.only is not None and name not in self.only:
+            yield
+            return
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         try:
