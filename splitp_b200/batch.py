@@ -159,6 +159,8 @@ class SplitScorer:
         elif method != Method.flattening:
             raise NotImplementedError("score_splits: Method.flattening or Method.subflattening")
 
+    REFIT_DAMPING = 0.5
+
     def _cut(self):
         """(Re)partitions the class-ordered split list from the current per-class costs."""
         from . import distributed as spd
@@ -192,7 +194,12 @@ class SplitScorer:
         middle = sorted(ratios)[len(ratios) // 2]
         if any(not 0.7 * middle <= r <= 1.3 * middle for r in ratios):
             return
-        self._per, self._fixed = spd.refit_costs(self._per, self._fixed, self._held, times)
+        per, fixed = spd.refit_costs(self._per, self._fixed, self._held, times)
+        # half a step towards the fitted costs: the measured call is not quite the steady state (2 GPUs: the rank holding 405 6|6
+        # matrices measured 25.3 ms in its second call but runs 24.2 ms later; the full step overshot, 23.3 | 24.9 ms)
+        d = self.REFIT_DAMPING
+        self._per = {a: self._per[a] + d * (per[a] - self._per[a]) for a in per}
+        self._fixed = {a: self._fixed[a] + d * (fixed[a] - self._fixed[a]) for a in fixed}
         self._cut()
 
     def device_scores(self, alignment, gram_hook=None):
