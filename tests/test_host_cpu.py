@@ -520,3 +520,35 @@ def test_refit_costs_recovers_class_costs_from_rank_times():
         if world == 8:
             assert max(after) <= 1.03 * (sum(after) / world), after
             assert abs(fitted[6] / truth[6] - 1) < 0.03 and abs(fitted[5] / truth[5] - 1) < 0.05
+
+
+def test_split_scorer_partition_covers_every_split_once():
+    """batch.SplitScorer(world = N): the ranks' shares of the flattening scores are disjoint, cover all 2,035 splits of 12 taxa,
+    are identical however often they are re-cut from the same costs, and a re-fit from made-up rank times keeps that property
+    (host logic only: no device is touched before the first scoring call)."""
+    import bench_inputs as BI
+    from splitp_b200 import batch
+    from splitp_b200 import distributed as spd
+    from splitp_b200.enums import Method
+    idx = BI.all_splits_idx(12)
+    for world in (2, 5, 8):
+        scorers = [batch.SplitScorer(idx, None, Method.flattening, r, world, sites="replicated") for r in range(world)]
+        seen = sorted(p for s in scorers for p in s.positions)
+        assert seen == list(range(len(idx)))
+        assert all(len(s.idx_mine) == len(s.positions) for s in scorers)
+        assert all(s._held == scorers[0]._held for s in scorers)            # every rank computes the same cut
+        assert sum(sum(h.values()) for h in scorers[0]._held) == len(idx)
+        # a re-fit with the same (made-up) rank times on every rank: still a partition, still identical on all ranks
+        times = [spd.RANK_BASE_US + sum(c * scorers[0]._per[a] * (1.2 if a == 6 else 0.9) + scorers[0]._fixed[a] for a, c in h.items())
+                 for h in scorers[0]._held]
+        for s in scorers:
+            per, fixed = spd.refit_costs(s._per, s._fixed, s._held, times)
+            s._per = {a: s._per[a] + s.REFIT_DAMPING * (per[a] - s._per[a]) for a in per}
+            s._fixed = {a: s._fixed[a] + s.REFIT_DAMPING * (fixed[a] - s._fixed[a]) for a in fixed}
+            s._cut()
+        assert sorted(p for s in scorers for p in s.positions) == list(range(len(idx)))
+        assert all(s._held == scorers[0]._held for s in scorers)
+    assert batch.replicate_sites(12, 1_000_000, 8) and not batch.replicate_sites(12, 1_000_000, 1)
+    assert not batch.replicate_sites(20, 100_000_000, 8)
+    with pytest.raises(ValueError):
+        batch.SplitScorer(idx, None, Method.flattening, 0, 2, sites="everything")
