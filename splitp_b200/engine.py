@@ -791,7 +791,7 @@ class CountScorer:
 
     def score_many(self, splits_idx, reduced=False, max_batch=512, max_batch_bytes=None, big_hook=None):
         """Scores of many splits.  Dense count flattenings of equal shape are batched: their Gram matrices are
-        built SPB_MAX_BATCH at a time into G[b] and ONE batched eigen-solver call scores up to `max_batch` of them
+        built up to 64 at a time into G[b] and ONE batched eigen-solver call scores up to `max_batch` of them
         (the Jacobi / Krylov kernels are latency-bound per matrix, so batching is what keeps all SMs busy)."""
         out = _empty(len(splits_idx), torch.float64)
         if reduced:

@@ -608,7 +608,7 @@ def test_int32_gram_with_correction_strip(sp, eng):
         G, k = scorer.gram(ia, ib)
         assert k == 4096
         assert torch.equal(buf["G"][b].to(torch.float64) + Cfull, G)
-    # (2) batched scores, int32 route against the fp64 route (20 splits = one batch of 16 and one of 4)
+    # (2) batched scores, int32 route against the fp64 route (20 splits in one batch)
     got = scorer.score_many(idx).cpu().numpy()
     scorer.int32_gram = False
     ref = scorer.score_many(idx).cpu().numpy()
